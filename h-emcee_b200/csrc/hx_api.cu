@@ -1,0 +1,583 @@
+// hx_api.cu — C-ABI of libhx.so (include/hx.h): argument validation, private workspace, kernel
+// dispatch.  No torch types, no exceptions across the boundary.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <new>
+
+#include "../../include/hx.h"
+#include "hx_common.cuh"
+#include "hx_rng.cuh"
+#include "hx_prep.cuh"
+#include "hx_launch.cuh"
+
+using namespace hx;
+
+// ---- error plumbing ---------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+int hx_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define fail hx_fail
+
+// ---- ctx / workspace ---------------------------------------------------------------------------------
+enum Slot { WS_C = 0, WS_M, WS_MEAN, WS_PART, WS_G, WS_S, WS_Q, WS_LA, WS_LP, WS_IDX, WS_GRAMP, WS_NSLOT };
+
+struct hx_ctx {
+  int device;
+  void* buf[WS_NSLOT];
+  size_t cap[WS_NSLOT];
+  int sm_count;
+};
+
+static int ws_get(hx_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (bytes == 0) bytes = 16;
+  if (ctx->cap[slot] < bytes) {
+    if (ctx->buf[slot]) HX_CUDA(cudaFree(ctx->buf[slot]));
+    ctx->buf[slot] = nullptr;
+    ctx->cap[slot] = 0;
+    size_t want = bytes + bytes / 4;
+    HX_CUDA(cudaMalloc(&ctx->buf[slot], want));
+    ctx->cap[slot] = want;
+  }
+  *out = ctx->buf[slot];
+  return 0;
+}
+
+extern "C" HX_API int hx_abi_version(void) { return HX_ABI_VERSION; }
+extern "C" HX_API const char* hx_last_error(void) { return g_err; }
+
+extern "C" HX_API int hx_ctx_create(hx_ctx** out, int device) {
+  if (!out) return fail(HX_E_NULL, "hx_ctx_create: out is NULL");
+  int ndev = 0;
+  HX_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(HX_E_SHAPE, "hx_ctx_create: device %d out of range (%d)", device, ndev);
+  HX_CUDA(cudaSetDevice(device));
+  hx_ctx* c = new (std::nothrow) hx_ctx();
+  if (!c) return fail(HX_E_NULL, "hx_ctx_create: out of host memory");
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  cudaDeviceProp prop;
+  HX_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    delete c;
+    return fail(HX_E_UNSUPPORTED, "libhx is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+  }
+  *out = c;
+  return 0;
+}
+
+extern "C" HX_API int hx_ctx_destroy(hx_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < WS_NSLOT; ++i)
+    if (ctx->buf[i]) cudaFree(ctx->buf[i]);
+  delete ctx;
+  return 0;
+}
+
+extern "C" HX_API size_t hx_ctx_workspace_bytes(const hx_ctx* ctx) {
+  size_t s = 0;
+  if (ctx) for (int i = 0; i < WS_NSLOT; ++i) s += ctx->cap[i];
+  return s;
+}
+
+// ---- helpers ---------------------------------------------------------------------------------------
+static inline int grid_for(uint64_t n, int block, int cap = 148 * 16) {
+  uint64_t g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > (uint64_t)cap) g = cap;
+  return (int)g;
+}
+static inline int round4(int d) { return (d + 3) & ~3; }
+static inline int check_dtype_impl(int dtype, int impl, const char* who) {
+  if (dtype != HX_F32 && dtype != HX_F64) return fail(HX_E_DTYPE, "%s: unknown dtype %d", who, dtype);
+  if (impl != HX_RNG_PARTITIONABLE && impl != HX_RNG_LEGACY) return fail(HX_E_DTYPE, "%s: unknown rng impl %d", who, impl);
+  return 0;
+}
+
+template <typename T>
+static int make_target(const hx_target* t, TargetDev<T>* o, const char* who) {
+  if (!t) return fail(HX_E_NULL, "%s: target is NULL", who);
+  if (t->dim < 1) return fail(HX_E_TARGET, "%s: target dim %d < 1", who, t->dim);
+  if (t->kind < HX_TARGET_GAUSS_ISO || t->kind > HX_TARGET_FUNNEL) return fail(HX_E_TARGET, "%s: unknown target kind %d", who, t->kind);
+  if (t->kind == HX_TARGET_GAUSS_FULL) {
+    if (!t->precision) return fail(HX_E_TARGET, "%s: GAUSS_FULL needs a precision matrix", who);
+    if (t->ld < t->dim || (t->ld & 3)) return fail(HX_E_TARGET, "%s: precision ld %d must be a multiple of 4 and >= dim %d", who, t->ld, t->dim);
+    if (((uintptr_t)t->precision) & 15) return fail(HX_E_ALIGN, "%s: precision must be 16-byte aligned", who);
+  }
+  if (t->kind == HX_TARGET_ROSENBROCK && t->dim < 2) return fail(HX_E_TARGET, "%s: rosenbrock needs dim >= 2", who);
+  if (t->kind == HX_TARGET_FUNNEL && !(t->a > 0)) return fail(HX_E_TARGET, "%s: funnel sigma must be > 0", who);
+  o->kind = t->kind; o->dim = t->dim; o->ld = t->ld; o->has_lower0 = t->has_lower0;
+  o->mean = (const T*)t->mean; o->prec = (const T*)t->precision;
+  o->a = (T)t->a; o->b = (T)t->b; o->lower0 = (T)t->lower0;
+  return 0;
+}
+
+// ---- (1) RNG entry points ----------------------------------------------------------------------------
+extern "C" HX_API int hx_split(const uint32_t key[2], int impl, int64_t num, uint32_t* out_dev, void* stream) {
+  if (!key || !out_dev) return fail(HX_E_NULL, "hx_split: NULL argument");
+  if (num < 0) return fail(HX_E_SHAPE, "hx_split: num %lld < 0", (long long)num);
+  if (int e = check_dtype_impl(HX_F32, impl, "hx_split")) return e;
+  if (impl == HX_RNG_LEGACY && (uint64_t)num * 2 > 0xFFFFFFFFull) return fail(HX_E_SHAPE, "hx_split: legacy split supports 2*num < 2^32");
+  if (num == 0) return 0;
+  Key k{key[0], key[1]};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (impl == HX_RNG_LEGACY) k_split<true><<<grid_for(num, 256), 256, 0, s>>>(k, (uint64_t)num, out_dev);
+  else k_split<false><<<grid_for(num, 256), 256, 0, s>>>(k, (uint64_t)num, out_dev);
+  HX_LAUNCH_CHECK("k_split");
+  return 0;
+}
+
+extern "C" HX_API int hx_random_bits(const uint32_t key[2], int impl, int bit_width, int64_t count, void* out_dev, void* stream) {
+  if (!key || !out_dev) return fail(HX_E_NULL, "hx_random_bits: NULL argument");
+  if (count < 0) return fail(HX_E_SHAPE, "hx_random_bits: count < 0");
+  if (bit_width != 32 && bit_width != 64) return fail(HX_E_DTYPE, "hx_random_bits: bit_width must be 32 or 64");
+  if (int e = check_dtype_impl(HX_F32, impl, "hx_random_bits")) return e;
+  if (impl == HX_RNG_LEGACY && (uint64_t)count * (bit_width / 32) > 0xFFFFFFFFull)
+    return fail(HX_E_SHAPE, "hx_random_bits: legacy layout supports < 2^32 words");
+  if (count == 0) return 0;
+  Key k{key[0], key[1]};
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = grid_for(count, 256);
+  if (bit_width == 32) {
+    if (impl == HX_RNG_LEGACY) k_bits32<true><<<g, 256, 0, s>>>(k, (uint64_t)count, (uint32_t*)out_dev);
+    else k_bits32<false><<<g, 256, 0, s>>>(k, (uint64_t)count, (uint32_t*)out_dev);
+  } else {
+    if (impl == HX_RNG_LEGACY) k_bits64<true><<<g, 256, 0, s>>>(k, (uint64_t)count, (uint64_t*)out_dev);
+    else k_bits64<false><<<g, 256, 0, s>>>(k, (uint64_t)count, (uint64_t*)out_dev);
+  }
+  HX_LAUNCH_CHECK("k_bits");
+  return 0;
+}
+
+extern "C" HX_API int hx_uniform(const uint32_t key[2], int impl, int dtype, double minval, double maxval, int64_t count,
+                          void* out_dev, void* stream) {
+  if (!key || !out_dev) return fail(HX_E_NULL, "hx_uniform: NULL argument");
+  if (count < 0) return fail(HX_E_SHAPE, "hx_uniform: count < 0");
+  if (int e = check_dtype_impl(dtype, impl, "hx_uniform")) return e;
+  if (count == 0) return 0;
+  Key k{key[0], key[1]};
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = grid_for(count, 256);
+  if (dtype == HX_F32) {
+    const float lo = (float)minval, hi = (float)maxval;
+    const float span = hi - lo;   // rounded in f32 like jax.random.uniform
+    if (impl == HX_RNG_LEGACY) k_uniform<float, true><<<g, 256, 0, s>>>(k, (uint64_t)count, lo, span, (float*)out_dev);
+    else k_uniform<float, false><<<g, 256, 0, s>>>(k, (uint64_t)count, lo, span, (float*)out_dev);
+  } else {
+    const double span = maxval - minval;
+    if (impl == HX_RNG_LEGACY) k_uniform<double, true><<<g, 256, 0, s>>>(k, (uint64_t)count, minval, span, (double*)out_dev);
+    else k_uniform<double, false><<<g, 256, 0, s>>>(k, (uint64_t)count, minval, span, (double*)out_dev);
+  }
+  HX_LAUNCH_CHECK("k_uniform");
+  return 0;
+}
+
+extern "C" HX_API int hx_normal(const uint32_t key[2], int impl, int dtype, int64_t count, void* out_dev, void* stream) {
+  if (!key || !out_dev) return fail(HX_E_NULL, "hx_normal: NULL argument");
+  if (count < 0) return fail(HX_E_SHAPE, "hx_normal: count < 0");
+  if (int e = check_dtype_impl(dtype, impl, "hx_normal")) return e;
+  if (count == 0) return 0;
+  Key k{key[0], key[1]};
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = grid_for(count, 256);
+  if (dtype == HX_F32) {
+    if (impl == HX_RNG_LEGACY) k_normal<float, true><<<g, 256, 0, s>>>(k, (uint64_t)count, (float*)out_dev);
+    else k_normal<float, false><<<g, 256, 0, s>>>(k, (uint64_t)count, (float*)out_dev);
+  } else {
+    if (impl == HX_RNG_LEGACY) k_normal<double, true><<<g, 256, 0, s>>>(k, (uint64_t)count, (double*)out_dev);
+    else k_normal<double, false><<<g, 256, 0, s>>>(k, (uint64_t)count, (double*)out_dev);
+  }
+  HX_LAUNCH_CHECK("k_normal");
+  return 0;
+}
+
+static int shuffle_rounds(int n) {
+  // jax.random._shuffle: ceil(3 * ln(max(1, n)) / ln(2^32 - 1))
+  const double r = std::ceil(3.0 * std::log((double)(n > 1 ? n : 1)) / std::log(4294967295.0));
+  return (int)r;
+}
+
+static int launch_choice2(const uint32_t* keys_dev, Key parent, const uint32_t* parent_ptr, uint64_t nsplit,
+                          int64_t first, int64_t nkeys, int impl, int n, int32_t* out_dev, cudaStream_t s) {
+  const int rounds = shuffle_rounds(n);
+  if (rounds > 2) return fail(HX_E_UNSUPPORTED, "choice: n=%d needs %d shuffle rounds (max 2 supported)", n, rounds);
+  const int g = (int)((nkeys < 148 * 8) ? nkeys : 148 * 8);
+  if (impl == HX_RNG_LEGACY) k_choice2<true><<<g, 256, 0, s>>>(keys_dev, parent, parent_ptr, nsplit, first, nkeys, n, rounds, out_dev);
+  else k_choice2<false><<<g, 256, 0, s>>>(keys_dev, parent, parent_ptr, nsplit, first, nkeys, n, rounds, out_dev);
+  HX_LAUNCH_CHECK("k_choice2");
+  return 0;
+}
+
+extern "C" HX_API int hx_choice2(hx_ctx* ctx, const uint32_t* keys_dev, int64_t nkeys, int impl, int32_t n, int32_t* out_dev,
+                          void* stream) {
+  (void)ctx;
+  if (!keys_dev || !out_dev) return fail(HX_E_NULL, "hx_choice2: NULL argument");
+  if (nkeys < 0 || n < 2) return fail(HX_E_SHAPE, "hx_choice2: need nkeys >= 0 and n >= 2 (got %lld, %d)", (long long)nkeys, n);
+  if (int e = check_dtype_impl(HX_F32, impl, "hx_choice2")) return e;
+  if (nkeys == 0) return 0;
+  return launch_choice2(keys_dev, Key{0, 0}, nullptr, 0, 0, nkeys, impl, n, out_dev, (cudaStream_t)stream);
+}
+
+// ---- prep: mean, C, M ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_pad_copy(const T* __restrict__ src, int n, int d, int ldd, T* __restrict__ dst) {
+  const size_t tot = (size_t)n * ldd;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ldd), c = (int)(i - (size_t)r * ldd);
+    dst[i] = (c < d) ? src[(size_t)r * d + c] : T(0);
+  }
+}
+
+// C = (X2 - mean_0(X2)) / sqrt(n), zero padded to ldd   (moves/hamiltonian/hmc_walk.py:35)
+template <typename T>
+static int center_complement(hx_ctx* ctx, const T* X2, int n, int d, int ldd, T** C_out, cudaStream_t s) {
+  void *pC, *pMean, *pPart;
+  const int nchunks = (n + kColChunk - 1) / kColChunk;
+  if (int e = ws_get(ctx, WS_C, (size_t)n * ldd * sizeof(T), &pC)) return e;
+  if (int e = ws_get(ctx, WS_MEAN, (size_t)d * sizeof(T), &pMean)) return e;
+  if (int e = ws_get(ctx, WS_PART, (size_t)nchunks * d * sizeof(T), &pPart)) return e;
+  dim3 g1((d + 127) / 128, nchunks);
+  k_colsum_partial<T><<<g1, 128, 0, s>>>(X2, n, d, (T*)pPart);
+  HX_LAUNCH_CHECK("k_colsum_partial");
+  k_mean_final<T><<<(d + 127) / 128, 128, 0, s>>>((const T*)pPart, nchunks, n, d, (T*)pMean);
+  HX_LAUNCH_CHECK("k_mean_final");
+  k_center<T><<<grid_for((uint64_t)n * ldd, 256), 256, 0, s>>>(X2, (const T*)pMean, n, d, ldd, (T*)pC);
+  HX_LAUNCH_CHECK("k_center");
+  *C_out = (T*)pC;
+  return 0;
+}
+
+// M = C^T C with a fixed-order split over rows (deterministic)
+template <typename T>
+static int gram_matrix(hx_ctx* ctx, const T* C, int n, int ldd, T** M_out, cudaStream_t s) {
+  void *pM, *pGram;
+  if (int e = ws_get(ctx, WS_M, (size_t)ldd * ldd * sizeof(T), &pM)) return e;
+  const int tiles = (ldd + 63) / 64;
+  int slices = (2 * ctx->sm_count) / (tiles * tiles);
+  const int max_slices = (n + 255) / 256;
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  int rows_per_slice = (n + slices - 1) / slices;
+  rows_per_slice = ((rows_per_slice + 15) / 16) * 16;
+  slices = (n + rows_per_slice - 1) / rows_per_slice;
+  dim3 gg(tiles, tiles, slices);
+  if (slices == 1) {
+    k_gram<T><<<gg, 256, 0, s>>>(C, n, ldd, rows_per_slice, (T*)pM);
+    HX_LAUNCH_CHECK("k_gram");
+  } else {
+    if (int e = ws_get(ctx, WS_GRAMP, (size_t)slices * ldd * ldd * sizeof(T), &pGram)) return e;
+    k_gram<T><<<gg, 256, 0, s>>>(C, n, ldd, rows_per_slice, (T*)pGram);
+    HX_LAUNCH_CHECK("k_gram");
+    k_sum_slices<T><<<grid_for((uint64_t)ldd * ldd, 256), 256, 0, s>>>((const T*)pGram, slices, (size_t)ldd * ldd, (T*)pM);
+    HX_LAUNCH_CHECK("k_sum_slices");
+  }
+  *M_out = (T*)pM;
+  return 0;
+}
+
+template <typename T>
+struct Fuse {       // batch-level fused accept + chain emit
+  const uint32_t* akey_ptr;
+  T* lp1w;
+  int32_t* accepts;
+  T* chain_out;
+  T* chain_lp;
+  int32_t* nonfinite;
+};
+
+static int check_move_args(const char* who, const void* X1, const void* X2, int n, int row0, int rows, int L,
+                           const void* lp1, const void* Q, const void* logacc, const void* lp_out, double eps) {
+  if (!X1 || !X2 || !lp1 || !Q || !logacc || !lp_out) return fail(HX_E_NULL, "%s: NULL state pointer", who);
+  if (n < 2) return fail(HX_E_SHAPE, "%s: group size n=%d must be >= 2", who, n);
+  if (row0 < 0 || rows < 1 || row0 + rows > n) return fail(HX_E_SHAPE, "%s: bad row shard [%d, %d) of %d", who, row0, row0 + rows, n);
+  if (L < 1) return fail(HX_E_SHAPE, "%s: L=%d must be >= 1", who, L);
+  if (!(eps == eps)) return fail(HX_E_SHAPE, "%s: step_size is NaN", who);
+  return 0;
+}
+
+// ---- walk move ---------------------------------------------------------------------------------------------------
+template <typename T>
+static int walk_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1, const T* X2, int n, int row0,
+                       int rows, double eps, Key key, const uint32_t* key_ptr, int L, const T* lp1, T* Q, T* logacc,
+                       T* pproj, T* lp_out, int flags, const Fuse<T>* fuse, cudaStream_t s) {
+  struct { WalkParams<T> P; } W;
+  memset(&W.P, 0, sizeof(W.P));
+  if (int e = make_target<T>(tgt, &W.P.tg, "hx_walk_move")) return e;
+  const int d = tgt->dim, ldd = round4(d);
+  T *C, *M;
+  if (int e = center_complement<T>(ctx, X2, n, d, ldd, &C, s)) return e;
+  if (int e = gram_matrix<T>(ctx, C, n, ldd, &M, s)) return e;
+  void* pG;
+  if (int e = ws_get(ctx, WS_G, (size_t)rows * d * sizeof(T), &pG)) return e;
+  if (!pproj) {
+    void* pS;
+    if (int e = ws_get(ctx, WS_S, (size_t)rows * d * sizeof(T), &pS)) return e;
+    pproj = (T*)pS;
+  }
+  W.P.X1 = X1; W.P.C = C; W.P.M = M; W.P.lp1 = lp1; W.P.Q = Q; W.P.S = pproj; W.P.G = (T*)pG;
+  W.P.logacc = logacc; W.P.lp_out = lp_out; W.P.dK_out = nullptr;
+  W.P.n = n; W.P.d = d; W.P.ldd = ldd; W.P.row0 = row0; W.P.rows = rows; W.P.L = L;
+  W.P.flags = (flags & HX_MOVE_FROZEN_GRAD) ? kFlagFrozen : 0;
+  W.P.eps = (T)eps; W.P.key = key; W.P.key_ptr = key_ptr;
+  if (fuse) {
+    W.P.fuse_accept = 1; W.P.akey_ptr = fuse->akey_ptr; W.P.X1w = const_cast<T*>(X1); W.P.lp1w = fuse->lp1w;
+    W.P.accepts = fuse->accepts; W.P.chain_out = fuse->chain_out; W.P.chain_lp = fuse->chain_lp;
+    W.P.nonfinite = fuse->nonfinite;
+  }
+  W.P.legacy = (impl == HX_RNG_LEGACY) ? 1 : 0;
+  return launch_walk<T>(W.P, ctx->sm_count, s);
+}
+
+extern "C" HX_API int hx_walk_move(hx_ctx* ctx, int dtype, int impl, const hx_target* tgt, const void* X1, const void* X2,
+                            int32_t n, int32_t row0, int32_t rows, double step_size, const uint32_t key[2], int32_t L,
+                            const void* lp1, void* Q, void* logacc, void* pproj, void* lp_out, int flags, void* stream) {
+  if (!ctx || !key) return fail(HX_E_NULL, "hx_walk_move: NULL ctx/key");
+  if (int e = check_dtype_impl(dtype, impl, "hx_walk_move")) return e;
+  if (int e = check_move_args("hx_walk_move", X1, X2, n, row0, rows, L, lp1, Q, logacc, lp_out, step_size)) return e;
+  HX_CUDA(cudaSetDevice(ctx->device));
+  const Key k{key[0], key[1]};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == HX_F32)
+    return walk_move_t<float>(ctx, impl, tgt, (const float*)X1, (const float*)X2, n, row0, rows, step_size, k, nullptr, L,
+                              (const float*)lp1, (float*)Q, (float*)logacc, (float*)pproj, (float*)lp_out, flags, nullptr, s);
+  return walk_move_t<double>(ctx, impl, tgt, (const double*)X1, (const double*)X2, n, row0, rows, step_size, k, nullptr, L,
+                             (const double*)lp1, (double*)Q, (double*)logacc, (double*)pproj, (double*)lp_out, flags, nullptr, s);
+}
+
+// ---- side move ---------------------------------------------------------------------------------------------------
+template <typename T>
+static int side_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1, const T* X2, int n, int row0,
+                       int rows, double eps, Key key, const uint32_t* key_ptr, int L, const T* lp1, T* Q, T* logacc,
+                       T* pproj, T* lp_out, int flags, const Fuse<T>* fuse, cudaStream_t s) {
+  struct { SideParams<T> P; } W;
+  memset(&W.P, 0, sizeof(W.P));
+  if (int e = make_target<T>(tgt, &W.P.tg, "hx_side_move")) return e;
+  const int d = tgt->dim, ldd = round4(d);
+  void *pG, *pIdx;
+  if (int e = ws_get(ctx, WS_G, (size_t)rows * d * sizeof(T), &pG)) return e;
+  if (int e = ws_get(ctx, WS_IDX, (size_t)rows * 2 * sizeof(int32_t), &pIdx)) return e;
+  if (!pproj) {
+    void* pS;
+    if (int e = ws_get(ctx, WS_S, (size_t)rows * d * sizeof(T), &pS)) return e;
+    pproj = (T*)pS;
+  }
+  // keys[0:n] of split(key, n + 2) drive the per-walker choices (hmc_side.py:37-47)
+  if (int e = launch_choice2(nullptr, key, key_ptr, (uint64_t)n + 2, row0, rows, impl, n, (int32_t*)pIdx, s)) return e;
+  W.P.X1 = X1; W.P.X2 = X2; W.P.idx2 = (const int32_t*)pIdx; W.P.lp1 = lp1; W.P.Q = Q; W.P.D = pproj; W.P.G = (T*)pG;
+  W.P.p_io = nullptr; W.P.logacc = logacc; W.P.lp_out = lp_out;
+  W.P.n = n; W.P.d = d; W.P.ldd = ldd; W.P.row0 = row0; W.P.rows = rows; W.P.L = L;
+  W.P.flags = (flags & HX_MOVE_FROZEN_GRAD) ? kFlagFrozen : 0;
+  W.P.eps = (T)eps; W.P.key = key; W.P.key_ptr = key_ptr;
+  if (fuse) {
+    W.P.fuse_accept = 1; W.P.akey_ptr = fuse->akey_ptr; W.P.X1w = const_cast<T*>(X1); W.P.lp1w = fuse->lp1w;
+    W.P.accepts = fuse->accepts; W.P.chain_out = fuse->chain_out; W.P.chain_lp = fuse->chain_lp;
+    W.P.nonfinite = fuse->nonfinite;
+  }
+  W.P.legacy = (impl == HX_RNG_LEGACY) ? 1 : 0;
+  return launch_side<T>(W.P, ctx->sm_count, s);
+}
+
+extern "C" HX_API int hx_side_move(hx_ctx* ctx, int dtype, int impl, const hx_target* tgt, const void* X1, const void* X2,
+                            int32_t n, int32_t row0, int32_t rows, double step_size, const uint32_t key[2], int32_t L,
+                            const void* lp1, void* Q, void* logacc, void* pproj, void* lp_out, int flags, void* stream) {
+  if (!ctx || !key) return fail(HX_E_NULL, "hx_side_move: NULL ctx/key");
+  if (int e = check_dtype_impl(dtype, impl, "hx_side_move")) return e;
+  if (int e = check_move_args("hx_side_move", X1, X2, n, row0, rows, L, lp1, Q, logacc, lp_out, step_size)) return e;
+  if (impl == HX_RNG_LEGACY && (uint64_t)(n + 2) * 2 > 0xFFFFFFFFull) return fail(HX_E_SHAPE, "hx_side_move: n too large for legacy split");
+  HX_CUDA(cudaSetDevice(ctx->device));
+  const Key k{key[0], key[1]};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == HX_F32)
+    return side_move_t<float>(ctx, impl, tgt, (const float*)X1, (const float*)X2, n, row0, rows, step_size, k, nullptr, L,
+                              (const float*)lp1, (float*)Q, (float*)logacc, (float*)pproj, (float*)lp_out, flags, nullptr, s);
+  return side_move_t<double>(ctx, impl, tgt, (const double*)X1, (const double*)X2, n, row0, rows, step_size, k, nullptr, L,
+                             (const double*)lp1, (double*)Q, (double*)logacc, (double*)pproj, (double*)lp_out, flags, nullptr, s);
+}
+
+// ---- integrator-only entries --------------------------------------------------------------------------------------
+template <typename T>
+static int leapfrog_walk_t(hx_ctx* ctx, const hx_target* tgt, T* q, T* S, const T* centered, int n2, int rows,
+                           double eps, int L, T* dK_out, cudaStream_t s) {
+  struct { WalkParams<T> P; } W;
+  memset(&W.P, 0, sizeof(W.P));
+  if (int e = make_target<T>(tgt, &W.P.tg, "hx_leapfrog_walk")) return e;
+  const int d = tgt->dim, ldd = round4(d);
+  void *pC, *pG, *pLa, *pLp;
+  if (int e = ws_get(ctx, WS_C, (size_t)n2 * ldd * sizeof(T), &pC)) return e;
+  k_pad_copy<T><<<grid_for((uint64_t)n2 * ldd, 256), 256, 0, s>>>(centered, n2, d, ldd, (T*)pC);
+  HX_LAUNCH_CHECK("k_pad_copy");
+  T* M;
+  if (int e = gram_matrix<T>(ctx, (const T*)pC, n2, ldd, &M, s)) return e;
+  if (int e = ws_get(ctx, WS_G, (size_t)rows * d * sizeof(T), &pG)) return e;
+  if (int e = ws_get(ctx, WS_LA, (size_t)rows * sizeof(T), &pLa)) return e;
+  if (int e = ws_get(ctx, WS_LP, (size_t)2 * rows * sizeof(T), &pLp)) return e;
+  HX_CUDA(cudaMemsetAsync(pLp, 0, (size_t)2 * rows * sizeof(T), s));
+  W.P.X1 = q; W.P.C = (const T*)pC; W.P.M = M; W.P.lp1 = (const T*)pLp; W.P.Q = q; W.P.S = S; W.P.G = (T*)pG;
+  W.P.logacc = (T*)pLa; W.P.lp_out = (T*)pLp + rows; W.P.dK_out = dK_out;
+  W.P.n = n2; W.P.d = d; W.P.ldd = ldd; W.P.row0 = 0; W.P.rows = rows; W.P.L = L;
+  W.P.flags = kFlagGivenMomentum | kFlagInPlaceQ;
+  W.P.eps = (T)eps;
+  return launch_walk<T>(W.P, ctx->sm_count, s);
+}
+
+extern "C" HX_API int hx_leapfrog_walk(hx_ctx* ctx, int dtype, const hx_target* tgt, void* q, void* S, const void* centered,
+                                int32_t n2, int32_t rows, double step_size, int32_t L, void* dK_out, void* stream) {
+  if (!ctx || !q || !S || !centered) return fail(HX_E_NULL, "hx_leapfrog_walk: NULL argument");
+  if (int e = check_dtype_impl(dtype, HX_RNG_PARTITIONABLE, "hx_leapfrog_walk")) return e;
+  if (n2 < 1 || rows < 1 || L < 1) return fail(HX_E_SHAPE, "hx_leapfrog_walk: need n2, rows, L >= 1");
+  HX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == HX_F32) return leapfrog_walk_t<float>(ctx, tgt, (float*)q, (float*)S, (const float*)centered, n2, rows, step_size, L, (float*)dK_out, s);
+  return leapfrog_walk_t<double>(ctx, tgt, (double*)q, (double*)S, (const double*)centered, n2, rows, step_size, L, (double*)dK_out, s);
+}
+
+template <typename T>
+static int leapfrog_side_t(hx_ctx* ctx, const hx_target* tgt, T* q, T* p, const T* diff, int rows, double eps, int L,
+                           cudaStream_t s) {
+  struct { SideParams<T> P; } W;
+  memset(&W.P, 0, sizeof(W.P));
+  if (int e = make_target<T>(tgt, &W.P.tg, "hx_leapfrog_side")) return e;
+  const int d = tgt->dim, ldd = round4(d);
+  void *pG, *pD, *pLa, *pLp;
+  if (int e = ws_get(ctx, WS_G, (size_t)rows * d * sizeof(T), &pG)) return e;
+  if (int e = ws_get(ctx, WS_S, (size_t)rows * d * sizeof(T), &pD)) return e;
+  if (int e = ws_get(ctx, WS_LA, (size_t)rows * sizeof(T), &pLa)) return e;
+  if (int e = ws_get(ctx, WS_LP, (size_t)2 * rows * sizeof(T), &pLp)) return e;
+  HX_CUDA(cudaMemcpyAsync(pD, diff, (size_t)rows * d * sizeof(T), cudaMemcpyDeviceToDevice, s));
+  HX_CUDA(cudaMemsetAsync(pLp, 0, (size_t)2 * rows * sizeof(T), s));
+  W.P.X1 = q; W.P.X2 = nullptr; W.P.idx2 = nullptr; W.P.lp1 = (const T*)pLp; W.P.Q = q; W.P.D = (T*)pD; W.P.G = (T*)pG;
+  W.P.p_io = p; W.P.logacc = (T*)pLa; W.P.lp_out = (T*)pLp + rows;
+  W.P.n = rows; W.P.d = d; W.P.ldd = ldd; W.P.row0 = 0; W.P.rows = rows; W.P.L = L;
+  W.P.flags = kFlagGivenMomentum | kFlagInPlaceQ;
+  W.P.eps = (T)eps;
+  return launch_side<T>(W.P, ctx->sm_count, s);
+}
+
+extern "C" HX_API int hx_leapfrog_side(hx_ctx* ctx, int dtype, const hx_target* tgt, void* q, void* p, const void* diff,
+                                int32_t rows, double step_size, int32_t L, void* stream) {
+  if (!ctx || !q || !p || !diff) return fail(HX_E_NULL, "hx_leapfrog_side: NULL argument");
+  if (int e = check_dtype_impl(dtype, HX_RNG_PARTITIONABLE, "hx_leapfrog_side")) return e;
+  if (rows < 1 || L < 1) return fail(HX_E_SHAPE, "hx_leapfrog_side: need rows, L >= 1");
+  HX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == HX_F32) return leapfrog_side_t<float>(ctx, tgt, (float*)q, (float*)p, (const float*)diff, rows, step_size, L, s);
+  return leapfrog_side_t<double>(ctx, tgt, (double*)q, (double*)p, (const double*)diff, rows, step_size, L, s);
+}
+
+// ---- log-density ----------------------------------------------------------------------------------------------------
+template <typename T>
+static int log_prob_t(hx_ctx* ctx, const hx_target* tgt, const T* X, int64_t rows, T* lp, T* grad, cudaStream_t s) {
+  struct { LogProbParams<T> P; } W;
+  memset(&W.P, 0, sizeof(W.P));
+  if (int e = make_target<T>(tgt, &W.P.tg, "hx_log_prob")) return e;
+  const int d = tgt->dim, ldd = round4(d);
+  T* G = grad;
+  if (!G) {
+    void* pG;
+    if (int e = ws_get(ctx, WS_G, (size_t)rows * d * sizeof(T), &pG)) return e;
+    G = (T*)pG;
+  }
+  W.P.X = X; W.P.G = G; W.P.lp = lp; W.P.rows = (int)rows; W.P.ldd = ldd; W.P.negate_grad = grad ? 1 : 0;
+  return launch_log_prob<T>(W.P, ctx->sm_count, s);
+}
+
+extern "C" HX_API int hx_log_prob(hx_ctx* ctx, int dtype, const hx_target* tgt, const void* X, int64_t rows, void* lp,
+                           void* grad, void* stream) {
+  if (!ctx || !X || !lp) return fail(HX_E_NULL, "hx_log_prob: NULL argument");
+  if (int e = check_dtype_impl(dtype, HX_RNG_PARTITIONABLE, "hx_log_prob")) return e;
+  if (rows < 0 || rows > 0x7FFFFFFF) return fail(HX_E_SHAPE, "hx_log_prob: bad rows");
+  if (rows == 0) return 0;
+  HX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == HX_F32) return log_prob_t<float>(ctx, tgt, (const float*)X, rows, (float*)lp, (float*)grad, s);
+  return log_prob_t<double>(ctx, tgt, (const double*)X, rows, (double*)lp, (double*)grad, s);
+}
+
+// ---- accept ---------------------------------------------------------------------------------------------------------
+extern "C" HX_API int hx_accept(hx_ctx* ctx, int dtype, int impl, void* cur, const void* prop, void* lp_cur,
+                         const void* lp_prop, const void* logacc, const uint32_t key[2], int32_t n, int32_t row0,
+                         int32_t rows, int32_t dim, int32_t* accepts, void* stream) {
+  if (!ctx || !cur || !prop || !lp_cur || !lp_prop || !logacc || !key || !accepts) return fail(HX_E_NULL, "hx_accept: NULL argument");
+  if (int e = check_dtype_impl(dtype, impl, "hx_accept")) return e;
+  if (n < 1 || row0 < 0 || rows < 1 || row0 + rows > n || dim < 1) return fail(HX_E_SHAPE, "hx_accept: bad shape");
+  HX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const Key k{key[0], key[1]};
+  const int grid = (rows + 7) / 8;
+  const bool leg = impl == HX_RNG_LEGACY;
+  if (dtype == HX_F32) {
+    if (leg) k_accept<float, true><<<grid, 256, 0, s>>>((float*)cur, (const float*)prop, (float*)lp_cur, (const float*)lp_prop, (const float*)logacc, k, n, row0, rows, dim, accepts);
+    else k_accept<float, false><<<grid, 256, 0, s>>>((float*)cur, (const float*)prop, (float*)lp_cur, (const float*)lp_prop, (const float*)logacc, k, n, row0, rows, dim, accepts);
+  } else {
+    if (leg) k_accept<double, true><<<grid, 256, 0, s>>>((double*)cur, (const double*)prop, (double*)lp_cur, (const double*)lp_prop, (const double*)logacc, k, n, row0, rows, dim, accepts);
+    else k_accept<double, false><<<grid, 256, 0, s>>>((double*)cur, (const double*)prop, (double*)lp_cur, (const double*)lp_prop, (const double*)logacc, k, n, row0, rows, dim, accepts);
+  }
+  HX_LAUNCH_CHECK("k_accept");
+  return 0;
+}
+
+// ---- batch level: T iterations of the main phase ----------------------------------------------------------------------
+template <typename T>
+static int run_iterations_t(hx_ctx* ctx, int impl, int move_kind, int key_order, const hx_target* tgt, T* X, T* lp, int n, double eps,
+                            int L, const uint32_t* keys, int64_t Tn, T* chain, T* chain_lp, int32_t* accepts,
+                            int32_t* nonfinite, cudaStream_t s) {
+  const int d = tgt->dim;
+  void *pQ, *pLa, *pLp;
+  if (int e = ws_get(ctx, WS_Q, (size_t)n * d * sizeof(T), &pQ)) return e;
+  if (int e = ws_get(ctx, WS_LA, (size_t)n * sizeof(T), &pLa)) return e;
+  if (int e = ws_get(ctx, WS_LP, (size_t)n * sizeof(T), &pLp)) return e;
+  const size_t W2 = (size_t)2 * n;
+  for (int64_t t = 0; t < Tn; ++t) {
+    const uint32_t* kt = keys + (size_t)t * 8;
+    for (int half = 0; half < 2; ++half) {
+      // main-phase key order (samplers/hamiltonian_ensemble.py:290,295,300,305):
+      //   move1 = keys[0], accept1 = keys[2], move2 = keys[1], accept2 = keys[3]
+      // warm-up order (:171,184,191,204): move1 = keys[0], accept1 = keys[1], move2 = keys[2], accept2 = keys[3]
+      const int im = key_order == 0 ? (half == 0 ? 0 : 1) : (half == 0 ? 0 : 2);
+      const int ia = key_order == 0 ? (half == 0 ? 2 : 3) : (half == 0 ? 1 : 3);
+      const uint32_t* kmove = kt + 2 * im;
+      const uint32_t* kacc = kt + 2 * ia;
+      T* Xa = X + (size_t)half * n * d;          // group being updated
+      T* Xb = X + (size_t)(1 - half) * n * d;    // complement (group 2 sees the updated group 1)
+      T* lpa = lp + (size_t)half * n;
+      Fuse<T> f;
+      f.akey_ptr = kacc; f.lp1w = lpa; f.accepts = accepts + (size_t)half * n;
+      f.chain_out = chain ? chain + ((size_t)t * W2 + (size_t)half * n) * d : nullptr;
+      f.chain_lp = chain_lp ? chain_lp + (size_t)t * W2 + (size_t)half * n : nullptr;
+      f.nonfinite = nonfinite;
+      int e;
+      if (move_kind == 0)
+        e = walk_move_t<T>(ctx, impl, tgt, Xa, Xb, n, 0, n, eps, Key{0, 0}, kmove, L, lpa, (T*)pQ, (T*)pLa, nullptr, (T*)pLp, 0, &f, s);
+      else
+        e = side_move_t<T>(ctx, impl, tgt, Xa, Xb, n, 0, n, eps, Key{0, 0}, kmove, L, lpa, (T*)pQ, (T*)pLa, nullptr, (T*)pLp, 0, &f, s);
+      if (e) return e;
+    }
+  }
+  return 0;
+}
+
+extern "C" HX_API int hx_run_iterations(hx_ctx* ctx, int dtype, int impl, int move_kind, int key_order, const hx_target* tgt, void* X,
+                                 void* lp, int32_t n, double step_size, int32_t L, const uint32_t* keys_dev, int64_t T,
+                                 void* chain_out, void* lp_out, int32_t* accepts, int32_t* nonfinite, void* stream) {
+  if (!ctx || !tgt || !X || !lp || !keys_dev || !accepts || !nonfinite) return fail(HX_E_NULL, "hx_run_iterations: NULL argument");
+  if (int e = check_dtype_impl(dtype, impl, "hx_run_iterations")) return e;
+  if (move_kind != 0 && move_kind != 1) return fail(HX_E_DTYPE, "hx_run_iterations: move_kind must be 0 (walk) or 1 (side)");
+  if (key_order != 0 && key_order != 1) return fail(HX_E_DTYPE, "hx_run_iterations: key_order must be 0 (main) or 1 (warm-up)");
+  if (n < 2 || L < 1 || T < 0) return fail(HX_E_SHAPE, "hx_run_iterations: need n >= 2, L >= 1, T >= 0");
+  HX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == HX_F32)
+    return run_iterations_t<float>(ctx, impl, move_kind, key_order, tgt, (float*)X, (float*)lp, n, step_size, L, keys_dev, T,
+                                   (float*)chain_out, (float*)lp_out, accepts, nonfinite, s);
+  return run_iterations_t<double>(ctx, impl, move_kind, key_order, tgt, (double*)X, (double*)lp, n, step_size, L, keys_dev, T,
+                                  (double*)chain_out, (double*)lp_out, accepts, nonfinite, s);
+}

@@ -1,0 +1,93 @@
+"""ctypes binding of libhx.so (include/hx.h).
+
+The CUDA extension is the only compute path of this package: if the shared
+library is missing or a call fails, an exception is raised — there is no CPU or
+PyTorch fallback (BASELINE.json north_star).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HX_F32, HX_F64 = 0, 1
+HX_RNG_PARTITIONABLE, HX_RNG_LEGACY = 0, 1
+HX_TARGET_GAUSS_ISO, HX_TARGET_GAUSS_FULL, HX_TARGET_ROSENBROCK, HX_TARGET_FUNNEL = 0, 1, 2, 3
+HX_MOVE_FROZEN_GRAD = 1
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libhx.so")
+
+
+class HxError(RuntimeError):
+    """A libhx call returned a non-zero status."""
+
+
+class hx_target(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("dim", C.c_int32), ("ld", C.c_int32), ("has_lower0", C.c_int32),
+        ("mean", C.c_void_p), ("precision", C.c_void_p),
+        ("a", C.c_double), ("b", C.c_double), ("lower0", C.c_double),
+    ]
+
+
+_P = C.c_void_p
+_KEY = C.POINTER(C.c_uint32)
+_PROTOS = {
+    "hx_abi_version": (C.c_int, []),
+    "hx_last_error": (C.c_char_p, []),
+    "hx_ctx_create": (C.c_int, [C.POINTER(_P), C.c_int]),
+    "hx_ctx_destroy": (C.c_int, [_P]),
+    "hx_ctx_workspace_bytes": (C.c_size_t, [_P]),
+    "hx_split": (C.c_int, [_KEY, C.c_int, C.c_int64, _P, _P]),
+    "hx_random_bits": (C.c_int, [_KEY, C.c_int, C.c_int, C.c_int64, _P, _P]),
+    "hx_uniform": (C.c_int, [_KEY, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int64, _P, _P]),
+    "hx_normal": (C.c_int, [_KEY, C.c_int, C.c_int, C.c_int64, _P, _P]),
+    "hx_choice2": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int32, _P, _P]),
+    "hx_log_prob": (C.c_int, [_P, C.c_int, C.POINTER(hx_target), _P, C.c_int64, _P, _P, _P]),
+    "hx_walk_move": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_double, _KEY, C.c_int32, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "hx_side_move": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_double, _KEY, C.c_int32, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "hx_leapfrog_walk": (C.c_int, [_P, C.c_int, C.POINTER(hx_target), _P, _P, _P, C.c_int32, C.c_int32, C.c_double,
+                                   C.c_int32, _P, _P]),
+    "hx_leapfrog_side": (C.c_int, [_P, C.c_int, C.POINTER(hx_target), _P, _P, _P, C.c_int32, C.c_double, C.c_int32, _P]),
+    "hx_accept": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _KEY, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                            _P, _P]),
+    "hx_run_iterations": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.c_double,
+                                    C.c_int32, _P, C.c_int64, _P, _P, _P, _P, _P]),
+}
+
+EXPORTS = tuple(_PROTOS)
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libhx.so (once) and attach prototypes.  Raises if the extension was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HxError(
+            f"libhx.so not found at {LIB_PATH}: build it with `make -C h-emcee_b200 -j8` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.hx_abi_version() != 1:
+        raise HxError(f"libhx ABI version {lib.hx_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "libhx"):
+    if status != 0:
+        msg = load().hx_last_error().decode("utf-8", "replace")
+        raise HxError(f"{what} failed with status {status}: {msg}")
+
+
+def key_arg(key):
+    """uint32[2] host key -> ctypes array."""
+    import numpy as np
+    k = np.asarray(key, dtype=np.uint32).reshape(2)
+    return (C.c_uint32 * 2)(int(k[0]), int(k[1]))

@@ -1,0 +1,97 @@
+"""Runtime plumbing: per-device libhx contexts, dtype codes, the current CUDA stream.
+
+PyTorch is used for device memory, streams and torch.distributed only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class _Config:
+    """Process-wide switches mirroring the JAX flags the reference depends on.
+
+    enable_x64 : like `jax_enable_x64` — float64 state and 64 random bits per draw
+                 (reference tests set it: src/hemcee/tests/test_proposal.py:7).
+    rng_impl   : "partitionable" (JAX >= 0.5 default, the mode the reference authors ran)
+                 or "legacy" (`jax_threefry_partitionable=False`).
+    """
+
+    def __init__(self):
+        self.enable_x64 = False
+        self.rng_impl = "partitionable"
+
+    def update(self, name, value):
+        if name in ("enable_x64", "jax_enable_x64"):
+            self.enable_x64 = bool(value)
+        elif name in ("rng_impl",):
+            if value not in ("partitionable", "legacy"):
+                raise ValueError("rng_impl must be 'partitionable' or 'legacy'")
+            self.rng_impl = value
+        elif name == "jax_threefry_partitionable":
+            self.rng_impl = "partitionable" if value else "legacy"
+        else:
+            raise ValueError(f"unknown config option {name}")
+
+
+config = _Config()
+_ctx = {}
+
+
+def default_dtype() -> torch.dtype:
+    return torch.float64 if config.enable_x64 else torch.float32
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return _lib.HX_F32
+    if dt == torch.float64:
+        return _lib.HX_F64
+    raise TypeError(f"libhx computes in float32 or float64, got {dt}")
+
+
+def impl_code(impl=None) -> int:
+    impl = config.rng_impl if impl is None else impl
+    return _lib.HX_RNG_LEGACY if impl == "legacy" else _lib.HX_RNG_PARTITIONABLE
+
+
+def device(dev=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.HxError("hemcee_b200 needs a CUDA device (sm_100a); none is visible and there is no CPU fallback")
+    if dev is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    dev = torch.device(dev)
+    if dev.type != "cuda":
+        raise _lib.HxError("hemcee_b200 runs on CUDA devices only")
+    return torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+
+
+def ctx(dev: torch.device) -> C.c_void_p:
+    """The libhx context (private scratch workspace) of a device."""
+    idx = dev.index
+    if idx not in _ctx:
+        h = C.c_void_p()
+        _lib.check(_lib.load().hx_ctx_create(C.byref(h), idx), "hx_ctx_create")
+        _ctx[idx] = h
+    return _ctx[idx]
+
+
+def stream(dev: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def as_key(key) -> np.ndarray:
+    if isinstance(key, torch.Tensor):
+        key = key.detach().cpu().numpy()
+    k = np.asarray(key)
+    if k.dtype != np.uint32:
+        k = k.astype(np.int64).astype(np.uint32) if k.dtype.kind in "iu" else k.view(np.uint32)
+    return k.reshape(2)

@@ -1,0 +1,354 @@
+"""`HamiltonianEnsembleSampler` with the reference's emcee-style API, driven by libhx kernels.
+
+Mirrors reference src/hemcee/samplers/hamiltonian_ensemble.py:12-346 and the BaseSampler of
+src/hemcee/samplers/sampler.py:12-102 (constructor, `run_mcmc`, `get_chain`, `get_logprob`,
+`get_acceptance_prob`, `get_autocorr`, `diagnostics_warmup/main`, `adapter`, `backend`).
+
+Differences a user switching over sees:
+  * `log_prob` is a built-in target (`hemcee_b200.targets`) instead of an arbitrary JAX callable;
+  * keys are uint32[2] arrays (`hemcee_b200.random.PRNGKey`); dtype / RNG layout follow
+    `hemcee_b200.config` (`enable_x64`, `rng_impl`) like the JAX flags they stand for;
+  * the chain is returned as a NumPy array on the host.
+
+The main phase replaces the reference's `lax.scan` (hamiltonian_ensemble.py:284-318 through
+sampler_utils.py:29-88) with `hx_run_iterations`: per half-move one fused kernel does momentum draw,
+projection, leapfrog, energy and Metropolis accept, and writes the new state straight into the
+on-device chain buffer, which is copied to pinned host memory per batch on a side stream.
+
+With `group=` (a torch.distributed process group) the walkers of both halves are row-sharded over
+the ranks; each half-move updates the local rows against the all-gathered complement (one NCCL
+all-gather per half-move).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib, _rt, adaptation, autocorr
+from . import random as hrandom
+from .backend import Backend
+from .moves import accept_proposal, hmc_side_move, hmc_walk_move
+from .targets import as_target
+
+
+def calculate_batch_size(total_chains, dim, total_iterations, user_batch_size=None):
+    """reference src/hemcee/samplers/sampler_utils.py:10-26."""
+    if user_batch_size is not None:
+        return user_batch_size
+    return min(max(50, 10000 // (total_chains * dim)), total_iterations)
+
+
+_NONFINITE_MSG = "Log probability returned NaN or inf value, please check your log probability function"
+
+
+class BaseSampler:
+    """reference src/hemcee/samplers/sampler.py:12-102."""
+
+    def __init__(self, total_chains, dim, log_prob, move, backend=None):
+        if total_chains < 4:
+            raise ValueError("`total_chains` must be at least 4 to form meaningful ensemble groups")
+        self.total_chains = int(total_chains)
+        self.dim = int(dim)
+        self.move = move
+        self.backend = Backend() if backend is None else backend
+        self.backend.reset(total_chains, dim)
+        self.target = as_target(log_prob)
+        if self.target.dim != self.dim:
+            raise ValueError(f"target has dim {self.target.dim}, sampler dim is {self.dim}")
+        # the reference builds jit(vmap(log_prob)) / jit(vmap(grad(log_prob))) here (sampler.py:52,55)
+        self.log_prob = self.target.log_prob
+        self.grad_log_prob = self.target.grad_log_prob
+        self.diagnostics_warmup = None
+        self.diagnostics_main = None
+
+    def _validate_mcmc_inputs(self, num_samples, warmup, thin_by, initial_state):
+        if thin_by < 1:
+            raise ValueError("`thin_by` must be 1 or greater.")
+        if warmup < 0:
+            raise ValueError("`warmup` must be 0 or greater.")
+        if num_samples < 0:
+            raise ValueError("`num_samples` must be 0 or greater.")
+        if tuple(initial_state.shape) != (self.total_chains, self.dim):
+            raise ValueError("`inital_state` needs to have shape ")
+
+    def get_chain(self, discard=0, thin=1, flat=False):
+        return self.backend.get_chain(discard=discard, thin=thin, flat=flat)
+
+    def get_logprob(self, discard=0, thin=1, flat=False):
+        return self.backend.get_log_prob(discard=discard, thin=thin, flat=flat)
+
+    def get_acceptance_prob(self):
+        return self.backend.accepted / self.backend.iteration
+
+    def get_autocorr(self, discard, thin):
+        return autocorr.integrated_time(self.get_chain(discard=discard, thin=thin, flat=False))
+
+
+class HamiltonianEnsembleSampler(BaseSampler):
+    def __init__(self, total_chains, dim, log_prob, step_size=0.1, L=10, move=hmc_walk_move, backend=None,
+                 adapt_inital_step_size=True, adapt_step_size=True, adapt_length=True, *, device=None, group=None,
+                 chain_store="full", verbose=True):
+        super().__init__(total_chains, dim, log_prob, move, backend)
+        if getattr(move, "__name__", None) not in ("hmc_walk_move", "hmc_side_move"):
+            raise ValueError("HamiltonianEnsembleSampler on B200 supports move=hmc_walk_move or hmc_side_move")
+        if self.total_chains % 2:
+            # the walk move needs equal halves (reference hmc_walk.py:36,91)
+            raise ValueError("`total_chains` must be even")
+        self.step_size = step_size
+        self.L = L
+        self.device = _rt.device(device)
+        self.dtype = _rt.default_dtype()
+        self.impl = _rt.config.rng_impl
+        self.verbose = verbose
+        self.group = group
+        self.chain_store = chain_store
+        if group is not None:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+            if (self.total_chains // 2) % self.world:
+                raise ValueError("total_chains/2 must be divisible by the number of ranks")
+        else:
+            self.world, self.rank = 1, 0
+        self.adapt_inital_step_size = adapt_inital_step_size
+        self.adapter = adaptation.select_adapter(adapt_step_size, adapt_length, self.move, self.step_size, self.L,
+                                                 self.dtype, self._allreduce)
+        self.adapter_state = self.adapter.init(self.dim)
+        self.kernel_launch_count = 0
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _say(self, msg):
+        if self.verbose and self.rank == 0:
+            print(msg)
+
+    def _allreduce(self, t):
+        if self.group is not None and self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.group)
+        return t
+
+    def _allgather(self, full, local):
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(full, local, group=self.group)
+
+    @property
+    def _move_kind(self):
+        return 0 if self.move.__name__ == "hmc_walk_move" else 1
+
+    # -- reference hamiltonian_ensemble.py:64-139 ----------------------------------------------------
+    def run_mcmc(self, key, initial_state, num_samples, warmup=1000, thin_by=1, batch_size=None, show_progress=False):
+        keys = hrandom.split(key, 3, self.device, self.impl)                        # :90
+        self._validate_mcmc_inputs(num_samples, warmup, thin_by, initial_state)     # :95
+        x0 = torch.as_tensor(np.asarray(initial_state) if not isinstance(initial_state, torch.Tensor) else initial_state)
+        x0 = x0.to(device=self.device, dtype=self.dtype, non_blocking=True).contiguous()
+        n = self.total_chains // 2
+        self._say(f"Using {self.total_chains} total chains: Group 1 ({n}), Group 2 ({self.total_chains - n})")
+        group1, group2 = x0[:n].clone(), x0[n:].clone()                             # :107-108
+        warmup_bs = calculate_batch_size(self.total_chains, self.dim, warmup, batch_size)
+        main_bs = calculate_batch_size(self.total_chains, self.dim, num_samples * thin_by, batch_size)
+
+        if self.adapt_inital_step_size:                                             # :115-118
+            self.step_size = adaptation.find_reasonable_step_size(
+                keys[0], group1, group2, self.target, self.target, self.step_size, self.move, self.impl)
+            self._say(f"Using inital step size of {float(self.step_size)!r}")
+
+        if warmup > 0:                                                              # :121-129
+            self._say("Starting warmup...")
+            group1, group2 = self._mcmc_warmup(keys[1], group1, group2, warmup, self.adapter, warmup_bs, show_progress)
+            self._say("Warmup complete.")
+            step_size, L = self.adapter.finalize(self.adapter_state)
+            self._say(f"Found step size {float(step_size)!r} and integration length: {int(L)}")
+        else:
+            step_size, L = self.step_size, self.L                                   # :131-132
+        self.found = (step_size, L)
+
+        self._say("Starting main sampling...")
+        self._mcmc_main(keys[2], group1, group2, num_samples, thin_by, step_size, L, main_bs, show_progress,
+                        warmup_offset=warmup)
+        self._say("Main sampling complete.")
+        return self.get_chain(discard=warmup, thin=thin_by)                         # :139
+
+    # -- batch-level engine (single GPU): T iterations per libhx call ----------------------------------
+    def _run_batches(self, key, X, lp, T, step_size, L, batch_size, offset, key_order, show_progress):
+        """Runs T iterations in batches; streams (chain, log-prob) batches to pinned host memory on a
+        side stream while the next batch computes.  Returns per-walker accept counts (numpy)."""
+        dev, W, d = self.device, self.total_chains, self.dim
+        n = W // 2
+        lib = _lib.load()
+        keys_dev = hrandom.split_device(key, 4 * T, dev, self.impl)                 # :227-228 / :328-330
+        accepts = torch.zeros(W, dtype=torch.int32, device=dev)
+        if T == 0:
+            return accepts.cpu().numpy()
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        nb = (T + batch_size - 1) // batch_size
+        host_chain = torch.empty((T, W, d), dtype=self.dtype, pin_memory=True)
+        host_lp = torch.empty((T, W), dtype=self.dtype, pin_memory=True)
+        host_flag = torch.zeros(nb, dtype=torch.int32, pin_memory=True)
+        bufs = [(torch.empty((min(batch_size, T), W, d), dtype=self.dtype, device=dev),
+                 torch.empty((min(batch_size, T), W), dtype=self.dtype, device=dev)) for _ in range(min(2, nb))]
+        copy_stream = torch.cuda.Stream(dev)
+        done = [None, None]
+        main = torch.cuda.current_stream(dev)
+        desc = self.target.descriptor(self.dtype, dev)
+        it = range(nb)
+        if show_progress:
+            from tqdm import tqdm
+            it = tqdm(it)
+        for b in it:
+            start, stop = b * batch_size, min((b + 1) * batch_size, T)
+            cbuf, lbuf = bufs[b % 2]
+            if done[b % 2] is not None:
+                main.wait_event(done[b % 2])          # the copy out of this buffer must be finished
+            st = lib.hx_run_iterations(_rt.ctx(dev), _rt.dtype_code(self.dtype), _rt.impl_code(self.impl),
+                                       self._move_kind, key_order, desc, _rt.ptr(X), _rt.ptr(lp), n, float(step_size),
+                                       int(L), _rt.ptr(keys_dev[4 * start:]), stop - start, _rt.ptr(cbuf), _rt.ptr(lbuf),
+                                       _rt.ptr(accepts), _rt.ptr(flag), _rt.stream(dev))
+            _lib.check(st, "hx_run_iterations")
+            ev = torch.cuda.Event()
+            ev.record(main)
+            copy_stream.wait_event(ev)
+            with torch.cuda.stream(copy_stream):
+                host_chain[start:stop].copy_(cbuf[: stop - start], non_blocking=True)
+                host_lp[start:stop].copy_(lbuf[: stop - start], non_blocking=True)
+                host_flag[b:b + 1].copy_(flag, non_blocking=True)
+                done[b % 2] = torch.cuda.Event()
+                done[b % 2].record(copy_stream)
+            if b >= 1 and int(host_flag[b - 1]) != 0 and done[(b - 1) % 2].query():
+                raise ValueError(_NONFINITE_MSG)                                     # sampler_utils.py:74-75
+        copy_stream.synchronize()
+        main.synchronize()
+        if int(host_flag.max()) != 0:
+            raise ValueError(_NONFINITE_MSG)
+        acc = accepts.cpu().numpy()
+        hc, hl = host_chain.numpy(), host_lp.numpy()
+        for b in range(nb):
+            start, stop = b * batch_size, min((b + 1) * batch_size, T)
+            self.backend.save_slice(hc[start:stop], hl[start:stop], acc if b == nb - 1 else np.zeros_like(acc),
+                                    offset + start)
+        self.kernel_launch_count += T * 2 * (6 if self._move_kind == 0 else 2)
+        return acc
+
+    # -- per-half-move engine (warm-up with adapters; row-sharded multi-GPU) ------------------------------
+    def _half(self, Xa_loc, Xb_full, lpa_loc, step, L, k_move, k_acc, acc_loc, n, row0, adapter_state):
+        prop, la, pproj, lpp = self.move(Xa_loc, Xb_full, step, k_move, self.target, self.target, int(L), lpa_loc,
+                                         row0=row0, n=n, impl=self.impl)
+        if adapter_state is not None:                                               # :176-182 (before the accept)
+            kw = dict(state=adapter_state, log_accept_rate=la, position_current=Xa_loc, position_proposed=prop,
+                      momentum_proposed=pproj, group2=Xb_full)
+            if isinstance(self.adapter, (adaptation.ChEESAdapter, adaptation.CompositeAdapter)):
+                kw["n_total"] = n
+            adapter_state = self.adapter.update(**kw)
+        accept_proposal(Xa_loc, prop, lpa_loc, lpp, la, k_acc, acc_loc, row0=row0, n=n, impl=self.impl)
+        return adapter_state
+
+    def _run_steps(self, key, g1, g2, T, batch_size, offset, key_order, fixed, adapter_state, show_progress):
+        """Python-driven loop: one libhx move + accept per half-move.  Used for warm-up with a live
+        adapter and for the row-sharded multi-GPU path."""
+        dev, W, d = self.device, self.total_chains, self.dim
+        n = W // 2
+        rows = n // self.world
+        row0 = self.rank * rows
+        keys = hrandom.split(key, 4 * T, dev, self.impl).reshape(T, 4, 2) if T > 0 else np.zeros((0, 4, 2), np.uint32)
+        sharded = self.world > 1
+        if sharded:
+            X1f, X2f = g1.contiguous(), g2.contiguous()
+            X1, X2 = X1f[row0:row0 + rows].clone(), X2f[row0:row0 + rows].clone()
+        else:
+            X1, X2 = g1, g2
+            X1f, X2f = X1, X2
+        lp1, lp2 = self.log_prob(X1), self.log_prob(X2)                              # :224-225 / :325-326
+        if sharded:
+            lp1f = torch.empty(n, dtype=self.dtype, device=dev)
+            lp2f = torch.empty(n, dtype=self.dtype, device=dev)
+        acc1 = torch.zeros(rows, dtype=torch.int32, device=dev)
+        acc2 = torch.zeros(rows, dtype=torch.int32, device=dev)
+        order = (0, 2, 1, 3) if key_order == 0 else (0, 1, 2, 3)     # move1, accept1, move2, accept2
+        full_store = (not sharded) or self.chain_store == "full"
+        Wst = W if full_store else 2 * rows
+        total_acc = np.zeros(Wst)
+        it = range(0, T, max(batch_size, 1))
+        if show_progress:
+            from tqdm import tqdm
+            it = tqdm(it)
+        for start in it:
+            stop = min(start + batch_size, T)
+            cbuf = torch.empty((stop - start, Wst, d), dtype=self.dtype, device=dev)
+            lbuf = torch.empty((stop - start, Wst), dtype=self.dtype, device=dev)
+            acc1.zero_(); acc2.zero_()
+            for t in range(start, stop):
+                k = keys[t]
+                if fixed is None:
+                    step, L = self.adapter.value(adapter_state)                      # :169
+                else:
+                    step, L = fixed
+                adapter_state = self._half(X1, X2f, lp1, step, L, k[order[0]], k[order[1]], acc1, n, row0, adapter_state)
+                if sharded:
+                    self._allgather(X1f, X1)
+                if fixed is None:
+                    step, L = self.adapter.value(adapter_state)                      # :189
+                adapter_state = self._half(X2, X1f, lp2, step, L, k[order[2]], k[order[3]], acc2, n, row0, adapter_state)
+                if sharded:
+                    self._allgather(X2f, X2)
+                i = t - start
+                if full_store:
+                    cbuf[i, :n].copy_(X1f); cbuf[i, n:].copy_(X2f)
+                    if sharded:
+                        self._allgather(lp1f, lp1); self._allgather(lp2f, lp2)
+                        lbuf[i, :n].copy_(lp1f); lbuf[i, n:].copy_(lp2f)
+                    else:
+                        lbuf[i, :n].copy_(lp1); lbuf[i, n:].copy_(lp2)
+                else:
+                    cbuf[i, :rows].copy_(X1); cbuf[i, rows:].copy_(X2)
+                    lbuf[i, :rows].copy_(lp1); lbuf[i, rows:].copy_(lp2)
+            bad = ~torch.isfinite(lbuf).all()
+            if sharded:
+                badt = bad.to(torch.int32).reshape(1)
+                self._allreduce(badt)
+                bad = badt[0] > 0
+            if bool(bad):                                                            # sampler_utils.py:74-75
+                raise ValueError(_NONFINITE_MSG)
+            if full_store and sharded:
+                a1f = torch.empty(n, dtype=torch.int32, device=dev); a2f = torch.empty(n, dtype=torch.int32, device=dev)
+                self._allgather(a1f, acc1); self._allgather(a2f, acc2)
+                acc = torch.cat([a1f, a2f]).cpu().numpy()
+            else:
+                acc = torch.cat([acc1, acc2]).cpu().numpy()
+            total_acc += acc
+            self.backend.save_slice(cbuf.cpu().numpy(), lbuf.cpu().numpy(), acc, offset + start)
+        self.kernel_launch_count += T * 2 * (8 if self._move_kind == 0 else 4)
+        if sharded:
+            g1.copy_(X1f); g2.copy_(X2f)
+        return total_acc, adapter_state
+
+    # -- reference hamiltonian_ensemble.py:141-248 --------------------------------------------------------
+    def _mcmc_warmup(self, key, group1, group2, warmup, adapter, batch_size, show_progress):
+        noop = isinstance(adapter, adaptation.NoOpAdapter)
+        if noop and self.world == 1:
+            step, L = adapter.value(self.adapter_state)
+            X = torch.cat([group1, group2]).contiguous()
+            lp = self.log_prob(X)
+            acc = self._run_batches(key, X, lp, warmup, step, L, batch_size, 0, 1, show_progress)
+            group1, group2 = X[: self.total_chains // 2].clone(), X[self.total_chains // 2:].clone()
+        else:
+            fixed = adapter.value(self.adapter_state) if noop else None
+            acc, st = self._run_steps(key, group1, group2, warmup, batch_size, 0, 1, fixed,
+                                      None if noop else self.adapter_state, show_progress)
+            if not noop:
+                self.adapter_state = st
+        self.diagnostics_warmup = {"accepts": acc, "acceptance_rate": acc / warmup}
+        self.backend.mark_warmup_end()
+        return group1, group2
+
+    # -- reference hamiltonian_ensemble.py:250-343 --------------------------------------------------------
+    def _mcmc_main(self, key, group1, group2, num_samples, thin_by, step_size, L, batch_size, show_progress,
+                   warmup_offset=0):
+        total = num_samples * thin_by
+        if self.world == 1:
+            X = torch.cat([group1, group2]).contiguous()
+            lp = self.log_prob(X)                                                    # :325-326
+            acc = self._run_batches(key, X, lp, total, step_size, L, batch_size, warmup_offset, 0, show_progress)
+            self.last_state = X
+        else:
+            acc, _ = self._run_steps(key, group1, group2, total, batch_size, warmup_offset, 0, (step_size, L), None,
+                                     show_progress)
+            self.last_state = torch.cat([group1, group2])
+        self.diagnostics_main = {"accepts": acc, "acceptance_rate": acc / total if total else acc}

@@ -1,0 +1,183 @@
+/*
+ * hx.h — C-ABI of libhx.so, the B200-native (sm_100a) implementation of h-emcee's
+ * ensemble-Hamiltonian hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own
+ * (pure JAX); every entry point below replaces one Python-level interface of the
+ * reference, cited as `file:line` relative to the reference repository root.  The
+ * Python mirror of the reference API (h-emcee_b200/hemcee_b200) binds these with
+ * ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross the boundary.
+ *   - every `*_dev` / `void*` state argument is a DEVICE pointer owned by the caller
+ *     (e.g. torch CUDA tensor .data_ptr()); the library allocates only private scratch.
+ *   - walker state is row-major [rows, dim] exactly like the reference's arrays.
+ *   - `dtype`: HX_F32 = JAX default mode, HX_F64 = `jax_enable_x64` (changes the RNG
+ *     stream: 64 random bits per draw).
+ *   - `impl`: threefry counter layout, HX_RNG_PARTITIONABLE (JAX >= 0.5 default) or
+ *     HX_RNG_LEGACY.
+ *   - keys are raw uint32[2] on the HOST unless the name says `_dev`.
+ *   - all launches are asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - return value: 0 ok; <0 invalid argument (HX_E_*); >0 a cudaError_t.  The message
+ *     is available from hx_last_error() (thread-local).  Nothing throws.
+ *   - a ctx is bound to one device and is not thread-safe (one host thread per ctx,
+ *     like the reference's single-threaded driver).
+ */
+#ifndef HX_H_
+#define HX_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HX_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define HX_API __attribute__((visibility("default")))
+#else
+#define HX_API
+#endif
+
+enum { HX_F32 = 0, HX_F64 = 1 };
+enum { HX_RNG_PARTITIONABLE = 0, HX_RNG_LEGACY = 1 };
+
+/* error codes (<0) */
+enum {
+  HX_E_NULL = -1,      /* required pointer is NULL */
+  HX_E_SHAPE = -2,     /* bad n / dim / rows / L */
+  HX_E_DTYPE = -3,     /* unknown dtype / impl / flag */
+  HX_E_TARGET = -4,    /* malformed target descriptor */
+  HX_E_UNSUPPORTED = -5,
+  HX_E_ALIGN = -6
+};
+
+/* Built-in targets.  The reference differentiates an arbitrary callable with
+ * jax.vmap(jax.grad(log_prob)) (src/hemcee/samplers/sampler.py:52,55); this library ships
+ * analytic log-density + gradient for the reference's own test targets
+ * (src/hemcee/tests/distribution.py:30-48,76-97,143-156; funnel per SURVEY §8a row T). */
+enum {
+  HX_TARGET_GAUSS_ISO = 0,   /* -1/2 |x - mean|^2                      (quickstart.ipynb cell 4) */
+  HX_TARGET_GAUSS_FULL = 1,  /* -1/2 (x-mean)^T P (x-mean), P = precision[dim, ld] symmetric    */
+  HX_TARGET_ROSENBROCK = 2,  /* -sum_i b (x_{i+1}-x_i^2)^2 + (a-x_i)^2  (distribution.py:155-156) */
+  HX_TARGET_FUNNEL = 3       /* x0=nu: -nu^2/(2 a^2) - 1/2 e^{-nu} sum x_i^2 - (dim-1) nu/2, a=sigma */
+};
+
+typedef struct hx_target {
+  int32_t kind;            /* HX_TARGET_* */
+  int32_t dim;
+  int32_t ld;              /* leading dimension (elements) of `precision`; multiple of 4, >= dim */
+  int32_t has_lower0;      /* if non-zero: log-density is -inf where x[0] < lower0 (hard constraint,
+                              reference src/hemcee/tests/test_log_prob_validation.py:95-155) */
+  const void* mean;        /* device [dim] in the run dtype, or NULL for zero mean */
+  const void* precision;   /* device [dim, ld] in the run dtype (GAUSS_FULL only), zero padded */
+  double a;                /* rosenbrock a / funnel sigma */
+  double b;                /* rosenbrock b */
+  double lower0;
+} hx_target;
+
+/* flags for the move entry points */
+enum {
+  HX_MOVE_FROZEN_GRAD = 1, /* use grad(log_prob) at the initial positions for every kick
+                              (src/hemcee/adaptation/reasonable_stepsize.py:34-38) */
+};
+
+typedef struct hx_ctx hx_ctx;
+
+HX_API int hx_abi_version(void);
+HX_API const char* hx_last_error(void);
+
+/* ctx = per-device scratch workspace (grow-only, private) */
+HX_API int hx_ctx_create(hx_ctx** out, int device);
+HX_API int hx_ctx_destroy(hx_ctx* ctx);
+/* bytes of private scratch currently held (diagnostics) */
+HX_API size_t hx_ctx_workspace_bytes(const hx_ctx* ctx);
+
+/* ---- (1) RNG: bit-exact jax.random subset ------------------------------------------------
+ * replaces jax.random.split   (call sites: samplers/hamiltonian_ensemble.py:90,228,330;
+ *                              moves/hamiltonian/hmc_side.py:37; adaptation/reasonable_stepsize.py:44)
+ *          jax.random.normal  (moves/hamiltonian/hmc_walk.py:36; moves/hamiltonian/hmc_side.py:54)
+ *          jax.random.uniform (samplers/sampler_utils.py:114)
+ *          jax.random.choice  (moves/hamiltonian/hmc_side.py:44-47)                              */
+HX_API int hx_split(const uint32_t key[2], int impl, int64_t num, uint32_t* out_dev /*[num,2]*/, void* stream);
+HX_API int hx_random_bits(const uint32_t key[2], int impl, int bit_width /*32|64*/, int64_t count,
+                   void* out_dev /*uint32|uint64 [count]*/, void* stream);
+HX_API int hx_uniform(const uint32_t key[2], int impl, int dtype, double minval, double maxval, int64_t count,
+               void* out_dev, void* stream);
+HX_API int hx_normal(const uint32_t key[2], int impl, int dtype, int64_t count, void* out_dev, void* stream);
+/* per-walker choice(key_i, arange(n), (2,), replace=False) for keys_dev[nkeys,2] -> int32 out_dev[nkeys,2] */
+HX_API int hx_choice2(hx_ctx* ctx, const uint32_t* keys_dev, int64_t nkeys, int impl, int32_t n,
+               int32_t* out_dev, void* stream);
+
+/* ---- (2) targets ---------------------------------------------------------------------------
+ * replaces the jitted vmap(log_prob) / vmap(grad(log_prob)) of samplers/sampler.py:52,55       */
+HX_API int hx_log_prob(hx_ctx* ctx, int dtype, const hx_target* tgt, const void* X_dev, int64_t rows,
+                void* lp_out_dev, void* grad_out_dev /*nullable [rows,dim]*/, void* stream);
+
+/* ---- (3) move level: mirrors the reference move protocol ------------------------------------
+ *   move(group1, group2, step_size, key, log_prob, grad_log_prob, L, log_prob_group1)
+ *     -> (proposed, log_accept_prob, momentum_projected, proposed_log_prob)
+ * (moves/hamiltonian/hmc_walk.py:6-59, moves/hamiltonian/hmc_side.py:6-77).
+ *
+ * `n` is the size of BOTH groups (the walk move needs equal halves, hmc_walk.py:36,91).
+ * `X1_dev` holds `rows` walkers of group 1 starting at global row `row0` (row0=0, rows=n on
+ * one GPU; a row shard otherwise — the RNG counters use the global row so results do not
+ * depend on the sharding).  `X2_dev` is the full complement [n, dim].                          */
+HX_API int hx_walk_move(hx_ctx* ctx, int dtype, int impl, const hx_target* tgt,
+                 const void* X1_dev, const void* X2_dev, int32_t n, int32_t row0, int32_t rows,
+                 double step_size, const uint32_t key[2], int32_t L, const void* lp1_dev,
+                 void* Q_out_dev, void* logacc_out_dev, void* pproj_out_dev /*nullable*/,
+                 void* lp_out_dev, int flags, void* stream);
+
+HX_API int hx_side_move(hx_ctx* ctx, int dtype, int impl, const hx_target* tgt,
+                 const void* X1_dev, const void* X2_dev, int32_t n, int32_t row0, int32_t rows,
+                 double step_size, const uint32_t key[2], int32_t L, const void* lp1_dev,
+                 void* Q_out_dev, void* logacc_out_dev, void* pproj_out_dev /*nullable*/,
+                 void* lp_out_dev, int flags, void* stream);
+
+/* integrator-only entries (moves/hamiltonian/hmc_walk.py:61-107, hmc_side.py:80-135), used by the
+ * reversibility / affine-invariance tests of the reference (tests/test_leapfrog.py:73-116,
+ * tests/affine_invariance/test_leapfrog.py:26-100).  `centered_dev` is the centred complement
+ * [n2, dim]; the walk momentum is given and returned in projected form S = p @ centered [rows,dim]
+ * (the n x n momentum is never materialised).                                     */
+HX_API int hx_leapfrog_walk(hx_ctx* ctx, int dtype, const hx_target* tgt, void* q_inout_dev,
+                     void* S_inout_dev, const void* centered_dev, int32_t n2, int32_t rows,
+                     double step_size, int32_t L, void* dK_out_dev /*nullable [rows]*/, void* stream);
+HX_API int hx_leapfrog_side(hx_ctx* ctx, int dtype, const hx_target* tgt, void* q_inout_dev,
+                     void* p_inout_dev /*[rows]*/, const void* diff_dev /*[rows,dim]*/, int32_t rows,
+                     double step_size, int32_t L, void* stream);
+
+/* Metropolis accept (samplers/sampler_utils.py:91-124): log(uniform(key,(n,),1e-10,1)) < logacc.
+ * Updates cur/lp_cur in place for rows [row0,row0+rows) of a group of n; accepts_inout (int32
+ * [rows]) is incremented.  The same key drives positions and log-probs, like the reference's two
+ * calls (samplers/hamiltonian_ensemble.py:295-296).                                              */
+HX_API int hx_accept(hx_ctx* ctx, int dtype, int impl, void* cur_inout_dev, const void* prop_dev,
+              void* lp_cur_inout_dev, const void* lp_prop_dev, const void* logacc_dev,
+              const uint32_t key[2], int32_t n, int32_t row0, int32_t rows, int32_t dim,
+              int32_t* accepts_inout_dev, void* stream);
+
+/* ---- (4) batch level: replaces the lax.scan of the MAIN phase -------------------------------
+ * (samplers/hamiltonian_ensemble.py:284-318 driven by samplers/sampler_utils.py:29-88).
+ * Runs T iterations: move(X1|X2) accept, move(X2|X1') accept, with the reference's main-phase
+ * key order (keys[t,0] move1, keys[t,2] accept1, keys[t,1] move2, keys[t,3] accept2).
+ *   keys_dev          uint32 [T,4,2] = split(key_main, 4T) (hx_split)
+ *   X_inout_dev       [2n, dim] (group 1 rows then group 2 rows), lp_inout_dev [2n]
+ *   chain_out_dev     [T, 2n, dim] or NULL; lp_out_dev [T, 2n] or NULL
+ *   accepts_inout_dev int32 [2n]
+ *   nonfinite_flag_dev int32[1], set to 1 if a stored log-prob is NaN/inf (sampler_utils.py:74-75)
+ * move_kind: 0 walk, 1 side.
+ * key_order: 0 = main phase (above); 1 = warm-up order keys[t,0] move1, keys[t,1] accept1,
+ *            keys[t,2] move2, keys[t,3] accept2 (samplers/hamiltonian_ensemble.py:171,184,191,204),
+ *            for warm-up runs whose adapter is the no-op one.                                    */
+HX_API int hx_run_iterations(hx_ctx* ctx, int dtype, int impl, int move_kind, int key_order, const hx_target* tgt,
+                      void* X_inout_dev, void* lp_inout_dev, int32_t n, double step_size, int32_t L,
+                      const uint32_t* keys_dev, int64_t T, void* chain_out_dev, void* lp_out_dev,
+                      int32_t* accepts_inout_dev, int32_t* nonfinite_flag_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HX_H_ */

@@ -1,0 +1,81 @@
+"""GPU parity of the libhx RNG entry points against the oracle restatement of jax.random.
+
+Bits, split keys and uniforms must be bit-exact; f32/f64 normals agree to a few ulp (log1p and FMA
+contraction differ between backends, also inside JAX itself — SURVEY App. B.5/B.6)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import jaxrng as R
+
+pytestmark = pytest.mark.gpu
+IMPLS = ["partitionable", "legacy"]
+
+
+def _u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("num", [1, 2, 3, 7, 1000, 4097])
+def test_split_exact(hx, impl, num):
+    key = R.PRNGKey(1234)
+    got = hx.random.split(key, num, impl=impl)
+    np.testing.assert_array_equal(got, R.split(key, num, impl))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("m", [1, 2, 3, 16, 255, 10001])
+def test_bits_exact(hx, impl, m):
+    key = R.PRNGKey(7)
+    np.testing.assert_array_equal(_u32(hx.random.random_bits(key, 32, (m,), impl=impl)), R.random_bits(key, 32, (m,), impl))
+    got64 = hx.random.random_bits(key, 64, (m,), impl=impl).cpu().numpy().view(np.uint64)
+    np.testing.assert_array_equal(got64, R.random_bits(key, 64, (m,), impl))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_uniform_exact(hx, impl, dtype):
+    key = R.PRNGKey(99)
+    npdt = np.float32 if dtype == torch.float32 else np.float64
+    for lo, hi in [(0.0, 1.0), (1e-10, 1.0), (-3.0, 5.0)]:
+        got = hx.random.uniform(key, (5001,), dtype, lo, hi, impl=impl).cpu().numpy()
+        np.testing.assert_array_equal(got, R.uniform(key, (5001,), npdt, lo, hi, impl))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_normal_f32_ulp(hx, impl):
+    key = R.PRNGKey(5)
+    got = hx.random.normal(key, (300, 301), torch.float32, impl=impl).cpu().numpy()
+    ref = R.normal(key, (300, 301), np.float32, impl)
+    ulp = np.spacing(np.abs(ref).astype(np.float32))
+    assert np.max(np.abs(got - ref) / ulp) <= 4.0          # tolerance: 4 ulp (f32)
+    assert np.mean(got == ref) > 0.5
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_normal_f64_tol(hx, impl):
+    key = R.PRNGKey(6)
+    got = hx.random.normal(key, (20000,), torch.float64, impl=impl).cpu().numpy()
+    ref = R.normal(key, (20000,), np.float64, impl)
+    np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-15)   # tolerance stated: 1e-13 relative
+
+
+def test_known_answers_on_device(hx):
+    # jax docs / tutorials (see tests/golden/rng_kat.json for provenance)
+    v = float(hx.random.normal(R.PRNGKey(42), (), torch.float32, impl="partitionable").cpu())
+    assert abs(v - (-0.028304616)) < 1e-7
+    v = float(hx.random.normal(R.PRNGKey(42), (), torch.float32, impl="legacy").cpu())
+    assert abs(v - (-0.18471177)) < 1e-6
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("n", [2, 3, 16, 100, 1625, 1626, 3000])
+def test_choice2_exact(hx, impl, n):
+    """hmc_side.py:43-47 per-walker choice; n > 1625 exercises the two-round shuffle."""
+    nkeys = 64 if n < 1000 else 24
+    keys = R.split(R.PRNGKey(n), nkeys, impl)
+    kd = torch.from_numpy(keys.view(np.int32).copy()).cuda()
+    got = hx.random.choice2(kd, n, impl=impl).cpu().numpy()
+    ref = np.stack([R.choice_no_replace(k, n, 2, impl) for k in keys])
+    np.testing.assert_array_equal(got, ref)
