@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — leapfrog walker-steps/s of the ensemble-Hamiltonian hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5] [--impl ours|reference]
+
+One "step" = one sampler iteration (two half-moves: every walker of both groups is proposed,
+integrated for L leapfrog steps and accepted/rejected).  Default workload = BASELINE.json's c5:
+1000-dim ill-conditioned Gaussian (kappa 1e4, full covariance), 65,536 walkers, walk move, L = 10,
+fp32 — the configuration the metric is quoted on; it fits one GPU because the walk move runs in
+projected form (no n x n momentum in HBM).  N > 1 shards the walkers of both halves by rows over the
+ranks (strong scaling: total work fixed) with one NCCL all-gather of the updated half per half-move.
+
+Prints ONE JSON line (contract in the task statement) with `roofline`, `cpu_baseline`, `e2e`,
+`clocks`, `gpu_launches`.  `--impl reference` times the reference algorithm on the host CPU: JAX is
+not installable in this image, so that arm runs the NumPy oracle port (dense n x n momentum form,
+exactly what the reference computes) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "h-emcee_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: target, d, kappa, W, L, eps, x64, move          (BASELINE.json configs / SURVEY §8d)
+    "c1": dict(target="gauss", d=10, kappa=1e3, W=32, L=10, eps=0.1, x64=True, move="walk"),
+    "c2": dict(target="gauss", d=100, kappa=1e4, W=1024, L=10, eps=0.1, x64=False, move="walk"),
+    "c2s": dict(target="gauss", d=100, kappa=1e4, W=1024, L=10, eps=0.1, x64=False, move="side"),
+    "c3": dict(target="rosenbrock", d=50, kappa=0, W=8192, L=10, eps=0.01, x64=False, move="walk"),
+    "c4": dict(target="funnel", d=25, kappa=0, W=16384, L=10, eps=0.05, x64=False, move="walk"),
+    "c5": dict(target="gauss", d=1000, kappa=1e4, W=65536, L=10, eps=0.1, x64=False, move="walk"),
+}
+CPU_SAMPLE_W = {"c1": 32, "c2": 1024, "c2s": 1024, "c3": 1024, "c4": 2048, "c5": 4096}
+
+
+def make_cov(d, kappa, seed=1):
+    """Sigma = Q diag(0.1 * linspace(1, kappa, d)) Q^T  (reference src/hemcee/tests/distribution.py:92-96)."""
+    rng = np.random.default_rng(seed)
+    Q, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    eig = 0.1 * np.linspace(1.0, kappa, d)
+    cov = (Q * eig) @ Q.T
+    prec = (Q / eig) @ Q.T
+    return 0.5 * (cov + cov.T), 0.5 * (prec + prec.T)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference's dense algorithm on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference(wl, steps, warmup, budget_s=None):
+    from oracle import jaxrng as R, moves as OM, targets as OT
+    cfg = WORKLOADS[wl]
+    Ws = min(cfg["W"], CPU_SAMPLE_W[wl])
+    d, L, eps = cfg["d"], cfg["L"], cfg["eps"]
+    dt = np.float64 if cfg["x64"] else np.float32
+    if cfg["target"] == "gauss":
+        cov, _ = make_cov(d, cfg["kappa"])
+        lp, grad = OT.make_gaussian(cov, np.zeros(d))
+    elif cfg["target"] == "rosenbrock":
+        lp, grad = OT.make_rosenbrock()
+    else:
+        lp, grad = OT.make_funnel()
+    move = OM.hmc_walk_move if cfg["move"] == "walk" else OM.hmc_side_move
+    k_init, k_run = R.split(R.PRNGKey(0), 2)
+    x = R.normal(k_init, (Ws, d), dt)
+    n = Ws // 2
+    g1, g2 = x[:n].copy(), x[n:].copy()
+    lp1, lp2 = lp(g1), lp(g2)
+    keys = R.split(k_run, 4 * (steps + warmup)).reshape(steps + warmup, 4, 2)
+    t0 = None
+    done = 0
+    for t in range(steps + warmup):
+        if t == warmup:
+            t0 = time.perf_counter()
+        k = keys[t]
+        q, la, _, lpq = move(g1, g2, eps, k[0], lp, grad, L, lp1)
+        g1, _ = OM.accept_proposal(g1, q, la, k[2]); lp1, _ = OM.accept_proposal(lp1, lpq, la, k[2])
+        q, la, _, lpq = move(g2, g1, eps, k[1], lp, grad, L, lp2)
+        g2, _ = OM.accept_proposal(g2, q, la, k[3]); lp2, _ = OM.accept_proposal(lp2, lpq, la, k[3])
+        if t >= warmup:
+            done += 1
+            if budget_s is not None and time.perf_counter() - t0 > budget_s:
+                break
+    el = time.perf_counter() - t0
+    value = Ws * L * done / el
+    sample = (f"{done} iterations of the {wl} workload at {Ws} of {cfg['W']} walkers (same dim {d}, L {L}, dtype "
+              f"{'f64' if cfg['x64'] else 'f32'}); the reference's cost per walker-step grows ~linearly with the "
+              f"walker count, so this sample flatters the CPU")
+    return dict(value=value, unit="walker-steps/s", cores=os.cpu_count(), kind="port", sample=sample), el / max(done, 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def algorithmic_flops_half_move(rows, n, d, L, target):
+    """minimal (projected-form) flops of one half-move over `rows` walkers."""
+    f = 2.0 * rows * n * d + (L + 1) * 2.0 * rows * d * d
+    if target == "gauss":
+        f += (L + 1) * 2.0 * rows * d * d + 2.0 * rows * d
+    elif target == "rosenbrock":
+        f += (L + 1) * 12.0 * rows * d
+    else:
+        f += (L + 1) * 8.0 * rows * d
+    return f
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    cfg = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    conf = dict(workload=f"{args.workload}: {cfg['d']}-dim {cfg['target']} (kappa {cfg['kappa']:g}), {cfg['W']} walkers, "
+                         f"{cfg['move']} move, L={cfg['L']}, eps={cfg['eps']}",
+                walkers=cfg["W"], dim=cfg["d"], L=cfg["L"], move=cfg["move"],
+                parallelism=f"walker rows sharded over {max(world, 1)} GPU(s), all-gather of the updated half per half-move"
+                if world > 1 else "single GPU",
+                l2="state (>=262 MB at c5) and centred complement exceed the 126 MB L2; chain slice written every step")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, per_iter = cpu_reference(args.workload, args.steps, max(args.warmup, 0))
+        line = dict(impl="reference", metric="leapfrog_walker_steps_per_sec", value=cb["value"], unit="walker-steps/s",
+                    n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=per_iter * 1e3,
+                    higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype="f64" if cfg["x64"] else "f32", data="synthetic", config=conf, cpu_baseline=cb,
+                    e2e=dict(value=cb["value"], unit="walker-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    gpu_launches=0, note="reference = NumPy oracle port of hemcee (JAX not installable here)")
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import hemcee_b200 as hx
+    from hemcee_b200 import _lib, _rt
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hx.config.update("enable_x64", cfg["x64"])
+    tdt = torch.float64 if cfg["x64"] else torch.float32
+    W, d, L, eps = cfg["W"], cfg["d"], cfg["L"], cfg["eps"]
+    n = W // 2
+    if n % world:
+        raise SystemExit("walkers/2 must divide by the number of GPUs")
+    rows = n // world
+    row0 = rank * rows
+    if cfg["target"] == "gauss":
+        _, prec = make_cov(d, cfg["kappa"])
+        tgt = hx.targets.GaussianFull(precision=prec)
+    elif cfg["target"] == "rosenbrock":
+        tgt = hx.targets.Rosenbrock(d)
+    else:
+        tgt = hx.targets.Funnel(d)
+    move = hx.hmc_walk_move if cfg["move"] == "walk" else hx.hmc_side_move
+    k_init, k_run = hx.random.split(hx.random.PRNGKey(0), 2)
+    x0 = hx.random.normal(k_init, (W, d), tdt)
+    if cfg["target"] == "rosenbrock":
+        x0 = x0 * 0.3 + 1.0
+    lib = _lib.load()
+    ctx = _rt.ctx(dev)
+    K, Wu = args.steps, args.warmup
+    keys_dev = hx.random.split_device(k_run, 4 * (K + Wu))
+    keys_host = keys_dev.cpu().numpy().view(np.uint32).reshape(K + Wu, 4, 2)
+    X = x0.clone()
+    lp = tgt.log_prob(X)
+    accepts = torch.zeros(W, dtype=torch.int32, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    desc = tgt.descriptor(tdt, dev)
+    mk = 0 if cfg["move"] == "walk" else 1
+
+    if world == 1:
+        chain = torch.empty((max(K, Wu), W, d), dtype=tdt, device=dev)
+        clp = torch.empty((max(K, Wu), W), dtype=tdt, device=dev)
+
+        def run(t0, T):
+            _lib.check(lib.hx_run_iterations(ctx, _rt.dtype_code(tdt), _rt.impl_code(), mk, 0, desc, _rt.ptr(X),
+                                             _rt.ptr(lp), n, eps, L, _rt.ptr(keys_dev[4 * t0:]), T, _rt.ptr(chain),
+                                             _rt.ptr(clp), _rt.ptr(accepts), _rt.ptr(flag), _rt.stream(dev)), "run")
+    else:
+        X1f, X2f = X[:n].contiguous(), X[n:].contiguous()
+        X1, X2 = X1f[row0:row0 + rows].clone(), X2f[row0:row0 + rows].clone()
+        lp1, lp2 = lp[:n][row0:row0 + rows].clone(), lp[n:][row0:row0 + rows].clone()
+        a1 = torch.zeros(rows, dtype=torch.int32, device=dev)
+        a2 = torch.zeros(rows, dtype=torch.int32, device=dev)
+        chain = torch.empty((max(K, Wu), 2 * rows, d), dtype=tdt, device=dev)
+
+        def half(Xa, Xbf, lpa, acc, km, ka, Xaf):
+            q, la, _, lpq = move(Xa, Xbf, eps, km, tgt, tgt, L, lpa, row0=row0, n=n)
+            hx.moves.accept_proposal(Xa, q, lpa, lpq, la, ka, acc, row0=row0, n=n)
+            dist.all_gather_into_tensor(Xaf, Xa)
+
+        def run(t0, T):
+            for t in range(t0, t0 + T):
+                k = keys_host[t]
+                half(X1, X2f, lp1, a1, k[0], k[2], X1f)
+                half(X2, X1f, lp2, a2, k[1], k[3], X2f)
+                chain[t - t0, :rows].copy_(X1); chain[t - t0, rows:].copy_(X2)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing (`value`) --------------------------------------------------------------
+    run(0, Wu)
+    barrier()
+    lib.hx_ctx_timing_enable(ctx, 1)
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    run(Wu, K)
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    kms, kn, alln = np.zeros(1), np.zeros(1, np.int64), np.zeros(1, np.int64)
+    import ctypes as C
+    c_ms, c_kn, c_all = C.c_double(), C.c_int64(), C.c_int64()
+    lib.hx_ctx_timing_read(ctx, C.byref(c_ms), C.byref(c_kn), C.byref(c_all))
+    lib.hx_ctx_timing_enable(ctx, 0)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    value = W * L * K / (ms * 1e-3)
+    acc_rate = None
+    if world == 1:
+        acc_rate = float(accepts.sum().item()) / (W * (K + Wu))
+
+    # ---- roofline of the dominant kernel (fused half-move) -------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+    k_launches = max(int(c_kn.value), 1)
+    k_ms = c_ms.value / k_launches
+    flops = algorithmic_flops_half_move(rows, n, d, L, cfg["target"])
+    achieved = flops / (k_ms * 1e-3) / 1e12
+    roofline = dict(bound="tensor", kernel="k_walk_half" if mk == 0 else "k_side_half", achieved=achieved, peak=peak_tf,
+                    unit="TFLOP/s", frac=achieved / peak_tf, traffic=None, peak_source=peak_src,
+                    flops_per_launch=flops, kernel_ms=k_ms, kernel_share_of_step=c_ms.value / ms,
+                    note="algorithmic flops = projected form 2*rows*n*d + (L+1)*(2*rows*d^2 [M] + grad) (SURVEY §8d)")
+
+    # ---- end-to-end through the public API with host buffers (`e2e`) -----------------------------------
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        x0_host = x0.cpu().pin_memory()
+        s = hx.HamiltonianEnsembleSampler(W, d, tgt, step_size=eps, L=L, move=move, adapt_inital_step_size=False,
+                                          adapt_step_size=False, adapt_length=False, verbose=False)
+        s.run_mcmc(k_run, x0_host, min(2, K), warmup=0, batch_size=1)      # warm the pinned allocations
+        torch.cuda.synchronize(dev)
+        s = hx.HamiltonianEnsembleSampler(W, d, tgt, step_size=eps, L=L, move=move, adapt_inital_step_size=False,
+                                          adapt_step_size=False, adapt_length=False, verbose=False)
+        t0 = time.perf_counter()
+        out = s.run_mcmc(k_run, x0_host, K, warmup=0, batch_size=max(1, K // 4))
+        torch.cuda.synchronize(dev)
+        el = time.perf_counter() - t0
+        isz = 8 if cfg["x64"] else 4
+        e2e = dict(value=W * L * K / el, unit="walker-steps/s",
+                   h2d_bytes_per_step=int(W * d * isz / K + 32), d2h_bytes_per_step=int(W * d * isz + W * isz),
+                   seconds=el, api="HamiltonianEnsembleSampler.run_mcmc (host initial_state -> host chain)",
+                   note="h2d = initial ensemble amortised over the steps + 4 keys; d2h = the step's chain slice and log-probs")
+        assert out.shape == (K, W, d)
+    elif world > 1:
+        e2e = dict(value=None, unit="walker-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0,
+                   note="multi-GPU e2e (host chain gather) not measured in this round")
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_reference(args.workload, 1000, 1, budget_s=15.0)
+
+    if rank == 0:
+        line = dict(metric="leapfrog_walker_steps_per_sec", value=value, unit="walker-steps/s", n_gpus=world, steps=K,
+                    warmup=Wu, ms_per_step=ms / K, higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype="f64" if cfg["x64"] else "f32", data="synthetic", config=conf, roofline=roofline,
+                    cpu_baseline=cb, clocks=clk, e2e=e2e, gpu_launches=int(c_all.value) if world == 1 else int(c_all.value),
+                    acceptance_rate=acc_rate, nonfinite=int(flag.item()))
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

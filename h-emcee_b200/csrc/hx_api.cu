@@ -5,6 +5,7 @@
 #include <cstring>
 #include <cmath>
 #include <new>
+#include <vector>
 
 #include "../../include/hx.h"
 #include "hx_common.cuh"
@@ -34,7 +35,57 @@ struct hx_ctx {
   void* buf[WS_NSLOT];
   size_t cap[WS_NSLOT];
   int sm_count;
+  // measurement hooks
+  int timing;
+  std::vector<cudaEvent_t>* ev;   // pairs (start, stop) around the dominant kernel
+  size_t ev_used;
+  int64_t launches;               // all kernels launched through this ctx
+  int last_gram_slices;
 };
+
+static int timing_begin(hx_ctx* ctx, cudaStream_t s) {
+  if (!ctx->timing) return 0;
+  if (!ctx->ev) ctx->ev = new (std::nothrow) std::vector<cudaEvent_t>();
+  if (!ctx->ev) return hx_fail(HX_E_NULL, "out of host memory");
+  while (ctx->ev->size() < ctx->ev_used + 2) {
+    cudaEvent_t e;
+    HX_CUDA(cudaEventCreate(&e));
+    ctx->ev->push_back(e);
+  }
+  HX_CUDA(cudaEventRecord((*ctx->ev)[ctx->ev_used], s));
+  return 0;
+}
+static int timing_end(hx_ctx* ctx, cudaStream_t s) {
+  if (!ctx->timing) return 0;
+  HX_CUDA(cudaEventRecord((*ctx->ev)[ctx->ev_used + 1], s));
+  ctx->ev_used += 2;
+  return 0;
+}
+
+extern "C" HX_API int hx_ctx_timing_enable(hx_ctx* ctx, int enable) {
+  if (!ctx) return hx_fail(HX_E_NULL, "hx_ctx_timing_enable: NULL ctx");
+  ctx->timing = enable ? 1 : 0;
+  ctx->ev_used = 0;
+  ctx->launches = 0;
+  return 0;
+}
+
+extern "C" HX_API int hx_ctx_timing_read(hx_ctx* ctx, double* kernel_ms, int64_t* kernel_launches, int64_t* all_launches) {
+  if (!ctx) return hx_fail(HX_E_NULL, "hx_ctx_timing_read: NULL ctx");
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+    HX_CUDA(cudaEventSynchronize((*ctx->ev)[i + 1]));
+    float t = 0.f;
+    HX_CUDA(cudaEventElapsedTime(&t, (*ctx->ev)[i], (*ctx->ev)[i + 1]));
+    ms += t;
+  }
+  if (kernel_ms) *kernel_ms = ms;
+  if (kernel_launches) *kernel_launches = (int64_t)(ctx->ev_used / 2);
+  if (all_launches) *all_launches = ctx->launches;
+  ctx->ev_used = 0;
+  ctx->launches = 0;
+  return 0;
+}
 
 static int ws_get(hx_ctx* ctx, int slot, size_t bytes, void** out) {
   if (bytes == 0) bytes = 16;
@@ -79,6 +130,10 @@ extern "C" HX_API int hx_ctx_destroy(hx_ctx* ctx) {
   cudaSetDevice(ctx->device);
   for (int i = 0; i < WS_NSLOT; ++i)
     if (ctx->buf[i]) cudaFree(ctx->buf[i]);
+  if (ctx->ev) {
+    for (cudaEvent_t e : *ctx->ev) cudaEventDestroy(e);
+    delete ctx->ev;
+  }
   delete ctx;
   return 0;
 }
@@ -270,6 +325,7 @@ static int gram_matrix(hx_ctx* ctx, const T* C, int n, int ldd, T** M_out, cudaS
   rows_per_slice = ((rows_per_slice + 15) / 16) * 16;
   slices = (n + rows_per_slice - 1) / rows_per_slice;
   dim3 gg(tiles, tiles, slices);
+  ctx->last_gram_slices = slices;
   if (slices == 1) {
     k_gram<T><<<gg, 256, 0, s>>>(C, n, ldd, rows_per_slice, (T*)pM);
     HX_LAUNCH_CHECK("k_gram");
@@ -334,7 +390,10 @@ static int walk_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1,
     W.P.nonfinite = fuse->nonfinite;
   }
   W.P.legacy = (impl == HX_RNG_LEGACY) ? 1 : 0;
-  return launch_walk<T>(W.P, ctx->sm_count, s);
+  ctx->launches += 5 + (ctx->last_gram_slices > 1 ? 1 : 0);   // colsum, mean, centre, gram(+reduce), half-move
+  if (int e = timing_begin(ctx, s)) return e;
+  if (int e = launch_walk<T>(W.P, ctx->sm_count, s)) return e;
+  return timing_end(ctx, s);
 }
 
 extern "C" HX_API int hx_walk_move(hx_ctx* ctx, int dtype, int impl, const hx_target* tgt, const void* X1, const void* X2,
@@ -383,7 +442,10 @@ static int side_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1,
     W.P.nonfinite = fuse->nonfinite;
   }
   W.P.legacy = (impl == HX_RNG_LEGACY) ? 1 : 0;
-  return launch_side<T>(W.P, ctx->sm_count, s);
+  ctx->launches += 2;   // choice, half-move
+  if (int e = timing_begin(ctx, s)) return e;
+  if (int e = launch_side<T>(W.P, ctx->sm_count, s)) return e;
+  return timing_end(ctx, s);
 }
 
 extern "C" HX_API int hx_side_move(hx_ctx* ctx, int dtype, int impl, const hx_target* tgt, const void* X1, const void* X2,

@@ -95,6 +95,12 @@ HX_API int hx_ctx_create(hx_ctx** out, int device);
 HX_API int hx_ctx_destroy(hx_ctx* ctx);
 /* bytes of private scratch currently held (diagnostics) */
 HX_API size_t hx_ctx_workspace_bytes(const hx_ctx* ctx);
+/* Measurement hooks (bench.py roofline): when enabled, every launch of the dominant half-move kernel
+ * is bracketed by CUDA events on its launch stream.  hx_ctx_timing_read synchronises those events and
+ * returns the summed kernel time [ms], the number of launches and the number of ALL kernels this
+ * library launched through `ctx` since the last reset; then it resets the counters.               */
+HX_API int hx_ctx_timing_enable(hx_ctx* ctx, int enable);
+HX_API int hx_ctx_timing_read(hx_ctx* ctx, double* kernel_ms, int64_t* kernel_launches, int64_t* all_launches);
 
 /* ---- (1) RNG: bit-exact jax.random subset ------------------------------------------------
  * replaces jax.random.split   (call sites: samplers/hamiltonian_ensemble.py:90,228,330;
