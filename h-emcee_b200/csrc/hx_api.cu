@@ -12,6 +12,9 @@
 #include "hx_rng.cuh"
 #include "hx_prep.cuh"
 #include "hx_launch.cuh"
+#include "hx_ctx.h"
+#include "hx_tc_walk.h"
+#include <type_traits>
 
 using namespace hx;
 
@@ -28,22 +31,21 @@ int hx_fail(int code, const char* fmt, ...) {
 #define fail hx_fail
 
 // ---- ctx / workspace ---------------------------------------------------------------------------------
-enum Slot { WS_C = 0, WS_M, WS_MEAN, WS_PART, WS_G, WS_S, WS_Q, WS_LA, WS_LP, WS_IDX, WS_GRAMP, WS_NSLOT };
+int ws_get(hx_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (bytes == 0) bytes = 16;
+  if (ctx->cap[slot] < bytes) {
+    if (ctx->buf[slot]) HX_CUDA(cudaFree(ctx->buf[slot]));
+    ctx->buf[slot] = nullptr;
+    ctx->cap[slot] = 0;
+    size_t want = bytes + bytes / 4;
+    HX_CUDA(cudaMalloc(&ctx->buf[slot], want));
+    ctx->cap[slot] = want;
+  }
+  *out = ctx->buf[slot];
+  return 0;
+}
 
-struct hx_ctx {
-  int device;
-  void* buf[WS_NSLOT];
-  size_t cap[WS_NSLOT];
-  int sm_count;
-  // measurement hooks
-  int timing;
-  std::vector<cudaEvent_t>* ev;   // pairs (start, stop) around the dominant kernel
-  size_t ev_used;
-  int64_t launches;               // all kernels launched through this ctx
-  int last_gram_slices;
-};
-
-static int timing_begin(hx_ctx* ctx, cudaStream_t s) {
+int timing_begin(hx_ctx* ctx, cudaStream_t s) {
   if (!ctx->timing) return 0;
   if (!ctx->ev) ctx->ev = new (std::nothrow) std::vector<cudaEvent_t>();
   if (!ctx->ev) return hx_fail(HX_E_NULL, "out of host memory");
@@ -55,12 +57,20 @@ static int timing_begin(hx_ctx* ctx, cudaStream_t s) {
   HX_CUDA(cudaEventRecord((*ctx->ev)[ctx->ev_used], s));
   return 0;
 }
-static int timing_end(hx_ctx* ctx, cudaStream_t s) {
+int timing_end(hx_ctx* ctx, cudaStream_t s) {
   if (!ctx->timing) return 0;
   HX_CUDA(cudaEventRecord((*ctx->ev)[ctx->ev_used + 1], s));
   ctx->ev_used += 2;
   return 0;
 }
+
+extern "C" HX_API int hx_ctx_set_precision(hx_ctx* ctx, int mode) {
+  if (!ctx) return hx_fail(HX_E_NULL, "hx_ctx_set_precision: NULL ctx");
+  if (mode < HX_PREC_AUTO || mode > HX_PREC_BF16) return hx_fail(HX_E_DTYPE, "hx_ctx_set_precision: unknown mode %d", mode);
+  ctx->precision = mode;
+  return 0;
+}
+extern "C" HX_API int hx_ctx_last_path(const hx_ctx* ctx) { return ctx ? ctx->last_path : -1; }
 
 extern "C" HX_API int hx_ctx_timing_enable(hx_ctx* ctx, int enable) {
   if (!ctx) return hx_fail(HX_E_NULL, "hx_ctx_timing_enable: NULL ctx");
@@ -84,20 +94,6 @@ extern "C" HX_API int hx_ctx_timing_read(hx_ctx* ctx, double* kernel_ms, int64_t
   if (all_launches) *all_launches = ctx->launches;
   ctx->ev_used = 0;
   ctx->launches = 0;
-  return 0;
-}
-
-static int ws_get(hx_ctx* ctx, int slot, size_t bytes, void** out) {
-  if (bytes == 0) bytes = 16;
-  if (ctx->cap[slot] < bytes) {
-    if (ctx->buf[slot]) HX_CUDA(cudaFree(ctx->buf[slot]));
-    ctx->buf[slot] = nullptr;
-    ctx->cap[slot] = 0;
-    size_t want = bytes + bytes / 4;
-    HX_CUDA(cudaMalloc(&ctx->buf[slot], want));
-    ctx->cap[slot] = want;
-  }
-  *out = ctx->buf[slot];
   return 0;
 }
 
@@ -311,6 +307,22 @@ static int center_complement(hx_ctx* ctx, const T* X2, int n, int d, int ldd, T*
   return 0;
 }
 
+// mean_0(X2) only (tensor-core path builds its own transposed planes)
+template <typename T>
+static int complement_mean(hx_ctx* ctx, const T* X2, int n, int d, T** mean_out, cudaStream_t s) {
+  void *pMean, *pPart;
+  const int nchunks = (n + kColChunk - 1) / kColChunk;
+  if (int e = ws_get(ctx, WS_MEAN, (size_t)d * sizeof(T), &pMean)) return e;
+  if (int e = ws_get(ctx, WS_PART, (size_t)nchunks * d * sizeof(T), &pPart)) return e;
+  dim3 g1((d + 127) / 128, nchunks);
+  k_colsum_partial<T><<<g1, 128, 0, s>>>(X2, n, d, (T*)pPart);
+  HX_LAUNCH_CHECK("k_colsum_partial");
+  k_mean_final<T><<<(d + 127) / 128, 128, 0, s>>>((const T*)pPart, nchunks, n, d, (T*)pMean);
+  HX_LAUNCH_CHECK("k_mean_final");
+  *mean_out = (T*)pMean;
+  return 0;
+}
+
 // M = C^T C with a fixed-order split over rows (deterministic)
 template <typename T>
 static int gram_matrix(hx_ctx* ctx, const T* C, int n, int ldd, T** M_out, cudaStream_t s) {
@@ -369,6 +381,27 @@ static int walk_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1,
   memset(&W.P, 0, sizeof(W.P));
   if (int e = make_target<T>(tgt, &W.P.tg, "hx_walk_move")) return e;
   const int d = tgt->dim, ldd = round4(d);
+  if constexpr (std::is_same<T, float>::value) {
+    if (tc::walk_eligible(ctx, HX_F32, tgt, n, rows, flags)) {
+      float* mean;
+      if (int e = complement_mean<float>(ctx, X2, n, d, &mean, s)) return e;
+      if (!pproj) {
+        void* pS;
+        if (int e = ws_get(ctx, WS_S, (size_t)rows * d * sizeof(float), &pS)) return e;
+        pproj = (float*)pS;
+      }
+      tc::FuseF32 f32;
+      if (fuse) {
+        f32.akey_ptr = fuse->akey_ptr; f32.lp1w = fuse->lp1w; f32.accepts = fuse->accepts;
+        f32.chain_out = fuse->chain_out; f32.chain_lp = fuse->chain_lp; f32.nonfinite = fuse->nonfinite;
+      }
+      ctx->launches += 2;
+      ctx->last_path = 1;
+      return tc::walk_half(ctx, impl, tgt, mean, X1, X2, n, row0, rows, eps, key, key_ptr, L, lp1, Q, logacc, pproj,
+                           lp_out, fuse ? &f32 : nullptr, s);
+    }
+  }
+  ctx->last_path = 0;
   T *C, *M;
   if (int e = center_complement<T>(ctx, X2, n, d, ldd, &C, s)) return e;
   if (int e = gram_matrix<T>(ctx, C, n, ldd, &M, s)) return e;

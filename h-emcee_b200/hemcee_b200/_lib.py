@@ -13,6 +13,7 @@ HX_F32, HX_F64 = 0, 1
 HX_RNG_PARTITIONABLE, HX_RNG_LEGACY = 0, 1
 HX_TARGET_GAUSS_ISO, HX_TARGET_GAUSS_FULL, HX_TARGET_ROSENBROCK, HX_TARGET_FUNNEL = 0, 1, 2, 3
 HX_MOVE_FROZEN_GRAD = 1
+HX_PREC_AUTO, HX_PREC_EXACT, HX_PREC_BF16X3, HX_PREC_BF16 = 0, 1, 2, 3
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libhx.so")
 
@@ -37,6 +38,8 @@ _PROTOS = {
     "hx_ctx_create": (C.c_int, [C.POINTER(_P), C.c_int]),
     "hx_ctx_destroy": (C.c_int, [_P]),
     "hx_ctx_workspace_bytes": (C.c_size_t, [_P]),
+    "hx_ctx_set_precision": (C.c_int, [_P, C.c_int]),
+    "hx_ctx_last_path": (C.c_int, [_P]),
     "hx_ctx_timing_enable": (C.c_int, [_P, C.c_int]),
     "hx_ctx_timing_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "hx_split": (C.c_int, [_KEY, C.c_int, C.c_int64, _P, _P]),

@@ -19,11 +19,17 @@ class _Config:
                  (reference tests set it: src/hemcee/tests/test_proposal.py:7).
     rng_impl   : "partitionable" (JAX >= 0.5 default, the mode the reference authors ran)
                  or "legacy" (`jax_threefry_partitionable=False`).
+    precision  : how the walk move's dense contractions are evaluated (include/hx.h HX_PREC_*):
+                 "auto" (exact fp32/fp64 SIMT kernels; split-bf16 tensor cores for large fp32
+                 full-covariance Gaussian problems), "exact", "bf16x3", "bf16".
     """
+
+    PRECISIONS = {"auto": 0, "exact": 1, "bf16x3": 2, "bf16": 3}
 
     def __init__(self):
         self.enable_x64 = False
         self.rng_impl = "partitionable"
+        self.precision = "auto"
 
     def update(self, name, value):
         if name in ("enable_x64", "jax_enable_x64"):
@@ -32,6 +38,12 @@ class _Config:
             if value not in ("partitionable", "legacy"):
                 raise ValueError("rng_impl must be 'partitionable' or 'legacy'")
             self.rng_impl = value
+        elif name == "precision":
+            if value not in self.PRECISIONS:
+                raise ValueError(f"precision must be one of {sorted(self.PRECISIONS)}")
+            self.precision = value
+            for h in _ctx.values():
+                _lib.check(_lib.load().hx_ctx_set_precision(h, self.PRECISIONS[value]), "hx_ctx_set_precision")
         elif name == "jax_threefry_partitionable":
             self.rng_impl = "partitionable" if value else "legacy"
         else:
@@ -76,6 +88,7 @@ def ctx(dev: torch.device) -> C.c_void_p:
     if idx not in _ctx:
         h = C.c_void_p()
         _lib.check(_lib.load().hx_ctx_create(C.byref(h), idx), "hx_ctx_create")
+        _lib.check(_lib.load().hx_ctx_set_precision(h, config.PRECISIONS[config.precision]), "hx_ctx_set_precision")
         _ctx[idx] = h
     return _ctx[idx]
 

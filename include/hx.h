@@ -95,6 +95,18 @@ HX_API int hx_ctx_create(hx_ctx** out, int device);
 HX_API int hx_ctx_destroy(hx_ctx* ctx);
 /* bytes of private scratch currently held (diagnostics) */
 HX_API size_t hx_ctx_workspace_bytes(const hx_ctx* ctx);
+/* Precision policy of the walk move's dense contractions:
+ *   HX_PREC_AUTO   exact SIMT fp32/fp64 kernels, except fp32 full-covariance Gaussian targets with
+ *                  dim >= 256 and >= 2048 walkers per group, which use HX_PREC_BF16X3
+ *   HX_PREC_EXACT  always the exact SIMT kernels (fp32 FMA / fp64)
+ *   HX_PREC_BF16X3 tcgen05 tensor cores, operands split into bf16 hi+lo, three products, fp32
+ *                  accumulation in TMEM (fp32-class accuracy, ~2^-16 per product)
+ *   HX_PREC_BF16   tcgen05, single bf16 product (statistical parity only)                         */
+enum { HX_PREC_AUTO = 0, HX_PREC_EXACT = 1, HX_PREC_BF16X3 = 2, HX_PREC_BF16 = 3 };
+HX_API int hx_ctx_set_precision(hx_ctx* ctx, int mode);
+/* which kernel the timing hooks bracketed last: 0 = fused SIMT half-move, 1 = tcgen05 projection GEMM */
+HX_API int hx_ctx_last_path(const hx_ctx* ctx);
+
 /* Measurement hooks (bench.py roofline): when enabled, every launch of the dominant half-move kernel
  * is bracketed by CUDA events on its launch stream.  hx_ctx_timing_read synchronises those events and
  * returns the summed kernel time [ms], the number of launches and the number of ALL kernels this

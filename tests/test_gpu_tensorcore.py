@@ -1,0 +1,95 @@
+"""tcgen05 path of the walk half-move (split-bf16 operands, fp32 TMEM accumulation) against the exact
+SIMT kernels and the dense oracle.
+
+Tolerances (stated): bf16x3 — positions within 2e-4 of the ensemble scale, log-accept within 5e-3
+(fp32-class: the three-product split carries ~2^-16 relative error per product, the same order as fp32
+accumulation over n terms); bf16 single pass — statistical parity only, positions within 2e-2."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import jaxrng as R, moves as OM, targets as OT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def prec(hx):
+    def set_(mode):
+        hx.config.update("precision", mode)
+    yield set_
+    hx.config.update("precision", "auto")
+
+
+def _problem(hx, n, d, seed=0, kappa=100.0):
+    ks = R.split(R.PRNGKey(seed), 4)
+    cov = OT.make_covariance_skewed(ks[0], d, kappa, np.float64)
+    mean = R.normal(ks[3], (d,), np.float64) * 0.1
+    g1 = (R.normal(ks[1], (n, d), np.float32) * 0.5).astype(np.float32)
+    g2 = (R.normal(ks[2], (n, d), np.float32) * 0.8).astype(np.float32)
+    return hx.targets.GaussianFull(cov=cov, mean=mean), OT.make_gaussian(cov, mean), g1, g2, ks[3]
+
+
+@pytest.mark.parametrize("n,d", [(128, 64), (256, 200), (640, 256), (384, 300)])
+@pytest.mark.parametrize("L", [1, 4])
+def test_bf16x3_matches_exact_and_oracle(hx, prec, n, d, L):
+    tgt, (olp, og), g1, g2, key = _problem(hx, n, d)
+    G1, G2 = torch.from_numpy(g1).cuda(), torch.from_numpy(g2).cuda()
+    LP1 = tgt.log_prob(G1)
+    prec("exact")
+    qe, lae, ppe, lpe = hx.hmc_walk_move(G1, G2, 0.03, key, tgt, tgt, L, LP1)
+    prec("bf16x3")
+    qt, lat, ppt, lpt = hx.hmc_walk_move(G1, G2, 0.03, key, tgt, tgt, L, LP1)
+    a64, b64 = g1.astype(np.float64), g2.astype(np.float64)
+    q64, la64, pp64, lp64 = OM.hmc_walk_move(a64, b64, 0.03, key, olp, og, L, olp(a64), rng_dtype=np.float32)
+    scale = np.abs(q64).max()
+    for q in (qe, qt):
+        np.testing.assert_allclose(q.cpu().numpy(), q64, rtol=0, atol=2e-4 * scale)
+    np.testing.assert_allclose(ppt.cpu().numpy(), pp64, rtol=0, atol=2e-4 * np.abs(pp64).max())
+    np.testing.assert_allclose(lpt.cpu().numpy(), lp64, rtol=2e-4, atol=2e-3)
+    np.testing.assert_allclose(lat.cpu().numpy(), la64, rtol=0, atol=5e-3)
+    np.testing.assert_allclose(lae.cpu().numpy(), la64, rtol=0, atol=5e-3)
+
+
+def test_bf16_single_pass_statistical(hx, prec):
+    tgt, (olp, og), g1, g2, key = _problem(hx, 256, 128)
+    G1, G2 = torch.from_numpy(g1).cuda(), torch.from_numpy(g2).cuda()
+    LP1 = tgt.log_prob(G1)
+    prec("bf16")
+    qt, lat, _, _ = hx.hmc_walk_move(G1, G2, 0.03, key, tgt, tgt, 4, LP1)
+    a64, b64 = g1.astype(np.float64), g2.astype(np.float64)
+    q64, la64, _, _ = OM.hmc_walk_move(a64, b64, 0.03, key, olp, og, 4, olp(a64), rng_dtype=np.float32)
+    np.testing.assert_allclose(qt.cpu().numpy(), q64, rtol=0, atol=2e-2 * np.abs(q64).max())
+    assert np.all(np.isfinite(lat.cpu().numpy()))
+
+
+def test_tc_shard_invariance_and_determinism(hx, prec):
+    prec("bf16x3")
+    tgt, _, g1, g2, key = _problem(hx, 512, 96)
+    G1, G2 = torch.from_numpy(g1).cuda(), torch.from_numpy(g2).cuda()
+    LP1 = tgt.log_prob(G1)
+    full = hx.hmc_walk_move(G1, G2, 0.03, key, tgt, tgt, 3, LP1)
+    again = hx.hmc_walk_move(G1, G2, 0.03, key, tgt, tgt, 3, LP1)
+    for a, b in zip(full, again):
+        assert torch.equal(a, b)
+    parts = [hx.hmc_walk_move(G1[r * 128:(r + 1) * 128], G2, 0.03, key, tgt, tgt, 3, LP1[r * 128:(r + 1) * 128],
+                              row0=r * 128, n=512) for r in range(4)]
+    for i in range(4):
+        assert torch.equal(torch.cat([p[i] for p in parts]), full[i])
+
+
+def test_tc_sampler_chain_close_to_exact(hx, prec):
+    """Whole run_mcmc on the tensor-core path vs the exact path: same accept decisions for the first
+    iterations and chains within the bf16x3 tolerance."""
+    W, d, T = 512, 64, 4
+    tgt, _, g1, g2, key = _problem(hx, W // 2, d)
+    x0 = np.concatenate([g1, g2])
+    out = {}
+    for mode in ("exact", "bf16x3"):
+        prec(mode)
+        s = hx.HamiltonianEnsembleSampler(W, d, tgt, step_size=0.03, L=5, adapt_inital_step_size=False,
+                                          adapt_step_size=False, adapt_length=False, verbose=False)
+        out[mode] = (s.run_mcmc(R.PRNGKey(5), x0, T, warmup=0), s.diagnostics_main["accepts"].sum())
+    same = np.all(np.abs(out["exact"][0] - out["bf16x3"][0]) <= 5e-4 * np.abs(out["exact"][0]).max(), axis=2)
+    assert same.mean() > 0.98
+    assert abs(int(out["exact"][1]) - int(out["bf16x3"][1])) <= 0.02 * W * T
