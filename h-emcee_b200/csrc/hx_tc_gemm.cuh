@@ -8,7 +8,7 @@
 // accumulator (~2^-16 relative product error, fp32-class); nprod = 1 uses the hi planes only.
 //
 // One CTA per 128 x BN output tile; warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread),
-// warps 2-5 = epilogue (TMEM -> registers -> smem transpose -> coalesced global access).
+// warps 2-5 = epilogue (TMEM -> registers; one thread per output row, 128-byte runs per thread).
 #pragma once
 #include "hx_tc.cuh"
 #include "hx_common.cuh"
@@ -53,7 +53,7 @@ struct SmemLayout {
   static constexpr int B_PLANE = BN * 128;
   static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
   static constexpr int STAGES = (BN >= 256) ? 2 : 3;
-  static constexpr int STG = 4 * 32 * 33 * 4;        // epilogue transpose staging (4 warps)
+  static constexpr int STG = 0;
   static constexpr int BYTES = STAGES * STAGE + STG + 256 + 1024;   // + barriers + alignment slack
 };
 
@@ -64,7 +64,6 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
-  float* stg_all = (float*)(smem + L::STAGES * L::STAGE);
   uint64_t* bars = (uint64_t*)(smem + L::STAGES * L::STAGE + L::STG);
   uint64_t* full = bars;                  // [STAGES]
   uint64_t* empty = bars + L::STAGES;     // [STAGES]
@@ -132,13 +131,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       umma_commit(tmem_full);       // accumulator complete
     }
   } else {
-    // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) ------------------------------------
+    // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); thread = one output row ----------
     const int q = warp & 3;
-    float* stg = stg_all + (warp - 2) * 32 * 33;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const int row_base = m0 + 32 * q;
-    float rowacc = 0.f;                 // lane r holds the partial of row (row_base + r)
+    const int row = m0 + 32 * q + lane;
+    const bool rok = row < g.M;
+    const bool vec = (g.N & 3) == 0 && (EPI == EPI_STORE ? (g.ldo & 3) == 0 : true);
+    float rowacc = 0.f;
     const int NC = BN / 32;
 #pragma unroll 1
     for (int cc = 0; cc < NC; ++cc) {
@@ -146,61 +146,136 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (col0 >= g.N) break;           // warp-uniform
       float v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cc * 32), v);
+      if (!rok) continue;
+      const int nval = min(32, g.N - col0);
+      const bool fast = vec && nval == 32;
+      if (EPI == EPI_STORE) {
+        float* o = g.out + (size_t)row * g.ldo + col0;
+        if (fast) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
-      __syncwarp();
-      const int col = col0 + lane;
-      const bool cok = col < g.N;
-      const float mu = (EPI != EPI_STORE && g.mu && cok) ? g.mu[col] : 0.f;
-#pragma unroll 4
-      for (int r = 0; r < 32; ++r) {
-        const int row = row_base + r;
-        if (row >= g.M) break;          // warp-uniform
-        const float acc = stg[r * 33 + lane];
-        float x = 0.f;
-        if (cok) {
-          if (EPI == EPI_STORE) {
-            g.out[(size_t)row * g.ldo + col] = acc;
-          } else if (EPI == EPI_GRAD) {
-            const size_t idx = (size_t)row * g.N + col;
-            g.G[idx] = acc;
-            __nv_bfloat16 hi, lo;
-            split_bf16(acc, hi, lo);
-            const size_t pidx = (size_t)row * g.Kout_p + col;
-            g.planes_out[pidx] = hi;
-            g.planes_out[(size_t)g.rows_out_pad * g.Kout_p + pidx] = lo;
-            if (g.want_lp) x = acc * (g.Q[idx] - mu);
+          for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) o[j] = v[j];
+        }
+      } else {
+        const size_t base = (size_t)row * g.N + col0;
+        const size_t pbase = (size_t)row * g.Kout_p + col0;
+        const size_t plane = (size_t)g.rows_out_pad * g.Kout_p;
+        float mu[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mu[j] = 0.f;
+        if (g.mu) {
+          if (fast) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(g.mu + col0) + j);
+              mu[4 * j] = t.x; mu[4 * j + 1] = t.y; mu[4 * j + 2] = t.z; mu[4 * j + 3] = t.w;
+            }
           } else {
-            const size_t idx = (size_t)row * g.N + col;
-            const float s_old = g.S[idx];
-            const float s_new = s_old - g.a * acc;
-            x = g.a * g.G[idx] * (s_old + s_new);
-            g.S[idx] = s_new;
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) mu[j] = g.mu[col0 + j];
+          }
+        }
+        if (EPI == EPI_GRAD) {
+          // g = acc: store fp32 + bf16 planes; optional lp partial sum_j g_j (q_j - mu_j)
+          float* Gp = g.G + base;
+          if (fast) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(Gp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) Gp[j] = v[j];
+          }
+          __align__(16) __nv_bfloat16 hi[32], lo[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) split_bf16(j < nval ? v[j] : 0.f, hi[j], lo[j]);
+          if (fast) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              reinterpret_cast<uint4*>(g.planes_out + pbase)[j] = reinterpret_cast<const uint4*>(hi)[j];
+              reinterpret_cast<uint4*>(g.planes_out + plane + pbase)[j] = reinterpret_cast<const uint4*>(lo)[j];
+            }
+          } else {
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) { g.planes_out[pbase + j] = hi[j]; g.planes_out[plane + pbase + j] = lo[j]; }
+          }
+          if (g.want_lp) {
+            const float* Qp = g.Q + base;
+            if (fast) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = reinterpret_cast<const float4*>(Qp)[j];
+                rowacc = fmaf(v[4 * j], t.x - mu[4 * j], rowacc);
+                rowacc = fmaf(v[4 * j + 1], t.y - mu[4 * j + 1], rowacc);
+                rowacc = fmaf(v[4 * j + 2], t.z - mu[4 * j + 2], rowacc);
+                rowacc = fmaf(v[4 * j + 3], t.w - mu[4 * j + 3], rowacc);
+              }
+            } else {
+              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) rowacc = fmaf(v[j], Qp[j] - mu[j], rowacc);
+            }
+          }
+        } else {
+          // kick: S -= a * acc ; dK += a * g * (S- + S+) ; optional drift q += eps * S+ (+ centred planes)
+          float sv[32], gv[32], qv[32];
+          float* Sp = g.S + base;
+          const float* Gp = g.G + base;
+          float* Qp = g.Q + base;
+          if (fast) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = reinterpret_cast<const float4*>(Sp)[j];
+              sv[4 * j] = t.x; sv[4 * j + 1] = t.y; sv[4 * j + 2] = t.z; sv[4 * j + 3] = t.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = reinterpret_cast<const float4*>(Gp)[j];
+              gv[4 * j] = t.x; gv[4 * j + 1] = t.y; gv[4 * j + 2] = t.z; gv[4 * j + 3] = t.w;
+            }
             if (g.drift) {
-              const float qn = g.Q[idx] + g.eps * s_new;
-              g.Q[idx] = qn;
-              __nv_bfloat16 hi, lo;
-              split_bf16(qn - mu, hi, lo);
-              const size_t pidx = (size_t)row * g.Kout_p + col;
-              g.planes_out[pidx] = hi;
-              g.planes_out[(size_t)g.rows_out_pad * g.Kout_p + pidx] = lo;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = reinterpret_cast<const float4*>(Qp)[j];
+                qv[4 * j] = t.x; qv[4 * j + 1] = t.y; qv[4 * j + 2] = t.z; qv[4 * j + 3] = t.w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { sv[j] = 0.f; gv[j] = 0.f; qv[j] = 0.f; }
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) { sv[j] = Sp[j]; gv[j] = Gp[j]; if (g.drift) qv[j] = Qp[j]; }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float s_new = sv[j] - g.a * v[j];
+            rowacc = fmaf(g.a * gv[j], sv[j] + s_new, rowacc);
+            sv[j] = s_new;
+            qv[j] = qv[j] + g.eps * s_new;
+          }
+          if (fast) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(Sp)[j] = make_float4(sv[4 * j], sv[4 * j + 1], sv[4 * j + 2], sv[4 * j + 3]);
+          } else {
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) Sp[j] = sv[j];
+          }
+          if (g.drift) {
+            __align__(16) __nv_bfloat16 hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) split_bf16(j < nval ? qv[j] - mu[j] : 0.f, hi[j], lo[j]);
+            if (fast) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(Qp)[j] = make_float4(qv[4 * j], qv[4 * j + 1], qv[4 * j + 2], qv[4 * j + 3]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                reinterpret_cast<uint4*>(g.planes_out + pbase)[j] = reinterpret_cast<const uint4*>(hi)[j];
+                reinterpret_cast<uint4*>(g.planes_out + plane + pbase)[j] = reinterpret_cast<const uint4*>(lo)[j];
+              }
+            } else {
+              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) { Qp[j] = qv[j]; g.planes_out[pbase + j] = hi[j]; g.planes_out[plane + pbase + j] = lo[j]; }
             }
           }
         }
-        if (EPI != EPI_STORE) {
-          const float s = warp_sum(x);
-          if (lane == r) rowacc += s;
-        }
       }
-      __syncwarp();
     }
-    if (EPI != EPI_STORE) {
-      const int row = row_base + lane;
-      if (row < g.M) {
-        float* p = g.part + (size_t)row * g.NT + blockIdx.x;
-        if (EPI == EPI_GRAD) { if (g.want_lp) *p = rowacc; }
-        else *p += rowacc;
-      }
+    if (EPI != EPI_STORE && rok) {
+      float* p = g.part + (size_t)row * g.NT + blockIdx.x;
+      if (EPI == EPI_GRAD) { if (g.want_lp) *p = rowacc; }
+      else *p += rowacc;
     }
     tc_fence_before();
   }
