@@ -298,12 +298,24 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
     k_launches = max(int(c_kn.value), 1)
     k_ms = c_ms.value / k_launches
-    flops = algorithmic_flops_half_move(rows, n, d, L, cfg["target"])
+    path = lib.hx_ctx_last_path(ctx)
+    if path == 1:
+        # tensor-core path: the bracketed kernel sequence is the momentum projection S0 = P0 C of one half-move
+        # (tcgen05 GEMM chunks, with the counter-based draw of the next chunk overlapped on a side stream)
+        kname = "tc::k_tc_gemm<256,EPI_STORE> (projection S0 = P0 C, bf16x3) + overlapped tc::k_rng_planes"
+        flops = 2.0 * rows * n * d
+        note = ("algorithmic flops = 2*rows*n*d of the projection (SURVEY §8d first term); the kernel executes 3 bf16 "
+                "products per algorithmic product (split-bf16 operands for fp32-class accuracy)")
+    else:
+        kname = "k_walk_half" if mk == 0 else "k_side_half"
+        flops = algorithmic_flops_half_move(rows, n, d, L, cfg["target"])
+        note = "algorithmic flops = projected form 2*rows*n*d + (L+1)*(2*rows*d^2 [M] + grad) (SURVEY §8d)"
     achieved = flops / (k_ms * 1e-3) / 1e12
-    roofline = dict(bound="tensor", kernel="k_walk_half" if mk == 0 else "k_side_half", achieved=achieved, peak=peak_tf,
+    roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=peak_tf,
                     unit="TFLOP/s", frac=achieved / peak_tf, traffic=None, peak_source=peak_src,
-                    flops_per_launch=flops, kernel_ms=k_ms, kernel_share_of_step=c_ms.value / ms,
-                    note="algorithmic flops = projected form 2*rows*n*d + (L+1)*(2*rows*d^2 [M] + grad) (SURVEY §8d)")
+                    flops_per_launch=flops, kernel_ms=k_ms, kernel_share_of_step=c_ms.value / ms, note=note,
+                    half_move_algorithmic_tflops=algorithmic_flops_half_move(rows, n, d, L, cfg["target"]) * 2 * K
+                    / (ms * 1e-3) / 1e12)
 
     # ---- end-to-end through the public API with host buffers (`e2e`) -----------------------------------
     e2e = None

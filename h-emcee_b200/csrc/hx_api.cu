@@ -130,6 +130,11 @@ extern "C" HX_API int hx_ctx_destroy(hx_ctx* ctx) {
     for (cudaEvent_t e : *ctx->ev) cudaEventDestroy(e);
     delete ctx->ev;
   }
+  if (ctx->side_ready) {
+    cudaStreamDestroy(ctx->side);
+    cudaEventDestroy(ctx->ev_fork);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_rng[i]); cudaEventDestroy(ctx->ev_gemm[i]); }
+  }
   delete ctx;
   return 0;
 }

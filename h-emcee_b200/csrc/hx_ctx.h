@@ -28,6 +28,10 @@ struct hx_ctx {
   int precision;                  // HX_PREC_*
   int last_path;                  // 0 fused SIMT half-move, 1 tcgen05 projection GEMM
   void* encode_fn;                // cuTensorMapEncodeTiled (resolved lazily)
+  // side stream + events used to overlap the momentum draw (ALU) with the projection GEMM (tensor pipe)
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_rng[2], ev_gemm[2];
+  int side_ready;
 };
 
 // grow-only scratch slot

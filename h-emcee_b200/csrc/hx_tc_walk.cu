@@ -11,6 +11,8 @@
 //              S  <- S - a g M ; dK += a<g, S- + S+> ; q += eps S   tc_gemm(G, MPlanes)   epilogue KICK
 //   finish:    dH = (lp1 - lp') - dK/2 ; log_acc ; optional Metropolis accept + chain emit
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 
 #include "../../include/hx.h"
 #include "hx_ctx.h"
@@ -235,7 +237,12 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   if (int e = ws_get(ctx, WS_M, (size_t)d * d * sizeof(float), &pM)) return e;
   if (int e = ws_get(ctx, WS_TC_MP, (size_t)2 * dB * dK * sizeof(bf), &pMP)) return e;
   if (int e = ws_get(ctx, WS_TC_PP, (size_t)2 * dB * dK * sizeof(bf), &pPP)) return e;
-  if (int e = ws_get(ctx, WS_TC_P0, (size_t)2 * rA * nK * sizeof(bf), &pP0)) return e;
+  // momentum-draw pipeline: chunks of >= 1024 rows (multiple of 128), ~8 per shard, two buffers in flight
+  int chunk = pad_to((rows + 7) / 8, kBM);
+  if (chunk < 1024) chunk = pad_to(rows < 1024 ? rows : 1024, kBM);
+  const int nchunks = (rows + chunk - 1) / chunk;
+  const size_t buf_elems = (size_t)2 * chunk * nK;            // one buffer = [2 planes, chunk, nK]
+  if (int e = ws_get(ctx, WS_TC_P0, (nchunks > 1 ? 2 : 1) * buf_elems * sizeof(bf), &pP0)) return e;
   if (int e = ws_get(ctx, WS_TC_QC, (size_t)2 * rA * dK * sizeof(bf), &pQC)) return e;
   if (int e = ws_get(ctx, WS_TC_GP, (size_t)2 * rA * dK * sizeof(bf), &pGP)) return e;
   if (int e = ws_get(ctx, WS_G, (size_t)rows * d * sizeof(float), &pG)) return e;
@@ -258,14 +265,62 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   k_split_planes<<<grid_for((size_t)dB * dK, 256), 256, 0, s>>>((const float*)tgt->precision, d, d, tgt->ld, dB, dK, (bf*)pPP);
   HX_LAUNCH_CHECK("k_split_planes(P)");
 
-  // (2) momentum draw (hmc_walk.py:36) and projection S0 = P0 C
-  k_rng_planes<<<grid_for((size_t)rA * nK / 8, 256), 256, 0, s>>>(key, key_ptr, impl == HX_RNG_LEGACY ? 1 : 0, n, row0, rows,
-                                                                  rA, nK, (bf*)pP0);
-  HX_LAUNCH_CHECK("k_rng_planes");
-  if (int e = timing_begin(ctx, s)) return e;
-  ga.M = rows; ga.N = d; ga.out = S; ga.ldo = d;
-  if (int e = launch_gemm<EPI_STORE>(ctx, (const bf*)pP0, rA, (const bf*)pCT, dAB, nK, ga, s)) return e;
-  if (int e = timing_end(ctx, s)) return e;
+  // (2) momentum draw (hmc_walk.py:36) and projection S0 = P0 C, pipelined over row chunks: the
+  //     counter-based draw of chunk c+1 (ALU pipes, side stream) overlaps the tcgen05 GEMM of chunk c.
+  {
+    if (!ctx->side_ready) {
+      int prio_lo = 0, prio_hi = 0;
+      HX_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      HX_CUDA(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo));
+      HX_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+      for (int i = 0; i < 2; ++i) {
+        HX_CUDA(cudaEventCreateWithFlags(&ctx->ev_rng[i], cudaEventDisableTiming));
+        HX_CUDA(cudaEventCreateWithFlags(&ctx->ev_gemm[i], cudaEventDisableTiming));
+      }
+      // same L1/shared carve-out as the GEMM kernel, otherwise the two kernels cannot share an SM
+      HX_CUDA(cudaFuncSetAttribute(k_rng_planes, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      ctx->side_ready = 1;
+    }
+    bf* Pbuf[2] = {(bf*)pP0, (bf*)pP0 + (nchunks > 1 ? buf_elems : 0)};
+    const bool trace = getenv("HX_TRACE") != nullptr;
+    cudaEvent_t tev[4][64];
+    if (trace) for (int a = 0; a < 4; ++a) for (int c = 0; c < nchunks && c < 64; ++c) cudaEventCreate(&tev[a][c]);
+    HX_CUDA(cudaEventRecord(ctx->ev_fork, s));
+    HX_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    if (int e = timing_begin(ctx, s)) return e;
+    for (int c = 0; c < nchunks; ++c) {
+      const int r0 = c * chunk;
+      const int rc = (rows - r0) < chunk ? (rows - r0) : chunk;
+      const int b = c & 1;
+      if (c >= 2) HX_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_gemm[b], 0));     // buffer b free again
+      // at most 4 CTAs (1024 threads) per SM so a GEMM CTA (192 threads, ~215 KB smem) always fits beside them
+      int rng_grid = grid_for((size_t)chunk * nK / 8, 256);
+      { const char* e_ = getenv("HX_RNG_CTAS"); const int per = e_ ? atoi(e_) : 4; if (rng_grid > ctx->sm_count * per) rng_grid = ctx->sm_count * per; }
+      if (trace && c < 64) cudaEventRecord(tev[0][c], ctx->side);
+      k_rng_planes<<<rng_grid, 256, 0, ctx->side>>>(
+          key, key_ptr, impl == HX_RNG_LEGACY ? 1 : 0, n, row0 + r0, rc, chunk, nK, Pbuf[b]);
+      HX_LAUNCH_CHECK("k_rng_planes");
+      if (trace && c < 64) cudaEventRecord(tev[1][c], ctx->side);
+      HX_CUDA(cudaEventRecord(ctx->ev_rng[b], ctx->side));
+      HX_CUDA(cudaStreamWaitEvent(s, ctx->ev_rng[b], 0));
+      if (trace && c < 64) cudaEventRecord(tev[2][c], s);
+      ga.M = rc; ga.N = d; ga.out = S + (size_t)r0 * d; ga.ldo = d;
+      if (int e = launch_gemm<EPI_STORE>(ctx, Pbuf[b], chunk, (const bf*)pCT, dAB, nK, ga, s)) return e;
+      HX_CUDA(cudaEventRecord(ctx->ev_gemm[b], s));
+      if (trace && c < 64) cudaEventRecord(tev[3][c], s);
+      ctx->launches += 1;
+    }
+    if (trace) {
+      cudaStreamSynchronize(s); cudaStreamSynchronize(ctx->side);
+      for (int c = 0; c < nchunks && c < 64; ++c) {
+        float t[4];
+        for (int a = 0; a < 4; ++a) cudaEventElapsedTime(&t[a], tev[0][0], tev[a][c]);
+        fprintf(stderr, "[hx trace] chunk %d rng %.3f-%.3f gemm %.3f-%.3f ms\n", c, t[0], t[1], t[2], t[3]);
+      }
+      for (int a = 0; a < 4; ++a) for (int c = 0; c < nchunks && c < 64; ++c) cudaEventDestroy(tev[a][c]);
+    }
+    if (int e = timing_end(ctx, s)) return e;
+  }
 
   // (3) leapfrog: L+1 kicks, every kick but the last followed by a drift (hmc_walk.py:85-102)
   const float* mu = (const float*)tgt->mean;
@@ -303,7 +358,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   }
   k_tc_finish<<<(rows + 7) / 8, 256, 0, s>>>(fa);
   HX_LAUNCH_CHECK("k_tc_finish");
-  ctx->launches += 7;
+  ctx->launches += 6;
   return 0;
 }
 
