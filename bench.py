@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--precision", default="auto", choices=["auto", "exact", "bf16x3", "bf16", "tf32x3"])
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -196,6 +197,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     hx.config.update("enable_x64", cfg["x64"])
+    hx.config.update("precision", args.precision)
     tdt = torch.float64 if cfg["x64"] else torch.float32
     W, d, L, eps = cfg["W"], cfg["d"], cfg["L"], cfg["eps"]
     n = W // 2
@@ -350,7 +352,7 @@ def main():
                     warmup=Wu, ms_per_step=ms / K, higher_is_better=True, scaling="strong", vs_baseline=None,
                     dtype="f64" if cfg["x64"] else "f32", data="synthetic", config=conf, roofline=roofline,
                     cpu_baseline=cb, clocks=clk, e2e=e2e, gpu_launches=int(c_all.value) if world == 1 else int(c_all.value),
-                    acceptance_rate=acc_rate, nonfinite=int(flag.item()))
+                    acceptance_rate=acc_rate, nonfinite=int(flag.item()), precision=args.precision)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

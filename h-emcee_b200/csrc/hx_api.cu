@@ -66,7 +66,7 @@ int timing_end(hx_ctx* ctx, cudaStream_t s) {
 
 extern "C" HX_API int hx_ctx_set_precision(hx_ctx* ctx, int mode) {
   if (!ctx) return hx_fail(HX_E_NULL, "hx_ctx_set_precision: NULL ctx");
-  if (mode < HX_PREC_AUTO || mode > HX_PREC_BF16) return hx_fail(HX_E_DTYPE, "hx_ctx_set_precision: unknown mode %d", mode);
+  if (mode < HX_PREC_AUTO || mode > HX_PREC_TF32X3) return hx_fail(HX_E_DTYPE, "hx_ctx_set_precision: unknown mode %d", mode);
   ctx->precision = mode;
   return 0;
 }

@@ -1,11 +1,14 @@
-// hx_tc_gemm.cuh — tcgen05 / TMEM / TMA GEMM with split-bf16 operands and fused leapfrog epilogues.
+// hx_tc_gemm.cuh — tcgen05 / TMEM / TMA GEMM with split operands and fused leapfrog epilogues.
 //
 //   D[M x N] (fp32, TMEM) = A[M x K] * B[N x K]^T
 //
-// A and B live in HBM as two bf16 "planes" each (hi = bf16(x), lo = bf16(x - hi)), K-major, zero padded:
-// plane p of a matrix with R_pad rows is rows [p*R_pad, (p+1)*R_pad) of one [2*R_pad, K_pad] bf16 array.
-// With nprod = 3 the kernel accumulates A_hi*B_hi + A_hi*B_lo + A_lo*B_hi in the same fp32 TMEM
-// accumulator (~2^-16 relative product error, fp32-class); nprod = 1 uses the hi planes only.
+// A and B live in HBM as two "planes" each (hi, lo with x ~= hi + lo), K-major, zero padded: plane p of a
+// matrix with R_pad rows is rows [p*R_pad, (p+1)*R_pad) of one [2*R_pad, K_pad] array.  The kernel
+// accumulates A_hi*B_hi + A_hi*B_lo + A_lo*B_hi in one fp32 TMEM accumulator (nprod = 3), or only the
+// first product (nprod = 1).  Two operand kinds:
+//   KIND_BF16  hi = bf16(x), lo = bf16(x - hi)            kind::f16, ~2^-16 per product   (momentum projection, Gram)
+//   KIND_TF32  hi = x with 13 low mantissa bits cleared,   kind::tf32, ~2^-21 per product  (leapfrog kicks: the
+//              lo = x - hi (fp32 containers)                                                energy error budget needs it)
 //
 // One CTA per 128 x BN output tile; warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread),
 // warps 2-5 = epilogue (TMEM -> registers; one thread per output row, 128-byte runs per thread).
@@ -17,11 +20,23 @@
 namespace hx {
 namespace tc {
 
-constexpr int kBM = 128;    // UMMA M
-constexpr int kBKe = 64;    // K elements per stage (= 128 B of bf16 = one swizzle atom)
+constexpr int kBM = 128;      // UMMA M
 constexpr int kThreads = 192;
 
-enum : int { EPI_STORE = 0, EPI_GRAD = 1, EPI_KICK = 2 };
+enum : int { KIND_BF16 = 0, KIND_TF32 = 1 };
+enum : int { EPI_STORE = 0, EPI_KICKB = 1, EPI_DOT = 2 };
+
+template <int KIND> struct Kind;
+template <> struct Kind<KIND_BF16> {
+  typedef __nv_bfloat16 elem;
+  static constexpr int ROW_ELEMS = 64;   // elements per 128-byte swizzle row = K per stage
+  static constexpr int UMMA_K = 16;
+};
+template <> struct Kind<KIND_TF32> {
+  typedef float elem;
+  static constexpr int ROW_ELEMS = 32;
+  static constexpr int UMMA_K = 8;
+};
 
 struct GemmArgs {
   int M, N;          // valid output rows / cols
@@ -29,22 +44,77 @@ struct GemmArgs {
   int rowsA_pad;     // rows per plane of A (multiple of 128)
   int rowsB_pad;     // rows per plane of B (multiple of BN)
   int nprod;         // 1 or 3
-  // EPI_STORE
+  // EPI_STORE: out[row*ldo + col] = acc
   float* out; int ldo;
-  // leapfrog epilogues (row-major [M x N] fp32 state, ld = N)
-  float* S; float* Q; float* G;
+  // EPI_KICKB (acc = (q - mu) @ Bop): S = S_in - a*acc ; Qs (+)= a*(Q - mu) ; if drift: Q += eps*S, planes <- split(Q - mu)
+  const float* S_in; float* S; float* Q; float* Qs;
   const float* mu;                 // [N] or nullptr
-  __nv_bfloat16* planes_out;       // EPI_GRAD: G planes; EPI_KICK: (Q - mu) planes; [2, rows_out_pad, Kout_p]
+  void* planes_out;                // [2, rows_out_pad, Kout_p] in the kernel's operand kind
   int rows_out_pad, Kout_p;
-  float* part;                     // EPI_GRAD: lp partial [M x NT] (written); EPI_KICK: dK partial [M x NT] (accumulated)
-  int NT;                          // number of N tiles (row stride of `part`)
   float a, eps;
-  int drift, want_lp;
+  int drift, first;
+  // EPI_DOT: part[row*NT + ntile] = sum_cols acc * (X + Y - mu)   (Y, mu optional)
+  const float* X; const float* Y;
+  float* part; int NT;
 };
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+
+// 32 contiguous floats of one row: vector path when `fast`, predicated scalar path otherwise
+__device__ __forceinline__ void load32(const float* p, float (&v)[32], int nval, bool fast) {
+  if (fast) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = reinterpret_cast<const float4*>(p)[j];
+      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (j < nval) ? p[j] : 0.f;
+  }
+}
+__device__ __forceinline__ void store32(float* p, const float (&v)[32], int nval, bool fast) {
+  if (fast) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(p)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (j < nval) p[j] = v[j];
+  }
+}
+// split 32 values into the hi/lo planes of the given kind (plane stride in elements)
+template <int KIND>
+__device__ __forceinline__ void store_planes32(void* planes, size_t pbase, size_t plane, const float (&v)[32], int nval, bool fast) {
+  if (KIND == KIND_BF16) {
+    __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(planes);
+    __align__(16) __nv_bfloat16 hi[32], lo[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) split_bf16(j < nval ? v[j] : 0.f, hi[j], lo[j]);
+    if (fast) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        reinterpret_cast<uint4*>(P + pbase)[j] = reinterpret_cast<const uint4*>(hi)[j];
+        reinterpret_cast<uint4*>(P + plane + pbase)[j] = reinterpret_cast<const uint4*>(lo)[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < nval) { P[pbase + j] = hi[j]; P[plane + pbase + j] = lo[j]; }
+    }
+  } else {
+    float* P = reinterpret_cast<float*>(planes);
+    float hi[32], lo[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) split_tf32(j < nval ? v[j] : 0.f, hi[j], lo[j]);
+    store32(P + pbase, hi, nval, fast);
+    store32(P + plane + pbase, lo, nval, fast);
+  }
 }
 
 template <int BN>
@@ -53,18 +123,34 @@ struct SmemLayout {
   static constexpr int B_PLANE = BN * 128;
   static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
   static constexpr int STAGES = (BN >= 256) ? 2 : 3;
-  static constexpr int STG = 0;
-  static constexpr int BYTES = STAGES * STAGE + STG + 256 + 1024;   // + barriers + alignment slack
+  static constexpr int BYTES = STAGES * STAGE + 256 + 1024;   // + barriers + alignment slack
 };
 
-template <int BN, int EPI>
+template <int KIND>
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  if (KIND == KIND_BF16) {
+    umma_bf16(tmem_d, ad, bd, idesc, acc);
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(ad), "l"(bd), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+
+template <int BN, int EPI, int KIND>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   using L = SmemLayout<BN>;
+  using KD = Kind<KIND>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
-  uint64_t* bars = (uint64_t*)(smem + L::STAGES * L::STAGE + L::STG);
+  uint64_t* bars = (uint64_t*)(smem + L::STAGES * L::STAGE);
   uint64_t* full = bars;                  // [STAGES]
   uint64_t* empty = bars + L::STAGES;     // [STAGES]
   uint64_t* tmem_full = bars + 2 * L::STAGES;
@@ -72,7 +158,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
-  const int num_kb = g.Kp / kBKe;
+  const int num_kb = g.Kp / KD::ROW_ELEMS;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -96,17 +182,20 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         mbar_wait(&empty[s], ph ^ 1u);
         uint8_t* st = stage_base + s * L::STAGE;
         mbar_expect_tx(&full[s], bytes);
-        tma_load_2d(st, &tmA, &full[s], kb * kBKe, m0);
-        tma_load_2d(st + 2 * L::A_PLANE, &tmB, &full[s], kb * kBKe, n0);
+        const int kc = kb * KD::ROW_ELEMS;
+        tma_load_2d(st, &tmA, &full[s], kc, m0);
+        tma_load_2d(st + 2 * L::A_PLANE, &tmB, &full[s], kc, n0);
         if (g.nprod == 3) {
-          tma_load_2d(st + L::A_PLANE, &tmA, &full[s], kb * kBKe, g.rowsA_pad + m0);
-          tma_load_2d(st + 2 * L::A_PLANE + L::B_PLANE, &tmB, &full[s], kb * kBKe, g.rowsB_pad + n0);
+          tma_load_2d(st + L::A_PLANE, &tmA, &full[s], kc, g.rowsA_pad + m0);
+          tma_load_2d(st + 2 * L::A_PLANE + L::B_PLANE, &tmB, &full[s], kc, g.rowsB_pad + n0);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      // kind::f16 / kind::tf32 instruction descriptor: D = F32, A/B format (1 = BF16, 2 = TF32), K-major, N>>3, M>>4
+      constexpr uint32_t fmt = (KIND == KIND_BF16) ? 1u : 2u;
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % L::STAGES;
         const uint32_t ph = (uint32_t)(kb / L::STAGES) & 1u;
@@ -122,8 +211,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const uint64_t ad = umma_desc_k128(p == 2 ? a_lo : a_hi);
           const uint64_t bd = umma_desc_k128(p == 1 ? b_lo : b_hi);
 #pragma unroll
-          for (int k = 0; k < kBKe / 16; ++k) {
-            umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | p | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < KD::ROW_ELEMS / KD::UMMA_K; ++k) {   // 4 steps of 32 bytes inside the 128-byte swizzle row
+            umma_issue<KIND>(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | p | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&empty[s]);     // frees the smem stage when these MMAs have read it
@@ -150,133 +239,55 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int nval = min(32, g.N - col0);
       const bool fast = vec && nval == 32;
       if (EPI == EPI_STORE) {
-        float* o = g.out + (size_t)row * g.ldo + col0;
-        if (fast) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-          _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) o[j] = v[j];
-        }
+        store32(g.out + (size_t)row * g.ldo + col0, v, nval, fast);
       } else {
         const size_t base = (size_t)row * g.N + col0;
-        const size_t pbase = (size_t)row * g.Kout_p + col0;
-        const size_t plane = (size_t)g.rows_out_pad * g.Kout_p;
         float mu[32];
+        if (g.mu) load32(g.mu + col0, mu, nval, fast);
+        else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mu[j] = 0.f;
-        if (g.mu) {
-          if (fast) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(g.mu + col0) + j);
-              mu[4 * j] = t.x; mu[4 * j + 1] = t.y; mu[4 * j + 2] = t.z; mu[4 * j + 3] = t.w;
-            }
-          } else {
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) mu[j] = g.mu[col0 + j];
-          }
+          for (int j = 0; j < 32; ++j) mu[j] = 0.f;
         }
-        if (EPI == EPI_GRAD) {
-          // g = acc: store fp32 + bf16 planes; optional lp partial sum_j g_j (q_j - mu_j)
-          float* Gp = g.G + base;
-          if (fast) {
+        if (EPI == EPI_DOT) {
+          float x[32];
+          load32(g.X + base, x, nval, fast);
+          if (g.Y) {
+            float y[32];
+            load32(g.Y + base, y, nval, fast);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(Gp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) Gp[j] = v[j];
+            for (int j = 0; j < 32; ++j) x[j] += y[j];
           }
-          __align__(16) __nv_bfloat16 hi[32], lo[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) split_bf16(j < nval ? v[j] : 0.f, hi[j], lo[j]);
-          if (fast) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              reinterpret_cast<uint4*>(g.planes_out + pbase)[j] = reinterpret_cast<const uint4*>(hi)[j];
-              reinterpret_cast<uint4*>(g.planes_out + plane + pbase)[j] = reinterpret_cast<const uint4*>(lo)[j];
-            }
-          } else {
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) { g.planes_out[pbase + j] = hi[j]; g.planes_out[plane + pbase + j] = lo[j]; }
-          }
-          if (g.want_lp) {
-            const float* Qp = g.Q + base;
-            if (fast) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 t = reinterpret_cast<const float4*>(Qp)[j];
-                rowacc = fmaf(v[4 * j], t.x - mu[4 * j], rowacc);
-                rowacc = fmaf(v[4 * j + 1], t.y - mu[4 * j + 1], rowacc);
-                rowacc = fmaf(v[4 * j + 2], t.z - mu[4 * j + 2], rowacc);
-                rowacc = fmaf(v[4 * j + 3], t.w - mu[4 * j + 3], rowacc);
-              }
-            } else {
-              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) rowacc = fmaf(v[j], Qp[j] - mu[j], rowacc);
-            }
-          }
+          for (int j = 0; j < 32; ++j) rowacc = fmaf(v[j], x[j] - mu[j], rowacc);   // padded lanes hold acc = 0
         } else {
-          // kick: S -= a * acc ; dK += a * g * (S- + S+) ; optional drift q += eps * S+ (+ centred planes)
-          float sv[32], gv[32], qv[32];
-          float* Sp = g.S + base;
-          const float* Gp = g.G + base;
-          float* Qp = g.Q + base;
-          if (fast) {
+          // EPI_KICKB
+          float sv[32], qv[32], ws[32];
+          load32(g.S_in + base, sv, nval, fast);
+          load32(g.Q + base, qv, nval, fast);
+          if (g.first) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 t = reinterpret_cast<const float4*>(Sp)[j];
-              sv[4 * j] = t.x; sv[4 * j + 1] = t.y; sv[4 * j + 2] = t.z; sv[4 * j + 3] = t.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 t = reinterpret_cast<const float4*>(Gp)[j];
-              gv[4 * j] = t.x; gv[4 * j + 1] = t.y; gv[4 * j + 2] = t.z; gv[4 * j + 3] = t.w;
-            }
-            if (g.drift) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 t = reinterpret_cast<const float4*>(Qp)[j];
-                qv[4 * j] = t.x; qv[4 * j + 1] = t.y; qv[4 * j + 2] = t.z; qv[4 * j + 3] = t.w;
-              }
-            }
+            for (int j = 0; j < 32; ++j) ws[j] = 0.f;
           } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { sv[j] = 0.f; gv[j] = 0.f; qv[j] = 0.f; }
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) { sv[j] = Sp[j]; gv[j] = Gp[j]; if (g.drift) qv[j] = Qp[j]; }
+            load32(g.Qs + base, ws, nval, fast);
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float s_new = sv[j] - g.a * v[j];
-            rowacc = fmaf(g.a * gv[j], sv[j] + s_new, rowacc);
-            sv[j] = s_new;
-            qv[j] = qv[j] + g.eps * s_new;
+            ws[j] = fmaf(g.a, qv[j] - mu[j], ws[j]);        // impulse-weighted position sum (G_total = Qs @ P)
+            sv[j] = sv[j] - g.a * v[j];
+            qv[j] = qv[j] + g.eps * sv[j];
           }
-          if (fast) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(Sp)[j] = make_float4(sv[4 * j], sv[4 * j + 1], sv[4 * j + 2], sv[4 * j + 3]);
-          } else {
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) Sp[j] = sv[j];
-          }
+          store32(g.S + base, sv, nval, fast);
+          store32(g.Qs + base, ws, nval, fast);
           if (g.drift) {
-            __align__(16) __nv_bfloat16 hi[32], lo[32];
+            store32(g.Q + base, qv, nval, fast);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) split_bf16(j < nval ? qv[j] - mu[j] : 0.f, hi[j], lo[j]);
-            if (fast) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(Qp)[j] = make_float4(qv[4 * j], qv[4 * j + 1], qv[4 * j + 2], qv[4 * j + 3]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                reinterpret_cast<uint4*>(g.planes_out + pbase)[j] = reinterpret_cast<const uint4*>(hi)[j];
-                reinterpret_cast<uint4*>(g.planes_out + plane + pbase)[j] = reinterpret_cast<const uint4*>(lo)[j];
-              }
-            } else {
-              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nval) { Qp[j] = qv[j]; g.planes_out[pbase + j] = hi[j]; g.planes_out[plane + pbase + j] = lo[j]; }
-            }
+            for (int j = 0; j < 32; ++j) qv[j] -= mu[j];
+            store_planes32<KIND>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, qv, nval, fast);
           }
         }
       }
     }
-    if (EPI != EPI_STORE && rok) {
-      float* p = g.part + (size_t)row * g.NT + blockIdx.x;
-      if (EPI == EPI_GRAD) { if (g.want_lp) *p = rowacc; }
-      else *p += rowacc;
-    }
+    if (EPI == EPI_DOT && rok) g.part[(size_t)row * g.NT + blockIdx.x] = rowacc;
     tc_fence_before();
   }
   __syncthreads();

@@ -2,14 +2,18 @@
 // dim / walker counts (fp32 state, split-bf16 operands on tcgen05, fp32 accumulation in TMEM).
 //
 // Same projected-form algorithm as the exact SIMT kernel (hx_move.cuh; reference
-// moves/hamiltonian/hmc_walk.py:6-107), expressed as GEMMs:
-//   C^T planes    <- ((X2 - mean)/sqrt(n))^T                    (hmc_walk.py:35)
-//   M             <- C^T C                                       tc_gemm(CT, CT)
-//   P0 planes     <- normal(key, (n, n))[row shard]              (hmc_walk.py:36), counter-based, bf16 hi/lo
-//   S0            <- P0 C                                        tc_gemm(P0, CT)
-//   per kick:  g  <- (q - mu) Prec                               tc_gemm(QC, PrecPlanes)  epilogue GRAD
-//              S  <- S - a g M ; dK += a<g, S- + S+> ; q += eps S   tc_gemm(G, MPlanes)   epilogue KICK
-//   finish:    dH = (lp1 - lp') - dK/2 ; log_acc ; optional Metropolis accept + chain emit
+// moves/hamiltonian/hmc_walk.py:6-107), expressed as GEMMs, with the two per-kick products folded into
+// one ("B-form"): for a Gaussian target grad U = (q - mu) P, so  g @ M = (q - mu) @ (P M).
+//   C^T planes    <- ((X2 - mean)/sqrt(n))^T                      (hmc_walk.py:35)            bf16 hi/lo
+//   M             <- C^T C                                         tc_gemm(CT, CT)             bf16 x3
+//   Bop           <- M P  (exact fp32 SIMT, d^3 flops)            k_small_gemm
+//   P0 planes     <- normal(key, (n, n))[row shard]                (hmc_walk.py:36)            bf16 hi/lo
+//   S0            <- P0 C                                          tc_gemm(P0, CT)             bf16 x3
+//   per kick:  S  <- S - a (q - mu) Bop^T ; Qs += a (q - mu) ; q += eps S    tc_gemm(QC, Bop)   tf32 x3
+//   energies:  G = Qs P ; dK = -1/2 <G, S0 + S_L> ; g_L = (q_L - mu) P ; lp' = -1/2 <g_L, q_L - mu>   tf32 x3
+//   finish:    dH = (lp1 - lp') + dK ; log_acc ; optional Metropolis accept + chain emit
+// The kicks and energy products use tf32 hi/lo operands (2^-21 per product): with bf16 hi/lo (2^-16) the
+// energy error of an ill-conditioned target (kappa 1e4) is ~0.3 and visibly lowers the acceptance rate.
 #include <cstring>
 #include <cstdio>
 #include <cstdlib>
@@ -43,17 +47,19 @@ static int get_encode(hx_ctx* ctx, EncodeFn* fn) {
   return 0;
 }
 
-// bf16 planes array [rows_total, Kp], K-major; box = [64 k-elements (128 B), box_rows], 128B swizzle
-static int make_tmap(hx_ctx* ctx, CUtensorMap* out, const void* base, uint64_t rows_total, uint64_t Kp, uint32_t box_rows) {
+// planes array [rows_total, Kp], K-major; box = [one 128-byte swizzle row of K, box_rows], 128B swizzle
+static int make_tmap(hx_ctx* ctx, CUtensorMap* out, const void* base, uint64_t rows_total, uint64_t Kp, uint32_t box_rows,
+                     int kind) {
   EncodeFn enc;
   if (int e = get_encode(ctx, &enc)) return e;
+  const uint64_t esz = kind == KIND_BF16 ? 2 : 4;
   cuuint64_t dims[2] = {Kp, rows_total};
-  cuuint64_t strides[1] = {Kp * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {Kp * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(out, kind == KIND_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return hx_fail(HX_E_UNSUPPORTED, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
 }
@@ -82,17 +88,70 @@ __global__ void k_center_planes_T(const float* __restrict__ X2, const float* __r
   }
 }
 
-// planes [2, rows_pad, Kp] <- split(src[r*ld + k]) for r, k < dim, zero elsewhere
+// planes [2, rows_pad, Kp] <- split(src[r*ld + k]) for r < dim_r, k < dim_k, zero elsewhere
+template <int KIND>
 __global__ void k_split_planes(const float* __restrict__ src, int dim_r, int dim_k, int ld, int rows_pad, int Kp,
-                               __nv_bfloat16* __restrict__ planes) {
+                               typename Kind<KIND>::elem* __restrict__ planes) {
   const size_t tot = (size_t)rows_pad * Kp, plane = tot;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / Kp), k = (int)(i - (size_t)r * Kp);
     const float v = (r < dim_r && k < dim_k) ? src[(size_t)r * ld + k] : 0.f;
-    __nv_bfloat16 hi, lo;
-    split_bf16(v, hi, lo);
-    planes[i] = hi;
-    planes[plane + i] = lo;
+    if (KIND == KIND_BF16) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      reinterpret_cast<__nv_bfloat16*>(planes)[i] = hi;
+      reinterpret_cast<__nv_bfloat16*>(planes)[plane + i] = lo;
+    } else {
+      float hi, lo;
+      split_tf32(v, hi, lo);
+      reinterpret_cast<float*>(planes)[i] = hi;
+      reinterpret_cast<float*>(planes)[plane + i] = lo;
+    }
+  }
+}
+
+// out[i][j] = sum_k A[i][k] * B[k][j]  (dim x dim, exact fp32 FMA; 64x64 tile, 4x4 per thread)
+__global__ void __launch_bounds__(256) k_small_gemm(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                    int dim, float* __restrict__ out, int ldo) {
+  constexpr int TB = 64, KB = 16;
+  __shared__ __align__(16) float sa[KB][TB + 4];
+  __shared__ __align__(16) float sb[KB][TB + 4];
+  const int ti = blockIdx.y * TB, tj = blockIdx.x * TB;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < dim; k0 += KB) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < KB * TB; idx += 256) {
+      const int i = idx / KB, kk = idx - i * KB;
+      sa[kk][i] = (ti + i < dim && k0 + kk < dim) ? A[(size_t)(ti + i) * lda + k0 + kk] : 0.f;
+      const int k2 = idx / TB, j = idx - k2 * TB;
+      sb[k2][j] = (k0 + k2 < dim && tj + j < dim) ? B[(size_t)(k0 + k2) * ldb + tj + j] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) {
+      float a[4], b[4];
+      ld4(&sa[kk][4 * ty], a);
+      ld4(&sb[kk][4 * tx], b);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gi = ti + 4 * ty + i;
+    if (gi >= dim) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gj = tj + 4 * tx + j;
+      if (gj < dim) out[(size_t)gi * ldo + gj] = acc[i][j];
+    }
   }
 }
 
@@ -119,9 +178,10 @@ __global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key
   }
 }
 
-// Q <- X1 ; QC planes <- split(X1 - mu) (zero padded) ; dK partials <- 0
+// Q <- X1 ; QC planes (hi/lo of the leapfrog operand kind) <- split(X1 - mu), zero padded
+template <int KIND>
 __global__ void k_tc_init(const float* __restrict__ X1, const float* __restrict__ mu, int rows, int d, int rows_pad, int Kp,
-                          float* __restrict__ Q, __nv_bfloat16* __restrict__ planes, float* __restrict__ dkp, int NT) {
+                          float* __restrict__ Q, typename Kind<KIND>::elem* __restrict__ planes) {
   const size_t tot = (size_t)rows_pad * Kp, plane = tot;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / Kp), k = (int)(i - (size_t)r * Kp);
@@ -131,11 +191,17 @@ __global__ void k_tc_init(const float* __restrict__ X1, const float* __restrict_
       Q[(size_t)r * d + k] = x;
       v = x - (mu ? mu[k] : 0.f);
     }
-    __nv_bfloat16 hi, lo;
-    split_bf16(v, hi, lo);
-    planes[i] = hi;
-    planes[plane + i] = lo;
-    if (k < NT && r < rows) dkp[(size_t)r * NT + k] = 0.f;
+    if (KIND == KIND_BF16) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      reinterpret_cast<__nv_bfloat16*>(planes)[i] = hi;
+      reinterpret_cast<__nv_bfloat16*>(planes)[plane + i] = lo;
+    } else {
+      float hi, lo;
+      split_tf32(v, hi, lo);
+      reinterpret_cast<float*>(planes)[i] = hi;
+      reinterpret_cast<float*>(planes)[plane + i] = lo;
+    }
   }
 }
 
@@ -185,20 +251,20 @@ __global__ void __launch_bounds__(256) k_tc_finish(FinishArgs a) {
 }
 
 // ---- GEMM launcher ---------------------------------------------------------------------------------------------------
-template <int EPI>
-static int launch_gemm(hx_ctx* ctx, const __nv_bfloat16* A, int rowsA_pad, const __nv_bfloat16* B, int rowsB_pad, int Kp,
-                       GemmArgs g, cudaStream_t s) {
+template <int EPI, int KIND>
+static int launch_gemm(hx_ctx* ctx, const void* A, int rowsA_pad, const void* B, int rowsB_pad, int Kp, GemmArgs g,
+                       cudaStream_t s) {
   CUtensorMap tmA, tmB;
-  if (int e = make_tmap(ctx, &tmA, A, 2ull * rowsA_pad, Kp, kBM)) return e;
-  if (int e = make_tmap(ctx, &tmB, B, 2ull * rowsB_pad, Kp, BN)) return e;
+  if (int e = make_tmap(ctx, &tmA, A, 2ull * rowsA_pad, Kp, kBM, KIND)) return e;
+  if (int e = make_tmap(ctx, &tmB, B, 2ull * rowsB_pad, Kp, BN, KIND)) return e;
   g.Kp = Kp; g.rowsA_pad = rowsA_pad; g.rowsB_pad = rowsB_pad;
-  static bool attr_done[3] = {false, false, false};
-  if (!attr_done[EPI]) {
-    HX_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::BYTES));
-    attr_done[EPI] = true;
+  static bool attr_done = false;
+  if (!attr_done) {
+    HX_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::BYTES));
+    attr_done = true;
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + kBM - 1) / kBM);
-  k_tc_gemm<BN, EPI><<<grid, kThreads, SmemLayout<BN>::BYTES, s>>>(tmA, tmB, g);
+  k_tc_gemm<BN, EPI, KIND><<<grid, kThreads, SmemLayout<BN>::BYTES, s>>>(tmA, tmB, g);
   HX_LAUNCH_CHECK("k_tc_gemm");
   ctx->launches += 1;
   return 0;
@@ -212,6 +278,45 @@ static inline int grid_for(size_t n, int block) {
   return (int)g;
 }
 
+struct LeapArgs {
+  const float* X1; const float* mu; int rows, d, rA, dK, dB, NT, L; double eps;
+  float* Q; float* S; float* S0; float* Qs; const float* Bo; const float* prec; int ld_prec;
+  void* pBoP; void* pPP; void* pQC; void* pQsP; float* lpp; float* dkp;
+};
+
+// L+1 kicks in B-form (every kick but the last followed by a drift; hmc_walk.py:85-102), then the two energy products.
+template <int KIND>
+static int leapfrog_bform(hx_ctx* ctx, const LeapArgs& a, cudaStream_t s) {
+  typedef typename Kind<KIND>::elem E;
+  const int rows = a.rows, d = a.d, rA = a.rA, dK = a.dK, dB = a.dB;
+  k_split_planes<KIND><<<grid_for((size_t)dB * dK, 256), 256, 0, s>>>(a.Bo, d, d, d, dB, dK, (E*)a.pBoP);
+  HX_LAUNCH_CHECK("k_split_planes(Bop)");
+  k_split_planes<KIND><<<grid_for((size_t)dB * dK, 256), 256, 0, s>>>(a.prec, d, d, a.ld_prec, dB, dK, (E*)a.pPP);
+  HX_LAUNCH_CHECK("k_split_planes(P)");
+  k_tc_init<KIND><<<grid_for((size_t)rA * dK, 256), 256, 0, s>>>(a.X1, a.mu, rows, d, rA, dK, a.Q, (E*)a.pQC);
+  HX_LAUNCH_CHECK("k_tc_init");
+  GemmArgs gg;
+  memset(&gg, 0, sizeof(gg));
+  gg.nprod = 3; gg.M = rows; gg.N = d; gg.mu = a.mu; gg.NT = a.NT; gg.eps = (float)a.eps;
+  for (int k = 0; k <= a.L; ++k) {
+    GemmArgs x = gg;
+    x.S_in = (k == 0) ? a.S0 : a.S; x.S = a.S; x.Q = a.Q; x.Qs = a.Qs; x.first = (k == 0) ? 1 : 0;
+    x.planes_out = a.pQC; x.rows_out_pad = rA; x.Kout_p = dK;
+    x.a = (float)((k == 0 || k == a.L) ? 0.5 * (float)a.eps : (float)a.eps);
+    x.drift = k < a.L ? 1 : 0;
+    if (int e = launch_gemm<EPI_KICKB, KIND>(ctx, a.pQC, rA, a.pBoP, dB, dK, x, s)) return e;
+  }
+  // energies: dK = -1/2 <Qs P, S0 + S_L> ; lp' = -1/2 <(q_L - mu) P, q_L - mu>
+  k_split_planes<KIND><<<grid_for((size_t)rA * dK, 256), 256, 0, s>>>(a.Qs, rows, d, d, rA, dK, (E*)a.pQsP);
+  HX_LAUNCH_CHECK("k_split_planes(Qs)");
+  GemmArgs x = gg;
+  x.mu = nullptr; x.X = a.S0; x.Y = a.S; x.part = a.dkp;
+  if (int e = launch_gemm<EPI_DOT, KIND>(ctx, a.pQsP, rA, a.pPP, dB, dK, x, s)) return e;
+  GemmArgs y = gg;
+  y.X = a.Q; y.Y = nullptr; y.part = a.lpp;
+  return launch_gemm<EPI_DOT, KIND>(ctx, a.pQC, rA, a.pPP, dB, dK, y, s);
+}
+
 bool walk_eligible(const hx_ctx* ctx, int dtype, const hx_target* tgt, int n, int rows, int flags) {
   if (ctx->precision == HX_PREC_EXACT) return false;
   if (dtype != HX_F32 || tgt->kind != HX_TARGET_GAUSS_FULL || flags != 0) return false;
@@ -223,33 +328,37 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
               int row0, int rows, double eps, Key key, const uint32_t* key_ptr, int L, const float* lp1, float* Q,
               float* logacc, float* S, float* lp_out, const FuseF32* fuse, cudaStream_t s) {
   const int d = tgt->dim;
-  const int nprod = (ctx->precision == HX_PREC_BF16) ? 1 : 3;
+  const int nprod = (ctx->precision == HX_PREC_BF16) ? 1 : 3;   // momentum projection / Gram only
   const int dB = pad_to(d, BN);            // rows of B-operand planes (N side)
   const int dK = pad_to(d, 64);            // K padding when dim is the reduction axis
   const int nK = pad_to(n, 64);            // K padding when the walker index is the reduction axis
   const int rA = pad_to(rows, kBM);        // rows of A-operand planes over walkers
-  const int dA = pad_to(d, kBM);           // rows of A-operand planes over dim (Gram)
+  const int dA = pad_to(d, kBM);
   const int dAB = dB > dA ? dB : dA;       // CT planes serve as both A (128-row boxes) and B (BN-row boxes)
   const int NT = (d + BN - 1) / BN;
   typedef __nv_bfloat16 bf;
-  void *pCT, *pM, *pMP, *pPP, *pP0, *pQC, *pGP, *pG, *pLPP, *pDKP;
-  if (int e = ws_get(ctx, WS_TC_CT, (size_t)2 * dAB * nK * sizeof(bf), &pCT)) return e;
-  if (int e = ws_get(ctx, WS_M, (size_t)d * d * sizeof(float), &pM)) return e;
-  if (int e = ws_get(ctx, WS_TC_MP, (size_t)2 * dB * dK * sizeof(bf), &pMP)) return e;
-  if (int e = ws_get(ctx, WS_TC_PP, (size_t)2 * dB * dK * sizeof(bf), &pPP)) return e;
   // momentum-draw pipeline: chunks of >= 1024 rows (multiple of 128), ~8 per shard, two buffers in flight
   int chunk = pad_to((rows + 7) / 8, kBM);
   if (chunk < 1024) chunk = pad_to(rows < 1024 ? rows : 1024, kBM);
   const int nchunks = (rows + chunk - 1) / chunk;
   const size_t buf_elems = (size_t)2 * chunk * nK;            // one buffer = [2 planes, chunk, nK]
+  void *pCT, *pM, *pBo, *pBoP, *pPP, *pP0, *pQC, *pQsP, *pS0, *pQs, *pLPP, *pDKP;
+  if (int e = ws_get(ctx, WS_TC_CT, (size_t)2 * dAB * nK * sizeof(bf), &pCT)) return e;
+  if (int e = ws_get(ctx, WS_M, (size_t)d * d * sizeof(float), &pM)) return e;
+  if (int e = ws_get(ctx, WS_TC_BO, (size_t)d * d * sizeof(float), &pBo)) return e;
+  if (int e = ws_get(ctx, WS_TC_MP, (size_t)2 * dB * dK * sizeof(float), &pBoP)) return e;
+  if (int e = ws_get(ctx, WS_TC_PP, (size_t)2 * dB * dK * sizeof(float), &pPP)) return e;
   if (int e = ws_get(ctx, WS_TC_P0, (nchunks > 1 ? 2 : 1) * buf_elems * sizeof(bf), &pP0)) return e;
-  if (int e = ws_get(ctx, WS_TC_QC, (size_t)2 * rA * dK * sizeof(bf), &pQC)) return e;
-  if (int e = ws_get(ctx, WS_TC_GP, (size_t)2 * rA * dK * sizeof(bf), &pGP)) return e;
-  if (int e = ws_get(ctx, WS_G, (size_t)rows * d * sizeof(float), &pG)) return e;
+  if (int e = ws_get(ctx, WS_TC_QC, (size_t)2 * rA * dK * sizeof(float), &pQC)) return e;
+  if (int e = ws_get(ctx, WS_TC_GP, (size_t)2 * rA * dK * sizeof(float), &pQsP)) return e;
+  if (int e = ws_get(ctx, WS_TC_S0, (size_t)rows * d * sizeof(float), &pS0)) return e;
+  if (int e = ws_get(ctx, WS_G, (size_t)rows * d * sizeof(float), &pQs)) return e;
   if (int e = ws_get(ctx, WS_TC_LPP, (size_t)rows * NT * sizeof(float), &pLPP)) return e;
   if (int e = ws_get(ctx, WS_TC_DKP, (size_t)rows * NT * sizeof(float), &pDKP)) return e;
+  float* S0 = (float*)pS0;
+  float* Qs = (float*)pQs;
 
-  // (1) complement statistics: mean_dev already holds mean_0(X2) (hx_api.cu); C^T planes, M = C^T C
+  // (1) complement statistics: mean_dev already holds mean_0(X2) (hx_api.cu); C^T planes, M = C^T C, Bop = M P
   {
     dim3 g((nK + 31) / 32, (dAB + 31) / 32), b(32, 8);
     k_center_planes_T<<<g, b, 0, s>>>(X2, mean_dev, n, d, dAB, nK, (bf*)pCT);
@@ -259,11 +368,12 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   memset(&ga, 0, sizeof(ga));
   ga.nprod = nprod;
   ga.M = d; ga.N = d; ga.out = (float*)pM; ga.ldo = d;
-  if (int e = launch_gemm<EPI_STORE>(ctx, (const bf*)pCT, dAB, (const bf*)pCT, dAB, nK, ga, s)) return e;
-  k_split_planes<<<grid_for((size_t)dB * dK, 256), 256, 0, s>>>((const float*)pM, d, d, d, dB, dK, (bf*)pMP);
-  HX_LAUNCH_CHECK("k_split_planes(M)");
-  k_split_planes<<<grid_for((size_t)dB * dK, 256), 256, 0, s>>>((const float*)tgt->precision, d, d, tgt->ld, dB, dK, (bf*)pPP);
-  HX_LAUNCH_CHECK("k_split_planes(P)");
+  if (int e = launch_gemm<EPI_STORE, KIND_BF16>(ctx, pCT, dAB, pCT, dAB, nK, ga, s)) return e;
+  {
+    dim3 g((d + 63) / 64, (d + 63) / 64);
+    k_small_gemm<<<g, 256, 0, s>>>((const float*)pM, d, (const float*)tgt->precision, tgt->ld, d, (float*)pBo, d);
+    HX_LAUNCH_CHECK("k_small_gemm");
+  }
 
   // (2) momentum draw (hmc_walk.py:36) and projection S0 = P0 C, pipelined over row chunks: the
   //     counter-based draw of chunk c+1 (ALU pipes, side stream) overlaps the tcgen05 GEMM of chunk c.
@@ -282,9 +392,6 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
       ctx->side_ready = 1;
     }
     bf* Pbuf[2] = {(bf*)pP0, (bf*)pP0 + (nchunks > 1 ? buf_elems : 0)};
-    const bool trace = getenv("HX_TRACE") != nullptr;
-    cudaEvent_t tev[4][64];
-    if (trace) for (int a = 0; a < 4; ++a) for (int c = 0; c < nchunks && c < 64; ++c) cudaEventCreate(&tev[a][c]);
     HX_CUDA(cudaEventRecord(ctx->ev_fork, s));
     HX_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
     if (int e = timing_begin(ctx, s)) return e;
@@ -293,57 +400,31 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
       const int rc = (rows - r0) < chunk ? (rows - r0) : chunk;
       const int b = c & 1;
       if (c >= 2) HX_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_gemm[b], 0));     // buffer b free again
-      // at most 4 CTAs (1024 threads) per SM so a GEMM CTA (192 threads, ~215 KB smem) always fits beside them
+      // at most 2 CTAs (16 warps) per SM so the GEMM's TMA / MMA issue threads are not starved of issue slots
       int rng_grid = grid_for((size_t)chunk * nK / 8, 256);
-      { const char* e_ = getenv("HX_RNG_CTAS"); const int per = e_ ? atoi(e_) : 4; if (rng_grid > ctx->sm_count * per) rng_grid = ctx->sm_count * per; }
-      if (trace && c < 64) cudaEventRecord(tev[0][c], ctx->side);
-      k_rng_planes<<<rng_grid, 256, 0, ctx->side>>>(
-          key, key_ptr, impl == HX_RNG_LEGACY ? 1 : 0, n, row0 + r0, rc, chunk, nK, Pbuf[b]);
+      if (rng_grid > ctx->sm_count * 2) rng_grid = ctx->sm_count * 2;
+      k_rng_planes<<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, impl == HX_RNG_LEGACY ? 1 : 0, n, row0 + r0, rc, chunk, nK,
+                                                    Pbuf[b]);
       HX_LAUNCH_CHECK("k_rng_planes");
-      if (trace && c < 64) cudaEventRecord(tev[1][c], ctx->side);
       HX_CUDA(cudaEventRecord(ctx->ev_rng[b], ctx->side));
       HX_CUDA(cudaStreamWaitEvent(s, ctx->ev_rng[b], 0));
-      if (trace && c < 64) cudaEventRecord(tev[2][c], s);
-      ga.M = rc; ga.N = d; ga.out = S + (size_t)r0 * d; ga.ldo = d;
-      if (int e = launch_gemm<EPI_STORE>(ctx, Pbuf[b], chunk, (const bf*)pCT, dAB, nK, ga, s)) return e;
+      ga.M = rc; ga.N = d; ga.out = S0 + (size_t)r0 * d; ga.ldo = d;
+      if (int e = launch_gemm<EPI_STORE, KIND_BF16>(ctx, Pbuf[b], chunk, pCT, dAB, nK, ga, s)) return e;
       HX_CUDA(cudaEventRecord(ctx->ev_gemm[b], s));
-      if (trace && c < 64) cudaEventRecord(tev[3][c], s);
       ctx->launches += 1;
-    }
-    if (trace) {
-      cudaStreamSynchronize(s); cudaStreamSynchronize(ctx->side);
-      for (int c = 0; c < nchunks && c < 64; ++c) {
-        float t[4];
-        for (int a = 0; a < 4; ++a) cudaEventElapsedTime(&t[a], tev[0][0], tev[a][c]);
-        fprintf(stderr, "[hx trace] chunk %d rng %.3f-%.3f gemm %.3f-%.3f ms\n", c, t[0], t[1], t[2], t[3]);
-      }
-      for (int a = 0; a < 4; ++a) for (int c = 0; c < nchunks && c < 64; ++c) cudaEventDestroy(tev[a][c]);
     }
     if (int e = timing_end(ctx, s)) return e;
   }
 
-  // (3) leapfrog: L+1 kicks, every kick but the last followed by a drift (hmc_walk.py:85-102)
+  // (3) leapfrog + energy products in the operand kind chosen by the precision policy
   const float* mu = (const float*)tgt->mean;
-  k_tc_init<<<grid_for((size_t)rA * dK, 256), 256, 0, s>>>(X1, mu, rows, d, rA, dK, Q, (bf*)pQC, (float*)pDKP, NT);
-  HX_LAUNCH_CHECK("k_tc_init");
-  HX_CUDA(cudaMemsetAsync(pGP, 0, (size_t)2 * rA * dK * sizeof(bf), s));
-  GemmArgs gg;
-  memset(&gg, 0, sizeof(gg));
-  gg.nprod = nprod; gg.M = rows; gg.N = d; gg.S = S; gg.Q = Q; gg.G = (float*)pG; gg.mu = mu;
-  gg.rows_out_pad = rA; gg.Kout_p = dK; gg.NT = NT; gg.eps = (float)eps;
-  auto grad = [&](int want_lp) -> int {
-    GemmArgs x = gg;
-    x.planes_out = (bf*)pGP; x.part = (float*)pLPP; x.want_lp = want_lp;
-    return launch_gemm<EPI_GRAD>(ctx, (const bf*)pQC, rA, (const bf*)pPP, dB, dK, x, s);
-  };
-  if (int e = grad(0)) return e;
-  for (int k = 0; k <= L; ++k) {
-    GemmArgs x = gg;
-    x.planes_out = (bf*)pQC; x.part = (float*)pDKP;
-    x.a = (float)((k == 0 || k == L) ? 0.5 * (float)eps : (float)eps);
-    x.drift = k < L ? 1 : 0;
-    if (int e = launch_gemm<EPI_KICK>(ctx, (const bf*)pGP, rA, (const bf*)pMP, dB, dK, x, s)) return e;
-    if (k < L) { if (int e = grad(k == L - 1 ? 1 : 0)) return e; }
+  {
+    LeapArgs la;
+    la.X1 = X1; la.mu = mu; la.rows = rows; la.d = d; la.rA = rA; la.dK = dK; la.dB = dB; la.NT = NT; la.L = L; la.eps = eps;
+    la.Q = Q; la.S = S; la.S0 = S0; la.Qs = Qs; la.Bo = (const float*)pBo; la.prec = (const float*)tgt->precision;
+    la.ld_prec = tgt->ld; la.pBoP = pBoP; la.pPP = pPP; la.pQC = pQC; la.pQsP = pQsP; la.lpp = (float*)pLPP; la.dkp = (float*)pDKP;
+    const int e = (ctx->precision == HX_PREC_TF32X3) ? leapfrog_bform<KIND_TF32>(ctx, la, s) : leapfrog_bform<KIND_BF16>(ctx, la, s);
+    if (e) return e;
   }
 
   // (4) energies, log-accept, optional fused accept + chain emit
@@ -358,7 +439,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   }
   k_tc_finish<<<(rows + 7) / 8, 256, 0, s>>>(fa);
   HX_LAUNCH_CHECK("k_tc_finish");
-  ctx->launches += 6;
+  ctx->launches += 8;
   return 0;
 }
 

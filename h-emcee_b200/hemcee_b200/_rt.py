@@ -24,7 +24,7 @@ class _Config:
                  full-covariance Gaussian problems), "exact", "bf16x3", "bf16".
     """
 
-    PRECISIONS = {"auto": 0, "exact": 1, "bf16x3": 2, "bf16": 3}
+    PRECISIONS = {"auto": 0, "exact": 1, "bf16x3": 2, "bf16": 3, "tf32x3": 4}
 
     def __init__(self):
         self.enable_x64 = False

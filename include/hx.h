@@ -101,8 +101,10 @@ HX_API size_t hx_ctx_workspace_bytes(const hx_ctx* ctx);
  *   HX_PREC_EXACT  always the exact SIMT kernels (fp32 FMA / fp64)
  *   HX_PREC_BF16X3 tcgen05 tensor cores, operands split into bf16 hi+lo, three products, fp32
  *                  accumulation in TMEM (fp32-class accuracy, ~2^-16 per product)
- *   HX_PREC_BF16   tcgen05, single bf16 product (statistical parity only)                         */
-enum { HX_PREC_AUTO = 0, HX_PREC_EXACT = 1, HX_PREC_BF16X3 = 2, HX_PREC_BF16 = 3 };
+ *   HX_PREC_BF16   tcgen05, single bf16 product for the momentum projection (statistical parity only)
+ *   HX_PREC_TF32X3 like BF16X3 but the leapfrog kicks / energy products use tf32 hi+lo operands
+ *                  (~2^-21 per product) — for targets conditioned worse than ~1e6                  */
+enum { HX_PREC_AUTO = 0, HX_PREC_EXACT = 1, HX_PREC_BF16X3 = 2, HX_PREC_BF16 = 3, HX_PREC_TF32X3 = 4 };
 HX_API int hx_ctx_set_precision(hx_ctx* ctx, int mode);
 /* which kernel the timing hooks bracketed last: 0 = fused SIMT half-move, 1 = tcgen05 projection GEMM */
 HX_API int hx_ctx_last_path(const hx_ctx* ctx);
