@@ -337,9 +337,11 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   const int dAB = dB > dA ? dB : dA;       // CT planes serve as both A (128-row boxes) and B (BN-row boxes)
   const int NT = (d + BN - 1) / BN;
   typedef __nv_bfloat16 bf;
-  // momentum-draw pipeline: chunks of >= 1024 rows (multiple of 128), ~8 per shard, two buffers in flight
-  int chunk = pad_to((rows + 7) / 8, kBM);
-  if (chunk < 1024) chunk = pad_to(rows < 1024 ? rows : 1024, kBM);
+  // momentum-draw pipeline: row chunks whose projection GEMM is exactly one wave (sm_count CTAs of 128 x BN),
+  // two P0 buffers in flight
+  int chunk = (ctx->sm_count / NT) * kBM;
+  if (chunk < kBM) chunk = kBM;
+  if (chunk > rA) chunk = rA;
   const int nchunks = (rows + chunk - 1) / chunk;
   const size_t buf_elems = (size_t)2 * chunk * nK;            // one buffer = [2 planes, chunk, nK]
   void *pCT, *pM, *pBo, *pBoP, *pPP, *pP0, *pQC, *pQsP, *pS0, *pQs, *pLPP, *pDKP;
