@@ -28,7 +28,7 @@ class Backend:
             raise AttributeError("you must run the sampler with 'store == True' before accessing the results")
         v = getattr(self, name)
         if name in ("chain", "log_prob"):
-            v = np.concatenate(v, axis=0)
+            v = v[0] if len(v) == 1 else np.concatenate(v, axis=0)   # single slice: no copy
         v = v[discard::thin]
         if flat:
             s = list(v.shape[1:])

@@ -219,11 +219,8 @@ class HamiltonianEnsembleSampler(BaseSampler):
         if int(host_flag.max()) != 0:
             raise ValueError(_NONFINITE_MSG)
         acc = accepts.cpu().numpy()
-        hc, hl = host_chain.numpy(), host_lp.numpy()
-        for b in range(nb):
-            start, stop = b * batch_size, min((b + 1) * batch_size, T)
-            self.backend.save_slice(hc[start:stop], hl[start:stop], acc if b == nb - 1 else np.zeros_like(acc),
-                                    offset + start)
+        # one slice for the whole phase: the pinned host buffer becomes the stored chain without another copy
+        self.backend.save_slice(host_chain.numpy(), host_lp.numpy(), acc, offset)
         self.kernel_launch_count += T * 2 * (6 if self._move_kind == 0 else 2)
         return acc
 
