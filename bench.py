@@ -114,7 +114,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -155,13 +155,14 @@ def algorithmic_flops_half_move(rows, n, d, L, target):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--precision", default="auto", choices=["auto", "exact", "bf16x3", "bf16", "tf32x3"])
+    ap.add_argument("--leapfrog-form", default="auto", choices=["auto", "stepwise", "propagator"])
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -198,6 +199,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     hx.config.update("enable_x64", cfg["x64"])
     hx.config.update("precision", args.precision)
+    hx.config.update("leapfrog_form", args.leapfrog_form)
     tdt = torch.float64 if cfg["x64"] else torch.float32
     W, d, L, eps = cfg["W"], cfg["d"], cfg["L"], cfg["eps"]
     n = W // 2
@@ -245,7 +247,9 @@ def main():
         a2 = torch.zeros(rows, dtype=torch.int32, device=dev)
         chain = torch.empty((max(K, Wu), 2 * rows, d), dtype=tdt, device=dev)
 
-        def half(Xa, Xbf, lpa, acc, km, ka, Xaf):
+        def half(Xa, Xbf, lpa, acc, km, ka, Xaf, knext):
+            if mk == 0 and knext is not None:      # the following half-move's momentum draw only needs its key
+                hx.moves.walk_prefetch(knext, n, row0, rows, dev)
             q, la, _, lpq = move(Xa, Xbf, eps, km, tgt, tgt, L, lpa, row0=row0, n=n)
             hx.moves.accept_proposal(Xa, q, lpa, lpq, la, ka, acc, row0=row0, n=n)
             dist.all_gather_into_tensor(Xaf, Xa)
@@ -253,8 +257,8 @@ def main():
         def run(t0, T):
             for t in range(t0, t0 + T):
                 k = keys_host[t]
-                half(X1, X2f, lp1, a1, k[0], k[2], X1f)
-                half(X2, X1f, lp2, a2, k[1], k[3], X2f)
+                half(X1, X2f, lp1, a1, k[0], k[2], X1f, k[1])
+                half(X2, X1f, lp2, a2, k[1], k[3], X2f, keys_host[t + 1][0] if t + 1 < K + Wu else None)
                 chain[t - t0, :rows].copy_(X1); chain[t - t0, rows:].copy_(X2)
 
     def barrier():
@@ -359,7 +363,7 @@ def main():
                     warmup=Wu, ms_per_step=ms / K, higher_is_better=True, scaling="strong", vs_baseline=None,
                     dtype="f64" if cfg["x64"] else "f32", data="synthetic", config=conf, roofline=roofline,
                     cpu_baseline=cb, clocks=clk, e2e=e2e, gpu_launches=int(c_all.value) if world == 1 else int(c_all.value),
-                    acceptance_rate=acc_rate, nonfinite=int(flag.item()), precision=args.precision)
+                    acceptance_rate=acc_rate, nonfinite=int(flag.item()), precision=args.precision, leapfrog_form=args.leapfrog_form)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

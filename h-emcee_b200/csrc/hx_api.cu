@@ -70,6 +70,33 @@ extern "C" HX_API int hx_ctx_set_precision(hx_ctx* ctx, int mode) {
   ctx->precision = mode;
   return 0;
 }
+extern "C" HX_API int hx_ctx_set_leapfrog_form(hx_ctx* ctx, int form) {
+  if (!ctx) return hx_fail(HX_E_NULL, "hx_ctx_set_leapfrog_form: NULL ctx");
+  if (form < HX_LEAP_AUTO || form > HX_LEAP_PROPAGATOR) return hx_fail(HX_E_DTYPE, "hx_ctx_set_leapfrog_form: unknown form %d", form);
+  ctx->leap_form = form;
+  return 0;
+}
+extern "C" HX_API int hx_walk_prefetch(hx_ctx* ctx, int impl, int32_t n, int32_t row0, int32_t rows, const uint32_t key[2]) {
+  if (!ctx || !key) return hx_fail(HX_E_NULL, "hx_walk_prefetch: NULL ctx/key");
+  if (impl != HX_RNG_PARTITIONABLE && impl != HX_RNG_LEGACY) return hx_fail(HX_E_DTYPE, "hx_walk_prefetch: unknown rng impl %d", impl);
+  if (n < 2 || row0 < 0 || rows < 1 || row0 + rows > n) return hx_fail(HX_E_SHAPE, "hx_walk_prefetch: bad row shard");
+  ctx->hint.valid = 1; ctx->hint.impl = impl; ctx->hint.n = n; ctx->hint.row0 = row0; ctx->hint.rows = rows;
+  ctx->hint.k0 = key[0]; ctx->hint.k1 = key[1]; ctx->hint.key_ptr = nullptr;
+  ctx->hint_valid = 1;
+  return 0;
+}
+extern "C" HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value) {
+  if (!ctx) return hx_fail(HX_E_NULL, "hx_ctx_set_tuning: NULL ctx");
+  if (what == 0) ctx->rng_ctas_per_sm = value;
+  else return hx_fail(HX_E_DTYPE, "hx_ctx_set_tuning: unknown knob %d", what);
+  return 0;
+}
+extern "C" HX_API int hx_tc_microbench(hx_ctx* ctx, int mode, int32_t n, int32_t rows, int32_t dim, int32_t reps, double* ms_out, void* stream) {
+  if (!ctx || !ms_out) return hx_fail(HX_E_NULL, "hx_tc_microbench: NULL argument");
+  if (mode < 0 || mode > 2 || n < 64 || rows < 1 || dim < 16 || reps < 1) return hx_fail(HX_E_SHAPE, "hx_tc_microbench: bad argument");
+  HX_CUDA(cudaSetDevice(ctx->device));
+  return tc::microbench(ctx, mode, n, rows, dim, reps, ms_out, (cudaStream_t)stream);
+}
 extern "C" HX_API int hx_ctx_last_path(const hx_ctx* ctx) { return ctx ? ctx->last_path : -1; }
 
 extern "C" HX_API int hx_ctx_timing_enable(hx_ctx* ctx, int enable) {
@@ -133,7 +160,11 @@ extern "C" HX_API int hx_ctx_destroy(hx_ctx* ctx) {
   if (ctx->side_ready) {
     cudaStreamDestroy(ctx->side);
     cudaEventDestroy(ctx->ev_fork);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_rng[i]); cudaEventDestroy(ctx->ev_gemm[i]); }
+    for (int b = 0; b < 2; ++b) {
+      if (!ctx->ev_chunk[b]) continue;
+      for (cudaEvent_t e : *ctx->ev_chunk[b]) cudaEventDestroy(e);
+      delete ctx->ev_chunk[b];
+    }
   }
   delete ctx;
   return 0;
@@ -381,7 +412,7 @@ static int check_move_args(const char* who, const void* X1, const void* X2, int 
 template <typename T>
 static int walk_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1, const T* X2, int n, int row0,
                        int rows, double eps, Key key, const uint32_t* key_ptr, int L, const T* lp1, T* Q, T* logacc,
-                       T* pproj, T* lp_out, int flags, const Fuse<T>* fuse, cudaStream_t s) {
+                       T* pproj, T* lp_out, int flags, const Fuse<T>* fuse, const tc::NextDraw* next, cudaStream_t s) {
   struct { WalkParams<T> P; } W;
   memset(&W.P, 0, sizeof(W.P));
   if (int e = make_target<T>(tgt, &W.P.tg, "hx_walk_move")) return e;
@@ -403,7 +434,7 @@ static int walk_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1,
       ctx->launches += 2;
       ctx->last_path = 1;
       return tc::walk_half(ctx, impl, tgt, mean, X1, X2, n, row0, rows, eps, key, key_ptr, L, lp1, Q, logacc, pproj,
-                           lp_out, fuse ? &f32 : nullptr, s);
+                           lp_out, fuse ? &f32 : nullptr, next, s);
     }
   }
   ctx->last_path = 0;
@@ -443,11 +474,20 @@ extern "C" HX_API int hx_walk_move(hx_ctx* ctx, int dtype, int impl, const hx_ta
   HX_CUDA(cudaSetDevice(ctx->device));
   const Key k{key[0], key[1]};
   cudaStream_t s = (cudaStream_t)stream;
+  tc::NextDraw nd;
+  const tc::NextDraw* next = nullptr;
+  if (ctx->hint_valid) {           // hx_walk_prefetch: start the following half-move's momentum draw under this one
+    ctx->hint_valid = 0;
+    if (ctx->hint.impl == impl && ctx->hint.n == n) {
+      nd.key = Key{ctx->hint.k0, ctx->hint.k1}; nd.key_ptr = nullptr; nd.row0 = ctx->hint.row0; nd.rows = ctx->hint.rows;
+      next = &nd;
+    }
+  }
   if (dtype == HX_F32)
     return walk_move_t<float>(ctx, impl, tgt, (const float*)X1, (const float*)X2, n, row0, rows, step_size, k, nullptr, L,
-                              (const float*)lp1, (float*)Q, (float*)logacc, (float*)pproj, (float*)lp_out, flags, nullptr, s);
+                              (const float*)lp1, (float*)Q, (float*)logacc, (float*)pproj, (float*)lp_out, flags, nullptr, next, s);
   return walk_move_t<double>(ctx, impl, tgt, (const double*)X1, (const double*)X2, n, row0, rows, step_size, k, nullptr, L,
-                             (const double*)lp1, (double*)Q, (double*)logacc, (double*)pproj, (double*)lp_out, flags, nullptr, s);
+                             (const double*)lp1, (double*)Q, (double*)logacc, (double*)pproj, (double*)lp_out, flags, nullptr, nullptr, s);
 }
 
 // ---- side move ---------------------------------------------------------------------------------------------------
@@ -655,8 +695,16 @@ static int run_iterations_t(hx_ctx* ctx, int impl, int move_kind, int key_order,
       f.chain_lp = chain_lp ? chain_lp + (size_t)t * W2 + (size_t)half * n : nullptr;
       f.nonfinite = nonfinite;
       int e;
+      // the half-move after this one (its momentum draw only needs the key): move2 of this iteration or move1 of the next
+      tc::NextDraw nd;
+      const tc::NextDraw* next = nullptr;
+      if (half == 0 || t + 1 < Tn) {
+        const uint32_t* kn = half == 0 ? kt + 2 * (key_order == 0 ? 1 : 2) : kt + 8;
+        nd.key = Key{0, 0}; nd.key_ptr = kn; nd.row0 = 0; nd.rows = n;
+        next = &nd;
+      }
       if (move_kind == 0)
-        e = walk_move_t<T>(ctx, impl, tgt, Xa, Xb, n, 0, n, eps, Key{0, 0}, kmove, L, lpa, (T*)pQ, (T*)pLa, nullptr, (T*)pLp, 0, &f, s);
+        e = walk_move_t<T>(ctx, impl, tgt, Xa, Xb, n, 0, n, eps, Key{0, 0}, kmove, L, lpa, (T*)pQ, (T*)pLa, nullptr, (T*)pLp, 0, &f, next, s);
       else
         e = side_move_t<T>(ctx, impl, tgt, Xa, Xb, n, 0, n, eps, Key{0, 0}, kmove, L, lpa, (T*)pQ, (T*)pLa, nullptr, (T*)pLp, 0, &f, s);
       if (e) return e;

@@ -11,7 +11,16 @@ enum Slot {
   WS_C = 0, WS_M, WS_MEAN, WS_PART, WS_G, WS_S, WS_Q, WS_LA, WS_LP, WS_IDX, WS_GRAMP,
   // tensor-core path
   WS_TC_CT, WS_TC_MP, WS_TC_PP, WS_TC_P0, WS_TC_QC, WS_TC_GP, WS_TC_LPP, WS_TC_DKP, WS_TC_MASK, WS_TC_BO, WS_TC_S0,
+  // propagator form of the Gaussian leapfrog
+  WS_TC_BX, WS_TC_BS, WS_TC_TQ, WS_TC_TS, WS_TC_TW, WS_TC_WP, WS_TC_B1, WS_TC_B2, WS_TC_ZB, WS_TC_ZT, WS_TC_QC2,
   WS_NSLOT
+};
+
+// one momentum draw P0 = normal(key, (n, n))[row0 : row0 + rows] held (or being written) in a draw buffer
+struct P0Job {
+  int valid, impl, n, row0, rows;
+  uint32_t k0, k1;
+  const uint32_t* key_ptr;       // device-resident key (batch loop) or NULL (key by value)
 };
 
 struct hx_ctx {
@@ -30,8 +39,14 @@ struct hx_ctx {
   void* encode_fn;                // cuTensorMapEncodeTiled (resolved lazily)
   // side stream + events used to overlap the momentum draw (ALU) with the projection GEMM (tensor pipe)
   cudaStream_t side;
-  cudaEvent_t ev_fork, ev_rng[2], ev_gemm[2];
+  cudaEvent_t ev_fork;
   int side_ready;
+  P0Job job[2];                            // contents of the two draw buffers
+  std::vector<cudaEvent_t>* ev_chunk[2];   // per buffer: "chunk c drawn" events
+  void* p0_base; size_t p0_elems;          // identity of the draw workspace the jobs refer to
+  P0Job hint; int hint_valid;              // hx_walk_prefetch: the walk half-move after the next one
+  int leap_form;                           // HX_LEAP_*
+  int rng_ctas_per_sm;                     // resident CTAs/SM of the draw kernel (0: default 4)
 };
 
 // grow-only scratch slot

@@ -24,7 +24,7 @@ constexpr int kBM = 128;      // UMMA M
 constexpr int kThreads = 192;
 
 enum : int { KIND_BF16 = 0, KIND_TF32 = 1 };
-enum : int { EPI_STORE = 0, EPI_KICKB = 1, EPI_DOT = 2 };
+enum : int { EPI_STORE = 0, EPI_KICKB = 1, EPI_DOT = 2, EPI_PROP = 3 };
 
 template <int KIND> struct Kind;
 template <> struct Kind<KIND_BF16> {
@@ -56,15 +56,27 @@ struct GemmArgs {
   // EPI_DOT: part[row*NT + ntile] = sum_cols acc * (X + Y - mu)   (Y, mu optional)
   const float* X; const float* Y;
   float* part; int NT;
+  // EPI_PROP (acc = [q0 - mu | S0] @ [Tq | Ts], the L-step leapfrog propagator of a Gaussian target): the N axis holds
+  // two column blocks of blk_cols (padded) columns each; block 0: Q = acc + mu, planes_out (tf32 hi/lo) <- split(acc);
+  // block 1: S = acc.  blk_cols = 0 for the other epilogues (one block).
+  int blk_cols;
 };
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
+// hi = RN_tf32(x), lo = RN_tf32(x - hi): both parts are exact tf32 values, so the tensor core's own truncation of the fp32
+// container is a no-op.  (Masking the low 13 bits instead rounds hi AND the truncated lo toward zero: a systematic
+// -2^-22 relative bias per product that shows up as a ~1e-2 bias of the energy error on kappa = 1e4 targets.)
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  lo = x - hi;
+  hi = rn_tf32(x);
+  lo = rn_tf32(x - hi);
 }
 
 // 32 contiguous floats of one row: vector path when `fast`, predicated scalar path otherwise
@@ -105,15 +117,15 @@ __device__ __forceinline__ void store_planes32(void* planes, size_t pbase, size_
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < nval) { P[pbase + j] = hi[j]; P[plane + pbase + j] = lo[j]; }
+      for (int j = 0; j < 32; ++j) { P[pbase + j] = hi[j]; P[plane + pbase + j] = lo[j]; }   // zero K-padding
     }
   } else {
     float* P = reinterpret_cast<float*>(planes);
     float hi[32], lo[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) split_tf32(j < nval ? v[j] : 0.f, hi[j], lo[j]);
-    store32(P + pbase, hi, nval, fast);
-    store32(P + plane + pbase, lo, nval, fast);
+    store32(P + pbase, hi, 32, fast);        // values beyond nval are zero: keeps the K-padding of the planes zero
+    store32(P + plane + pbase, lo, 32, fast);
   }
 }
 
@@ -222,16 +234,18 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   } else {
     // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); thread = one output row ----------
     const int q = warp & 3;
-    mbar_wait(tmem_full, 0);
+    mbar_wait_backoff(tmem_full, 0, 512);
     tc_fence_after();
     const int row = m0 + 32 * q + lane;
     const bool rok = row < g.M;
     const bool vec = (g.N & 3) == 0 && (EPI == EPI_STORE ? (g.ldo & 3) == 0 : true);
     float rowacc = 0.f;
     const int NC = BN / 32;
+    const int blk = (EPI == EPI_PROP) ? n0 / g.blk_cols : 0;
+    const int cn0 = (EPI == EPI_PROP) ? n0 - blk * g.blk_cols : n0;
 #pragma unroll 1
     for (int cc = 0; cc < NC; ++cc) {
-      const int col0 = n0 + cc * 32;
+      const int col0 = cn0 + cc * 32;
       if (col0 >= g.N) break;           // warp-uniform
       float v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cc * 32), v);
@@ -240,6 +254,22 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const bool fast = vec && nval == 32;
       if (EPI == EPI_STORE) {
         store32(g.out + (size_t)row * g.ldo + col0, v, nval, fast);
+      } else if (EPI == EPI_PROP) {
+        const size_t base = (size_t)row * g.N + col0;
+        if (blk == 0) {
+          float qv[32];
+          if (g.mu) {
+            load32(g.mu + col0, qv, nval, fast);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) qv[j] += v[j];
+            store32(g.Q + base, qv, nval, fast);
+          } else {
+            store32(g.Q + base, v, nval, fast);
+          }
+          store_planes32<KIND_TF32>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, v, nval, fast);
+        } else {
+          store32(g.S + base, v, nval, fast);
+        }
       } else {
         const size_t base = (size_t)row * g.N + col0;
         float mu[32];

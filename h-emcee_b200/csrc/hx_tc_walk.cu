@@ -155,12 +155,12 @@ __global__ void __launch_bounds__(256) k_small_gemm(const float* __restrict__ A,
   }
 }
 
-// P0 planes [2, rows_pad, Kp]: P0[r][j] = normal(key, (n, n))[row0 + r, j]; 8 consecutive j per thread
+// Rows [0, rows_chunk) of the P0 planes (hi at `planes`, lo at `planes + plane`): P0[r][j] = normal(key, (n, n))[row0 + r, j],
+// zero for r >= rows or j >= n; 8 consecutive j per thread
 __global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key_ptr, int legacy, int n, int row0, int rows,
-                                                    int rows_pad, int Kp, __nv_bfloat16* __restrict__ planes) {
+                                                    int rows_chunk, int Kp, size_t plane, __nv_bfloat16* __restrict__ planes) {
   if (key_ptr) { key.k0 = key_ptr[0]; key.k1 = key_ptr[1]; }
-  const size_t plane = (size_t)rows_pad * Kp;
-  const size_t nvec = plane / 8;
+  const size_t nvec = (size_t)rows_chunk * Kp / 8;
   const uint64_t nn = (uint64_t)n * (uint64_t)n;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
     const size_t i = v * 8;
@@ -201,6 +201,87 @@ __global__ void k_tc_init(const float* __restrict__ X1, const float* __restrict_
       split_tf32(v, hi, lo);
       reinterpret_cast<float*>(planes)[i] = hi;
       reinterpret_cast<float*>(planes)[plane + i] = lo;
+    }
+  }
+}
+
+// basis of the propagator run: bX = [I; 0], bS = [0; I]  (each [2d, d])
+__global__ void k_basis_init(float* __restrict__ bX, float* __restrict__ bS, int d) {
+  const size_t tot = (size_t)2 * d * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / d), c = (int)(i - (size_t)r * d);
+    bX[i] = (r == c) ? 1.f : 0.f;
+    bS[i] = (r == c + d) ? 1.f : 0.f;
+  }
+}
+
+// z0 = [X1 - mu | S0] as A-operand planes with K2 = 2*dK columns (x part at [0, dK), S part at [dK, 2 dK)), zero padded:
+// zB = bf16 hi/lo [2, rA, K2] (nullable), zT = tf32 hi/lo [2, rA, K2] (nullable)
+__global__ void k_z0_planes(const float* __restrict__ X1, const float* __restrict__ mu, const float* __restrict__ S0, int rows,
+                            int d, int rA, int dK, __nv_bfloat16* __restrict__ zB, float* __restrict__ zT) {
+  const int K2 = 2 * dK;
+  const size_t tot4 = (size_t)rA * K2 / 4, plane = (size_t)rA * K2;
+  for (size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < tot4; i4 += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = i4 * 4;
+    const int r = (int)(i / K2), kk = (int)(i - (size_t)r * K2);
+    const int part = kk >= dK, c0 = kk - part * dK;
+    float v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int c = c0 + t;
+      float x = 0.f;
+      if (r < rows && c < d) x = part ? S0[(size_t)r * d + c] : X1[(size_t)r * d + c] - (mu ? mu[c] : 0.f);
+      v[t] = x;
+    }
+    if (zB) {
+      __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) split_bf16(v[t], hi[t], lo[t]);
+      *reinterpret_cast<uint2*>(zB + i) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(zB + plane + i) = *reinterpret_cast<const uint2*>(lo);
+    }
+    if (zT) {
+      float hi[4], lo[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) split_tf32(v[t], hi[t], lo[t]);
+      *reinterpret_cast<float4*>(zT + i) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(zT + plane + i) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
+// B-operand planes of a propagator block: planes[row_off + c][kk] = split(src[k(kk)][c]) for c < d, where src is
+// [2d, d] (basis index k major) and kk -> k maps the z0 column layout (kk < dK: k = kk; else k = d + kk - dK);
+// zero outside.  Covers rows [row_off, row_off + rows_blk) of both planes ([2, rows_pad, K2]).
+template <int KIND>
+__global__ void k_transpose_planes(const float* __restrict__ src, int d, int dK, int rows_blk, int rows_pad, int row_off,
+                                   typename Kind<KIND>::elem* __restrict__ planes) {
+  __shared__ float tile[32][33];
+  const int K2 = 2 * dK;
+  const int kk0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {       // i: kk index, threadIdx.x: c index (coalesced over c)
+    const int kk = kk0 + i, c = c0 + threadIdx.x;
+    const int part = kk >= dK, kc = kk - part * dK;
+    tile[i][threadIdx.x] = (kc < d && c < d) ? src[(size_t)(part * d + kc) * d + c] : 0.f;
+  }
+  __syncthreads();
+  const size_t plane = (size_t)rows_pad * K2;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {       // i: c index, threadIdx.x: kk index (coalesced over kk)
+    const int c = c0 + i, kk = kk0 + threadIdx.x;
+    if (c < rows_blk && kk < K2) {
+      const size_t o = (size_t)(row_off + c) * K2 + kk;
+      const float v = tile[threadIdx.x][i];
+      if (KIND == KIND_BF16) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        reinterpret_cast<__nv_bfloat16*>(planes)[o] = hi;
+        reinterpret_cast<__nv_bfloat16*>(planes)[plane + o] = lo;
+      } else {
+        float hi, lo;
+        split_tf32(v, hi, lo);
+        reinterpret_cast<float*>(planes)[o] = hi;
+        reinterpret_cast<float*>(planes)[plane + o] = lo;
+      }
     }
   }
 }
@@ -251,11 +332,13 @@ __global__ void __launch_bounds__(256) k_tc_finish(FinishArgs a) {
 }
 
 // ---- GEMM launcher ---------------------------------------------------------------------------------------------------
+// rowsA_pad / rowsB_pad = plane stride in rows; mapA_rows = rows covered by the A tensor map (0: both full planes);
+// n_grid = padded N the grid covers (0: g.N)
 template <int EPI, int KIND>
 static int launch_gemm(hx_ctx* ctx, const void* A, int rowsA_pad, const void* B, int rowsB_pad, int Kp, GemmArgs g,
-                       cudaStream_t s) {
+                       cudaStream_t s, uint64_t mapA_rows = 0, int n_grid = 0) {
   CUtensorMap tmA, tmB;
-  if (int e = make_tmap(ctx, &tmA, A, 2ull * rowsA_pad, Kp, kBM, KIND)) return e;
+  if (int e = make_tmap(ctx, &tmA, A, mapA_rows ? mapA_rows : 2ull * rowsA_pad, Kp, kBM, KIND)) return e;
   if (int e = make_tmap(ctx, &tmB, B, 2ull * rowsB_pad, Kp, BN, KIND)) return e;
   g.Kp = Kp; g.rowsA_pad = rowsA_pad; g.rowsB_pad = rowsB_pad;
   static bool attr_done = false;
@@ -263,7 +346,7 @@ static int launch_gemm(hx_ctx* ctx, const void* A, int rowsA_pad, const void* B,
     HX_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::BYTES));
     attr_done = true;
   }
-  dim3 grid((g.N + BN - 1) / BN, (g.M + kBM - 1) / kBM);
+  dim3 grid(((n_grid ? n_grid : g.N) + BN - 1) / BN, (g.M + kBM - 1) / kBM);
   k_tc_gemm<BN, EPI, KIND><<<grid, kThreads, SmemLayout<BN>::BYTES, s>>>(tmA, tmB, g);
   HX_LAUNCH_CHECK("k_tc_gemm");
   ctx->launches += 1;
@@ -281,7 +364,8 @@ static inline int grid_for(size_t n, int block) {
 struct LeapArgs {
   const float* X1; const float* mu; int rows, d, rA, dK, dB, NT, L; double eps;
   float* Q; float* S; float* S0; float* Qs; const float* Bo; const float* prec; int ld_prec;
-  void* pBoP; void* pPP; void* pQC; void* pQsP; float* lpp; float* dkp;
+  void* pBoP; void* pPP; void* pQC; void* pQC2; void* pQsP; float* lpp; float* dkp;
+  int energies;     // 0: integrate only (propagator basis run)
 };
 
 // L+1 kicks in B-form (every kick but the last followed by a drift; hmc_walk.py:85-102), then the two energy products.
@@ -295,26 +379,33 @@ static int leapfrog_bform(hx_ctx* ctx, const LeapArgs& a, cudaStream_t s) {
   HX_LAUNCH_CHECK("k_split_planes(P)");
   k_tc_init<KIND><<<grid_for((size_t)rA * dK, 256), 256, 0, s>>>(a.X1, a.mu, rows, d, rA, dK, a.Q, (E*)a.pQC);
   HX_LAUNCH_CHECK("k_tc_init");
+  ctx->launches += 3;
   GemmArgs gg;
   memset(&gg, 0, sizeof(gg));
   gg.nprod = 3; gg.M = rows; gg.N = d; gg.mu = a.mu; gg.NT = a.NT; gg.eps = (float)a.eps;
+  // The q - mu operand planes ping-pong between two buffers: a kick's epilogue writes the NEXT operand while sibling CTAs of the
+  // same row tile (other column tiles) may still be reading the current one (updating in place is a race).
+  void* planes[2] = {a.pQC, a.pQC2};
   for (int k = 0; k <= a.L; ++k) {
     GemmArgs x = gg;
     x.S_in = (k == 0) ? a.S0 : a.S; x.S = a.S; x.Q = a.Q; x.Qs = a.Qs; x.first = (k == 0) ? 1 : 0;
-    x.planes_out = a.pQC; x.rows_out_pad = rA; x.Kout_p = dK;
+    x.planes_out = planes[(k + 1) & 1]; x.rows_out_pad = rA; x.Kout_p = dK;
     x.a = (float)((k == 0 || k == a.L) ? 0.5 * (float)a.eps : (float)a.eps);
     x.drift = k < a.L ? 1 : 0;
-    if (int e = launch_gemm<EPI_KICKB, KIND>(ctx, a.pQC, rA, a.pBoP, dB, dK, x, s)) return e;
+    if (int e = launch_gemm<EPI_KICKB, KIND>(ctx, planes[k & 1], rA, a.pBoP, dB, dK, x, s)) return e;
   }
+  void* planes_L = planes[a.L & 1];      // q_L - mu (written by the last drift, kick L-1)
+  if (!a.energies) return 0;
   // energies: dK = -1/2 <Qs P, S0 + S_L> ; lp' = -1/2 <(q_L - mu) P, q_L - mu>
   k_split_planes<KIND><<<grid_for((size_t)rA * dK, 256), 256, 0, s>>>(a.Qs, rows, d, d, rA, dK, (E*)a.pQsP);
   HX_LAUNCH_CHECK("k_split_planes(Qs)");
+  ctx->launches += 1;
   GemmArgs x = gg;
   x.mu = nullptr; x.X = a.S0; x.Y = a.S; x.part = a.dkp;
   if (int e = launch_gemm<EPI_DOT, KIND>(ctx, a.pQsP, rA, a.pPP, dB, dK, x, s)) return e;
   GemmArgs y = gg;
   y.X = a.Q; y.Y = nullptr; y.part = a.lpp;
-  return launch_gemm<EPI_DOT, KIND>(ctx, a.pQC, rA, a.pPP, dB, dK, y, s);
+  return launch_gemm<EPI_DOT, KIND>(ctx, planes_L, rA, a.pPP, dB, dK, y, s);
 }
 
 bool walk_eligible(const hx_ctx* ctx, int dtype, const hx_target* tgt, int n, int rows, int flags) {
@@ -324,9 +415,77 @@ bool walk_eligible(const hx_ctx* ctx, int dtype, const hx_target* tgt, int n, in
   return tgt->dim >= 16 && n >= 64;      // forced tensor-core modes (tests)
 }
 
+// ---- momentum-draw jobs ------------------------------------------------------------------------------------------------
+// P0 = normal(key, (n, n))[row0 : row0 + rows] does not depend on the ensemble, only on the key.  A job draws it as bf16
+// hi/lo planes [2, rA, nK] into one of two buffers on the low-priority side stream, chunk by chunk (one event per
+// chunk), so that (a) the projection GEMM of chunk c overlaps the draw of chunk c+1 and (b) the draw for the NEXT
+// half-move (key known in advance) runs under the current half-move's tensor-core work.
+static int side_init(hx_ctx* ctx) {
+  if (ctx->side_ready) return 0;
+  int prio_lo = 0, prio_hi = 0;
+  HX_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  HX_CUDA(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo));
+  HX_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  for (int b = 0; b < 2; ++b) {
+    ctx->job[b].valid = 0;
+    ctx->ev_chunk[b] = new std::vector<cudaEvent_t>();
+  }
+  // same L1/shared carve-out as the GEMM kernel, otherwise the two kernels cannot share an SM
+  HX_CUDA(cudaFuncSetAttribute(k_rng_planes, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  ctx->side_ready = 1;
+  return 0;
+}
+
+static bool job_matches(const P0Job& j, int impl, int n, int row0, int rows, Key key, const uint32_t* key_ptr) {
+  if (!j.valid || j.impl != impl || j.n != n || j.row0 != row0 || j.rows != rows) return false;
+  if (key_ptr || j.key_ptr) return key_ptr == j.key_ptr;
+  return key.k0 == j.k0 && key.k1 == j.k1;
+}
+
+static int chunk_rows(const hx_ctx* ctx, int rA, int NT) {
+  int chunk = (ctx->sm_count / NT) * kBM;     // projection GEMM of one chunk = one wave of 128 x BN tiles
+  if (chunk < kBM) chunk = kBM;
+  if (chunk > rA) chunk = rA;
+  return chunk;
+}
+
+// enqueue the draw of (key, row0, rows) into buffer b on the side stream
+static int job_launch(hx_ctx* ctx, int b, __nv_bfloat16* buf, int impl, int n, int row0, int rows, int rA, int nK, int chunk,
+                      Key key, const uint32_t* key_ptr, cudaStream_t s) {
+  const int nchunks = (rows + chunk - 1) / chunk;
+  std::vector<cudaEvent_t>& evs = *ctx->ev_chunk[b];
+  while ((int)evs.size() < nchunks) {
+    cudaEvent_t e;
+    HX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    evs.push_back(e);
+  }
+  // ordered after everything already enqueued on s (the buffer's previous consumer in particular)
+  HX_CUDA(cudaEventRecord(ctx->ev_fork, s));
+  HX_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+  const size_t plane = (size_t)rA * nK;
+  for (int c = 0; c < nchunks; ++c) {
+    const int r0 = c * chunk;
+    const int rc = (rows - r0) < chunk ? (rows - r0) : chunk;
+    const int rcp = pad_to(rc, kBM);
+    // 4 CTAs (32 warps) per SM: measured (scripts/overlap_bench.py) to overlap fully with a co-resident GEMM CTA, whereas
+    // 1-2 CTAs/SM serialise (too few warps to cover the ALU latency once the GEMM's warps take issue slots)
+    int rng_grid = grid_for((size_t)rcp * nK / 8, 256);
+    const int cap = ctx->sm_count * (ctx->rng_ctas_per_sm > 0 ? ctx->rng_ctas_per_sm : 4);
+    if (rng_grid > cap) rng_grid = cap;
+    k_rng_planes<<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, impl == HX_RNG_LEGACY ? 1 : 0, n, row0 + r0, rc, rcp, nK, plane,
+                                                  buf + (size_t)r0 * nK);
+    HX_LAUNCH_CHECK("k_rng_planes");
+    HX_CUDA(cudaEventRecord(evs[c], ctx->side));
+    ctx->launches += 1;
+  }
+  P0Job& j = ctx->job[b];
+  j.valid = 1; j.impl = impl; j.n = n; j.row0 = row0; j.rows = rows; j.k0 = key.k0; j.k1 = key.k1; j.key_ptr = key_ptr;
+  return 0;
+}
+
 int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev, const float* X1, const float* X2, int n,
               int row0, int rows, double eps, Key key, const uint32_t* key_ptr, int L, const float* lp1, float* Q,
-              float* logacc, float* S, float* lp_out, const FuseF32* fuse, cudaStream_t s) {
+              float* logacc, float* S, float* lp_out, const FuseF32* fuse, const NextDraw* next, cudaStream_t s) {
   const int d = tgt->dim;
   const int nprod = (ctx->precision == HX_PREC_BF16) ? 1 : 3;   // momentum projection / Gram only
   const int dB = pad_to(d, BN);            // rows of B-operand planes (N side)
@@ -336,29 +495,56 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   const int dA = pad_to(d, kBM);
   const int dAB = dB > dA ? dB : dA;       // CT planes serve as both A (128-row boxes) and B (BN-row boxes)
   const int NT = (d + BN - 1) / BN;
+  const int K2 = 2 * dK;                   // K of the propagator GEMMs: z0 = [q0 - mu | S0]
+  const int bR = 2 * d, bRA = pad_to(bR, kBM);   // propagator basis rows
   typedef __nv_bfloat16 bf;
-  // momentum-draw pipeline: row chunks whose projection GEMM is exactly one wave (sm_count CTAs of 128 x BN),
-  // two P0 buffers in flight
-  int chunk = (ctx->sm_count / NT) * kBM;
-  if (chunk < kBM) chunk = kBM;
-  if (chunk > rA) chunk = rA;
-  const int nchunks = (rows + chunk - 1) / chunk;
-  const size_t buf_elems = (size_t)2 * chunk * nK;            // one buffer = [2 planes, chunk, nK]
-  void *pCT, *pM, *pBo, *pBoP, *pPP, *pP0, *pQC, *pQsP, *pS0, *pQs, *pLPP, *pDKP;
+  // leapfrog form: step-by-step kicks on every walker, or (Gaussian target => linear dynamics) the L-step propagator
+  // built once per half-move from 2d basis trajectories and applied to all walkers in one GEMM
+  bool prop = ctx->leap_form == HX_LEAP_PROPAGATOR || (ctx->leap_form == HX_LEAP_AUTO && rows >= 6 * d && L >= 4);
+  const bool g1_tf32 = ctx->precision == HX_PREC_TF32X3;
+  const int rQ = prop ? (rA > bRA ? rA : bRA) : rA;            // rows of the q - mu operand planes (basis run reuses them)
+
+  void *pCT, *pM, *pBo, *pBoP, *pPP, *pP0, *pQC, *pQC2, *pQsP, *pS0, *pQs, *pLPP, *pDKP;
   if (int e = ws_get(ctx, WS_TC_CT, (size_t)2 * dAB * nK * sizeof(bf), &pCT)) return e;
   if (int e = ws_get(ctx, WS_M, (size_t)d * d * sizeof(float), &pM)) return e;
   if (int e = ws_get(ctx, WS_TC_BO, (size_t)d * d * sizeof(float), &pBo)) return e;
   if (int e = ws_get(ctx, WS_TC_MP, (size_t)2 * dB * dK * sizeof(float), &pBoP)) return e;
   if (int e = ws_get(ctx, WS_TC_PP, (size_t)2 * dB * dK * sizeof(float), &pPP)) return e;
-  if (int e = ws_get(ctx, WS_TC_P0, (nchunks > 1 ? 2 : 1) * buf_elems * sizeof(bf), &pP0)) return e;
-  if (int e = ws_get(ctx, WS_TC_QC, (size_t)2 * rA * dK * sizeof(float), &pQC)) return e;
-  if (int e = ws_get(ctx, WS_TC_GP, (size_t)2 * rA * dK * sizeof(float), &pQsP)) return e;
+  const size_t buf_elems = (size_t)2 * rA * nK;               // one draw buffer = [2 planes, rA, nK]
+  if (int e = ws_get(ctx, WS_TC_P0, 2 * buf_elems * sizeof(bf), &pP0)) return e;
+  if (int e = ws_get(ctx, WS_TC_QC, (size_t)2 * rQ * dK * sizeof(float), &pQC)) return e;
+  if (int e = ws_get(ctx, WS_TC_QC2, (size_t)2 * (prop ? bRA : rA) * dK * sizeof(float), &pQC2)) return e;
+  if (int e = ws_get(ctx, WS_TC_GP, (size_t)2 * (prop ? bRA : rA) * dK * sizeof(float), &pQsP)) return e;
   if (int e = ws_get(ctx, WS_TC_S0, (size_t)rows * d * sizeof(float), &pS0)) return e;
   if (int e = ws_get(ctx, WS_G, (size_t)rows * d * sizeof(float), &pQs)) return e;
   if (int e = ws_get(ctx, WS_TC_LPP, (size_t)rows * NT * sizeof(float), &pLPP)) return e;
   if (int e = ws_get(ctx, WS_TC_DKP, (size_t)rows * NT * sizeof(float), &pDKP)) return e;
   float* S0 = (float*)pS0;
   float* Qs = (float*)pQs;
+  const float* mu = (const float*)tgt->mean;
+  if (int e = side_init(ctx)) return e;
+
+  // (0) momentum draw (hmc_walk.py:36): use the prefetched job if it is this half-move's, otherwise start it now; then
+  //     queue the next half-move's draw behind it
+  const int chunk = chunk_rows(ctx, rA, NT);
+  const int nchunks = (rows + chunk - 1) / chunk;
+  bf* Pbuf[2] = {(bf*)pP0, (bf*)pP0 + buf_elems};
+  if (ctx->p0_base != pP0 || ctx->p0_elems != buf_elems) {    // workspace moved or reshaped: prefetched draws are gone
+    ctx->job[0].valid = ctx->job[1].valid = 0;
+    ctx->p0_base = pP0; ctx->p0_elems = buf_elems;
+  }
+  int cur = -1;
+  for (int b = 0; b < 2; ++b)
+    if (job_matches(ctx->job[b], impl, n, row0, rows, key, key_ptr)) cur = b;
+  if (cur < 0) {
+    cur = ctx->job[0].valid ? (ctx->job[1].valid ? 0 : 1) : 0;
+    if (int e = job_launch(ctx, cur, Pbuf[cur], impl, n, row0, rows, rA, nK, chunk, key, key_ptr, s)) return e;
+  }
+  ctx->job[cur].valid = 0;       // consumed by this half-move
+  if (next && next->rows == rows) {
+    if (int e = job_launch(ctx, 1 - cur, Pbuf[1 - cur], impl, n, next->row0, next->rows, rA, nK, chunk, next->key, next->key_ptr, s))
+      return e;
+  }
 
   // (1) complement statistics: mean_dev already holds mean_0(X2) (hx_api.cu); C^T planes, M = C^T C, Bop = M P
   {
@@ -376,60 +562,104 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     k_small_gemm<<<g, 256, 0, s>>>((const float*)pM, d, (const float*)tgt->precision, tgt->ld, d, (float*)pBo, d);
     HX_LAUNCH_CHECK("k_small_gemm");
   }
+  ctx->launches += 2;
 
-  // (2) momentum draw (hmc_walk.py:36) and projection S0 = P0 C, pipelined over row chunks: the
-  //     counter-based draw of chunk c+1 (ALU pipes, side stream) overlaps the tcgen05 GEMM of chunk c.
-  {
-    if (!ctx->side_ready) {
-      int prio_lo = 0, prio_hi = 0;
-      HX_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-      HX_CUDA(cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo));
-      HX_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-      for (int i = 0; i < 2; ++i) {
-        HX_CUDA(cudaEventCreateWithFlags(&ctx->ev_rng[i], cudaEventDisableTiming));
-        HX_CUDA(cudaEventCreateWithFlags(&ctx->ev_gemm[i], cudaEventDisableTiming));
-      }
-      // same L1/shared carve-out as the GEMM kernel, otherwise the two kernels cannot share an SM
-      HX_CUDA(cudaFuncSetAttribute(k_rng_planes, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      ctx->side_ready = 1;
+  // (2) propagator (Gaussian target: the leapfrog is a linear map of z0 = [q0 - mu | S0]).  Integrate the 2d basis
+  //     trajectories with the same kick/drift recurrence (tf32 hi/lo operands), giving q_L - mu = z0 Tq, S_L = z0 Ts
+  //     and the impulse-weighted position sum Qs = z0 W; fold the precision into W for the kinetic-energy product.
+  void *pBX = nullptr, *pBS = nullptr, *pTQ = nullptr, *pTS = nullptr, *pTW = nullptr, *pWP = nullptr, *pB1 = nullptr,
+       *pB2 = nullptr, *pZB = nullptr, *pZT = nullptr;
+  if (prop) {
+    const size_t bsz = (size_t)bR * d * sizeof(float);
+    if (int e = ws_get(ctx, WS_TC_BX, bsz, &pBX)) return e;
+    if (int e = ws_get(ctx, WS_TC_BS, bsz, &pBS)) return e;
+    if (int e = ws_get(ctx, WS_TC_TQ, bsz, &pTQ)) return e;
+    if (int e = ws_get(ctx, WS_TC_TS, bsz, &pTS)) return e;
+    if (int e = ws_get(ctx, WS_TC_TW, bsz, &pTW)) return e;
+    if (int e = ws_get(ctx, WS_TC_WP, bsz, &pWP)) return e;
+    if (int e = ws_get(ctx, WS_TC_B1, (size_t)2 * (2 * dB) * K2 * sizeof(float), &pB1)) return e;
+    if (int e = ws_get(ctx, WS_TC_B2, (size_t)2 * dB * K2 * sizeof(float), &pB2)) return e;
+    if (int e = ws_get(ctx, WS_TC_ZB, g1_tf32 ? 16 : (size_t)2 * rA * K2 * sizeof(bf), &pZB)) return e;
+    if (int e = ws_get(ctx, WS_TC_ZT, (size_t)2 * rA * K2 * sizeof(float), &pZT)) return e;
+    k_basis_init<<<grid_for((size_t)bR * d, 256), 256, 0, s>>>((float*)pBX, (float*)pBS, d);
+    HX_LAUNCH_CHECK("k_basis_init");
+    LeapArgs la;
+    la.X1 = (const float*)pBX; la.mu = nullptr; la.rows = bR; la.d = d; la.rA = bRA; la.dK = dK; la.dB = dB; la.NT = NT; la.L = L;
+    la.eps = eps; la.Q = (float*)pTQ; la.S = (float*)pTS; la.S0 = (float*)pBS; la.Qs = (float*)pTW; la.Bo = (const float*)pBo;
+    la.prec = (const float*)tgt->precision; la.ld_prec = tgt->ld; la.pBoP = pBoP; la.pPP = pPP; la.pQC = pQC; la.pQC2 = pQC2; la.pQsP = pQsP;
+    la.lpp = nullptr; la.dkp = nullptr; la.energies = 0;
+    if (int e = leapfrog_bform<KIND_TF32>(ctx, la, s)) return e;
+    // WP = W P  (rows: basis index): A = planes of W, B = planes of P (symmetric)
+    k_split_planes<KIND_TF32><<<grid_for((size_t)bRA * dK, 256), 256, 0, s>>>((const float*)pTW, bR, d, d, bRA, dK, (float*)pQsP);
+    HX_LAUNCH_CHECK("k_split_planes(W)");
+    GemmArgs gw;
+    memset(&gw, 0, sizeof(gw));
+    gw.nprod = 3; gw.M = bR; gw.N = d; gw.out = (float*)pWP; gw.ldo = d;
+    if (int e = launch_gemm<EPI_STORE, KIND_TF32>(ctx, pQsP, bRA, pPP, dB, dK, gw, s)) return e;
+    // B operands: [Tq ; Ts]^T for the apply GEMM, (W P)^T for the kinetic-energy product
+    dim3 tg((K2 + 31) / 32, (dB + 31) / 32), tb(32, 8);
+    if (g1_tf32) {
+      k_transpose_planes<KIND_TF32><<<tg, tb, 0, s>>>((const float*)pTQ, d, dK, dB, 2 * dB, 0, (float*)pB1);
+      k_transpose_planes<KIND_TF32><<<tg, tb, 0, s>>>((const float*)pTS, d, dK, dB, 2 * dB, dB, (float*)pB1);
+    } else {
+      k_transpose_planes<KIND_BF16><<<tg, tb, 0, s>>>((const float*)pTQ, d, dK, dB, 2 * dB, 0, (bf*)pB1);
+      k_transpose_planes<KIND_BF16><<<tg, tb, 0, s>>>((const float*)pTS, d, dK, dB, 2 * dB, dB, (bf*)pB1);
     }
-    bf* Pbuf[2] = {(bf*)pP0, (bf*)pP0 + (nchunks > 1 ? buf_elems : 0)};
-    HX_CUDA(cudaEventRecord(ctx->ev_fork, s));
-    HX_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    k_transpose_planes<KIND_TF32><<<tg, tb, 0, s>>>((const float*)pWP, d, dK, dB, dB, 0, (float*)pB2);
+    HX_LAUNCH_CHECK("k_transpose_planes");
+    ctx->launches += 5;
+  }
+
+  // (3) projection S0 = P0 C, chunk by chunk as the draw completes
+  {
+    std::vector<cudaEvent_t>& evs = *ctx->ev_chunk[cur];
     if (int e = timing_begin(ctx, s)) return e;
     for (int c = 0; c < nchunks; ++c) {
       const int r0 = c * chunk;
       const int rc = (rows - r0) < chunk ? (rows - r0) : chunk;
-      const int b = c & 1;
-      if (c >= 2) HX_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_gemm[b], 0));     // buffer b free again
-      // at most 2 CTAs (16 warps) per SM so the GEMM's TMA / MMA issue threads are not starved of issue slots
-      int rng_grid = grid_for((size_t)chunk * nK / 8, 256);
-      if (rng_grid > ctx->sm_count * 2) rng_grid = ctx->sm_count * 2;
-      k_rng_planes<<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, impl == HX_RNG_LEGACY ? 1 : 0, n, row0 + r0, rc, chunk, nK,
-                                                    Pbuf[b]);
-      HX_LAUNCH_CHECK("k_rng_planes");
-      HX_CUDA(cudaEventRecord(ctx->ev_rng[b], ctx->side));
-      HX_CUDA(cudaStreamWaitEvent(s, ctx->ev_rng[b], 0));
+      HX_CUDA(cudaStreamWaitEvent(s, evs[c], 0));
       ga.M = rc; ga.N = d; ga.out = S0 + (size_t)r0 * d; ga.ldo = d;
-      if (int e = launch_gemm<EPI_STORE, KIND_BF16>(ctx, Pbuf[b], chunk, pCT, dAB, nK, ga, s)) return e;
-      HX_CUDA(cudaEventRecord(ctx->ev_gemm[b], s));
-      ctx->launches += 1;
+      if (int e = launch_gemm<EPI_STORE, KIND_BF16>(ctx, Pbuf[cur] + (size_t)r0 * nK, rA, pCT, dAB, nK, ga, s,
+                                                    (uint64_t)rA + pad_to(rc, kBM)))
+        return e;
     }
     if (int e = timing_end(ctx, s)) return e;
   }
 
-  // (3) leapfrog + energy products in the operand kind chosen by the precision policy
-  const float* mu = (const float*)tgt->mean;
-  {
+  // (4) leapfrog + energy products
+  if (prop) {
+    k_z0_planes<<<grid_for((size_t)rA * K2 / 4, 256), 256, 0, s>>>(X1, mu, S0, rows, d, rA, dK, g1_tf32 ? nullptr : (bf*)pZB,
+                                                                   (float*)pZT);
+    HX_LAUNCH_CHECK("k_z0_planes");
+    ctx->launches += 1;
+    GemmArgs g1;
+    memset(&g1, 0, sizeof(g1));
+    g1.nprod = 3; g1.M = rows; g1.N = d; g1.mu = mu; g1.Q = Q; g1.S = S; g1.blk_cols = dB;
+    g1.planes_out = pQC; g1.rows_out_pad = rQ; g1.Kout_p = dK;
+    if (g1_tf32) {
+      if (int e = launch_gemm<EPI_PROP, KIND_TF32>(ctx, pZT, rA, pB1, 2 * dB, K2, g1, s, 0, 2 * dB)) return e;
+    } else {
+      if (int e = launch_gemm<EPI_PROP, KIND_BF16>(ctx, pZB, rA, pB1, 2 * dB, K2, g1, s, 0, 2 * dB)) return e;
+    }
+    GemmArgs g2;
+    memset(&g2, 0, sizeof(g2));
+    g2.nprod = 3; g2.M = rows; g2.N = d; g2.NT = NT; g2.X = S0; g2.Y = S; g2.part = (float*)pDKP;
+    if (int e = launch_gemm<EPI_DOT, KIND_TF32>(ctx, pZT, rA, pB2, dB, K2, g2, s)) return e;
+    GemmArgs g3;
+    memset(&g3, 0, sizeof(g3));
+    g3.nprod = 3; g3.M = rows; g3.N = d; g3.NT = NT; g3.mu = mu; g3.X = Q; g3.part = (float*)pLPP;
+    if (int e = launch_gemm<EPI_DOT, KIND_TF32>(ctx, pQC, rQ, pPP, dB, dK, g3, s)) return e;
+  } else {
     LeapArgs la;
     la.X1 = X1; la.mu = mu; la.rows = rows; la.d = d; la.rA = rA; la.dK = dK; la.dB = dB; la.NT = NT; la.L = L; la.eps = eps;
     la.Q = Q; la.S = S; la.S0 = S0; la.Qs = Qs; la.Bo = (const float*)pBo; la.prec = (const float*)tgt->precision;
-    la.ld_prec = tgt->ld; la.pBoP = pBoP; la.pPP = pPP; la.pQC = pQC; la.pQsP = pQsP; la.lpp = (float*)pLPP; la.dkp = (float*)pDKP;
-    const int e = (ctx->precision == HX_PREC_TF32X3) ? leapfrog_bform<KIND_TF32>(ctx, la, s) : leapfrog_bform<KIND_BF16>(ctx, la, s);
+    la.ld_prec = tgt->ld; la.pBoP = pBoP; la.pPP = pPP; la.pQC = pQC; la.pQC2 = pQC2; la.pQsP = pQsP; la.lpp = (float*)pLPP; la.dkp = (float*)pDKP;
+    la.energies = 1;
+    const int e = g1_tf32 ? leapfrog_bform<KIND_TF32>(ctx, la, s) : leapfrog_bform<KIND_BF16>(ctx, la, s);
     if (e) return e;
   }
 
-  // (4) energies, log-accept, optional fused accept + chain emit
+  // (5) energies, log-accept, optional fused accept + chain emit
   FinishArgs fa;
   memset(&fa, 0, sizeof(fa));
   fa.lpp = (const float*)pLPP; fa.dkp = (const float*)pDKP; fa.NT = NT; fa.lp1 = lp1; fa.Q = Q; fa.logacc = logacc;
@@ -441,7 +671,62 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   }
   k_tc_finish<<<(rows + 7) / 8, 256, 0, s>>>(fa);
   HX_LAUNCH_CHECK("k_tc_finish");
-  ctx->launches += 8;
+  ctx->launches += 2;
+  return 0;
+}
+
+// ---- diagnostics: how well do the momentum draw (ALU) and the projection GEMM (tensor pipe) overlap? --------------------------
+// mode 0: `reps` draws alone; 1: `reps` projection GEMMs alone; 2: both at once (draw on the side stream into one buffer, GEMM on
+// `s` from the other).  Returns the wall time of the whole batch in ms (CUDA events spanning both streams).
+int microbench(hx_ctx* ctx, int mode, int n, int rows, int d, int reps, double* ms_out, cudaStream_t s) {
+  const int dB = pad_to(d, BN), nK = pad_to(n, 64), rA = pad_to(rows, kBM), dA = pad_to(d, kBM);
+  const int dAB = dB > dA ? dB : dA, NT = (d + BN - 1) / BN;
+  typedef __nv_bfloat16 bf;
+  void *pCT, *pP0, *pS0;
+  const size_t buf_elems = (size_t)2 * rA * nK;
+  if (int e = ws_get(ctx, WS_TC_CT, (size_t)2 * dAB * nK * sizeof(bf), &pCT)) return e;
+  if (int e = ws_get(ctx, WS_TC_P0, 2 * buf_elems * sizeof(bf), &pP0)) return e;
+  if (int e = ws_get(ctx, WS_TC_S0, (size_t)rows * d * sizeof(float), &pS0)) return e;
+  if (int e = side_init(ctx)) return e;
+  ctx->job[0].valid = ctx->job[1].valid = 0;
+  ctx->p0_base = nullptr;
+  HX_CUDA(cudaMemsetAsync(pCT, 0x3c, (size_t)2 * dAB * nK * sizeof(bf), s));     // finite bf16 pattern
+  bf* Pbuf[2] = {(bf*)pP0, (bf*)pP0 + buf_elems};
+  const int chunk = chunk_rows(ctx, rA, NT);
+  Key key{1u, 2u};
+  if (int e = job_launch(ctx, 0, Pbuf[0], 0, n, 0, rows, rA, nK, chunk, key, nullptr, s)) return e;   // valid operand for the GEMM
+  HX_CUDA(cudaStreamSynchronize(ctx->side));
+  cudaEvent_t e0, e1, eside, eg;
+  HX_CUDA(cudaEventCreate(&e0)); HX_CUDA(cudaEventCreate(&e1)); HX_CUDA(cudaEventCreate(&eside)); HX_CUDA(cudaEventCreate(&eg));
+  HX_CUDA(cudaEventRecord(e0, s));
+  for (int r = 0; r < reps; ++r) {
+    if (mode == 0 || mode == 2)
+      if (int e = job_launch(ctx, 1, Pbuf[1], 0, n, 0, rows, rA, nK, chunk, key, nullptr, s)) return e;
+    if (mode == 1 || mode == 2) {
+      GemmArgs ga;
+      memset(&ga, 0, sizeof(ga));
+      ga.nprod = 3;
+      const int nchunks = (rows + chunk - 1) / chunk;
+      for (int c = 0; c < nchunks; ++c) {
+        const int r0 = c * chunk, rc = (rows - r0) < chunk ? (rows - r0) : chunk;
+        ga.M = rc; ga.N = d; ga.out = (float*)pS0 + (size_t)r0 * d; ga.ldo = d;
+        if (int e = launch_gemm<EPI_STORE, KIND_BF16>(ctx, Pbuf[0] + (size_t)r0 * nK, rA, pCT, dAB, nK, ga, s, (uint64_t)rA + pad_to(rc, kBM)))
+          return e;
+      }
+    }
+  }
+  HX_CUDA(cudaEventRecord(eg, s));
+  HX_CUDA(cudaEventRecord(eside, ctx->side));
+  HX_CUDA(cudaStreamWaitEvent(s, eside, 0));
+  HX_CUDA(cudaEventRecord(e1, s));
+  HX_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f, msg = 0.f, msr = 0.f;
+  HX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  HX_CUDA(cudaEventElapsedTime(&msg, e0, eg));
+  HX_CUDA(cudaEventElapsedTime(&msr, e0, eside));
+  ms_out[0] = ms; ms_out[1] = msg; ms_out[2] = msr;      // total, GEMM stream done, draw stream done
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(eside); cudaEventDestroy(eg);
+  ctx->job[0].valid = ctx->job[1].valid = 0;
   return 0;
 }
 

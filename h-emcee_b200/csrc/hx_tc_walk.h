@@ -18,13 +18,21 @@ struct FuseF32 {      // batch-level fused accept + chain emit (same fields as F
   int32_t* nonfinite;
 };
 
+struct NextDraw {     // the walk half-move that follows this one (its momentum draw is started early)
+  Key key;
+  const uint32_t* key_ptr;
+  int row0, rows;
+};
+
 // true if this half-move should take the tcgen05 path under the ctx precision policy
 bool walk_eligible(const hx_ctx* ctx, int dtype, const hx_target* tgt, int n, int rows, int flags);
 
 // one walk half-move on tensor cores; `mean_dev` = mean_0(X2) [dim] already computed
 int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev, const float* X1, const float* X2, int n,
               int row0, int rows, double eps, Key key, const uint32_t* key_ptr, int L, const float* lp1, float* Q,
-              float* logacc, float* S, float* lp_out, const FuseF32* fuse, cudaStream_t s);
+              float* logacc, float* S, float* lp_out, const FuseF32* fuse, const NextDraw* next, cudaStream_t s);
+
+int microbench(hx_ctx* ctx, int mode, int n, int rows, int d, int reps, double* ms_out, cudaStream_t s);
 
 }  // namespace tc
 }  // namespace hx

@@ -39,6 +39,10 @@ _PROTOS = {
     "hx_ctx_destroy": (C.c_int, [_P]),
     "hx_ctx_workspace_bytes": (C.c_size_t, [_P]),
     "hx_ctx_set_precision": (C.c_int, [_P, C.c_int]),
+    "hx_ctx_set_leapfrog_form": (C.c_int, [_P, C.c_int]),
+    "hx_walk_prefetch": (C.c_int, [_P, C.c_int, C.c_int32, C.c_int32, C.c_int32, _KEY]),
+    "hx_tc_microbench": (C.c_int, [_P, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), _P]),
+    "hx_ctx_set_tuning": (C.c_int, [_P, C.c_int, C.c_int]),
     "hx_ctx_last_path": (C.c_int, [_P]),
     "hx_ctx_timing_enable": (C.c_int, [_P, C.c_int]),
     "hx_ctx_timing_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

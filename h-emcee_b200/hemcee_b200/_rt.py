@@ -21,15 +21,19 @@ class _Config:
                  or "legacy" (`jax_threefry_partitionable=False`).
     precision  : how the walk move's dense contractions are evaluated (include/hx.h HX_PREC_*):
                  "auto" (exact fp32/fp64 SIMT kernels; split-bf16 tensor cores for large fp32
-                 full-covariance Gaussian problems), "exact", "bf16x3", "bf16".
+                 full-covariance Gaussian problems), "exact", "bf16x3", "bf16", "tf32x3".
+    leapfrog_form : tensor-core walk path only (include/hx.h HX_LEAP_*): "stepwise" kicks on every walker,
+                 "propagator" (L-step linear map of a Gaussian target applied in one GEMM), or "auto".
     """
 
     PRECISIONS = {"auto": 0, "exact": 1, "bf16x3": 2, "bf16": 3, "tf32x3": 4}
+    LEAPFROG_FORMS = {"auto": 0, "stepwise": 1, "propagator": 2}
 
     def __init__(self):
         self.enable_x64 = False
         self.rng_impl = "partitionable"
         self.precision = "auto"
+        self.leapfrog_form = "auto"
 
     def update(self, name, value):
         if name in ("enable_x64", "jax_enable_x64"):
@@ -44,6 +48,12 @@ class _Config:
             self.precision = value
             for h in _ctx.values():
                 _lib.check(_lib.load().hx_ctx_set_precision(h, self.PRECISIONS[value]), "hx_ctx_set_precision")
+        elif name == "leapfrog_form":
+            if value not in self.LEAPFROG_FORMS:
+                raise ValueError(f"leapfrog_form must be one of {sorted(self.LEAPFROG_FORMS)}")
+            self.leapfrog_form = value
+            for h in _ctx.values():
+                _lib.check(_lib.load().hx_ctx_set_leapfrog_form(h, self.LEAPFROG_FORMS[value]), "hx_ctx_set_leapfrog_form")
         elif name == "jax_threefry_partitionable":
             self.rng_impl = "partitionable" if value else "legacy"
         else:
@@ -89,6 +99,8 @@ def ctx(dev: torch.device) -> C.c_void_p:
         h = C.c_void_p()
         _lib.check(_lib.load().hx_ctx_create(C.byref(h), idx), "hx_ctx_create")
         _lib.check(_lib.load().hx_ctx_set_precision(h, config.PRECISIONS[config.precision]), "hx_ctx_set_precision")
+        _lib.check(_lib.load().hx_ctx_set_leapfrog_form(h, config.LEAPFROG_FORMS[config.leapfrog_form]),
+                   "hx_ctx_set_leapfrog_form")
         _ctx[idx] = h
     return _ctx[idx]
 

@@ -51,6 +51,14 @@ def hmc_walk_move(group1, group2, step_size, key, log_prob, grad_log_prob, L, lo
     return _move("hx_walk_move", group1, group2, step_size, key, log_prob, grad_log_prob, L, log_prob_group1, row0, n, impl)
 
 
+def walk_prefetch(key, n, row0, rows, device=None, impl=None):
+    """Hint for the tensor-core walk path (include/hx.h hx_walk_prefetch): the walk half-move after the next
+    `hmc_walk_move` call will use `key` on the row shard [row0, row0+rows) of a group of n."""
+    dev = _rt.device(device)
+    _lib.check(_lib.load().hx_walk_prefetch(_rt.ctx(dev), _rt.impl_code(impl), int(n), int(row0), int(rows),
+                                            _lib.key_arg(_rt.as_key(key))), "hx_walk_prefetch")
+
+
 def hmc_side_move(group1, group2, step_size, key, log_prob, grad_log_prob, L, log_prob_group1, *, row0=0, n=None,
                   impl=None):
     """Hamiltonian side move (Alg. 4 of arXiv:2505.02987); reference hmc_side.py:6-77."""

@@ -27,7 +27,7 @@ import torch
 from . import _lib, _rt, adaptation, autocorr
 from . import random as hrandom
 from .backend import Backend
-from .moves import accept_proposal, hmc_side_move, hmc_walk_move
+from .moves import accept_proposal, hmc_side_move, hmc_walk_move, walk_prefetch
 from .targets import as_target
 
 
@@ -277,11 +277,15 @@ class HamiltonianEnsembleSampler(BaseSampler):
                     step, L = self.adapter.value(adapter_state)                      # :169
                 else:
                     step, L = fixed
+                if self._move_kind == 0:          # the draw of the following half-move only needs its key
+                    walk_prefetch(k[order[2]], n, row0, rows, dev, self.impl)
                 adapter_state = self._half(X1, X2f, lp1, step, L, k[order[0]], k[order[1]], acc1, n, row0, adapter_state)
                 if sharded:
                     self._allgather(X1f, X1)
                 if fixed is None:
                     step, L = self.adapter.value(adapter_state)                      # :189
+                if self._move_kind == 0 and t + 1 < T:
+                    walk_prefetch(keys[t + 1][order[0]], n, row0, rows, dev, self.impl)
                 adapter_state = self._half(X2, X1f, lp2, step, L, k[order[2]], k[order[3]], acc2, n, row0, adapter_state)
                 if sharded:
                     self._allgather(X2f, X2)

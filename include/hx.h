@@ -106,6 +106,20 @@ HX_API size_t hx_ctx_workspace_bytes(const hx_ctx* ctx);
  *                  (~2^-21 per product) — for targets conditioned worse than ~1e6                  */
 enum { HX_PREC_AUTO = 0, HX_PREC_EXACT = 1, HX_PREC_BF16X3 = 2, HX_PREC_BF16 = 3, HX_PREC_TF32X3 = 4 };
 HX_API int hx_ctx_set_precision(hx_ctx* ctx, int mode);
+/* Form of the walk move's leapfrog on the tensor-core path (full-covariance Gaussian targets):
+ *   HX_LEAP_STEPWISE    one kick GEMM per leapfrog step on every walker (hmc_walk.py:85-102 as written)
+ *   HX_LEAP_PROPAGATOR  the dynamics of a Gaussian target are linear, so the L-step map of (q - mean, p C) is a
+ *                       2dim x 2dim matrix: integrate 2*dim basis trajectories with the same recurrence, then apply the
+ *                       map to all walkers in one GEMM (cost independent of L per walker)
+ *   HX_LEAP_AUTO        propagator when rows >= 6*dim and L >= 4                                            */
+enum { HX_LEAP_AUTO = 0, HX_LEAP_STEPWISE = 1, HX_LEAP_PROPAGATOR = 2 };
+HX_API int hx_ctx_set_leapfrog_form(hx_ctx* ctx, int form);
+/* Diagnostics for the roofline discussion: wall time [ms] of `reps` repetitions of (mode 0) the momentum draw
+ * of a rows x n shard alone, (1) its projection GEMM alone, (2) both running concurrently on two streams.  */
+HX_API int hx_tc_microbench(hx_ctx* ctx, int mode, int32_t n, int32_t rows, int32_t dim, int32_t reps, double* ms_out /*[3]: total,
+                     GEMM stream, draw stream*/, void* stream);
+/* tuning knobs (what = 0: resident CTAs per SM of the momentum-draw kernel, default 4) */
+HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value);
 /* which kernel the timing hooks bracketed last: 0 = fused SIMT half-move, 1 = tcgen05 projection GEMM */
 HX_API int hx_ctx_last_path(const hx_ctx* ctx);
 
@@ -151,6 +165,11 @@ HX_API int hx_walk_move(hx_ctx* ctx, int dtype, int impl, const hx_target* tgt,
                  double step_size, const uint32_t key[2], int32_t L, const void* lp1_dev,
                  void* Q_out_dev, void* logacc_out_dev, void* pproj_out_dev /*nullable*/,
                  void* lp_out_dev, int flags, void* stream);
+
+/* Hint: the walk half-move AFTER the next hx_walk_move call will use (key, row0, rows) with the same n and impl.
+ * The momentum matrix normal(key, (n, n)) (hmc_walk.py:36) depends only on the key, so its draw is started on a
+ * side stream under the next call's tensor-core work.  Purely an optimisation: results never depend on it.   */
+HX_API int hx_walk_prefetch(hx_ctx* ctx, int impl, int32_t n, int32_t row0, int32_t rows, const uint32_t key[2]);
 
 HX_API int hx_side_move(hx_ctx* ctx, int dtype, int impl, const hx_target* tgt,
                  const void* X1_dev, const void* X2_dev, int32_t n, int32_t row0, int32_t rows,

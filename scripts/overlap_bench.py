@@ -1,0 +1,36 @@
+"""GPU diagnostic: draw (ALU) vs projection GEMM (tensor) overlap and power (hx_tc_microbench)."""
+import sys, os, subprocess, threading, time, ctypes as C
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "h-emcee_b200")]
+import hemcee_b200 as hx
+from hemcee_b200 import _lib, _rt
+dev = torch.device("cuda", 0); torch.cuda.set_device(0)
+lib = _lib.load(); ctx = _rt.ctx(dev)
+n = int(os.environ.get("N", 32768)); rows = int(os.environ.get("ROWS", n)); d = 1000
+reps = int(os.environ.get("REPS", 200))
+user = torch.cuda.Stream()
+def sample(stop, out):
+    p = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "50", "-i", "0"], stdout=subprocess.PIPE, text=True)
+    while not stop.is_set():
+        line = p.stdout.readline()
+        if line: out.append(line.strip().split(", "))
+    p.terminate()
+runs = [(1, 4, "gemm alone"), (2, 2, "both, draw 2 CTA/SM"), (2, 3, "both, draw 3 CTA/SM"), (2, 4, "both, draw 4 CTA/SM"), (2, 5, "both, draw 5 CTA/SM"), (2, 6, "both, draw 6 CTA/SM")]
+for mode, cps, name in runs:
+    lib.hx_ctx_set_tuning(ctx, 0, cps)
+    ms = (C.c_double * 3)()
+    with torch.cuda.stream(user):
+        st = _rt.stream(dev)
+        _lib.check(lib.hx_tc_microbench(ctx, mode, n, rows, d, 2, ms, st))   # warm
+        stop, out = threading.Event(), []
+        th = threading.Thread(target=sample, args=(stop, out)); th.start(); time.sleep(0.2)
+        _lib.check(lib.hx_tc_microbench(ctx, mode, n, rows, d, reps, ms, st))
+    stop.set(); th.join()
+    rows_ = [r for r in out if len(r) == 3]
+    busy = rows_[len(rows_) // 3:]          # later samples: power reading has settled
+    clk = np.median([float(r[0]) for r in busy]) if busy else float("nan")
+    pw = np.max([float(r[1]) for r in busy]) if busy else float("nan")
+    cap = sum(r[2].lower().startswith("active") for r in busy)
+    print(f"{name:22s} total {ms[0] / reps:7.3f} ms/rep  gemm-stream {ms[1] / reps:7.3f}  draw-stream {ms[2] / reps:7.3f}   sm clock {clk:.0f} MHz  max power {pw:.0f} W  power-cap {cap}/{len(busy)}", flush=True)
+    time.sleep(0.5)

@@ -62,4 +62,5 @@ def install(hx, oracle_target):
         return current, lp_current, accepts
 
     S.accept_proposal = accept_proposal
+    S.walk_prefetch = lambda *a, **k: None      # device-side optimisation hint: nothing to do for the stand-in
     return log_prob, make_move

@@ -21,6 +21,14 @@ def prec(hx):
     hx.config.update("precision", "auto")
 
 
+@pytest.fixture()
+def form(hx):
+    def set_(f):
+        hx.config.update("leapfrog_form", f)
+    yield set_
+    hx.config.update("leapfrog_form", "auto")
+
+
 def _problem(hx, n, d, seed=0, kappa=100.0):
     ks = R.split(R.PRNGKey(seed), 4)
     cov = OT.make_covariance_skewed(ks[0], d, kappa, np.float64)
@@ -32,7 +40,9 @@ def _problem(hx, n, d, seed=0, kappa=100.0):
 
 @pytest.mark.parametrize("n,d", [(128, 64), (256, 200), (640, 256), (384, 300)])
 @pytest.mark.parametrize("L", [1, 4])
-def test_bf16x3_matches_exact_and_oracle(hx, prec, n, d, L):
+@pytest.mark.parametrize("lf", ["stepwise", "propagator"])
+def test_bf16x3_matches_exact_and_oracle(hx, prec, form, n, d, L, lf):
+    form(lf)
     tgt, (olp, og), g1, g2, key = _problem(hx, n, d)
     G1, G2 = torch.from_numpy(g1).cuda(), torch.from_numpy(g2).cuda()
     LP1 = tgt.log_prob(G1)
@@ -93,3 +103,54 @@ def test_tc_sampler_chain_close_to_exact(hx, prec):
     same = np.all(np.abs(out["exact"][0] - out["bf16x3"][0]) <= 5e-4 * np.abs(out["exact"][0]).max(), axis=2)
     assert same.mean() > 0.98
     assert abs(int(out["exact"][1]) - int(out["bf16x3"][1])) <= 0.02 * W * T
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "tf32x3"])
+def test_propagator_matches_stepwise_long_trajectory(hx, prec, form, mode):
+    """L = 12 steps on an ill-conditioned target (kappa 1e3): the propagator form (2d basis trajectories + one
+    apply GEMM) against the step-by-step kicks and the f64 oracle."""
+    n, d, L, eps = 512, 128, 12, 0.05
+    tgt, (olp, og), g1, g2, key = _problem(hx, n, d, seed=3, kappa=1000.0)
+    G1, G2 = torch.from_numpy(g1).cuda(), torch.from_numpy(g2).cuda()
+    LP1 = tgt.log_prob(G1)
+    prec(mode)
+    out = {}
+    for lf in ("stepwise", "propagator"):
+        form(lf)
+        out[lf] = [t.cpu().numpy() for t in hx.hmc_walk_move(G1, G2, eps, key, tgt, tgt, L, LP1)]
+    a64, b64 = g1.astype(np.float64), g2.astype(np.float64)
+    q64, la64, pp64, lp64 = OM.hmc_walk_move(a64, b64, eps, key, olp, og, L, olp(a64), rng_dtype=np.float32)
+    scale = np.abs(q64).max()
+    for lf in out:
+        q, la, pp, lp = out[lf]
+        np.testing.assert_allclose(q, q64, rtol=0, atol=2e-4 * scale)
+        np.testing.assert_allclose(pp, pp64, rtol=0, atol=2e-4 * np.abs(pp64).max())
+        np.testing.assert_allclose(lp, lp64, rtol=2e-4, atol=2e-3)
+        np.testing.assert_allclose(la, la64, rtol=0, atol=5e-3)
+
+
+def test_prefetched_draw_is_transparent(hx, prec, form):
+    """hx_run_iterations starts the next half-move's momentum draw early (it depends only on the key); the chain must
+    equal, bit for bit, the one built from separate hx_walk_move + hx_accept calls without any prefetch."""
+    W, d, T, L, eps = 512, 64, 3, 5, 0.03
+    n = W // 2
+    prec("bf16x3")
+    form("propagator")
+    tgt, _, g1, g2, _ = _problem(hx, n, d, seed=7)
+    x0 = np.concatenate([g1, g2])
+    key = R.PRNGKey(11)
+    s = hx.HamiltonianEnsembleSampler(W, d, tgt, step_size=eps, L=L, adapt_inital_step_size=False, adapt_step_size=False,
+                                      adapt_length=False, verbose=False)
+    chain = s.run_mcmc(key, x0, T, warmup=0)
+    kmain = R.split(key, 3)[2]
+    keys = R.split(kmain, 4 * T).reshape(T, 4, 2)
+    X1, X2 = torch.from_numpy(g1).cuda(), torch.from_numpy(g2).cuda()
+    lp1, lp2 = tgt.log_prob(X1), tgt.log_prob(X2)
+    for t in range(T):
+        k = keys[t]
+        q, la, _, lpq = hx.hmc_walk_move(X1, X2, eps, k[0], tgt, tgt, L, lp1)
+        hx.moves.accept_proposal(X1, q, lp1, lpq, la, k[2])
+        q, la, _, lpq = hx.hmc_walk_move(X2, X1, eps, k[1], tgt, tgt, L, lp2)
+        hx.moves.accept_proposal(X2, q, lp2, lpq, la, k[3])
+        np.testing.assert_array_equal(chain[t, :n], X1.cpu().numpy())
+        np.testing.assert_array_equal(chain[t, n:], X2.cpu().numpy())
