@@ -284,6 +284,10 @@ def main():
     import ctypes as C
     c_ms, c_kn, c_all = C.c_double(), C.c_int64(), C.c_int64()
     lib.hx_ctx_timing_read(ctx, C.byref(c_ms), C.byref(c_kn), C.byref(c_all))
+    ph_ms, ph_n = (C.c_double * 8)(), (C.c_int64 * 8)()
+    lib.hx_ctx_timing_phases(ctx, ph_ms, ph_n)
+    names = ["main", "prep", "basis", "leapfrog", "finish"]
+    phases = {nm: round(ph_ms[i] / max(ph_n[i], 1), 4) for i, nm in enumerate(names) if ph_n[i] > 0}
     lib.hx_ctx_timing_enable(ctx, 0)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -363,7 +367,8 @@ def main():
                     warmup=Wu, ms_per_step=ms / K, higher_is_better=True, scaling="strong", vs_baseline=None,
                     dtype="f64" if cfg["x64"] else "f32", data="synthetic", config=conf, roofline=roofline,
                     cpu_baseline=cb, clocks=clk, e2e=e2e, gpu_launches=int(c_all.value) if world == 1 else int(c_all.value),
-                    acceptance_rate=acc_rate, nonfinite=int(flag.item()), precision=args.precision, leapfrog_form=args.leapfrog_form)
+                    acceptance_rate=acc_rate, nonfinite=int(flag.item()), precision=args.precision, leapfrog_form=args.leapfrog_form,
+                    phase_ms_per_half_move=phases)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

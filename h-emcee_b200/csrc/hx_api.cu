@@ -45,22 +45,19 @@ int ws_get(hx_ctx* ctx, int slot, size_t bytes, void** out) {
   return 0;
 }
 
-int timing_begin(hx_ctx* ctx, cudaStream_t s) {
+int timing_mark(hx_ctx* ctx, cudaStream_t s, int phase) {
   if (!ctx->timing) return 0;
-  if (!ctx->ev) ctx->ev = new (std::nothrow) std::vector<cudaEvent_t>();
-  if (!ctx->ev) return hx_fail(HX_E_NULL, "out of host memory");
-  while (ctx->ev->size() < ctx->ev_used + 2) {
+  if (!ctx->ev) { ctx->ev = new (std::nothrow) std::vector<cudaEvent_t>(); ctx->ev_tag = new (std::nothrow) std::vector<int>(); }
+  if (!ctx->ev || !ctx->ev_tag) return hx_fail(HX_E_NULL, "out of host memory");
+  if (ctx->ev->size() <= ctx->ev_used) {
     cudaEvent_t e;
     HX_CUDA(cudaEventCreate(&e));
     ctx->ev->push_back(e);
+    ctx->ev_tag->push_back(-1);
   }
   HX_CUDA(cudaEventRecord((*ctx->ev)[ctx->ev_used], s));
-  return 0;
-}
-int timing_end(hx_ctx* ctx, cudaStream_t s) {
-  if (!ctx->timing) return 0;
-  HX_CUDA(cudaEventRecord((*ctx->ev)[ctx->ev_used + 1], s));
-  ctx->ev_used += 2;
+  (*ctx->ev_tag)[ctx->ev_used] = phase;
+  ctx->ev_used += 1;
   return 0;
 }
 
@@ -107,20 +104,37 @@ extern "C" HX_API int hx_ctx_timing_enable(hx_ctx* ctx, int enable) {
   return 0;
 }
 
-extern "C" HX_API int hx_ctx_timing_read(hx_ctx* ctx, double* kernel_ms, int64_t* kernel_launches, int64_t* all_launches) {
-  if (!ctx) return hx_fail(HX_E_NULL, "hx_ctx_timing_read: NULL ctx");
-  double ms = 0.0;
-  for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+static int timing_collect(hx_ctx* ctx, double* phase_ms, int64_t* phase_n) {
+  for (int p = 0; p < HX_PH_COUNT; ++p) { phase_ms[p] = 0.0; phase_n[p] = 0; }
+  for (size_t i = 0; i + 1 < ctx->ev_used; ++i) {
+    const int tag = (*ctx->ev_tag)[i];
+    if (tag < 0 || tag >= HX_PH_COUNT) continue;
     HX_CUDA(cudaEventSynchronize((*ctx->ev)[i + 1]));
     float t = 0.f;
     HX_CUDA(cudaEventElapsedTime(&t, (*ctx->ev)[i], (*ctx->ev)[i + 1]));
-    ms += t;
+    phase_ms[tag] += t;
+    phase_n[tag] += 1;
   }
-  if (kernel_ms) *kernel_ms = ms;
-  if (kernel_launches) *kernel_launches = (int64_t)(ctx->ev_used / 2);
+  return 0;
+}
+
+extern "C" HX_API int hx_ctx_timing_read(hx_ctx* ctx, double* kernel_ms, int64_t* kernel_launches, int64_t* all_launches) {
+  if (!ctx) return hx_fail(HX_E_NULL, "hx_ctx_timing_read: NULL ctx");
+  double pm[HX_PH_COUNT];
+  int64_t pn[HX_PH_COUNT];
+  if (int e = timing_collect(ctx, pm, pn)) return e;
+  for (int p = 0; p < HX_PH_COUNT; ++p) { ctx->phase_ms[p] = pm[p]; ctx->phase_n[p] = pn[p]; }
+  if (kernel_ms) *kernel_ms = pm[HX_PH_MAIN];
+  if (kernel_launches) *kernel_launches = pn[HX_PH_MAIN];
   if (all_launches) *all_launches = ctx->launches;
   ctx->ev_used = 0;
   ctx->launches = 0;
+  return 0;
+}
+
+extern "C" HX_API int hx_ctx_timing_phases(hx_ctx* ctx, double* phase_ms, int64_t* phase_count) {
+  if (!ctx || !phase_ms || !phase_count) return hx_fail(HX_E_NULL, "hx_ctx_timing_phases: NULL argument");
+  for (int p = 0; p < HX_PH_COUNT; ++p) { phase_ms[p] = ctx->phase_ms[p]; phase_count[p] = ctx->phase_n[p]; }
   return 0;
 }
 
@@ -156,6 +170,7 @@ extern "C" HX_API int hx_ctx_destroy(hx_ctx* ctx) {
   if (ctx->ev) {
     for (cudaEvent_t e : *ctx->ev) cudaEventDestroy(e);
     delete ctx->ev;
+    delete ctx->ev_tag;
   }
   if (ctx->side_ready) {
     cudaStreamDestroy(ctx->side);

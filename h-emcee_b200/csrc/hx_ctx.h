@@ -30,8 +30,10 @@ struct hx_ctx {
   int sm_count;
   // measurement hooks
   int timing;
-  std::vector<cudaEvent_t>* ev;   // pairs (start, stop) around the dominant kernel
+  std::vector<cudaEvent_t>* ev;   // marks on the launch stream; the interval after mark i belongs to phase ev_tag[i]
+  std::vector<int>* ev_tag;       // HX_PH_* or -1 (end of a measured section)
   size_t ev_used;
+  double phase_ms[8]; int64_t phase_n[8];   // last hx_ctx_timing_read, by phase
   int64_t launches;               // all kernels launched through this ctx
   int last_gram_slices;
   int precision;                  // HX_PREC_*
@@ -51,5 +53,8 @@ struct hx_ctx {
 
 // grow-only scratch slot
 int ws_get(hx_ctx* ctx, int slot, size_t bytes, void** out);
-int timing_begin(hx_ctx* ctx, cudaStream_t s);
-int timing_end(hx_ctx* ctx, cudaStream_t s);
+// phases of a half-move for the timing hooks (hx_ctx_timing_read / hx_ctx_timing_phases)
+enum { HX_PH_MAIN = 0, HX_PH_PREP = 1, HX_PH_BASIS = 2, HX_PH_LEAP = 3, HX_PH_FINISH = 4, HX_PH_COUNT = 8 };
+int timing_mark(hx_ctx* ctx, cudaStream_t s, int phase);   // phase -1 closes the section
+inline int timing_begin(hx_ctx* ctx, cudaStream_t s) { return timing_mark(ctx, s, HX_PH_MAIN); }
+inline int timing_end(hx_ctx* ctx, cudaStream_t s) { return timing_mark(ctx, s, -1); }

@@ -103,8 +103,23 @@ __device__ __forceinline__ double uniform_from_bits(uint64_t b, double lo, doubl
 }
 
 // XLA erf_inv, f32 (Giles single precision).
+// w = -log1p(-x^2) is evaluated as -ln2 * lg2(1 - x2) with the SFU (MUFU.LG2, absolute error 2^-22.6 in log2), where
+// x2 = rn(x*x) is rounded FIRST exactly like XLA's log1p(-x*x) argument (near |x| = 1 that rounding is the dominant error of
+// the reference's own value, so it has to be reproduced, not improved on): the absolute error of w stays below ~2e-7, i.e. <= 1 ulp in the result (dp/dw ~ 0.3),
+// the same order as the backend-to-backend log1p differences inside JAX itself; libdevice's log1pf costs ~22 FMA-pipe
+// instructions per draw, which is 15 % of the whole draw (the walk move needs n^2 of them per half-move).
+__device__ __forceinline__ float fast_lg2(float t) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+  return r;
+}
+__device__ __forceinline__ float fast_sqrt(float t) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+  return r;
+}
 __device__ __forceinline__ float erfinv_xla(float x) {
-  float w = -log1pf(-x * x);
+  float w = -0.693147182f * fast_lg2(__fsub_rn(1.0f, __fmul_rn(x, x)));
   float p;
   if (w < 5.0f) {
     w = w - 2.5f;
@@ -118,7 +133,7 @@ __device__ __forceinline__ float erfinv_xla(float x) {
     p = fmaf(p, w, 0.246640727f);
     p = fmaf(p, w, 1.50140941f);
   } else {
-    w = sqrtf(w) - 3.0f;
+    w = fast_sqrt(w) - 3.0f;
     p = -0.000200214257f;
     p = fmaf(p, w, 0.000100950558f);
     p = fmaf(p, w, 0.00134934322f);

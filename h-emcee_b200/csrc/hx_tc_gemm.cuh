@@ -60,6 +60,9 @@ struct GemmArgs {
   // two column blocks of blk_cols (padded) columns each; block 0: Q = acc + mu, planes_out (tf32 hi/lo) <- split(acc);
   // block 1: S = acc.  blk_cols = 0 for the other epilogues (one block).
   int blk_cols;
+  // split-K (EPI_STORE only): grid.z slices of kb_per_slice K-blocks each, slice z stores to out + z * slice_stride; the
+  // caller adds the slices in a fixed order (also shortens the tensor core's truncating accumulation chains).  0 = no split.
+  int kb_per_slice; size_t slice_stride;
 };
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -170,7 +173,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
-  const int num_kb = g.Kp / KD::ROW_ELEMS;
+  const int num_kb_total = g.Kp / KD::ROW_ELEMS;
+  const int kb0 = g.kb_per_slice ? (int)blockIdx.z * g.kb_per_slice : 0;
+  const int num_kb = g.kb_per_slice ? min(g.kb_per_slice, num_kb_total - kb0) : num_kb_total;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -194,7 +199,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         mbar_wait(&empty[s], ph ^ 1u);
         uint8_t* st = stage_base + s * L::STAGE;
         mbar_expect_tx(&full[s], bytes);
-        const int kc = kb * KD::ROW_ELEMS;
+        const int kc = (kb0 + kb) * KD::ROW_ELEMS;
         tma_load_2d(st, &tmA, &full[s], kc, m0);
         tma_load_2d(st + 2 * L::A_PLANE, &tmB, &full[s], kc, n0);
         if (g.nprod == 3) {
@@ -253,7 +258,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int nval = min(32, g.N - col0);
       const bool fast = vec && nval == 32;
       if (EPI == EPI_STORE) {
-        store32(g.out + (size_t)row * g.ldo + col0, v, nval, fast);
+        store32(g.out + (size_t)blockIdx.z * g.slice_stride + (size_t)row * g.ldo + col0, v, nval, fast);
       } else if (EPI == EPI_PROP) {
         const size_t base = (size_t)row * g.N + col0;
         if (blk == 0) {

@@ -286,6 +286,15 @@ __global__ void k_transpose_planes(const float* __restrict__ src, int d, int dK,
   }
 }
 
+// out[i] = sum_z part[z][i] in fixed order (split-K slices)
+__global__ void k_sum_slices_f(const float* __restrict__ part, int nslices, size_t count, float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < nslices; ++z) s += part[(size_t)z * count + i];
+    out[i] = s;
+  }
+}
+
 struct FinishArgs {
   const float* lpp; const float* dkp; int NT;
   const float* lp1; const float* Q;
@@ -336,7 +345,7 @@ __global__ void __launch_bounds__(256) k_tc_finish(FinishArgs a) {
 // n_grid = padded N the grid covers (0: g.N)
 template <int EPI, int KIND>
 static int launch_gemm(hx_ctx* ctx, const void* A, int rowsA_pad, const void* B, int rowsB_pad, int Kp, GemmArgs g,
-                       cudaStream_t s, uint64_t mapA_rows = 0, int n_grid = 0) {
+                       cudaStream_t s, uint64_t mapA_rows = 0, int n_grid = 0, int slices = 1) {
   CUtensorMap tmA, tmB;
   if (int e = make_tmap(ctx, &tmA, A, mapA_rows ? mapA_rows : 2ull * rowsA_pad, Kp, kBM, KIND)) return e;
   if (int e = make_tmap(ctx, &tmB, B, 2ull * rowsB_pad, Kp, BN, KIND)) return e;
@@ -346,7 +355,7 @@ static int launch_gemm(hx_ctx* ctx, const void* A, int rowsA_pad, const void* B,
     HX_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::BYTES));
     attr_done = true;
   }
-  dim3 grid(((n_grid ? n_grid : g.N) + BN - 1) / BN, (g.M + kBM - 1) / kBM);
+  dim3 grid(((n_grid ? n_grid : g.N) + BN - 1) / BN, (g.M + kBM - 1) / kBM, slices);
   k_tc_gemm<BN, EPI, KIND><<<grid, kThreads, SmemLayout<BN>::BYTES, s>>>(tmA, tmB, g);
   HX_LAUNCH_CHECK("k_tc_gemm");
   ctx->launches += 1;
@@ -541,12 +550,9 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     if (int e = job_launch(ctx, cur, Pbuf[cur], impl, n, row0, rows, rA, nK, chunk, key, key_ptr, s)) return e;
   }
   ctx->job[cur].valid = 0;       // consumed by this half-move
-  if (next && next->rows == rows) {
-    if (int e = job_launch(ctx, 1 - cur, Pbuf[1 - cur], impl, n, next->row0, next->rows, rA, nK, chunk, next->key, next->key_ptr, s))
-      return e;
-  }
 
   // (1) complement statistics: mean_dev already holds mean_0(X2) (hx_api.cu); C^T planes, M = C^T C, Bop = M P
+  if (int e = timing_mark(ctx, s, HX_PH_PREP)) return e;
   {
     dim3 g((nK + 31) / 32, (dAB + 31) / 32), b(32, 8);
     k_center_planes_T<<<g, b, 0, s>>>(X2, mean_dev, n, d, dAB, nK, (bf*)pCT);
@@ -555,8 +561,28 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   GemmArgs ga;
   memset(&ga, 0, sizeof(ga));
   ga.nprod = nprod;
-  ga.M = d; ga.N = d; ga.out = (float*)pM; ga.ldo = d;
-  if (int e = launch_gemm<EPI_STORE, KIND_BF16>(ctx, pCT, dAB, pCT, dAB, nK, ga, s)) return e;
+  {
+    // Gram M = C^T C: only (d/128) x (d/256) output tiles with K = n, so split K over enough slices to fill the SMs
+    const int tiles = ((d + BN - 1) / BN) * ((d + kBM - 1) / kBM), nkb = nK / 64;
+    int slices = ctx->sm_count / tiles;
+    if (slices > 16) slices = 16;
+    if (slices > nkb) slices = nkb;
+    if (slices < 1) slices = 1;
+    const int kbs = (nkb + slices - 1) / slices;
+    slices = (nkb + kbs - 1) / kbs;
+    void* pMs = pM;
+    if (slices > 1)
+      if (int e = ws_get(ctx, WS_GRAMP, (size_t)slices * d * d * sizeof(float), &pMs)) return e;
+    ga.M = d; ga.N = d; ga.out = (float*)pMs; ga.ldo = d;
+    ga.kb_per_slice = slices > 1 ? kbs : 0; ga.slice_stride = (size_t)d * d;
+    if (int e = launch_gemm<EPI_STORE, KIND_BF16>(ctx, pCT, dAB, pCT, dAB, nK, ga, s, 0, 0, slices)) return e;
+    if (slices > 1) {
+      k_sum_slices_f<<<grid_for((size_t)d * d, 256), 256, 0, s>>>((const float*)pMs, slices, (size_t)d * d, (float*)pM);
+      HX_LAUNCH_CHECK("k_sum_slices_f");
+      ctx->launches += 1;
+    }
+    ga.kb_per_slice = 0; ga.slice_stride = 0;
+  }
   {
     dim3 g((d + 63) / 64, (d + 63) / 64);
     k_small_gemm<<<g, 256, 0, s>>>((const float*)pM, d, (const float*)tgt->precision, tgt->ld, d, (float*)pBo, d);
@@ -570,6 +596,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   void *pBX = nullptr, *pBS = nullptr, *pTQ = nullptr, *pTS = nullptr, *pTW = nullptr, *pWP = nullptr, *pB1 = nullptr,
        *pB2 = nullptr, *pZB = nullptr, *pZT = nullptr;
   if (prop) {
+    if (int e = timing_mark(ctx, s, HX_PH_BASIS)) return e;
     const size_t bsz = (size_t)bR * d * sizeof(float);
     if (int e = ws_get(ctx, WS_TC_BX, bsz, &pBX)) return e;
     if (int e = ws_get(ctx, WS_TC_BS, bsz, &pBS)) return e;
@@ -610,7 +637,13 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     ctx->launches += 5;
   }
 
-  // (3) projection S0 = P0 C, chunk by chunk as the draw completes
+  // (3) projection S0 = P0 C, chunk by chunk as the draw completes.  The NEXT half-move's draw is queued here: it then runs
+  //     under the throughput-bound projection / apply GEMMs (measured to overlap fully, scripts/overlap_bench.py) and stays
+  //     out of the way of the small latency-bound launches above, which it would slow 3-4x.
+  if (next && next->rows == rows) {
+    if (int e = job_launch(ctx, 1 - cur, Pbuf[1 - cur], impl, n, next->row0, next->rows, rA, nK, chunk, next->key, next->key_ptr, s))
+      return e;
+  }
   {
     std::vector<cudaEvent_t>& evs = *ctx->ev_chunk[cur];
     if (int e = timing_begin(ctx, s)) return e;
@@ -623,7 +656,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
                                                     (uint64_t)rA + pad_to(rc, kBM)))
         return e;
     }
-    if (int e = timing_end(ctx, s)) return e;
+    if (int e = timing_mark(ctx, s, HX_PH_LEAP)) return e;
   }
 
   // (4) leapfrog + energy products
@@ -660,6 +693,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   }
 
   // (5) energies, log-accept, optional fused accept + chain emit
+  if (int e = timing_mark(ctx, s, HX_PH_FINISH)) return e;
   FinishArgs fa;
   memset(&fa, 0, sizeof(fa));
   fa.lpp = (const float*)pLPP; fa.dkp = (const float*)pDKP; fa.NT = NT; fa.lp1 = lp1; fa.Q = Q; fa.logacc = logacc;
@@ -672,7 +706,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   k_tc_finish<<<(rows + 7) / 8, 256, 0, s>>>(fa);
   HX_LAUNCH_CHECK("k_tc_finish");
   ctx->launches += 2;
-  return 0;
+  return timing_mark(ctx, s, -1);
 }
 
 // ---- diagnostics: how well do the momentum draw (ALU) and the projection GEMM (tensor pipe) overlap? --------------------------

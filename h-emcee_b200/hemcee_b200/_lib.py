@@ -46,6 +46,7 @@ _PROTOS = {
     "hx_ctx_last_path": (C.c_int, [_P]),
     "hx_ctx_timing_enable": (C.c_int, [_P, C.c_int]),
     "hx_ctx_timing_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "hx_ctx_timing_phases": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "hx_split": (C.c_int, [_KEY, C.c_int, C.c_int64, _P, _P]),
     "hx_random_bits": (C.c_int, [_KEY, C.c_int, C.c_int, C.c_int64, _P, _P]),
     "hx_uniform": (C.c_int, [_KEY, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int64, _P, _P]),

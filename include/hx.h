@@ -129,6 +129,10 @@ HX_API int hx_ctx_last_path(const hx_ctx* ctx);
  * library launched through `ctx` since the last reset; then it resets the counters.               */
 HX_API int hx_ctx_timing_enable(hx_ctx* ctx, int enable);
 HX_API int hx_ctx_timing_read(hx_ctx* ctx, double* kernel_ms, int64_t* kernel_launches, int64_t* all_launches);
+/* per-phase breakdown of the last hx_ctx_timing_read (8 entries each): [0] dominant kernel section (fused SIMT half-move, or
+ * the projection GEMM on the tensor-core path), [1] complement statistics (centre, Gram, M P), [2] propagator basis run,
+ * [3] leapfrog apply / kicks + energy products, [4] finish (energies, accept, chain emit); summed ms and interval counts */
+HX_API int hx_ctx_timing_phases(hx_ctx* ctx, double* phase_ms, int64_t* phase_count);
 
 /* ---- (1) RNG: bit-exact jax.random subset ------------------------------------------------
  * replaces jax.random.split   (call sites: samplers/hamiltonian_ensemble.py:90,228,330;
