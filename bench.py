@@ -101,7 +101,8 @@ def cpu_reference(wl, steps, warmup, budget_s=None):
 
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  The sampler runs from before the
+    warm-up (nvidia-smi needs ~100 ms to start); only samples read between mark_begin() and mark_end() are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -110,6 +111,7 @@ class ClockSampler:
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -121,23 +123,33 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        sm, pw, mx, reasons = [], [], None, set()
+        for ts, r in self.rows:
             try:
-                sm.append(float(r[1])); mx = float(r[2])
+                mx = float(r[2])
+                if self.t0 is not None and not (self.t0 <= ts <= (self.t1 or ts) + 0.03):
+                    continue
+                sm.append(float(r[1])); pw.append(float(r[3]))
             except Exception:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
-                    samples=len(sm))
+                    samples=len(sm), power_w_max=max(pw) if pw else None)
 
 
 def algorithmic_flops_half_move(rows, n, d, L, target):
@@ -267,17 +279,19 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident timing (`value`) --------------------------------------------------------------
+    clocks = ClockSampler(local)
+    clocks.start()
     run(0, Wu)
     barrier()
     lib.hx_ctx_timing_enable(ctx, 1)
-    clocks = ClockSampler(local)
-    clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.mark_begin()
     e0.record()
     run(Wu, K)
     e1.record()
     barrier()
+    clocks.mark_end()
     clk = clocks.stop()
     ms = e0.elapsed_time(e1)
     kms, kn, alln = np.zeros(1), np.zeros(1, np.int64), np.zeros(1, np.int64)
