@@ -182,7 +182,7 @@ def main():
     conf = dict(workload=f"{args.workload}: {cfg['d']}-dim {cfg['target']} (kappa {cfg['kappa']:g}), {cfg['W']} walkers, "
                          f"{cfg['move']} move, L={cfg['L']}, eps={cfg['eps']}",
                 walkers=cfg["W"], dim=cfg["d"], L=cfg["L"], move=cfg["move"],
-                parallelism=f"walker rows sharded over {max(world, 1)} GPU(s), all-gather of the updated half per half-move"
+                parallelism=f"walker rows sharded over {max(world, 1)} GPU(s); updated rows stored into the peers' copies over NVLink by the kernels, one epoch barrier per half-move"
                 if world > 1 else "single GPU",
                 l2="state (>=262 MB at c5) and centred complement exceed the 126 MB L2; chain slice written every step")
 
@@ -252,26 +252,20 @@ def main():
                                              _rt.ptr(lp), n, eps, L, _rt.ptr(keys_dev[4 * t0:]), T, _rt.ptr(chain),
                                              _rt.ptr(clp), _rt.ptr(accepts), _rt.ptr(flag), _rt.stream(dev)), "run")
     else:
-        X1f, X2f = X[:n].contiguous(), X[n:].contiguous()
-        X1, X2 = X1f[row0:row0 + rows].clone(), X2f[row0:row0 + rows].clone()
-        lp1, lp2 = lp[:n][row0:row0 + rows].clone(), lp[n:][row0:row0 + rows].clone()
-        a1 = torch.zeros(rows, dtype=torch.int32, device=dev)
-        a2 = torch.zeros(rows, dtype=torch.int32, device=dev)
+        # row-sharded: every rank holds the full state in its peer-mapped exchange region and updates its own rows; the kernels
+        # store the updated rows into the peers' copies over NVLink (include/hx.h section 5)
+        Xf, lpf = _rt.dist_setup(dev, dist.group.WORLD, tdt, n, d)
+        Xf.copy_(X); lpf.copy_(lp)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        accepts = torch.zeros(2 * rows, dtype=torch.int32, device=dev)
         chain = torch.empty((max(K, Wu), 2 * rows, d), dtype=tdt, device=dev)
-
-        def half(Xa, Xbf, lpa, acc, km, ka, Xaf, knext):
-            if mk == 0 and knext is not None:      # the following half-move's momentum draw only needs its key
-                hx.moves.walk_prefetch(knext, n, row0, rows, dev)
-            q, la, _, lpq = move(Xa, Xbf, eps, km, tgt, tgt, L, lpa, row0=row0, n=n)
-            hx.moves.accept_proposal(Xa, q, lpa, lpq, la, ka, acc, row0=row0, n=n)
-            dist.all_gather_into_tensor(Xaf, Xa)
+        clp = torch.empty((max(K, Wu), 2 * rows), dtype=tdt, device=dev)
 
         def run(t0, T):
-            for t in range(t0, t0 + T):
-                k = keys_host[t]
-                half(X1, X2f, lp1, a1, k[0], k[2], X1f, k[1])
-                half(X2, X1f, lp2, a2, k[1], k[3], X2f, keys_host[t + 1][0] if t + 1 < K + Wu else None)
-                chain[t - t0, :rows].copy_(X1); chain[t - t0, rows:].copy_(X2)
+            _lib.check(lib.hx_run_iterations_sharded(ctx, _rt.dtype_code(tdt), _rt.impl_code(), mk, 0, desc, eps, L,
+                                                     _rt.ptr(keys_dev[4 * t0:]), T, _rt.ptr(chain), _rt.ptr(clp), _rt.ptr(accepts),
+                                                     _rt.ptr(flag), _rt.stream(dev)), "run_sharded")
 
     def barrier():
         if world > 1:
@@ -308,9 +302,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
     value = W * L * K / (ms * 1e-3)
-    acc_rate = None
-    if world == 1:
-        acc_rate = float(accepts.sum().item()) / (W * (K + Wu))
+    tot_acc = accepts.sum().to(torch.float64).reshape(1)
+    if world > 1:
+        dist.all_reduce(tot_acc)
+    acc_rate = float(tot_acc.item()) / (W * (K + Wu))
 
     # ---- roofline of the dominant kernel (fused half-move) -------------------------------------------
     peaks = {}
@@ -368,9 +363,32 @@ def main():
                    note="h2d = initial ensemble amortised over the steps + 4 keys; d2h = the step's chain slice and log-probs; "
                         "pinned host chain buffer reused from an untimed warm-up run of the same size")
         assert out.shape == (K, W, d)
-    elif world > 1:
-        e2e = dict(value=None, unit="walker-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0,
-                   note="multi-GPU e2e (host chain gather) not measured in this round")
+    elif world > 1 and not args.no_e2e:
+        # every rank streams the chain of ITS rows to its own pinned host buffer (chain_store='local'); max over ranks
+        x0_host = x0.cpu().pin_memory()
+        mkS = lambda: hx.HamiltonianEnsembleSampler(W, d, tgt, step_size=eps, L=L, move=move, adapt_inital_step_size=False,
+                                                    adapt_step_size=False, adapt_length=False, verbose=False,
+                                                    group=dist.group.WORLD, chain_store="local", exchange="peer")
+        s = mkS()
+        w = s.run_mcmc(k_run, x0_host, K, warmup=0, batch_size=max(1, K // 4))
+        del w, s
+        import gc
+        gc.collect()
+        s = mkS()
+        barrier()
+        t0 = time.perf_counter()
+        out = s.run_mcmc(k_run, x0_host, K, warmup=0, batch_size=max(1, K // 4))
+        torch.cuda.synchronize(dev)
+        el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        el = float(el[0])
+        isz = 8 if cfg["x64"] else 4
+        e2e = dict(value=W * L * K / el, unit="walker-steps/s", h2d_bytes_per_step=int(W * d * isz / K + 32),
+                   d2h_bytes_per_step=int((W * d * isz + W * isz) / world), seconds=el,
+                   api="HamiltonianEnsembleSampler.run_mcmc(group=..., chain_store='local') (host initial_state -> per-rank host chain)",
+                   note="per rank: h2d = the initial ensemble amortised over the steps + keys, d2h = the chain slice and log-probs of "
+                        "the rank's own rows; time = max over ranks")
+        assert out.shape == (K, 2 * rows, d)
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -14,6 +14,7 @@
 #include "hx_launch.cuh"
 #include "hx_ctx.h"
 #include "hx_tc_walk.h"
+#include "hx_dist.cuh"
 #include <type_traits>
 
 using namespace hx;
@@ -162,9 +163,11 @@ extern "C" HX_API int hx_ctx_create(hx_ctx** out, int device) {
   return 0;
 }
 
+extern "C" HX_API int hx_dist_destroy(hx_ctx* ctx);
 extern "C" HX_API int hx_ctx_destroy(hx_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
+  hx_dist_destroy(ctx);
   for (int i = 0; i < WS_NSLOT; ++i)
     if (ctx->buf[i]) cudaFree(ctx->buf[i]);
   if (ctx->ev) {
@@ -743,4 +746,160 @@ extern "C" HX_API int hx_run_iterations(hx_ctx* ctx, int dtype, int impl, int mo
                                    (float*)chain_out, (float*)lp_out, accepts, nonfinite, s);
   return run_iterations_t<double>(ctx, impl, move_kind, key_order, tgt, (double*)X, (double*)lp, n, step_size, L, keys_dev, T,
                                   (double*)chain_out, (double*)lp_out, accepts, nonfinite, s);
+}
+
+// ---- (5) row-sharded multi-GPU batch loop: exchange over NVLink peer memory (hx_dist.cuh) -------------------------------------
+extern "C" HX_API int hx_dist_init(hx_ctx* ctx, int dtype, int32_t rank, int32_t world, int32_t n, int32_t dim, void* handle_out) {
+  if (!ctx || !handle_out) return fail(HX_E_NULL, "hx_dist_init: NULL argument");
+  if (dtype != HX_F32 && dtype != HX_F64) return fail(HX_E_DTYPE, "hx_dist_init: unknown dtype %d", dtype);
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(HX_E_SHAPE, "hx_dist_init: bad rank %d / world %d (max %d)", rank, world, kMaxRanks);
+  if (n < 2 || dim < 1 || n % world) return fail(HX_E_SHAPE, "hx_dist_init: group size %d must be a multiple of the world size %d", n, world);
+  const size_t esz = dtype == HX_F32 ? 4 : 8;
+  if (((size_t)(n / world) * dim * esz) % 16 || ((size_t)(n / world) * esz) % 16)
+    return fail(HX_E_ALIGN, "hx_dist_init: a rank's rows (%d x %d) and log-probs must be multiples of 16 bytes", n / world, dim);
+  HX_CUDA(cudaSetDevice(ctx->device));
+  HxDist& D = ctx->dist;
+  if (D.on) return fail(HX_E_UNSUPPORTED, "hx_dist_init: already initialised (call hx_dist_destroy first)");
+  memset(&D, 0, sizeof(D));
+  const size_t xb = (size_t)2 * n * dim * esz, lb = (size_t)2 * n * esz;
+  D.lp_off = (xb + 255) & ~(size_t)255;
+  D.flag_off = (D.lp_off + lb + 255) & ~(size_t)255;
+  D.counter_off = D.flag_off + 256;
+  D.bytes = D.counter_off + 256;
+  void* base = nullptr;
+  HX_CUDA(cudaMalloc(&base, D.bytes));
+  HX_CUDA(cudaMemset(base, 0, D.bytes));
+  HX_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, base);
+  if (e != cudaSuccess) { cudaFree(base); return fail((int)e, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle_out, &h, 64);
+  D.base[rank] = base;
+  D.rank = rank; D.world = world; D.n = n; D.dim = dim; D.dtype = dtype; D.epoch = 0; D.on = 1;
+  return 0;
+}
+
+extern "C" HX_API int hx_dist_connect(hx_ctx* ctx, const void* handles) {
+  if (!ctx || !handles) return fail(HX_E_NULL, "hx_dist_connect: NULL argument");
+  HxDist& D = ctx->dist;
+  if (!D.on) return fail(HX_E_UNSUPPORTED, "hx_dist_connect: hx_dist_init first");
+  HX_CUDA(cudaSetDevice(ctx->device));
+  for (int p = 0; p < D.world; ++p) {
+    if (p == D.rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)p * 64, 64);
+    void* ptr = nullptr;
+    HX_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    D.base[p] = ptr;
+  }
+  D.on = 2;
+  return 0;
+}
+
+extern "C" HX_API int hx_dist_buffers(hx_ctx* ctx, void** X_full, void** lp_full) {
+  if (!ctx || !ctx->dist.on) return fail(HX_E_UNSUPPORTED, "hx_dist_buffers: not initialised");
+  if (X_full) *X_full = ctx->dist.base[ctx->dist.rank];
+  if (lp_full) *lp_full = (char*)ctx->dist.base[ctx->dist.rank] + ctx->dist.lp_off;
+  return 0;
+}
+
+extern "C" HX_API int hx_dist_destroy(hx_ctx* ctx) {
+  if (!ctx || !ctx->dist.on) return 0;
+  HxDist& D = ctx->dist;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (int p = 0; p < D.world; ++p)
+    if (p != D.rank && D.base[p]) cudaIpcCloseMemHandle(D.base[p]);
+  if (D.base[D.rank]) cudaFree(D.base[D.rank]);
+  memset(&D, 0, sizeof(D));
+  return 0;
+}
+
+template <typename T>
+static int run_iterations_sharded_t(hx_ctx* ctx, int impl, int move_kind, int key_order, const hx_target* tgt, double eps, int L,
+                                    const uint32_t* keys, int64_t Tn, T* chain, T* chain_lp, int32_t* accepts, int32_t* nonfinite,
+                                    cudaStream_t s) {
+  HxDist& D = ctx->dist;
+  const int n = D.n, d = D.dim, world = D.world, rank = D.rank;
+  const int rows = n / world, row0 = rank * rows;
+  T* Xf = (T*)D.base[rank];
+  T* lpf = (T*)((char*)D.base[rank] + D.lp_off);
+  const uint32_t* flags = (const uint32_t*)((char*)D.base[rank] + D.flag_off);
+  uint32_t* counter = (uint32_t*)((char*)D.base[rank] + D.counter_off);
+  PeerTable pt;
+  for (int p = 0; p < kMaxRanks; ++p) pt.base[p] = p < world ? D.base[p] : nullptr;
+  void *pQ, *pLa, *pLp;
+  if (int e = ws_get(ctx, WS_Q, (size_t)rows * d * sizeof(T), &pQ)) return e;
+  if (int e = ws_get(ctx, WS_LA, (size_t)rows * sizeof(T), &pLa)) return e;
+  if (int e = ws_get(ctx, WS_LP, (size_t)rows * sizeof(T), &pLp)) return e;
+  int clock_khz = 1900000;
+  cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, ctx->device);
+  const long long timeout = (long long)clock_khz * 1000ll * 20ll;      // ~20 s of SM clocks
+  for (int64_t t = 0; t < Tn; ++t) {
+    const uint32_t* kt = keys + (size_t)t * 8;
+    for (int half = 0; half < 2; ++half) {
+      const int im = key_order == 0 ? (half == 0 ? 0 : 1) : (half == 0 ? 0 : 2);
+      const int ia = key_order == 0 ? (half == 0 ? 2 : 3) : (half == 0 ? 1 : 3);
+      // the complement (and, from the previous iteration, this half) must be complete on this rank
+      if (D.epoch > 0) {
+        k_dist_wait<<<1, 32, 0, s>>>(flags, world, D.epoch, timeout, nonfinite);
+        HX_LAUNCH_CHECK("k_dist_wait");
+      }
+      T* Xa = Xf + ((size_t)half * n + row0) * d;
+      T* Xb = Xf + (size_t)(1 - half) * n * d;
+      T* lpa = lpf + (size_t)half * n + row0;
+      Fuse<T> f;
+      f.akey_ptr = kt + 2 * ia; f.lp1w = lpa; f.accepts = accepts + (size_t)half * rows;
+      f.chain_out = chain ? chain + ((size_t)t * 2 * rows + (size_t)half * rows) * d : nullptr;
+      f.chain_lp = chain_lp ? chain_lp + (size_t)t * 2 * rows + (size_t)half * rows : nullptr;
+      f.nonfinite = nonfinite;
+      tc::NextDraw nd;
+      const tc::NextDraw* next = nullptr;
+      if (half == 0 || t + 1 < Tn) {
+        nd.key = Key{0, 0}; nd.key_ptr = half == 0 ? kt + 2 * (key_order == 0 ? 1 : 2) : kt + 8; nd.row0 = row0; nd.rows = rows;
+        next = &nd;
+      }
+      int e;
+      if (move_kind == 0)
+        e = walk_move_t<T>(ctx, impl, tgt, Xa, Xb, n, row0, rows, eps, Key{0, 0}, kt + 2 * im, L, lpa, (T*)pQ, (T*)pLa, nullptr, (T*)pLp, 0, &f, next, s);
+      else
+        e = side_move_t<T>(ctx, impl, tgt, Xa, Xb, n, row0, rows, eps, Key{0, 0}, kt + 2 * im, L, lpa, (T*)pQ, (T*)pLa, nullptr, (T*)pLp, 0, &f, s);
+      if (e) return e;
+      // exchange: store the rank's updated rows (+ log-probs) into every peer's copy, then publish the epoch
+      D.epoch += 1;
+      const size_t x_off = ((size_t)half * n + row0) * d * sizeof(T), cnt = (size_t)rows * d * sizeof(T) / 16;
+      const size_t l_off = D.lp_off + ((size_t)half * n + row0) * sizeof(T), lcnt = (size_t)rows * sizeof(T) / 16;
+      int grid = (int)((cnt + 255) / 256);
+      if (grid > ctx->sm_count * 2) grid = ctx->sm_count * 2;
+      if (grid < 1) grid = 1;
+      k_dist_push<<<grid, 256, 0, s>>>(pt, rank, world, x_off, cnt, l_off, lcnt, D.flag_off, counter, D.epoch);
+      HX_LAUNCH_CHECK("k_dist_push");
+      ctx->launches += 2;
+    }
+  }
+  if (D.epoch > 0) {
+    k_dist_wait<<<1, 32, 0, s>>>(flags, world, D.epoch, timeout, nonfinite);
+    HX_LAUNCH_CHECK("k_dist_wait");
+  }
+  return 0;
+}
+
+extern "C" HX_API int hx_run_iterations_sharded(hx_ctx* ctx, int dtype, int impl, int move_kind, int key_order, const hx_target* tgt,
+                                         double step_size, int32_t L, const uint32_t* keys_dev, int64_t T, void* chain_out,
+                                         void* lp_out, int32_t* accepts, int32_t* nonfinite, void* stream) {
+  if (!ctx || !tgt || !keys_dev || !accepts || !nonfinite) return fail(HX_E_NULL, "hx_run_iterations_sharded: NULL argument");
+  if (ctx->dist.on != 2) return fail(HX_E_UNSUPPORTED, "hx_run_iterations_sharded: hx_dist_init + hx_dist_connect first");
+  if (int e = check_dtype_impl(dtype, impl, "hx_run_iterations_sharded")) return e;
+  if (dtype != ctx->dist.dtype || tgt->dim != ctx->dist.dim) return fail(HX_E_SHAPE, "hx_run_iterations_sharded: dtype/dim differ from hx_dist_init");
+  if (move_kind != 0 && move_kind != 1) return fail(HX_E_DTYPE, "hx_run_iterations_sharded: move_kind must be 0 (walk) or 1 (side)");
+  if (key_order != 0 && key_order != 1) return fail(HX_E_DTYPE, "hx_run_iterations_sharded: key_order must be 0 or 1");
+  if (L < 1 || T < 0) return fail(HX_E_SHAPE, "hx_run_iterations_sharded: need L >= 1, T >= 0");
+  HX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == HX_F32)
+    return run_iterations_sharded_t<float>(ctx, impl, move_kind, key_order, tgt, step_size, L, keys_dev, T, (float*)chain_out,
+                                           (float*)lp_out, accepts, nonfinite, s);
+  return run_iterations_sharded_t<double>(ctx, impl, move_kind, key_order, tgt, step_size, L, keys_dev, T, (double*)chain_out,
+                                          (double*)lp_out, accepts, nonfinite, s);
 }

@@ -23,6 +23,14 @@ struct P0Job {
   const uint32_t* key_ptr;       // device-resident key (batch loop) or NULL (key by value)
 };
 
+// row-sharded multi-GPU state (hx_dist.cuh)
+struct HxDist {
+  int on, rank, world, n, dim, dtype;
+  void* base[8];          // own region + peers' regions mapped through CUDA IPC
+  size_t bytes, lp_off, flag_off, counter_off;
+  uint32_t epoch;         // half-moves pushed so far
+};
+
 struct hx_ctx {
   int device;
   void* buf[WS_NSLOT];
@@ -48,6 +56,7 @@ struct hx_ctx {
   void* p0_base; size_t p0_elems;          // identity of the draw workspace the jobs refer to
   P0Job hint; int hint_valid;              // hx_walk_prefetch: the walk half-move after the next one
   int leap_form;                           // HX_LEAP_*
+  HxDist dist;
   int rng_ctas_per_sm;                     // resident CTAs/SM of the draw kernel (0: default 4)
 };
 

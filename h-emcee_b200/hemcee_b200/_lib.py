@@ -64,6 +64,12 @@ _PROTOS = {
                             _P, _P]),
     "hx_run_iterations": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.c_double,
                                     C.c_int32, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    "hx_dist_init": (C.c_int, [_P, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "hx_dist_connect": (C.c_int, [_P, _P]),
+    "hx_dist_buffers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
+    "hx_dist_destroy": (C.c_int, [_P]),
+    "hx_run_iterations_sharded": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), C.c_double, C.c_int32, _P,
+                                            C.c_int64, _P, _P, _P, _P, _P]),
 }
 
 EXPORTS = tuple(_PROTOS)

@@ -120,3 +120,45 @@ def as_key(key) -> np.ndarray:
     if k.dtype != np.uint32:
         k = k.astype(np.int64).astype(np.uint32) if k.dtype.kind in "iu" else k.view(np.uint32)
     return k.reshape(2)
+
+
+# ---- row-sharded multi-GPU plumbing (include/hx.h section 5) ---------------------------------------------------------
+_dist = {}
+
+
+class _DevMem:
+    """A libhx-owned device buffer exposed through __cuda_array_interface__ so torch can view it without a copy."""
+
+    def __init__(self, ptr, shape, dtype):
+        typestr = {torch.float32: "<f4", torch.float64: "<f8"}[dtype]
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def dist_setup(dev: torch.device, group, dtype: torch.dtype, n: int, dim: int):
+    """Create (once per shape) the peer-mapped exchange region of this rank and connect it to the other ranks of `group`.
+    torch.distributed only carries the 64-byte IPC handles.  Returns (X_full [2n, dim], lp_full [2n]) torch views."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    key = (dev.index, id(group))
+    want = (n, dim, dtype, world)
+    lib = _lib.load()
+    h = ctx(dev)
+    if key in _dist and _dist[key][0] != want:
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)
+        _lib.check(lib.hx_dist_destroy(h), "hx_dist_destroy")
+        del _dist[key]
+    if key not in _dist:
+        handle = (C.c_uint8 * 64)()
+        _lib.check(lib.hx_dist_init(h, dtype_code(dtype), rank, world, n, dim, handle), "hx_dist_init")
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=dev)
+        allh = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        buf = (C.c_uint8 * (world * 64)).from_buffer_copy(bytes(allh.cpu().numpy().tobytes()))
+        _lib.check(lib.hx_dist_connect(h, buf), "hx_dist_connect")
+        px, pl = C.c_void_p(), C.c_void_p()
+        _lib.check(lib.hx_dist_buffers(h, C.byref(px), C.byref(pl)), "hx_dist_buffers")
+        X = torch.as_tensor(_DevMem(px.value, (2 * n, dim), dtype), device=dev)
+        lp = torch.as_tensor(_DevMem(pl.value, (2 * n,), dtype), device=dev)
+        _dist[key] = (want, X, lp)
+    return _dist[key][1], _dist[key][2]

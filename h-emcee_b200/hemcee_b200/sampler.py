@@ -87,7 +87,7 @@ class BaseSampler:
 class HamiltonianEnsembleSampler(BaseSampler):
     def __init__(self, total_chains, dim, log_prob, step_size=0.1, L=10, move=hmc_walk_move, backend=None,
                  adapt_inital_step_size=True, adapt_step_size=True, adapt_length=True, *, device=None, group=None,
-                 chain_store="full", verbose=True):
+                 chain_store="full", exchange="peer", verbose=True):
         super().__init__(total_chains, dim, log_prob, move, backend)
         if getattr(move, "__name__", None) not in ("hmc_walk_move", "hmc_side_move"):
             raise ValueError("HamiltonianEnsembleSampler on B200 supports move=hmc_walk_move or hmc_side_move")
@@ -102,11 +102,16 @@ class HamiltonianEnsembleSampler(BaseSampler):
         self.verbose = verbose
         self.group = group
         self.chain_store = chain_store
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' (NVLink peer-memory stores from the kernels) or 'nccl' (all-gather)")
+        self.exchange = exchange
         if group is not None:
             import torch.distributed as dist
             self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
             if (self.total_chains // 2) % self.world:
                 raise ValueError("total_chains/2 must be divisible by the number of ranks")
+            if chain_store == "local":      # this rank stores only the chain of its own rows (half 1 rows, then half 2 rows)
+                self.backend.reset(2 * ((self.total_chains // 2) // self.world), self.dim)
         else:
             self.world, self.rank = 1, 0
         self.adapt_inital_step_size = adapt_inital_step_size
@@ -224,6 +229,97 @@ class HamiltonianEnsembleSampler(BaseSampler):
         self.kernel_launch_count += T * 2 * (6 if self._move_kind == 0 else 2)
         return acc
 
+    # -- batch-level engine, row-sharded over the ranks of `group`: exchange over NVLink peer memory -------------
+    def _run_batches_sharded(self, key, g1, g2, T, step_size, L, batch_size, offset, key_order, show_progress):
+        """hx_run_iterations_sharded (include/hx.h section 5): every rank updates its rows of both halves; the updated rows
+        are stored into the peers' copies by the kernels themselves.  Chain slices of the LOCAL rows stream to pinned host
+        memory; with chain_store='full' they are all-gathered per batch (NCCL, off the hot path) before the host copy."""
+        import torch.distributed as dist
+        dev, W, d = self.device, self.total_chains, self.dim
+        n = W // 2
+        rows = n // self.world
+        lib = _lib.load()
+        keys_dev = hrandom.split_device(key, 4 * T, dev, self.impl)
+        Xf, lpf = _rt.dist_setup(dev, self.group, self.dtype, n, d)
+        Xf[:n].copy_(g1); Xf[n:].copy_(g2)
+        lpf.copy_(self.log_prob(Xf))
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.group)            # nobody stores rows into a peer before that peer loaded its initial state
+        accepts = torch.zeros(2 * rows, dtype=torch.int32, device=dev)
+        full = self.chain_store == "full"
+        Wst = W if full else 2 * rows
+        if T == 0:
+            return np.zeros(Wst)
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        nb = (T + batch_size - 1) // batch_size
+        B = min(batch_size, T)
+        host_chain = torch.empty((T, Wst, d), dtype=self.dtype, pin_memory=True)
+        host_lp = torch.empty((T, Wst), dtype=self.dtype, pin_memory=True)
+        bufs = [(torch.empty((B, 2, rows, d), dtype=self.dtype, device=dev),
+                 torch.empty((B, 2, rows), dtype=self.dtype, device=dev)) for _ in range(min(2, nb))]
+        copy_stream = torch.cuda.Stream(dev)
+        done = [None, None]
+        main = torch.cuda.current_stream(dev)
+        desc = self.target.descriptor(self.dtype, dev)
+        it = range(nb)
+        if show_progress and self.rank == 0:
+            from tqdm import tqdm
+            it = tqdm(it)
+        for b in it:
+            start, stop = b * batch_size, min((b + 1) * batch_size, T)
+            nbt = stop - start
+            cbuf, lbuf = bufs[b % 2]
+            if done[b % 2] is not None:
+                main.wait_event(done[b % 2])
+            st = lib.hx_run_iterations_sharded(_rt.ctx(dev), _rt.dtype_code(self.dtype), _rt.impl_code(self.impl), self._move_kind,
+                                               key_order, desc, float(step_size), int(L), _rt.ptr(keys_dev[4 * start:]), nbt,
+                                               _rt.ptr(cbuf), _rt.ptr(lbuf), _rt.ptr(accepts), _rt.ptr(flag), _rt.stream(dev))
+            _lib.check(st, "hx_run_iterations_sharded")
+            if full:
+                gc = torch.empty((self.world, nbt, 2, rows, d), dtype=self.dtype, device=dev)
+                gl = torch.empty((self.world, nbt, 2, rows), dtype=self.dtype, device=dev)
+                dist.all_gather_into_tensor(gc, cbuf[:nbt].contiguous(), group=self.group)
+                dist.all_gather_into_tensor(gl, lbuf[:nbt].contiguous(), group=self.group)
+                src_c = gc.permute(1, 2, 0, 3, 4).reshape(nbt, W, d)
+                src_l = gl.permute(1, 2, 0, 3).reshape(nbt, W)
+            else:
+                src_c, src_l = cbuf[:nbt].reshape(nbt, 2 * rows, d), lbuf[:nbt].reshape(nbt, 2 * rows)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            copy_stream.wait_event(ev)
+            with torch.cuda.stream(copy_stream):
+                host_chain[start:stop].copy_(src_c, non_blocking=True)
+                host_lp[start:stop].copy_(src_l, non_blocking=True)
+                src_c.record_stream(copy_stream); src_l.record_stream(copy_stream)
+                done[b % 2] = torch.cuda.Event()
+                done[b % 2].record(copy_stream)
+        copy_stream.synchronize()
+        main.synchronize()
+        self._allreduce_max(flag)
+        code = int(flag.item())
+        if code & 2:
+            raise _lib.HxError("row exchange timed out: a peer rank stopped")
+        if code & 1:
+            raise ValueError(_NONFINITE_MSG)                                         # sampler_utils.py:74-75
+        if full:
+            ga = torch.empty((self.world, 2, rows), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(ga, accepts.reshape(2, rows).contiguous(), group=self.group)
+            acc = ga.permute(1, 0, 2).reshape(W).cpu().numpy()
+        else:
+            acc = accepts.cpu().numpy()
+        self.backend.save_slice(host_chain.numpy(), host_lp.numpy(), acc, offset)
+        self.kernel_launch_count += T * 2 * (8 if self._move_kind == 0 else 4)
+        g1.copy_(Xf[:n]); g2.copy_(Xf[n:])
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.group)
+        return acc
+
+    def _allreduce_max(self, t):
+        if self.group is not None and self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
     # -- per-half-move engine (warm-up with adapters; row-sharded multi-GPU) ------------------------------
     def _half(self, Xa_loc, Xb_full, lpa_loc, step, L, k_move, k_acc, acc_loc, n, row0, adapter_state):
         prop, la, pproj, lpp = self.move(Xa_loc, Xb_full, step, k_move, self.target, self.target, int(L), lpa_loc,
@@ -329,6 +425,9 @@ class HamiltonianEnsembleSampler(BaseSampler):
             lp = self.log_prob(X)
             acc = self._run_batches(key, X, lp, warmup, step, L, batch_size, 0, 1, show_progress)
             group1, group2 = X[: self.total_chains // 2].clone(), X[self.total_chains // 2:].clone()
+        elif noop and self.exchange == "peer":
+            step, L = adapter.value(self.adapter_state)
+            acc = self._run_batches_sharded(key, group1, group2, warmup, step, L, batch_size, 0, 1, show_progress)
         else:
             fixed = adapter.value(self.adapter_state) if noop else None
             acc, st = self._run_steps(key, group1, group2, warmup, batch_size, 0, 1, fixed,
@@ -348,6 +447,9 @@ class HamiltonianEnsembleSampler(BaseSampler):
             lp = self.log_prob(X)                                                    # :325-326
             acc = self._run_batches(key, X, lp, total, step_size, L, batch_size, warmup_offset, 0, show_progress)
             self.last_state = X
+        elif self.exchange == "peer":
+            acc = self._run_batches_sharded(key, group1, group2, total, step_size, L, batch_size, warmup_offset, 0, show_progress)
+            self.last_state = torch.cat([group1, group2])
         else:
             acc, _ = self._run_steps(key, group1, group2, total, batch_size, warmup_offset, 0, (step_size, L), None,
                                      show_progress)

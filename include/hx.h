@@ -220,6 +220,28 @@ HX_API int hx_run_iterations(hx_ctx* ctx, int dtype, int impl, int move_kind, in
                       const uint32_t* keys_dev, int64_t T, void* chain_out_dev, void* lp_out_dev,
                       int32_t* accepts_inout_dev, int32_t* nonfinite_flag_dev, void* stream);
 
+/* ---- (5) row-sharded multi-GPU batch loop (the reference is single-device) ---------------------------
+ * One process per GPU.  Rows of BOTH halves are split over `world` ranks (rank r owns rows [r n/world, (r+1) n/world) of each
+ * half); every rank keeps a full copy [2n, dim] + log-probs [2n] in a library-owned region that its peers map with CUDA
+ * IPC.  After a half-move the rank's updated rows are stored directly into every peer's copy over NVLink and an epoch
+ * flag is published (csrc/hx_dist.cuh): this replaces the per-half-move NCCL all-gather, no staging copy, no collective
+ * library on the data path.  RNG counters use global rows, so the chain equals the single-GPU chain bit for bit.
+ *   hx_dist_init     allocate the region, return its 64-byte IPC handle (exchange the handles with any host-side
+ *                    all-gather, e.g. torch.distributed)
+ *   hx_dist_connect  map the peers' regions (`handles` = world x 64 bytes, indexed by rank)
+ *   hx_dist_buffers  device pointers of the local full copy: load the initial ensemble / log-probs there (every rank the
+ *                    full arrays), synchronise all ranks, then call hx_run_iterations_sharded; read the final state there
+ *   hx_run_iterations_sharded  like hx_run_iterations for this rank's rows; chain_out [T, 2 n/world, dim] and lp_out
+ *                    [T, 2 n/world] (rows of half 1, then of half 2), accepts int32 [2 n/world]; bit 1 of the
+ *                    non-finite flag reports an exchange timeout (a peer stopped)                                   */
+HX_API int hx_dist_init(hx_ctx* ctx, int dtype, int32_t rank, int32_t world, int32_t n, int32_t dim, void* handle_out /*64 B*/);
+HX_API int hx_dist_connect(hx_ctx* ctx, const void* handles /*world x 64 B*/);
+HX_API int hx_dist_buffers(hx_ctx* ctx, void** X_full_dev, void** lp_full_dev);
+HX_API int hx_dist_destroy(hx_ctx* ctx);
+HX_API int hx_run_iterations_sharded(hx_ctx* ctx, int dtype, int impl, int move_kind, int key_order, const hx_target* tgt,
+                              double step_size, int32_t L, const uint32_t* keys_dev, int64_t T, void* chain_out_dev,
+                              void* lp_out_dev, int32_t* accepts_inout_dev, int32_t* nonfinite_flag_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

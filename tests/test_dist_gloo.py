@@ -39,7 +39,7 @@ def _worker(rank, world, port, move_kind, warm, out_dir):
     move = make_move(move_kind)
     s = S.HamiltonianEnsembleSampler(W, d, tgt, step_size=0.05, L=4, move=move, adapt_inital_step_size=False,
                                      adapt_step_size=bool(warm), adapt_length=False, group=dist.group.WORLD,
-                                     verbose=False)
+                                     exchange="nccl", verbose=False)   # collective path; 'peer' needs NVLink GPUs
     k_init, k_run = R.split(R.PRNGKey(0), 2)
     x0 = R.normal(k_init, (W, d), np.float64)
     chain = s.run_mcmc(k_run, x0, T, warmup=warm)

@@ -24,12 +24,26 @@ cov = OT.make_covariance_skewed(R.PRNGKey(7), d, 100.0, np.float64)
 tgt = hx.targets.GaussianFull(cov=cov)
 k_init, k_run = R.split(R.PRNGKey(0), 2)
 x0 = R.normal(k_init, (W, d), np.float32)
-for move in (hx.hmc_walk_move, hx.hmc_side_move):
-    s = hx.HamiltonianEnsembleSampler(W, d, tgt, step_size=0.05, L=4, move=move, adapt_inital_step_size=False,
-                                      adapt_step_size=False, adapt_length=False, group=dist.group.WORLD, verbose=False)
-    chain = s.run_mcmc(k_run, x0, T, warmup=0)
-    if rank == 0:
-        np.save(os.path.join({out!r}, "chain_" + move.__name__ + ".npy"), chain)
+for exchange in ("peer", "nccl"):
+    for move in (hx.hmc_walk_move, hx.hmc_side_move):
+        s = hx.HamiltonianEnsembleSampler(W, d, tgt, step_size=0.05, L=4, move=move, adapt_inital_step_size=False,
+                                          adapt_step_size=False, adapt_length=False, group=dist.group.WORLD,
+                                          exchange=exchange, verbose=False)
+        chain = s.run_mcmc(k_run, x0, T, warmup=0, batch_size=2)
+        if rank == 0:
+            np.save(os.path.join({out!r}, "chain_" + exchange + "_" + move.__name__ + ".npy"), chain)
+            np.save(os.path.join({out!r}, "acc_" + exchange + "_" + move.__name__ + ".npy"), s.diagnostics_main["accepts"])
+# tensor-core walk path, sharded, peer exchange vs single GPU (rows = 128 per rank)
+hx.config.update("precision", "bf16x3")
+d2, W2 = 64, 512
+cov2 = OT.make_covariance_skewed(R.PRNGKey(8), d2, 100.0, np.float64)
+tgt2 = hx.targets.GaussianFull(cov=cov2)
+x02 = R.normal(k_init, (W2, d2), np.float32)
+s = hx.HamiltonianEnsembleSampler(W2, d2, tgt2, step_size=0.03, L=4, adapt_inital_step_size=False, adapt_step_size=False,
+                                  adapt_length=False, group=dist.group.WORLD, exchange="peer", verbose=False)
+chain = s.run_mcmc(k_run, x02, 3, warmup=0)
+if rank == 0:
+    np.save(os.path.join({out!r}, "chain_tc.npy"), chain)
 dist.destroy_process_group()
 '''
 
@@ -52,5 +66,20 @@ def test_two_rank_chain_equals_single_gpu(hx, tmp_path):
         s = hx.HamiltonianEnsembleSampler(W, d, tgt, step_size=0.05, L=4, move=move, adapt_inital_step_size=False,
                                           adapt_step_size=False, adapt_length=False, verbose=False)
         ref = s.run_mcmc(k_run, x0, T, warmup=0)
-        got = np.load(tmp_path / f"chain_{move.__name__}.npy")
-        np.testing.assert_array_equal(got, ref)
+        for exchange in ("peer", "nccl"):
+            got = np.load(tmp_path / f"chain_{exchange}_{move.__name__}.npy")
+            np.testing.assert_array_equal(got, ref)
+            np.testing.assert_array_equal(np.load(tmp_path / f"acc_{exchange}_{move.__name__}.npy"), s.diagnostics_main["accepts"])
+    # tensor-core path: the sharded chain equals the single-GPU tensor-core chain bit for bit
+    hx.config.update("precision", "bf16x3")
+    try:
+        d2, W2 = 64, 512
+        cov2 = OT.make_covariance_skewed(R.PRNGKey(8), d2, 100.0, np.float64)
+        tgt2 = hx.targets.GaussianFull(cov=cov2)
+        x02 = R.normal(k_init, (W2, d2), np.float32)
+        s = hx.HamiltonianEnsembleSampler(W2, d2, tgt2, step_size=0.03, L=4, adapt_inital_step_size=False, adapt_step_size=False,
+                                          adapt_length=False, verbose=False)
+        ref = s.run_mcmc(k_run, x02, 3, warmup=0)
+        np.testing.assert_array_equal(np.load(tmp_path / "chain_tc.npy"), ref)
+    finally:
+        hx.config.update("precision", "auto")
