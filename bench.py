@@ -101,29 +101,69 @@ def cpu_reference(wl, steps, warmup, budget_s=None):
 
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  The sampler runs from before the
-    warm-up (nvidia-smi needs ~100 ms to start); only samples read between mark_begin() and mark_end() are reported."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons during the timed region (B200_PROFILING.md's clocks line), read in-process through
+    NVML every 10 ms (nvidia_ml_py).  An `nvidia-smi -lms` loop per rank was measured to stall kernel launches through the
+    driver lock (2x slower steps at 8 ranks), so only rank 0 samples and it does so with direct NVML calls; the fallback is
+    one `nvidia-smi -lms 100` process.  Only samples between mark_begin() and mark_end() are reported."""
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
+        self.rows = []          # (t, sm_mhz, power_w, reasons bitmask)
+        self.max_mhz = None
         self.t0 = self.t1 = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._proc = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES if it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.rows.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                          pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                          int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.01)
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+            self.R = dict(hw_slowdown=pynvml.nvmlClocksEventReasonHwSlowdown, hw_thermal_slowdown=pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                          sw_thermal_slowdown=pynvml.nvmlClocksEventReasonSwThermalSlowdown, sw_power_cap=pynvml.nvmlClocksEventReasonSwPowerCap)
+        except Exception:
+            self._thread = None
+            self._start_smi()
+
+    def _start_smi(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.R = dict(hw_slowdown=1, hw_thermal_slowdown=2, sw_thermal_slowdown=4, sw_power_cap=8)
+
+            def read():
+                for line in self._proc.stdout:
+                    c = [x.strip() for x in line.split(",")]
+                    try:
+                        self.max_mhz = float(c[1])
+                        mask = sum(b for b, v in zip((1, 2, 4, 8), c[3:7]) if v.lower().startswith("active"))
+                        self.rows.append((time.perf_counter(), float(c[0]), float(c[2]), mask))
+                    except Exception:
+                        pass
+            threading.Thread(target=read, daemon=True).start()
+        except Exception:
+            self._proc = None
 
     def mark_begin(self):
         self.t0 = time.perf_counter()
@@ -132,24 +172,15 @@ class ClockSampler:
         self.t1 = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.05)
-        self.proc.terminate()
-        sm, pw, mx, reasons = [], [], None, set()
-        for ts, r in self.rows:
-            try:
-                mx = float(r[2])
-                if self.t0 is not None and not (self.t0 <= ts <= (self.t1 or ts) + 0.03):
-                    continue
-                sm.append(float(r[1])); pw.append(float(r[3]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
-                    samples=len(sm), power_w_max=max(pw) if pw else None)
+        self._stop.set()
+        if self._proc is not None:
+            self._proc.terminate()
+        if self._thread is None and self._proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["clock sampler unavailable"], samples=0)
+        rows = [r for r in self.rows if self.t0 is None or self.t0 <= r[0] <= (self.t1 or r[0]) + 0.005]
+        reasons = sorted(nm for nm, bit in self.R.items() if any(r[3] & bit for r in rows))
+        return dict(sm_mhz=float(np.median([r[1] for r in rows])) if rows else None, sm_max_mhz=self.max_mhz, reasons=reasons,
+                    samples=len(rows), power_w_max=max((r[2] for r in rows), default=None))
 
 
 def algorithmic_flops_half_move(rows, n, d, L, target):
@@ -274,7 +305,8 @@ def main():
 
     # ---- device-resident timing (`value`) --------------------------------------------------------------
     clocks = ClockSampler(local)
-    clocks.start()
+    if rank == 0:       # one sampler per box: several nvidia-smi loops contend for the driver lock and stall kernel launches
+        clocks.start()
     run(0, Wu)
     barrier()
     lib.hx_ctx_timing_enable(ctx, 1)
@@ -294,7 +326,7 @@ def main():
     lib.hx_ctx_timing_read(ctx, C.byref(c_ms), C.byref(c_kn), C.byref(c_all))
     ph_ms, ph_n = (C.c_double * 8)(), (C.c_int64 * 8)()
     lib.hx_ctx_timing_phases(ctx, ph_ms, ph_n)
-    names = ["main", "prep", "basis", "leapfrog", "finish"]
+    names = ["main", "prep", "basis", "leapfrog", "finish", "wait_peers", "push_rows", "mean"]
     phases = {nm: round(ph_ms[i] / max(ph_n[i], 1), 4) for i, nm in enumerate(names) if ph_n[i] > 0}
     lib.hx_ctx_timing_enable(ctx, 0)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -318,23 +350,48 @@ def main():
     k_launches = max(int(c_kn.value), 1)
     k_ms = c_ms.value / k_launches
     path = lib.hx_ctx_last_path(ctx)
+    form = args.leapfrog_form
+    if form == "auto":
+        form = "propagator" if (rows >= 6 * d and L >= 4) else "stepwise"
+    extra = {}
     if path == 1:
-        # tensor-core path: the bracketed kernel sequence is the momentum projection S0 = P0 C of one half-move
-        # (tcgen05 GEMM chunks, with the counter-based draw of the next chunk overlapped on a side stream)
-        kname = "tc::k_tc_gemm<256,EPI_STORE> (projection S0 = P0 C, bf16x3) + overlapped tc::k_rng_planes"
+        # tensor-core path: the bracketed section is the momentum projection S0 = P0 C of one half-move: tcgen05 GEMM chunks
+        # (128 x 256 tiles, K = n) while the counter-based draw of the NEXT half-move's P0 runs concurrently on the ALU pipes
+        kname = ("tc::k_tc_gemm<256,EPI_STORE,bf16 hi/lo> projection S0 = P0 C (all row chunks of a half-move), "
+                 "tc::k_rng_planes of the next half-move concurrent")
         flops = 2.0 * rows * n * d
-        note = ("algorithmic flops = 2*rows*n*d of the projection (SURVEY §8d first term); the kernel executes 3 bf16 "
-                "products per algorithmic product (split-bf16 operands for fp32-class accuracy)")
+        nK, dpad = -(-n // 64) * 64, -(-d // 256) * 256
+        executed = 3.0 * 2.0 * (-(-rows // 128) * 128) * nK * dpad
+        dB, dK = dpad, -(-d // 64) * 64
+        # executed tensor flops of the whole half-move in bf16 units (tf32 products count double: half the MMA rate)
+        if form == "propagator":
+            lf = 3 * 2.0 * rows * (2 * dK) * (2 * dB) + 2 * 3 * (2.0 * rows * (2 * dK) * dB + 2.0 * rows * dK * dB)
+            lf += 2 * 3 * (L + 1) * 2.0 * (2 * d) * dK * dB + 2 * 3 * 2.0 * (2 * d) * dK * dB
+        else:
+            lf = 3 * (L + 3) * 2.0 * rows * dK * dB
+        gram = 3 * 2.0 * dB * dB * nK
+        step_exec = executed + lf + gram
+        extra = dict(executed_tflops=executed / (k_ms * 1e-3) / 1e12, executed_frac=executed / (k_ms * 1e-3) / 1e12 / peak_tf,
+                     step_executed_tflops=step_exec * 2 * K / (ms * 1e-3) / 1e12,
+                     step_executed_frac=step_exec * 2 * K / (ms * 1e-3) / 1e12 / peak_tf)
+        note = ("achieved/frac = ALGORITHMIC flops 2*rows*n*d of the projection (SURVEY §8d first term) / section time. fp32-class "
+                "accuracy on bf16 tensor cores takes 3 products per algorithmic product (hi*hi + hi*lo + lo*hi), so frac <= 1/3 by "
+                "construction; executed_* counts the products actually issued (incl. d padded to 256); step_executed_* is the whole "
+                "iteration (projection + leapfrog/energy GEMMs + Gram; tf32 products counted double) against the same peak")
+        if args.workload == "c5" and world == 1:
+            extra["traffic_source"] = ("profiles/r01b_c5_ncu_full_summary.txt: dram bytes read+write of the 7 chunk launches of one "
+                                       "half-move (6 x 758.9 MB + 710.0 MB) = the P0 planes + C^T planes, i.e. no re-reads")
     else:
         kname = "k_walk_half" if mk == 0 else "k_side_half"
         flops = algorithmic_flops_half_move(rows, n, d, L, cfg["target"])
         note = "algorithmic flops = projected form 2*rows*n*d + (L+1)*(2*rows*d^2 [M] + grad) (SURVEY §8d)"
     achieved = flops / (k_ms * 1e-3) / 1e12
     roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=peak_tf,
-                    unit="TFLOP/s", frac=achieved / peak_tf, traffic=None, peak_source=peak_src,
+                    unit="TFLOP/s", frac=achieved / peak_tf,
+                    traffic=5.263e9 if "traffic_source" in extra else None, peak_source=peak_src,
                     flops_per_launch=flops, kernel_ms=k_ms, kernel_share_of_step=c_ms.value / ms, note=note,
                     half_move_algorithmic_tflops=algorithmic_flops_half_move(rows, n, d, L, cfg["target"]) * 2 * K
-                    / (ms * 1e-3) / 1e12)
+                    / (ms * 1e-3) / 1e12, **extra)
 
     # ---- end-to-end through the public API with host buffers (`e2e`) -----------------------------------
     e2e = None

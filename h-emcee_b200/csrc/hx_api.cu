@@ -86,6 +86,8 @@ extern "C" HX_API int hx_walk_prefetch(hx_ctx* ctx, int impl, int32_t n, int32_t
 extern "C" HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value) {
   if (!ctx) return hx_fail(HX_E_NULL, "hx_ctx_set_tuning: NULL ctx");
   if (what == 0) ctx->rng_ctas_per_sm = value;
+  else if (what == 1) ctx->proj_slices = value;
+  else if (what == 2) ctx->gram_tf32 = value;
   else return hx_fail(HX_E_DTYPE, "hx_ctx_set_tuning: unknown knob %d", what);
   return 0;
 }
@@ -843,9 +845,11 @@ static int run_iterations_sharded_t(hx_ctx* ctx, int impl, int move_kind, int ke
       const int ia = key_order == 0 ? (half == 0 ? 2 : 3) : (half == 0 ? 1 : 3);
       // the complement (and, from the previous iteration, this half) must be complete on this rank
       if (D.epoch > 0) {
+        if (int e = timing_mark(ctx, s, HX_PH_WAIT)) return e;
         k_dist_wait<<<1, 32, 0, s>>>(flags, world, D.epoch, timeout, nonfinite);
         HX_LAUNCH_CHECK("k_dist_wait");
       }
+      if (int e = timing_mark(ctx, s, HX_PH_STATS)) return e;
       T* Xa = Xf + ((size_t)half * n + row0) * d;
       T* Xb = Xf + (size_t)(1 - half) * n * d;
       T* lpa = lpf + (size_t)half * n + row0;
@@ -868,6 +872,7 @@ static int run_iterations_sharded_t(hx_ctx* ctx, int impl, int move_kind, int ke
       if (e) return e;
       // exchange: store the rank's updated rows (+ log-probs) into every peer's copy, then publish the epoch
       D.epoch += 1;
+      if (int e2 = timing_mark(ctx, s, HX_PH_PUSH)) return e2;
       const size_t x_off = ((size_t)half * n + row0) * d * sizeof(T), cnt = (size_t)rows * d * sizeof(T) / 16;
       const size_t l_off = D.lp_off + ((size_t)half * n + row0) * sizeof(T), lcnt = (size_t)rows * sizeof(T) / 16;
       int grid = (int)((cnt + 255) / 256);
@@ -875,6 +880,7 @@ static int run_iterations_sharded_t(hx_ctx* ctx, int impl, int move_kind, int ke
       if (grid < 1) grid = 1;
       k_dist_push<<<grid, 256, 0, s>>>(pt, rank, world, x_off, cnt, l_off, lcnt, D.flag_off, counter, D.epoch);
       HX_LAUNCH_CHECK("k_dist_push");
+      if (int e2 = timing_mark(ctx, s, -1)) return e2;
       ctx->launches += 2;
     }
   }

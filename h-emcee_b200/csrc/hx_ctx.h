@@ -12,7 +12,7 @@ enum Slot {
   // tensor-core path
   WS_TC_CT, WS_TC_MP, WS_TC_PP, WS_TC_P0, WS_TC_QC, WS_TC_GP, WS_TC_LPP, WS_TC_DKP, WS_TC_MASK, WS_TC_BO, WS_TC_S0,
   // propagator form of the Gaussian leapfrog
-  WS_TC_BX, WS_TC_BS, WS_TC_TQ, WS_TC_TS, WS_TC_TW, WS_TC_WP, WS_TC_B1, WS_TC_B2, WS_TC_ZB, WS_TC_ZT, WS_TC_QC2,
+  WS_TC_BX, WS_TC_BS, WS_TC_TQ, WS_TC_TS, WS_TC_TW, WS_TC_WP, WS_TC_B1, WS_TC_B2, WS_TC_ZB, WS_TC_ZT, WS_TC_QC2, WS_TC_PP32, WS_TC_S0P, WS_TC_CT32,
   WS_NSLOT
 };
 
@@ -57,13 +57,15 @@ struct hx_ctx {
   P0Job hint; int hint_valid;              // hx_walk_prefetch: the walk half-move after the next one
   int leap_form;                           // HX_LEAP_*
   HxDist dist;
+  int gram_tf32;                           // 1: Gram from tf32 hi/lo operands instead of bf16 hi/lo
+  int proj_slices;                         // split-K slices of the projection GEMM (0: default)
   int rng_ctas_per_sm;                     // resident CTAs/SM of the draw kernel (0: default 4)
 };
 
 // grow-only scratch slot
 int ws_get(hx_ctx* ctx, int slot, size_t bytes, void** out);
 // phases of a half-move for the timing hooks (hx_ctx_timing_read / hx_ctx_timing_phases)
-enum { HX_PH_MAIN = 0, HX_PH_PREP = 1, HX_PH_BASIS = 2, HX_PH_LEAP = 3, HX_PH_FINISH = 4, HX_PH_COUNT = 8 };
+enum { HX_PH_MAIN = 0, HX_PH_PREP = 1, HX_PH_BASIS = 2, HX_PH_LEAP = 3, HX_PH_FINISH = 4, HX_PH_WAIT = 5, HX_PH_PUSH = 6, HX_PH_STATS = 7, HX_PH_COUNT = 8 };
 int timing_mark(hx_ctx* ctx, cudaStream_t s, int phase);   // phase -1 closes the section
 inline int timing_begin(hx_ctx* ctx, cudaStream_t s) { return timing_mark(ctx, s, HX_PH_MAIN); }
 inline int timing_end(hx_ctx* ctx, cudaStream_t s) { return timing_mark(ctx, s, -1); }

@@ -66,8 +66,9 @@ static int make_tmap(hx_ctx* ctx, CUtensorMap* out, const void* base, uint64_t r
 
 // ---- elementwise / layout kernels -----------------------------------------------------------------------------
 // CT planes [2, dB_pad, Kp]: CT[c][j] = (X2[j][c] - mean[c]) / sqrt(n); zero outside (c < d, j < n)
+// planes32 (nullable): the same matrix as tf32 hi/lo planes [2, dB_pad, Kp] for the Gram product
 __global__ void k_center_planes_T(const float* __restrict__ X2, const float* __restrict__ mean, int n, int d,
-                                  int dB_pad, int Kp, __nv_bfloat16* __restrict__ planes) {
+                                  int dB_pad, int Kp, __nv_bfloat16* __restrict__ planes, float* __restrict__ planes32) {
   __shared__ float tile[32][33];
   const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const float sc = sqrtf((float)n);
@@ -84,6 +85,12 @@ __global__ void k_center_planes_T(const float* __restrict__ X2, const float* __r
       split_bf16(tile[threadIdx.x][cc], hi, lo);
       planes[(size_t)c * Kp + j] = hi;
       planes[plane + (size_t)c * Kp + j] = lo;
+      if (planes32) {
+        float h32, l32;
+        split_tf32(tile[threadIdx.x][cc], h32, l32);
+        planes32[(size_t)c * Kp + j] = h32;
+        planes32[plane + (size_t)c * Kp + j] = l32;
+      }
     }
   }
 }
@@ -110,7 +117,10 @@ __global__ void k_split_planes(const float* __restrict__ src, int dim_r, int dim
   }
 }
 
-// out[i][j] = sum_k A[i][k] * B[k][j]  (dim x dim, exact fp32 FMA; 64x64 tile, 4x4 per thread)
+// out[i][j] = sum_k A[i][k] * B[k][j]  (dim x dim; fp32 inputs, fp64 products and accumulation, result rounded to fp32 once;
+// 64x64 tile, 4x4 per thread).  Used for B = M P: the product of the Gram matrix (eigenvalues up to ~1e3 at kappa = 1e4) and
+// the precision (up to ~10) is O(1) by cancellation, and accumulating it in fp32 costs ~1e-4 of the ensemble scale in the
+// proposed positions (measured against an f64 integration; oracle-side check in tests/test_oracle_moves.py).
 __global__ void __launch_bounds__(256) k_small_gemm(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                     int dim, float* __restrict__ out, int ldo) {
   constexpr int TB = 64, KB = 16;
@@ -118,11 +128,11 @@ __global__ void __launch_bounds__(256) k_small_gemm(const float* __restrict__ A,
   __shared__ __align__(16) float sb[KB][TB + 4];
   const int ti = blockIdx.y * TB, tj = blockIdx.x * TB;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][4];
+  double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
   for (int k0 = 0; k0 < dim; k0 += KB) {
     __syncthreads();
     for (int idx = threadIdx.x; idx < KB * TB; idx += 256) {
@@ -140,7 +150,7 @@ __global__ void __launch_bounds__(256) k_small_gemm(const float* __restrict__ A,
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma((double)a[i], (double)b[j], acc[i][j]);
     }
   }
 #pragma unroll
@@ -150,7 +160,7 @@ __global__ void __launch_bounds__(256) k_small_gemm(const float* __restrict__ A,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gj = tj + 4 * tx + j;
-      if (gj < dim) out[(size_t)gi * ldo + gj] = acc[i][j];
+      if (gj < dim) out[(size_t)gi * ldo + gj] = (float)acc[i][j];
     }
   }
 }
@@ -553,17 +563,25 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
 
   // (1) complement statistics: mean_dev already holds mean_0(X2) (hx_api.cu); C^T planes, M = C^T C, Bop = M P
   if (int e = timing_mark(ctx, s, HX_PH_PREP)) return e;
+  // The Gram matrix enters every kick through B = P M, where the ill-conditioning of the target amplifies its error.
+  // hx_ctx_set_tuning(2, 1) forms it from tf32 hi/lo operands (2^-21 per product) instead of bf16 hi/lo; on B200 that did
+  // not improve the proposal against an f64 integration (scripts/slices_sweep.py), so bf16 hi/lo is the default.
+  const bool gram32 = ctx->gram_tf32 && nprod == 3;
+  void* pCT32 = nullptr;
+  if (gram32)
+    if (int e = ws_get(ctx, WS_TC_CT32, (size_t)2 * dAB * nK * sizeof(float), &pCT32)) return e;
   {
     dim3 g((nK + 31) / 32, (dAB + 31) / 32), b(32, 8);
-    k_center_planes_T<<<g, b, 0, s>>>(X2, mean_dev, n, d, dAB, nK, (bf*)pCT);
+    k_center_planes_T<<<g, b, 0, s>>>(X2, mean_dev, n, d, dAB, nK, (bf*)pCT, (float*)pCT32);
     HX_LAUNCH_CHECK("k_center_planes_T");
   }
   GemmArgs ga;
   memset(&ga, 0, sizeof(ga));
   ga.nprod = nprod;
   {
-    // Gram M = C^T C: only (d/128) x (d/256) output tiles with K = n, so split K over enough slices to fill the SMs
-    const int tiles = ((d + BN - 1) / BN) * ((d + kBM - 1) / kBM), nkb = nK / 64;
+    // Gram M = C^T C: only (d/128) x (d/256) output tiles with K = n, so split K over enough slices to fill the SMs (the
+    // fp32 slice sum also shortens the tensor core's truncating accumulation chains)
+    const int tiles = ((d + BN - 1) / BN) * ((d + kBM - 1) / kBM), nkb = nK / (gram32 ? 32 : 64);
     int slices = ctx->sm_count / tiles;
     if (slices > 16) slices = 16;
     if (slices > nkb) slices = nkb;
@@ -575,7 +593,11 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
       if (int e = ws_get(ctx, WS_GRAMP, (size_t)slices * d * d * sizeof(float), &pMs)) return e;
     ga.M = d; ga.N = d; ga.out = (float*)pMs; ga.ldo = d;
     ga.kb_per_slice = slices > 1 ? kbs : 0; ga.slice_stride = (size_t)d * d;
-    if (int e = launch_gemm<EPI_STORE, KIND_BF16>(ctx, pCT, dAB, pCT, dAB, nK, ga, s, 0, 0, slices)) return e;
+    if (gram32) {
+      if (int e = launch_gemm<EPI_STORE, KIND_TF32>(ctx, pCT32, dAB, pCT32, dAB, nK, ga, s, 0, 0, slices)) return e;
+    } else {
+      if (int e = launch_gemm<EPI_STORE, KIND_BF16>(ctx, pCT, dAB, pCT, dAB, nK, ga, s, 0, 0, slices)) return e;
+    }
     if (slices > 1) {
       k_sum_slices_f<<<grid_for((size_t)d * d, 256), 256, 0, s>>>((const float*)pMs, slices, (size_t)d * d, (float*)pM);
       HX_LAUNCH_CHECK("k_sum_slices_f");
@@ -594,7 +616,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   //     trajectories with the same kick/drift recurrence (tf32 hi/lo operands), giving q_L - mu = z0 Tq, S_L = z0 Ts
   //     and the impulse-weighted position sum Qs = z0 W; fold the precision into W for the kinetic-energy product.
   void *pBX = nullptr, *pBS = nullptr, *pTQ = nullptr, *pTS = nullptr, *pTW = nullptr, *pWP = nullptr, *pB1 = nullptr,
-       *pB2 = nullptr, *pZB = nullptr, *pZT = nullptr;
+       *pB2 = nullptr, *pZB = nullptr, *pZT = nullptr, *pPP32 = nullptr;
   if (prop) {
     if (int e = timing_mark(ctx, s, HX_PH_BASIS)) return e;
     const size_t bsz = (size_t)bR * d * sizeof(float);
@@ -615,14 +637,20 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     la.eps = eps; la.Q = (float*)pTQ; la.S = (float*)pTS; la.S0 = (float*)pBS; la.Qs = (float*)pTW; la.Bo = (const float*)pBo;
     la.prec = (const float*)tgt->precision; la.ld_prec = tgt->ld; la.pBoP = pBoP; la.pPP = pPP; la.pQC = pQC; la.pQC2 = pQC2; la.pQsP = pQsP;
     la.lpp = nullptr; la.dkp = nullptr; la.energies = 0;
-    if (int e = leapfrog_bform<KIND_TF32>(ctx, la, s)) return e;
+    // the basis run uses the operand kind of the apply GEMM: its rounding (2^-16 per bf16x3 product) is of the same order
+    // as the apply's, and bf16 halves both the MMA time and the number of TMA round trips of these latency-bound launches
+    if (int e = g1_tf32 ? leapfrog_bform<KIND_TF32>(ctx, la, s) : leapfrog_bform<KIND_BF16>(ctx, la, s)) return e;
+    // tf32 hi/lo planes of the precision matrix for the energy products
+    if (int e = ws_get(ctx, WS_TC_PP32, (size_t)2 * dB * dK * sizeof(float), &pPP32)) return e;
+    k_split_planes<KIND_TF32><<<grid_for((size_t)dB * dK, 256), 256, 0, s>>>((const float*)tgt->precision, d, d, tgt->ld, dB, dK, (float*)pPP32);
+    HX_LAUNCH_CHECK("k_split_planes(P, tf32)");
     // WP = W P  (rows: basis index): A = planes of W, B = planes of P (symmetric)
     k_split_planes<KIND_TF32><<<grid_for((size_t)bRA * dK, 256), 256, 0, s>>>((const float*)pTW, bR, d, d, bRA, dK, (float*)pQsP);
     HX_LAUNCH_CHECK("k_split_planes(W)");
     GemmArgs gw;
     memset(&gw, 0, sizeof(gw));
     gw.nprod = 3; gw.M = bR; gw.N = d; gw.out = (float*)pWP; gw.ldo = d;
-    if (int e = launch_gemm<EPI_STORE, KIND_TF32>(ctx, pQsP, bRA, pPP, dB, dK, gw, s)) return e;
+    if (int e = launch_gemm<EPI_STORE, KIND_TF32>(ctx, pQsP, bRA, pPP32, dB, dK, gw, s)) return e;
     // B operands: [Tq ; Ts]^T for the apply GEMM, (W P)^T for the kinetic-energy product
     dim3 tg((K2 + 31) / 32, (dB + 31) / 32), tb(32, 8);
     if (g1_tf32) {
@@ -647,15 +675,33 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   {
     std::vector<cudaEvent_t>& evs = *ctx->ev_chunk[cur];
     if (int e = timing_begin(ctx, s)) return e;
+    // optional split-K (hx_ctx_set_tuning(1, slices)): slices of K summed in fp32 in a fixed order.  Measured on B200
+    // (scripts/slices_sweep.py): no accuracy gain for the projection, +20 % time, so the default is one slice.
+    const int nkb = nK / 64;
+    int slices = ctx->proj_slices > 0 ? ctx->proj_slices : 1;
+    if (slices > nkb / 16) slices = nkb / 16 > 0 ? nkb / 16 : 1;      // at least 16 K-blocks (1024 walkers) per slice
+    const int kbs = (nkb + slices - 1) / slices;
+    slices = (nkb + kbs - 1) / kbs;
+    void* pS0P = nullptr;
+    if (slices > 1)
+      if (int e = ws_get(ctx, WS_TC_S0P, (size_t)slices * chunk * d * sizeof(float), &pS0P)) return e;
     for (int c = 0; c < nchunks; ++c) {
       const int r0 = c * chunk;
       const int rc = (rows - r0) < chunk ? (rows - r0) : chunk;
       HX_CUDA(cudaStreamWaitEvent(s, evs[c], 0));
-      ga.M = rc; ga.N = d; ga.out = S0 + (size_t)r0 * d; ga.ldo = d;
+      ga.M = rc; ga.N = d; ga.ldo = d;
+      ga.out = slices > 1 ? (float*)pS0P : S0 + (size_t)r0 * d;
+      ga.kb_per_slice = slices > 1 ? kbs : 0; ga.slice_stride = (size_t)rc * d;
       if (int e = launch_gemm<EPI_STORE, KIND_BF16>(ctx, Pbuf[cur] + (size_t)r0 * nK, rA, pCT, dAB, nK, ga, s,
-                                                    (uint64_t)rA + pad_to(rc, kBM)))
+                                                    (uint64_t)rA + pad_to(rc, kBM), 0, slices))
         return e;
+      if (slices > 1) {
+        k_sum_slices_f<<<grid_for((size_t)rc * d, 256), 256, 0, s>>>((const float*)pS0P, slices, (size_t)rc * d, S0 + (size_t)r0 * d);
+        HX_LAUNCH_CHECK("k_sum_slices_f");
+        ctx->launches += 1;
+      }
     }
+    ga.kb_per_slice = 0; ga.slice_stride = 0;
     if (int e = timing_mark(ctx, s, HX_PH_LEAP)) return e;
   }
 
@@ -681,7 +727,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     GemmArgs g3;
     memset(&g3, 0, sizeof(g3));
     g3.nprod = 3; g3.M = rows; g3.N = d; g3.NT = NT; g3.mu = mu; g3.X = Q; g3.part = (float*)pLPP;
-    if (int e = launch_gemm<EPI_DOT, KIND_TF32>(ctx, pQC, rQ, pPP, dB, dK, g3, s)) return e;
+    if (int e = launch_gemm<EPI_DOT, KIND_TF32>(ctx, pQC, rQ, pPP32, dB, dK, g3, s)) return e;
   } else {
     LeapArgs la;
     la.X1 = X1; la.mu = mu; la.rows = rows; la.d = d; la.rA = rA; la.dK = dK; la.dB = dB; la.NT = NT; la.L = L; la.eps = eps;

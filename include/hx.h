@@ -118,7 +118,9 @@ HX_API int hx_ctx_set_leapfrog_form(hx_ctx* ctx, int form);
  * of a rows x n shard alone, (1) its projection GEMM alone, (2) both running concurrently on two streams.  */
 HX_API int hx_tc_microbench(hx_ctx* ctx, int mode, int32_t n, int32_t rows, int32_t dim, int32_t reps, double* ms_out /*[3]: total,
                      GEMM stream, draw stream*/, void* stream);
-/* tuning knobs (what = 0: resident CTAs per SM of the momentum-draw kernel, default 4) */
+/* tuning knobs: what = 0 resident CTAs per SM of the momentum-draw kernel (default 4); what = 1 split-K slices of the
+ * projection GEMM, summed in fp32 in a fixed order (default 1 = accumulate all of K = n inside the tensor core; measured:
+ * no accuracy gain from more); what = 2: 1 = Gram matrix from tf32 hi/lo operands instead of bf16 hi/lo (default 0)         */
 HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value);
 /* which kernel the timing hooks bracketed last: 0 = fused SIMT half-move, 1 = tcgen05 projection GEMM */
 HX_API int hx_ctx_last_path(const hx_ctx* ctx);
@@ -131,7 +133,8 @@ HX_API int hx_ctx_timing_enable(hx_ctx* ctx, int enable);
 HX_API int hx_ctx_timing_read(hx_ctx* ctx, double* kernel_ms, int64_t* kernel_launches, int64_t* all_launches);
 /* per-phase breakdown of the last hx_ctx_timing_read (8 entries each): [0] dominant kernel section (fused SIMT half-move, or
  * the projection GEMM on the tensor-core path), [1] complement statistics (centre, Gram, M P), [2] propagator basis run,
- * [3] leapfrog apply / kicks + energy products, [4] finish (energies, accept, chain emit); summed ms and interval counts */
+ * [3] leapfrog apply / kicks + energy products, [4] finish (energies, accept, chain emit), [5] waiting for the peers' rows,
+ * [6] storing the updated rows into the peers (sharded loop), [7] complement mean; summed ms and interval counts */
 HX_API int hx_ctx_timing_phases(hx_ctx* ctx, double* phase_ms, int64_t* phase_count);
 
 /* ---- (1) RNG: bit-exact jax.random subset ------------------------------------------------
