@@ -206,6 +206,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--precision", default="auto", choices=["auto", "exact", "bf16x3", "bf16", "tf32x3"])
     ap.add_argument("--leapfrog-form", default="auto", choices=["auto", "stepwise", "propagator"])
+    ap.add_argument("--tune", action="append", default=[], help="hx_ctx_set_tuning knob as what=value (diagnostics)")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -264,6 +265,9 @@ def main():
         x0 = x0 * 0.3 + 1.0
     lib = _lib.load()
     ctx = _rt.ctx(dev)
+    for kv in args.tune:
+        w_, v_ = kv.split("=")
+        _lib.check(lib.hx_ctx_set_tuning(ctx, int(w_), int(v_)), "hx_ctx_set_tuning")
     K, Wu = args.steps, args.warmup
     keys_dev = hx.random.split_device(k_run, 4 * (K + Wu))
     keys_host = keys_dev.cpu().numpy().view(np.uint32).reshape(K + Wu, 4, 2)

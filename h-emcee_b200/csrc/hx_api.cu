@@ -88,6 +88,7 @@ extern "C" HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value) {
   if (what == 0) ctx->rng_ctas_per_sm = value;
   else if (what == 1) ctx->proj_slices = value;
   else if (what == 2) ctx->gram_tf32 = value;
+  else if (what == 3) ctx->energy_bf16 = value;
   else return hx_fail(HX_E_DTYPE, "hx_ctx_set_tuning: unknown knob %d", what);
   return 0;
 }

@@ -57,6 +57,7 @@ struct hx_ctx {
   P0Job hint; int hint_valid;              // hx_walk_prefetch: the walk half-move after the next one
   int leap_form;                           // HX_LEAP_*
   HxDist dist;
+  int energy_bf16;                         // 1: propagator-form energy products from bf16 hi/lo operands (default tf32 hi/lo)
   int gram_tf32;                           // 1: Gram from tf32 hi/lo operands instead of bf16 hi/lo
   int proj_slices;                         // split-K slices of the projection GEMM (0: default)
   int rng_ctas_per_sm;                     // resident CTAs/SM of the draw kernel (0: default 4)

@@ -60,6 +60,7 @@ struct GemmArgs {
   // two column blocks of blk_cols (padded) columns each; block 0: Q = acc + mu, planes_out (tf32 hi/lo) <- split(acc);
   // block 1: S = acc.  blk_cols = 0 for the other epilogues (one block).
   int blk_cols;
+  int planes_bf16;   // EPI_PROP: kind of planes_out (1 bf16 hi/lo, 0 tf32 hi/lo)
   // split-K (EPI_STORE only): grid.z slices of kb_per_slice K-blocks each, slice z stores to out + z * slice_stride; the
   // caller adds the slices in a fixed order (also shortens the tensor core's truncating accumulation chains).  0 = no split.
   int kb_per_slice; size_t slice_stride;
@@ -184,7 +185,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  // two fp32 accumulators: columns [0, BN) take the hi*hi products, [BN, 2 BN) the two hi*lo correction products.  The tensor
+  // core truncates at every accumulation step; keeping the 2^-9-sized corrections out of the main chain cuts the number of
+  // truncations of the large partial sum by 3x, and the two parts are added once, round-to-nearest, in the epilogue.
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -229,7 +233,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const uint64_t bd = umma_desc_k128(p == 1 ? b_lo : b_hi);
 #pragma unroll
           for (int k = 0; k < KD::ROW_ELEMS / KD::UMMA_K; ++k) {   // 4 steps of 32 bytes inside the 128-byte swizzle row
-            umma_issue<KIND>(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | p | k) != 0 ? 1u : 0u);
+            const uint32_t acc = p == 0 ? ((kb | k) != 0 ? 1u : 0u) : ((kb | (p - 1) | k) != 0 ? 1u : 0u);
+            umma_issue<KIND>(tmem_base + (p == 0 ? 0u : (uint32_t)BN), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, acc);
           }
         }
         umma_commit(&empty[s]);     // frees the smem stage when these MMAs have read it
@@ -254,6 +259,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (col0 >= g.N) break;           // warp-uniform
       float v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cc * 32), v);
+      if (g.nprod == 3) {
+        float vc[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(BN + cc * 32), vc);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += vc[j];
+      }
       if (!rok) continue;
       const int nval = min(32, g.N - col0);
       const bool fast = vec && nval == 32;
@@ -271,7 +282,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           } else {
             store32(g.Q + base, v, nval, fast);
           }
-          store_planes32<KIND_TF32>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, v, nval, fast);
+          if (g.planes_bf16)
+            store_planes32<KIND_BF16>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, v, nval, fast);
+          else
+            store_planes32<KIND_TF32>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, v, nval, fast);
         } else {
           store32(g.S + base, v, nval, fast);
         }
@@ -328,7 +342,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 

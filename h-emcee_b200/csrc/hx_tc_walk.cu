@@ -521,6 +521,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   // built once per half-move from 2d basis trajectories and applied to all walkers in one GEMM
   bool prop = ctx->leap_form == HX_LEAP_PROPAGATOR || (ctx->leap_form == HX_LEAP_AUTO && rows >= 6 * d && L >= 4);
   const bool g1_tf32 = ctx->precision == HX_PREC_TF32X3;
+  const bool e_bf16 = ctx->energy_bf16 && !g1_tf32;          // propagator form: energy products from bf16 hi/lo operands
   const int rQ = prop ? (rA > bRA ? rA : bRA) : rA;            // rows of the q - mu operand planes (basis run reuses them)
 
   void *pCT, *pM, *pBo, *pBoP, *pPP, *pP0, *pQC, *pQC2, *pQsP, *pS0, *pQs, *pLPP, *pDKP;
@@ -629,7 +630,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     if (int e = ws_get(ctx, WS_TC_B1, (size_t)2 * (2 * dB) * K2 * sizeof(float), &pB1)) return e;
     if (int e = ws_get(ctx, WS_TC_B2, (size_t)2 * dB * K2 * sizeof(float), &pB2)) return e;
     if (int e = ws_get(ctx, WS_TC_ZB, g1_tf32 ? 16 : (size_t)2 * rA * K2 * sizeof(bf), &pZB)) return e;
-    if (int e = ws_get(ctx, WS_TC_ZT, (size_t)2 * rA * K2 * sizeof(float), &pZT)) return e;
+    if (int e = ws_get(ctx, WS_TC_ZT, e_bf16 ? 16 : (size_t)2 * rA * K2 * sizeof(float), &pZT)) return e;
     k_basis_init<<<grid_for((size_t)bR * d, 256), 256, 0, s>>>((float*)pBX, (float*)pBS, d);
     HX_LAUNCH_CHECK("k_basis_init");
     LeapArgs la;
@@ -660,7 +661,8 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
       k_transpose_planes<KIND_BF16><<<tg, tb, 0, s>>>((const float*)pTQ, d, dK, dB, 2 * dB, 0, (bf*)pB1);
       k_transpose_planes<KIND_BF16><<<tg, tb, 0, s>>>((const float*)pTS, d, dK, dB, 2 * dB, dB, (bf*)pB1);
     }
-    k_transpose_planes<KIND_TF32><<<tg, tb, 0, s>>>((const float*)pWP, d, dK, dB, dB, 0, (float*)pB2);
+    if (e_bf16) k_transpose_planes<KIND_BF16><<<tg, tb, 0, s>>>((const float*)pWP, d, dK, dB, dB, 0, (bf*)pB2);
+    else k_transpose_planes<KIND_TF32><<<tg, tb, 0, s>>>((const float*)pWP, d, dK, dB, dB, 0, (float*)pB2);
     HX_LAUNCH_CHECK("k_transpose_planes");
     ctx->launches += 5;
   }
@@ -708,13 +710,13 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   // (4) leapfrog + energy products
   if (prop) {
     k_z0_planes<<<grid_for((size_t)rA * K2 / 4, 256), 256, 0, s>>>(X1, mu, S0, rows, d, rA, dK, g1_tf32 ? nullptr : (bf*)pZB,
-                                                                   (float*)pZT);
+                                                                   e_bf16 ? nullptr : (float*)pZT);
     HX_LAUNCH_CHECK("k_z0_planes");
     ctx->launches += 1;
     GemmArgs g1;
     memset(&g1, 0, sizeof(g1));
     g1.nprod = 3; g1.M = rows; g1.N = d; g1.mu = mu; g1.Q = Q; g1.S = S; g1.blk_cols = dB;
-    g1.planes_out = pQC; g1.rows_out_pad = rQ; g1.Kout_p = dK;
+    g1.planes_out = pQC; g1.rows_out_pad = rQ; g1.Kout_p = dK; g1.planes_bf16 = e_bf16 ? 1 : 0;
     if (g1_tf32) {
       if (int e = launch_gemm<EPI_PROP, KIND_TF32>(ctx, pZT, rA, pB1, 2 * dB, K2, g1, s, 0, 2 * dB)) return e;
     } else {
@@ -723,11 +725,19 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     GemmArgs g2;
     memset(&g2, 0, sizeof(g2));
     g2.nprod = 3; g2.M = rows; g2.N = d; g2.NT = NT; g2.X = S0; g2.Y = S; g2.part = (float*)pDKP;
-    if (int e = launch_gemm<EPI_DOT, KIND_TF32>(ctx, pZT, rA, pB2, dB, K2, g2, s)) return e;
+    if (e_bf16) {
+      if (int e = launch_gemm<EPI_DOT, KIND_BF16>(ctx, pZB, rA, pB2, dB, K2, g2, s)) return e;
+    } else {
+      if (int e = launch_gemm<EPI_DOT, KIND_TF32>(ctx, pZT, rA, pB2, dB, K2, g2, s)) return e;
+    }
     GemmArgs g3;
     memset(&g3, 0, sizeof(g3));
     g3.nprod = 3; g3.M = rows; g3.N = d; g3.NT = NT; g3.mu = mu; g3.X = Q; g3.part = (float*)pLPP;
-    if (int e = launch_gemm<EPI_DOT, KIND_TF32>(ctx, pQC, rQ, pPP32, dB, dK, g3, s)) return e;
+    if (e_bf16) {
+      if (int e = launch_gemm<EPI_DOT, KIND_BF16>(ctx, pQC, rQ, pPP, dB, dK, g3, s)) return e;      // pPP: bf16 planes from the basis run
+    } else {
+      if (int e = launch_gemm<EPI_DOT, KIND_TF32>(ctx, pQC, rQ, pPP32, dB, dK, g3, s)) return e;
+    }
   } else {
     LeapArgs la;
     la.X1 = X1; la.mu = mu; la.rows = rows; la.d = d; la.rA = rA; la.dK = dK; la.dB = dB; la.NT = NT; la.L = L; la.eps = eps;
