@@ -207,6 +207,7 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "exact", "bf16x3", "bf16", "tf32x3"])
     ap.add_argument("--leapfrog-form", default="auto", choices=["auto", "stepwise", "propagator"])
     ap.add_argument("--tune", action="append", default=[], help="hx_ctx_set_tuning knob as what=value (diagnostics)")
+    ap.add_argument("--ess-iters", type=int, default=160, help="iterations of the ESS/s leg (0 = skip)")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -451,6 +452,42 @@ def main():
                         "the rank's own rows; time = max over ranks")
         assert out.shape == (K, 2 * rows, d)
 
+    # ---- ESS/s leg (BASELINE metric): tau_int via the reference's estimator (autocorr.py:44-118, c=5, tol=50,
+    #      quiet) on a fixed subset of <= 16 dims x <= 1024 walkers, after a burn-in; device-resident state, untimed by `value`
+    ess = None
+    if world == 1 and args.ess_iters > 0 and not args.no_e2e:
+        from hemcee_b200 import autocorr as hac
+        Tb, Te, Bq = 48, args.ess_iters, 8
+        Xe = x0.clone(); lpe = tgt.log_prob(Xe)
+        ke = hx.random.split_device(hx.random.PRNGKey(12345), 4 * (Tb + Te))
+        acc_e = torch.zeros(W, dtype=torch.int32, device=dev)
+        cbuf = torch.empty((Bq, W, d), dtype=tdt, device=dev)
+        dims = torch.linspace(0, d - 1, min(16, d)).long().to(dev)
+        wsel = torch.linspace(0, W - 1, min(1024, W)).long().to(dev)
+        sub = torch.empty((Te, wsel.numel(), dims.numel()), dtype=tdt, device=dev)
+
+        def run_e(t0, T, store):
+            for b0 in range(0, T, Bq):
+                nb_ = min(Bq, T - b0)
+                _lib.check(lib.hx_run_iterations(ctx, _rt.dtype_code(tdt), _rt.impl_code(), mk, 0, desc, _rt.ptr(Xe), _rt.ptr(lpe), n,
+                                                 eps, L, _rt.ptr(ke[4 * (t0 + b0):]), nb_, _rt.ptr(cbuf), None, _rt.ptr(acc_e),
+                                                 _rt.ptr(flag), _rt.stream(dev)), "run_ess")
+                if store:
+                    sub[b0:b0 + nb_] = cbuf[:nb_][:, wsel][:, :, dims]
+        run_e(0, Tb, False)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        run_e(Tb, Te, True)
+        torch.cuda.synchronize(dev)
+        el = time.perf_counter() - t0
+        tau = np.asarray(hac.integrated_time(sub, c=5, tol=50, quiet=True))
+        tmax = float(np.nanmax(tau))
+        ess = dict(value=Te * W / tmax / el, unit="ESS/s", tau_max=tmax, tau_min=float(np.nanmin(tau)), iterations=Te, burn_in=Tb,
+                   seconds=el, reliable=bool(50 * tmax <= Te), dims=int(dims.numel()), walkers_in_estimate=int(wsel.numel()),
+                   note="min over the sampled dims of (iterations * walkers / tau_int) / wall time of those iterations; fixed "
+                        "step size and L (no adaptation), chain started from N(0, I)")
+        del sub, cbuf
+
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_reference(args.workload, 1000, 1, budget_s=15.0)
@@ -461,7 +498,7 @@ def main():
                     dtype="f64" if cfg["x64"] else "f32", data="synthetic", config=conf, roofline=roofline,
                     cpu_baseline=cb, clocks=clk, e2e=e2e, gpu_launches=int(c_all.value) if world == 1 else int(c_all.value),
                     acceptance_rate=acc_rate, nonfinite=int(flag.item()), precision=args.precision, leapfrog_form=args.leapfrog_form,
-                    phase_ms_per_half_move=phases)
+                    phase_ms_per_half_move=phases, ess=ess)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
