@@ -106,8 +106,9 @@ class ClockSampler:
     driver lock (2x slower steps at 8 ranks), so only rank 0 samples and it does so with direct NVML calls; the fallback is
     one `nvidia-smi -lms 100` process.  Only samples between mark_begin() and mark_end() are reported."""
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period=0.01):
         self.gpu = gpu_index
+        self.period = period
         self.rows = []          # (t, sm_mhz, power_w, reasons bitmask)
         self.max_mhz = None
         self.t0 = self.t1 = None
@@ -135,7 +136,7 @@ class ClockSampler:
                                           int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
                     except Exception:
                         pass
-                    time.sleep(0.01)
+                    time.sleep(self.period)
             self._thread = threading.Thread(target=loop, daemon=True)
             self._thread.start()
             self.R = dict(hw_slowdown=pynvml.nvmlClocksEventReasonHwSlowdown, hw_thermal_slowdown=pynvml.nvmlClocksEventReasonHwThermalSlowdown,
@@ -207,6 +208,7 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "exact", "bf16x3", "bf16", "tf32x3"])
     ap.add_argument("--leapfrog-form", default="auto", choices=["auto", "stepwise", "propagator"])
     ap.add_argument("--tune", action="append", default=[], help="hx_ctx_set_tuning knob as what=value (diagnostics)")
+    ap.add_argument("--clock-period", type=float, default=0.01, help="NVML sampling period in s (0 = no clock sampling)")
     ap.add_argument("--ess-iters", type=int, default=160, help="iterations of the ESS/s leg (0 = skip)")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
@@ -309,8 +311,8 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident timing (`value`) --------------------------------------------------------------
-    clocks = ClockSampler(local)
-    if rank == 0:       # one sampler per box: several nvidia-smi loops contend for the driver lock and stall kernel launches
+    clocks = ClockSampler(local, args.clock_period)
+    if rank == 0 and args.clock_period > 0:       # one sampler per box: several nvidia-smi loops contend for the driver lock and stall kernel launches
         clocks.start()
     run(0, Wu)
     barrier()
@@ -319,7 +321,9 @@ def main():
     barrier()
     clocks.mark_begin()
     e0.record()
+    t_host0 = time.perf_counter()
     run(Wu, K)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / K      # host time to enqueue one iteration (launches are async)
     e1.record()
     barrier()
     clocks.mark_end()
@@ -498,7 +502,7 @@ def main():
                     dtype="f64" if cfg["x64"] else "f32", data="synthetic", config=conf, roofline=roofline,
                     cpu_baseline=cb, clocks=clk, e2e=e2e, gpu_launches=int(c_all.value) if world == 1 else int(c_all.value),
                     acceptance_rate=acc_rate, nonfinite=int(flag.item()), precision=args.precision, leapfrog_form=args.leapfrog_form,
-                    phase_ms_per_half_move=phases, ess=ess)
+                    phase_ms_per_half_move=phases, ess=ess, host_enqueue_ms_per_step=host_enqueue_ms)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -32,7 +32,9 @@ static int dispatch_tile(int ldd, int rows, int sm_count, F&& f) {
     if (CG >= 128) return f.template run<Cfg<T>::BMa, Cfg<T>::TMa, 256>();
     return f.template run<Cfg<T>::BMb, Cfg<T>::TMb, 256>();
   }
-  if (small) return f.template run<8, 1, 256>();
+  // narrow targets (dim < 128) are RNG/latency-bound: prefer the 8-row tile unless the 32-row tile already gives >= 16
+  // resident warps per SM (4 warps per CTA)
+  if (small || (long long)((rows + 31) / 32) * 4 < 16ll * sm_count) return f.template run<8, 1, 256>();
   return f.template run<32, 4, 256>();
 }
 

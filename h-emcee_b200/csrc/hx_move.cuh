@@ -101,20 +101,70 @@ __device__ __forceinline__ void gemm_rows(T (&acc)[TM][4], const TileMap<T, BM, 
   constexpr int LDA = BM + 4;
 #pragma unroll
   for (int r = 0; r < TM; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = T(0); }
+  // Small row tiles (TM <= 4) are latency-bound: the B rows of a K-chunk are fetched into registers BEFORE the A tile is
+  // produced (for the momentum projection that is the RNG), so the L2 latency of the kBK independent loads overlaps the fill
+  // instead of being paid 4 rows at a time inside the FMA loop.  Same FMA order => bit-identical results.
+  constexpr int PRE = (TM <= 4 && BM >= 8) ? ((sizeof(T) == 4) ? kBK / 2 : kBK / 4) : 0;   // not the 1024-thread wide-dim tiles
   for (int k0 = 0; k0 < K; k0 += kBK) {
+    const T* Bp = B + 4 * (tm.active ? tm.cg : 0);
+    T breg[PRE > 0 ? PRE : 1][4];
+    if constexpr (PRE > 0) {
+      if (tm.active) {
+#pragma unroll
+        for (int kk = 0; kk < PRE; ++kk) {
+          int k = k0 + kk;
+          k = (k < K) ? k : (K - 1);
+          ld4_ro(Bp + (size_t)k * ldb, breg[kk]);
+        }
+      }
+    }
     __syncthreads();
     load(As, k0, tm.tid, tm.nthreads);
     __syncthreads();
     if (tm.active) {
-      const T* Bp = B + 4 * tm.cg;
       const T* Ap = As + tm.rg * TM;
+      if constexpr (PRE > 0) {
+#pragma unroll
+        for (int h = 0; h < kBK / PRE; ++h) {
+          if (h > 0) {
+#pragma unroll
+            for (int kk = 0; kk < PRE; ++kk) {
+              int k = k0 + h * PRE + kk;
+              k = (k < K) ? k : (K - 1);
+              ld4_ro(Bp + (size_t)k * ldb, breg[kk]);
+            }
+          }
+#pragma unroll
+          for (int kk = 0; kk < PRE; ++kk) {
+            const int ka = h * PRE + kk;
+            if constexpr (TM % 4 == 0) {
+#pragma unroll
+              for (int r4 = 0; r4 < TM / 4; ++r4) {
+                T a[4];
+                ld4(Ap + ka * LDA + 4 * r4, a);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) acc[4 * r4 + i][j] = fma_t(a[i], breg[kk][j], acc[4 * r4 + i][j]);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int r = 0; r < TM; ++r) {
+                const T a = Ap[ka * LDA + r];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[r][j] = fma_t(a, breg[kk][j], acc[r][j]);
+              }
+            }
+          }
+        }
+      } else {
 #pragma unroll 4
-      for (int kk = 0; kk < kBK; ++kk) {
-        int k = k0 + kk;
-        k = (k < K) ? k : (K - 1);  // tail rows multiply zero-filled A
-        T b[4];
-        ld4_ro(Bp + (size_t)k * ldb, b);
-        if constexpr (TM % 4 == 0) {
+        for (int kk = 0; kk < kBK; ++kk) {
+          int k = k0 + kk;
+          k = (k < K) ? k : (K - 1);  // tail rows multiply zero-filled A
+          T b[4];
+          ld4_ro(Bp + (size_t)k * ldb, b);
 #pragma unroll
           for (int r4 = 0; r4 < TM / 4; ++r4) {
             T a[4];
@@ -124,13 +174,6 @@ __device__ __forceinline__ void gemm_rows(T (&acc)[TM][4], const TileMap<T, BM, 
 #pragma unroll
               for (int j = 0; j < 4; ++j) acc[4 * r4 + i][j] = fma_t(a[i], b[j], acc[4 * r4 + i][j]);
             }
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < TM; ++r) {
-            const T a = Ap[kk * LDA + r];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[r][j] = fma_t(a, b[j], acc[r][j]);
           }
         }
       }
