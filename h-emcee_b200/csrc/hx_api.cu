@@ -417,6 +417,7 @@ struct Fuse {       // batch-level fused accept + chain emit
   T* chain_out;
   T* chain_lp;
   int32_t* nonfinite;
+  const DistPush* push;   // sharded runs, tensor-core path: the finish kernel pushes the rows itself
 };
 
 static int check_move_args(const char* who, const void* X1, const void* X2, int n, int row0, int rows, int L,
@@ -451,6 +452,7 @@ static int walk_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1,
       if (fuse) {
         f32.akey_ptr = fuse->akey_ptr; f32.lp1w = fuse->lp1w; f32.accepts = fuse->accepts;
         f32.chain_out = fuse->chain_out; f32.chain_lp = fuse->chain_lp; f32.nonfinite = fuse->nonfinite;
+        f32.push = fuse->push;
       }
       ctx->launches += 2;
       ctx->last_path = 1;
@@ -715,6 +717,7 @@ static int run_iterations_t(hx_ctx* ctx, int impl, int move_kind, int key_order,
       f.chain_out = chain ? chain + ((size_t)t * W2 + (size_t)half * n) * d : nullptr;
       f.chain_lp = chain_lp ? chain_lp + (size_t)t * W2 + (size_t)half * n : nullptr;
       f.nonfinite = nonfinite;
+      f.push = nullptr;
       int e;
       // the half-move after this one (its momentum draw only needs the key): move2 of this iteration or move1 of the next
       tc::NextDraw nd;
@@ -859,6 +862,17 @@ static int run_iterations_sharded_t(hx_ctx* ctx, int impl, int move_kind, int ke
       f.chain_out = chain ? chain + ((size_t)t * 2 * rows + (size_t)half * rows) * d : nullptr;
       f.chain_lp = chain_lp ? chain_lp + (size_t)t * 2 * rows + (size_t)half * rows : nullptr;
       f.nonfinite = nonfinite;
+      // exchange: the rank's updated rows (+ log-probs) are stored into every peer's copy and the epoch is published, either by
+      // the tensor-core path's finish kernel itself or by k_dist_push after the SIMT half-move
+      D.epoch += 1;
+      const size_t x_off = ((size_t)half * n + row0) * d * sizeof(T), cnt = (size_t)rows * d * sizeof(T) / 16;
+      const size_t l_off = D.lp_off + ((size_t)half * n + row0) * sizeof(T), lcnt = (size_t)rows * sizeof(T) / 16;
+      DistPush dp;
+      dp.pt = pt; dp.rank = rank; dp.world = world; dp.x_off = x_off; dp.lp_off = l_off; dp.flag_off = D.flag_off;
+      dp.counter = counter; dp.epoch = D.epoch;
+      bool fused_push = false;
+      if constexpr (std::is_same<T, float>::value) fused_push = move_kind == 0 && tc::walk_eligible(ctx, HX_F32, tgt, n, rows, 0);
+      f.push = fused_push ? &dp : nullptr;
       tc::NextDraw nd;
       const tc::NextDraw* next = nullptr;
       if (half == 0 || t + 1 < Tn) {
@@ -871,16 +885,14 @@ static int run_iterations_sharded_t(hx_ctx* ctx, int impl, int move_kind, int ke
       else
         e = side_move_t<T>(ctx, impl, tgt, Xa, Xb, n, row0, rows, eps, Key{0, 0}, kt + 2 * im, L, lpa, (T*)pQ, (T*)pLa, nullptr, (T*)pLp, 0, &f, s);
       if (e) return e;
-      // exchange: store the rank's updated rows (+ log-probs) into every peer's copy, then publish the epoch
-      D.epoch += 1;
-      if (int e2 = timing_mark(ctx, s, HX_PH_PUSH)) return e2;
-      const size_t x_off = ((size_t)half * n + row0) * d * sizeof(T), cnt = (size_t)rows * d * sizeof(T) / 16;
-      const size_t l_off = D.lp_off + ((size_t)half * n + row0) * sizeof(T), lcnt = (size_t)rows * sizeof(T) / 16;
-      int grid = (int)((cnt + 255) / 256);
-      if (grid > ctx->sm_count * 2) grid = ctx->sm_count * 2;
-      if (grid < 1) grid = 1;
-      k_dist_push<<<grid, 256, 0, s>>>(pt, rank, world, x_off, cnt, l_off, lcnt, D.flag_off, counter, D.epoch);
-      HX_LAUNCH_CHECK("k_dist_push");
+      if (!fused_push) {
+        if (int e2 = timing_mark(ctx, s, HX_PH_PUSH)) return e2;
+        int grid = (int)((cnt + 255) / 256);
+        if (grid > ctx->sm_count * 2) grid = ctx->sm_count * 2;
+        if (grid < 1) grid = 1;
+        k_dist_push<<<grid, 256, 0, s>>>(pt, rank, world, x_off, cnt, l_off, lcnt, D.flag_off, counter, D.epoch);
+        HX_LAUNCH_CHECK("k_dist_push");
+      }
       if (int e2 = timing_mark(ctx, s, -1)) return e2;
       ctx->launches += 2;
     }

@@ -312,61 +312,91 @@ struct FinishArgs {
   int rows, d, n, row0, has_lower0; float lower0;
   int fuse, legacy; Key akey; const uint32_t* akey_ptr;
   float* X1w; float* lp1w; int32_t* accepts; float* chain_out; float* chain_lp; int32_t* nonfinite;
+  int push; DistPush dp;
 };
 
-// one warp per walker: energies, log-accept and (optionally) the Metropolis accept + chain emit
+// one warp per walker: energies, log-accept and (optionally) the Metropolis accept + chain emit.  In row-sharded runs the
+// same stores also go into every peer's copy of the ensemble over NVLink (the exchange step of the half-move, fused), and
+// the last CTA publishes the half-move's epoch (hx_dist.cuh).
 __global__ void __launch_bounds__(256) k_tc_finish(FinishArgs a) {
   const int lane = threadIdx.x & 31;
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (r >= a.rows) return;
-  float lp = 0.f, dk = 0.f;
-  for (int t = 0; t < a.NT; ++t) { lp += a.lpp[(size_t)r * a.NT + t]; dk += a.dkp[(size_t)r * a.NT + t]; }
-  lp *= -0.5f;
-  dk *= -0.5f;
-  if (a.has_lower0 && a.Q[(size_t)r * a.d] < a.lower0) lp = -CUDART_INF_F;
-  const float lp1 = a.lp1[r];
-  float dH = (lp1 - lp) + dk;                              // hmc_walk.py:54
-  if (isnan(dH)) dH = CUDART_INF_F;                        // hmc_walk.py:55
-  const float la = fminf(0.f, -dH);                        // hmc_walk.py:56
-  if (lane == 0) { a.logacc[r] = la; a.lp_out[r] = lp; }
-  if (!a.fuse) return;
-  Key akey = a.akey;
-  if (a.akey_ptr) { akey.k0 = a.akey_ptr[0]; akey.k1 = a.akey_ptr[1]; }
-  const float lo = 1e-10f, span = 1.0f - lo;
-  const float u = uniform_rt<float>(akey, (uint64_t)(a.row0 + r), (uint64_t)a.n, lo, span, a.legacy != 0);
-  const bool acc = logf(u) < la;                           // sampler_utils.py:114-115
-  const float lps = acc ? lp : lp1;
-  if (lane == 0) {
-    a.lp1w[r] = lps;
-    if (a.chain_lp) a.chain_lp[r] = lps;
-    a.accepts[r] += acc ? 1 : 0;
-    if (!isfinite(lps) && a.nonfinite) atomicOr(a.nonfinite, 1);
+  if (r < a.rows) {
+    float lp = 0.f, dk = 0.f;
+    for (int t = 0; t < a.NT; ++t) { lp += a.lpp[(size_t)r * a.NT + t]; dk += a.dkp[(size_t)r * a.NT + t]; }
+    lp *= -0.5f;
+    dk *= -0.5f;
+    if (a.has_lower0 && a.Q[(size_t)r * a.d] < a.lower0) lp = -CUDART_INF_F;
+    const float lp1 = a.lp1[r];
+    float dH = (lp1 - lp) + dk;                              // hmc_walk.py:54
+    if (isnan(dH)) dH = CUDART_INF_F;                        // hmc_walk.py:55
+    const float la = fminf(0.f, -dH);                        // hmc_walk.py:56
+    if (lane == 0) { a.logacc[r] = la; a.lp_out[r] = lp; }
+    if (a.fuse) {
+      Key akey = a.akey;
+      if (a.akey_ptr) { akey.k0 = a.akey_ptr[0]; akey.k1 = a.akey_ptr[1]; }
+      const float lo = 1e-10f, span = 1.0f - lo;
+      const float u = uniform_rt<float>(akey, (uint64_t)(a.row0 + r), (uint64_t)a.n, lo, span, a.legacy != 0);
+      const bool acc = logf(u) < la;                           // sampler_utils.py:114-115
+      const float lps = acc ? lp : lp1;
+      if (lane == 0) {
+        a.lp1w[r] = lps;
+        if (a.chain_lp) a.chain_lp[r] = lps;
+        a.accepts[r] += acc ? 1 : 0;
+        if (!isfinite(lps) && a.nonfinite) atomicOr(a.nonfinite, 1);
+        if (a.push)
+          for (int p = 0; p < a.dp.world; ++p)
+            if (p != a.dp.rank) reinterpret_cast<float*>(static_cast<char*>(a.dp.pt.base[p]) + a.dp.lp_off)[r] = lps;
+      }
+      const size_t off = (size_t)r * a.d;
+      if (a.push && (a.d & 3) == 0) {
+        // 16-byte stores: one float4 per lane and step, replicated to every peer
+        const int d4 = a.d >> 2;
+        const float4* q4 = reinterpret_cast<const float4*>(a.Q + off);
+        float4* x4 = reinterpret_cast<float4*>(a.X1w + off);
+        float4* c4 = a.chain_out ? reinterpret_cast<float4*>(a.chain_out + off) : nullptr;
+        const bool cvec = a.chain_out && ((reinterpret_cast<uintptr_t>(a.chain_out + off) & 15) == 0);
+        for (int c = lane; c < d4; c += 32) {
+          const float4 v = acc ? q4[c] : x4[c];
+          if (acc) x4[c] = v;
+          if (cvec) c4[c] = v;
+          else if (a.chain_out) { float* co = a.chain_out + off + 4 * c; co[0] = v.x; co[1] = v.y; co[2] = v.z; co[3] = v.w; }
+#pragma unroll 1
+          for (int p = 0; p < a.dp.world; ++p)
+            if (p != a.dp.rank) reinterpret_cast<float4*>(static_cast<char*>(a.dp.pt.base[p]) + a.dp.x_off)[(off >> 2) + c] = v;
+        }
+      } else {
+        for (int c = lane; c < a.d; c += 32) {
+          const float v = acc ? a.Q[off + c] : a.X1w[off + c];
+          a.X1w[off + c] = v;
+          if (a.chain_out) a.chain_out[off + c] = v;
+          if (a.push)
+            for (int p = 0; p < a.dp.world; ++p)
+              if (p != a.dp.rank) reinterpret_cast<float*>(static_cast<char*>(a.dp.pt.base[p]) + a.dp.x_off)[off + c] = v;
+        }
+      }
+    }
   }
-  const size_t off = (size_t)r * a.d;
-  for (int c = lane; c < a.d; c += 32) {
-    const float v = acc ? a.Q[off + c] : a.X1w[off + c];
-    a.X1w[off + c] = v;
-    if (a.chain_out) a.chain_out[off + c] = v;
-  }
+  if (a.push) dist_publish(a.dp);
 }
 
 // ---- GEMM launcher ---------------------------------------------------------------------------------------------------
 // rowsA_pad / rowsB_pad = plane stride in rows; mapA_rows = rows covered by the A tensor map (0: both full planes);
 // n_grid = padded N the grid covers (0: g.N)
-template <int EPI, int KIND>
+template <int EPI, int KIND, int BNT = BN>
 static int launch_gemm(hx_ctx* ctx, const void* A, int rowsA_pad, const void* B, int rowsB_pad, int Kp, GemmArgs g,
                        cudaStream_t s, uint64_t mapA_rows = 0, int n_grid = 0, int slices = 1) {
   CUtensorMap tmA, tmB;
   if (int e = make_tmap(ctx, &tmA, A, mapA_rows ? mapA_rows : 2ull * rowsA_pad, Kp, kBM, KIND)) return e;
-  if (int e = make_tmap(ctx, &tmB, B, 2ull * rowsB_pad, Kp, BN, KIND)) return e;
+  if (int e = make_tmap(ctx, &tmB, B, 2ull * rowsB_pad, Kp, BNT, KIND)) return e;
   g.Kp = Kp; g.rowsA_pad = rowsA_pad; g.rowsB_pad = rowsB_pad;
   static bool attr_done = false;
   if (!attr_done) {
-    HX_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, EPI, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::BYTES));
+    HX_CUDA(cudaFuncSetAttribute(k_tc_gemm<BNT, EPI, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BNT>::BYTES));
     attr_done = true;
   }
-  dim3 grid(((n_grid ? n_grid : g.N) + BN - 1) / BN, (g.M + kBM - 1) / kBM, slices);
-  k_tc_gemm<BN, EPI, KIND><<<grid, kThreads, SmemLayout<BN>::BYTES, s>>>(tmA, tmB, g);
+  dim3 grid(((n_grid ? n_grid : g.N) + BNT - 1) / BNT, (g.M + kBM - 1) / kBM, slices);
+  k_tc_gemm<BNT, EPI, KIND><<<grid, kThreads, SmemLayout<BNT>::BYTES, s>>>(tmA, tmB, g);
   HX_LAUNCH_CHECK("k_tc_gemm");
   ctx->launches += 1;
   return 0;
@@ -405,13 +435,20 @@ static int leapfrog_bform(hx_ctx* ctx, const LeapArgs& a, cudaStream_t s) {
   // The q - mu operand planes ping-pong between two buffers: a kick's epilogue writes the NEXT operand while sibling CTAs of the
   // same row tile (other column tiles) may still be reading the current one (updating in place is a race).
   void* planes[2] = {a.pQC, a.pQC2};
+  const bool narrow = ((rows + kBM - 1) / kBM) * ((d + BN - 1) / BN) * 2 <= ctx->sm_count;
   for (int k = 0; k <= a.L; ++k) {
     GemmArgs x = gg;
     x.S_in = (k == 0) ? a.S0 : a.S; x.S = a.S; x.Q = a.Q; x.Qs = a.Qs; x.first = (k == 0) ? 1 : 0;
     x.planes_out = planes[(k + 1) & 1]; x.rows_out_pad = rA; x.Kout_p = dK;
     x.a = (float)((k == 0 || k == a.L) ? 0.5 * (float)a.eps : (float)a.eps);
     x.drift = k < a.L ? 1 : 0;
-    if (int e = launch_gemm<EPI_KICKB, KIND>(ctx, planes[k & 1], rA, a.pBoP, dB, dK, x, s)) return e;
+    // few rows (the propagator's 2d basis trajectories): 128-wide tiles double the CTAs and halve both the MMA chain and
+    // the per-thread epilogue of these latency-bound launches
+    if (narrow) {
+      if (int e = launch_gemm<EPI_KICKB, KIND, 128>(ctx, planes[k & 1], rA, a.pBoP, dB, dK, x, s)) return e;
+    } else {
+      if (int e = launch_gemm<EPI_KICKB, KIND>(ctx, planes[k & 1], rA, a.pBoP, dB, dK, x, s)) return e;
+    }
   }
   void* planes_L = planes[a.L & 1];      // q_L - mu (written by the last drift, kick L-1)
   if (!a.energies) return 0;
@@ -758,6 +795,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   if (fuse) {
     fa.fuse = 1; fa.akey_ptr = fuse->akey_ptr; fa.X1w = const_cast<float*>(X1); fa.lp1w = fuse->lp1w;
     fa.accepts = fuse->accepts; fa.chain_out = fuse->chain_out; fa.chain_lp = fuse->chain_lp; fa.nonfinite = fuse->nonfinite;
+    if (fuse->push) { fa.push = 1; fa.dp = *fuse->push; }
   }
   k_tc_finish<<<(rows + 7) / 8, 256, 0, s>>>(fa);
   HX_LAUNCH_CHECK("k_tc_finish");

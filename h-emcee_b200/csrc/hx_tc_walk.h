@@ -5,6 +5,7 @@
 #include "../../include/hx.h"
 #include "hx_ctx.h"
 #include "hx_rng.cuh"
+#include "hx_dist.cuh"
 
 namespace hx {
 namespace tc {
@@ -16,6 +17,7 @@ struct FuseF32 {      // batch-level fused accept + chain emit (same fields as F
   float* chain_out;
   float* chain_lp;
   int32_t* nonfinite;
+  const DistPush* push;   // row-sharded runs: store the accepted rows into the peers' copies and publish the epoch (nullable)
 };
 
 struct NextDraw {     // the walk half-move that follows this one (its momentum draw is started early)

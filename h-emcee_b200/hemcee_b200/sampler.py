@@ -136,6 +136,13 @@ class HamiltonianEnsembleSampler(BaseSampler):
         dist.all_gather_into_tensor(full, local, group=self.group)
 
     @property
+    def _peer_ok(self):
+        """Peer-memory exchange needs a rank's rows and log-probs to be multiples of 16 bytes (vector stores)."""
+        rows = (self.total_chains // 2) // max(self.world, 1)
+        esz = 8 if self.dtype == torch.float64 else 4
+        return self.exchange == "peer" and (rows * self.dim * esz) % 16 == 0 and (rows * esz) % 16 == 0
+
+    @property
     def _move_kind(self):
         return 0 if self.move.__name__ == "hmc_walk_move" else 1
 
@@ -425,7 +432,7 @@ class HamiltonianEnsembleSampler(BaseSampler):
             lp = self.log_prob(X)
             acc = self._run_batches(key, X, lp, warmup, step, L, batch_size, 0, 1, show_progress)
             group1, group2 = X[: self.total_chains // 2].clone(), X[self.total_chains // 2:].clone()
-        elif noop and self.exchange == "peer":
+        elif noop and self._peer_ok:
             step, L = adapter.value(self.adapter_state)
             acc = self._run_batches_sharded(key, group1, group2, warmup, step, L, batch_size, 0, 1, show_progress)
         else:
@@ -447,7 +454,7 @@ class HamiltonianEnsembleSampler(BaseSampler):
             lp = self.log_prob(X)                                                    # :325-326
             acc = self._run_batches(key, X, lp, total, step_size, L, batch_size, warmup_offset, 0, show_progress)
             self.last_state = X
-        elif self.exchange == "peer":
+        elif self._peer_ok:
             acc = self._run_batches_sharded(key, group1, group2, total, step_size, L, batch_size, warmup_offset, 0, show_progress)
             self.last_state = torch.cat([group1, group2])
         else:
