@@ -15,6 +15,7 @@
 #include "hx_ctx.h"
 #include "hx_tc_walk.h"
 #include "hx_dist.cuh"
+#include "hx_adapt.cuh"
 #include <type_traits>
 
 using namespace hx;
@@ -440,7 +441,7 @@ static int walk_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1,
   if (int e = make_target<T>(tgt, &W.P.tg, "hx_walk_move")) return e;
   const int d = tgt->dim, ldd = round4(d);
   if constexpr (std::is_same<T, float>::value) {
-    if (tc::walk_eligible(ctx, HX_F32, tgt, n, rows, flags)) {
+    if (!ctx->ctl_eps && tc::walk_eligible(ctx, HX_F32, tgt, n, rows, flags)) {
       float* mean;
       if (int e = complement_mean<float>(ctx, X2, n, d, &mean, s)) return e;
       if (!pproj) {
@@ -476,6 +477,7 @@ static int walk_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1,
   W.P.n = n; W.P.d = d; W.P.ldd = ldd; W.P.row0 = row0; W.P.rows = rows; W.P.L = L;
   W.P.flags = (flags & HX_MOVE_FROZEN_GRAD) ? kFlagFrozen : 0;
   W.P.eps = (T)eps; W.P.key = key; W.P.key_ptr = key_ptr;
+  W.P.eps_ptr = (const T*)ctx->ctl_eps; W.P.L_ptr = ctx->ctl_L;
   if (fuse) {
     W.P.fuse_accept = 1; W.P.akey_ptr = fuse->akey_ptr; W.P.X1w = const_cast<T*>(X1); W.P.lp1w = fuse->lp1w;
     W.P.accepts = fuse->accepts; W.P.chain_out = fuse->chain_out; W.P.chain_lp = fuse->chain_lp;
@@ -537,6 +539,7 @@ static int side_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1,
   W.P.n = n; W.P.d = d; W.P.ldd = ldd; W.P.row0 = row0; W.P.rows = rows; W.P.L = L;
   W.P.flags = (flags & HX_MOVE_FROZEN_GRAD) ? kFlagFrozen : 0;
   W.P.eps = (T)eps; W.P.key = key; W.P.key_ptr = key_ptr;
+  W.P.eps_ptr = (const T*)ctx->ctl_eps; W.P.L_ptr = ctx->ctl_L;
   if (fuse) {
     W.P.fuse_accept = 1; W.P.akey_ptr = fuse->akey_ptr; W.P.X1w = const_cast<T*>(X1); W.P.lp1w = fuse->lp1w;
     W.P.accepts = fuse->accepts; W.P.chain_out = fuse->chain_out; W.P.chain_lp = fuse->chain_lp;
@@ -752,6 +755,123 @@ extern "C" HX_API int hx_run_iterations(hx_ctx* ctx, int dtype, int impl, int mo
                                    (float*)chain_out, (float*)lp_out, accepts, nonfinite, s);
   return run_iterations_t<double>(ctx, impl, move_kind, key_order, tgt, (double*)X, (double*)lp, n, step_size, L, keys_dev, T,
                                   (double*)chain_out, (double*)lp_out, accepts, nonfinite, s);
+}
+
+// ---- (4b) warm-up scan with live adapters: adapter state, value() and update() on the device (hx_adapt.cuh) ---------------------
+template <typename T>
+static int column_mean(hx_ctx* ctx, const T* X, int rows, int d, T* mean_out, cudaStream_t s) {
+  void* pPart;
+  const int nchunks = (rows + kColChunk - 1) / kColChunk;
+  if (int e = ws_get(ctx, WS_AD_PART, (size_t)nchunks * d * sizeof(T), &pPart)) return e;
+  dim3 g1((d + 127) / 128, nchunks);
+  k_colsum_partial<T><<<g1, 128, 0, s>>>(X, rows, d, (T*)pPart);
+  HX_LAUNCH_CHECK("k_colsum_partial");
+  k_mean_final<T><<<(d + 127) / 128, 128, 0, s>>>((const T*)pPart, nchunks, rows, d, mean_out);
+  HX_LAUNCH_CHECK("k_mean_final");
+  return 0;
+}
+
+template <typename T>
+static int run_warmup_t(hx_ctx* ctx, int impl, int move_kind, const hx_target* tgt, T* X, T* lp, int n, const hx_adapt_params& P,
+                        hx_adapt_state* st_host, const uint32_t* keys, int64_t Tn, T* chain, T* chain_lp, int32_t* accepts,
+                        int32_t* nonfinite, cudaStream_t s) {
+  const int d = tgt->dim, ldd = round4(d);
+  if (P.use_chees && d > kAdaptMaxDim) return fail(HX_E_UNSUPPORTED, "hx_run_warmup: ChEES on the device needs dim <= %d (got %d)", kAdaptMaxDim, d);
+  void *pQ, *pLa, *pLp, *pS, *pSt, *pMean, *pChol, *pStat;
+  if (int e = ws_get(ctx, WS_AD_PROP, (size_t)n * d * sizeof(T), &pQ)) return e;
+  if (int e = ws_get(ctx, WS_LA, (size_t)n * sizeof(T), &pLa)) return e;
+  if (int e = ws_get(ctx, WS_LP, (size_t)n * sizeof(T), &pLp)) return e;
+  if (int e = ws_get(ctx, WS_S, (size_t)n * d * sizeof(T), &pS)) return e;
+  if (int e = ws_get(ctx, WS_AD_STATE, sizeof(AdaptDev<T>), &pSt)) return e;
+  if (int e = ws_get(ctx, WS_AD_MEAN, (size_t)2 * d * sizeof(T), &pMean)) return e;
+  if (int e = ws_get(ctx, WS_AD_CHOL, (size_t)d * d * sizeof(T), &pChol)) return e;
+  if (int e = ws_get(ctx, WS_AD_STAT, (size_t)3 * n * sizeof(T), &pStat)) return e;
+  AdaptDev<T>* st = (AdaptDev<T>*)pSt;
+  T* mean_prev = (T*)pMean;
+  T* mean_prop = (T*)pMean + d;
+  T* stat_da = (T*)pStat;
+  T* stat_acc = stat_da + n;
+  T* stat_accg = stat_acc + n;
+  AdaptDev<T> h;
+  memset(&h, 0, sizeof(h));
+  h.da_it = (int)st_host->da_iteration; h.da_ls = (T)st_host->da_log_step; h.da_lsb = (T)st_host->da_log_step_bar;
+  h.da_H = (T)st_host->da_H_bar; h.ch_lT = (T)st_host->ch_log_T; h.ch_lTb = (T)st_host->ch_log_T_bar; h.ch_m1 = (T)st_host->ch_m1;
+  h.ch_m2 = (T)st_host->ch_m2; h.ch_it = (T)st_host->ch_iteration; h.ch_halton = (float)st_host->ch_halton;
+  HX_CUDA(cudaMemcpyAsync(st, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+  HX_CUDA(cudaStreamSynchronize(s));                    // `h` is a stack object
+  k_adapt_value<T><<<1, 32, 0, s>>>(st, P);
+  HX_LAUNCH_CHECK("k_adapt_value");
+  ctx->ctl_eps = &st->eps;
+  ctx->ctl_L = &st->L;
+  const size_t W2 = (size_t)2 * n;
+  int err = 0;
+  for (int64_t t = 0; t < Tn && !err; ++t) {
+    const uint32_t* kt = keys + (size_t)t * 8;
+    for (int half = 0; half < 2 && !err; ++half) {
+      // warm-up key order (samplers/hamiltonian_ensemble.py:171,184,191,204)
+      const uint32_t* kmove = kt + 2 * (half == 0 ? 0 : 2);
+      const uint32_t* kacc = kt + 2 * (half == 0 ? 1 : 3);
+      T* Xa = X + (size_t)half * n * d;
+      T* Xb = X + (size_t)(1 - half) * n * d;
+      T* lpa = lp + (size_t)half * n;
+      if (move_kind == 0)
+        err = walk_move_t<T>(ctx, impl, tgt, Xa, Xb, n, 0, n, 0.0, Key{0, 0}, kmove, 1, lpa, (T*)pQ, (T*)pLa, (T*)pS, (T*)pLp, 0, nullptr, nullptr, s);
+      else
+        err = side_move_t<T>(ctx, impl, tgt, Xa, Xb, n, 0, n, 0.0, Key{0, 0}, kmove, 1, lpa, (T*)pQ, (T*)pLa, (T*)pS, (T*)pLp, 0, nullptr, s);
+      if (err) break;
+      // adapter.update(state, log_accept, position_current = X (pre-accept), position_proposed, momentum_proposed, group2)  :176-182
+      const T* Lf = nullptr;
+      if (P.use_chees) {
+        T* M = (T*)ctx->buf[WS_M];
+        if (move_kind != 0) {        // the side move does not form the Gram matrix of the complement
+          T* C;
+          if ((err = center_complement<T>(ctx, Xb, n, d, ldd, &C, s))) break;
+          if ((err = gram_matrix<T>(ctx, C, n, ldd, &M, s))) break;
+        }
+        if ((err = column_mean<T>(ctx, Xa, n, d, mean_prev, s))) break;
+        if ((err = column_mean<T>(ctx, (const T*)pQ, n, d, mean_prop, s))) break;
+        k_chol<T><<<1, 256, 0, s>>>(M, ldd, d, (T)n / (T)(n - 1), (T*)pChol, d);
+        Lf = (const T*)pChol;
+      }
+      k_adapt_rows<T><<<(n + 127) / 128, 128, 0, s>>>((const T*)pLa, Xa, (const T*)pQ, (const T*)pS, mean_prev, mean_prop, Lf, d, n, d,
+                                                      st, P, stat_da, stat_acc, stat_accg);
+      k_adapt_update<T><<<1, 1024, 0, s>>>(st, P, stat_da, stat_acc, stat_accg, n);
+      k_accept_emit<T><<<(n + 7) / 8, 256, 0, s>>>(Xa, (const T*)pQ, lpa, (const T*)pLp, (const T*)pLa, kacc, impl == HX_RNG_LEGACY ? 1 : 0,
+                                                   n, 0, n, d, accepts + (size_t)half * n,
+                                                   chain ? chain + ((size_t)t * W2 + (size_t)half * n) * d : nullptr,
+                                                   chain_lp ? chain_lp + (size_t)t * W2 + (size_t)half * n : nullptr, nonfinite);
+      cudaError_t ce = cudaGetLastError();
+      if (ce != cudaSuccess) err = fail((int)ce, "hx_run_warmup: launch failed: %s", cudaGetErrorString(ce));
+      ctx->launches += 8;
+    }
+  }
+  ctx->ctl_eps = nullptr;
+  ctx->ctl_L = nullptr;
+  if (err) return err;
+  HX_CUDA(cudaMemcpyAsync(&h, st, sizeof(h), cudaMemcpyDeviceToHost, s));
+  HX_CUDA(cudaStreamSynchronize(s));
+  st_host->da_iteration = h.da_it; st_host->da_log_step = (double)h.da_ls; st_host->da_log_step_bar = (double)h.da_lsb;
+  st_host->da_H_bar = (double)h.da_H; st_host->ch_log_T = (double)h.ch_lT; st_host->ch_log_T_bar = (double)h.ch_lTb;
+  st_host->ch_m1 = (double)h.ch_m1; st_host->ch_m2 = (double)h.ch_m2; st_host->ch_iteration = (double)h.ch_it;
+  st_host->ch_halton = (double)h.ch_halton;
+  return 0;
+}
+
+extern "C" HX_API int hx_run_warmup(hx_ctx* ctx, int dtype, int impl, int move_kind, const hx_target* tgt, void* X, void* lp, int32_t n,
+                             const hx_adapt_params* params, hx_adapt_state* state, const uint32_t* keys_dev, int64_t T,
+                             void* chain_out, void* lp_out, int32_t* accepts, int32_t* nonfinite, void* stream) {
+  if (!ctx || !tgt || !X || !lp || !params || !state || !keys_dev || !accepts || !nonfinite) return fail(HX_E_NULL, "hx_run_warmup: NULL argument");
+  if (int e = check_dtype_impl(dtype, impl, "hx_run_warmup")) return e;
+  if (move_kind != 0 && move_kind != 1) return fail(HX_E_DTYPE, "hx_run_warmup: move_kind must be 0 (walk) or 1 (side)");
+  if (!params->use_da && !params->use_chees) return fail(HX_E_DTYPE, "hx_run_warmup: no adapter enabled (use hx_run_iterations with key_order 1)");
+  if (n < 2 || T < 0) return fail(HX_E_SHAPE, "hx_run_warmup: need n >= 2, T >= 0");
+  HX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == HX_F32)
+    return run_warmup_t<float>(ctx, impl, move_kind, tgt, (float*)X, (float*)lp, n, *params, state, keys_dev, T, (float*)chain_out,
+                               (float*)lp_out, accepts, nonfinite, s);
+  return run_warmup_t<double>(ctx, impl, move_kind, tgt, (double*)X, (double*)lp, n, *params, state, keys_dev, T, (double*)chain_out,
+                              (double*)lp_out, accepts, nonfinite, s);
 }
 
 // ---- (5) row-sharded multi-GPU batch loop: exchange over NVLink peer memory (hx_dist.cuh) -------------------------------------

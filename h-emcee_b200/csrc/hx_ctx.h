@@ -13,6 +13,8 @@ enum Slot {
   WS_TC_CT, WS_TC_MP, WS_TC_PP, WS_TC_P0, WS_TC_QC, WS_TC_GP, WS_TC_LPP, WS_TC_DKP, WS_TC_MASK, WS_TC_BO, WS_TC_S0,
   // propagator form of the Gaussian leapfrog
   WS_TC_BX, WS_TC_BS, WS_TC_TQ, WS_TC_TS, WS_TC_TW, WS_TC_WP, WS_TC_B1, WS_TC_B2, WS_TC_ZB, WS_TC_ZT, WS_TC_QC2, WS_TC_PP32, WS_TC_S0P, WS_TC_CT32,
+  // device-resident adaptation
+  WS_AD_STATE, WS_AD_MEAN, WS_AD_PART, WS_AD_CHOL, WS_AD_STAT, WS_AD_PROP,
   WS_NSLOT
 };
 
@@ -57,6 +59,7 @@ struct hx_ctx {
   P0Job hint; int hint_valid;              // hx_walk_prefetch: the walk half-move after the next one
   int leap_form;                           // HX_LEAP_*
   HxDist dist;
+  const void* ctl_eps; const int* ctl_L;   // device-resident (step, L) the SIMT move kernels read during adaptive warm-up
   int energy_bf16;                         // 1: propagator-form energy products from bf16 hi/lo operands (default tf32 hi/lo)
   int gram_tf32;                           // 1: Gram from tf32 hi/lo operands instead of bf16 hi/lo
   int proj_slices;                         // split-K slices of the projection GEMM (0: default)

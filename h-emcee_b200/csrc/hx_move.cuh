@@ -332,6 +332,8 @@ struct WalkParams {
   Key key;
   const uint32_t* key_ptr;   // if non-null the move key is read from device memory
   // fused Metropolis accept + chain emit (batch level); off when fuse_accept == 0
+  const T* eps_ptr;      // device-resident step size / trajectory length (adaptive warm-up); override eps / L when set
+  const int* L_ptr;
   int fuse_accept;
   Key akey;
   const uint32_t* akey_ptr;
@@ -393,6 +395,8 @@ __global__ void __launch_bounds__(MAXT) k_walk_half(WalkParams<T> P) {
   T* S = P.S + off;
   T* G = P.G + off;
   const bool frozen = (P.flags & kFlagFrozen) != 0;
+  const T eps_ = P.eps_ptr ? *P.eps_ptr : P.eps;
+  const int L_ = P.L_ptr ? *P.L_ptr : P.L;
 
   Key key = P.key;
   if (P.key_ptr) { key.k0 = P.key_ptr[0]; key.k1 = P.key_ptr[1]; }
@@ -427,11 +431,11 @@ __global__ void __launch_bounds__(MAXT) k_walk_half(WalkParams<T> P) {
 #pragma unroll
   for (int r = 0; r < TM; ++r) dK[r] = T(0);
 
-  eval_target<T, BM, TM>(P.tg, tm, Q, G, As, red, lp_rows, rows_valid, P.L == 0);
+  eval_target<T, BM, TM>(P.tg, tm, Q, G, As, red, lp_rows, rows_valid, L_ == 0);
   // L+1 kicks (half, L-1 full, half), every kick but the last followed by a drift (hmc_walk.py:85-102)
-  for (int k = 0; k <= P.L; ++k) {
-    const T a = (k == 0 || k == P.L) ? T(0.5) * P.eps : P.eps;
-    const bool drift = k < P.L;
+  for (int k = 0; k <= L_; ++k) {
+    const T a = (k == 0 || k == L_) ? T(0.5) * eps_ : eps_;
+    const bool drift = k < L_;
     RowsLoader<T, BM> ld{G, d, nullptr, rows_valid, d};
     gemm_rows<T, BM, TM>(acc, tm, As, ld, P.M, P.ldd, d);   // g @ M
     if (tm.active) {
@@ -448,14 +452,14 @@ __global__ void __launch_bounds__(MAXT) k_walk_half(WalkParams<T> P) {
               const T s_new = s_old - a * acc[r][j];
               dK[r] = fma_t(a * G[idx], s_old + s_new, dK[r]);
               S[idx] = s_new;
-              if (drift) Q[idx] = Q[idx] + P.eps * s_new;
+              if (drift) Q[idx] = Q[idx] + eps_ * s_new;
             }
           }
         }
       }
     }
     __syncthreads();
-    if (drift && !frozen) eval_target<T, BM, TM>(P.tg, tm, Q, G, As, red, lp_rows, rows_valid, k == P.L - 1);
+    if (drift && !frozen) eval_target<T, BM, TM>(P.tg, tm, Q, G, As, red, lp_rows, rows_valid, k == L_ - 1);
   }
   if (frozen) eval_target<T, BM, TM>(P.tg, tm, Q, G, As, red, lp_rows, rows_valid, true);
 
@@ -501,6 +505,8 @@ struct SideParams {
   T eps;
   Key key;
   const uint32_t* key_ptr;
+  const T* eps_ptr;      // device-resident step size / trajectory length (adaptive warm-up); override eps / L when set
+  const int* L_ptr;
   int fuse_accept;
   Key akey;
   const uint32_t* akey_ptr;
@@ -536,6 +542,8 @@ __global__ void __launch_bounds__(MAXT) k_side_half(SideParams<T> P) {
   T* D = P.D + off;
   T* G = P.G + off;
   const bool frozen = (P.flags & kFlagFrozen) != 0;
+  const T eps_ = P.eps_ptr ? *P.eps_ptr : P.eps;
+  const int L_ = P.L_ptr ? *P.L_ptr : P.L;
   const bool given = (P.flags & kFlagGivenMomentum) != 0;
 
   Key key = P.key;
@@ -565,10 +573,10 @@ __global__ void __launch_bounds__(MAXT) k_side_half(SideParams<T> P) {
   }
   __syncthreads();
 
-  eval_target<T, BM, TM>(P.tg, tm, Q, G, As, red, lp_rows, rows_valid, P.L == 0);
-  for (int k = 0; k <= P.L; ++k) {
-    const T a = (k == 0 || k == P.L) ? T(0.5) * P.eps : P.eps;
-    const bool drift = k < P.L;
+  eval_target<T, BM, TM>(P.tg, tm, Q, G, As, red, lp_rows, rows_valid, L_ == 0);
+  for (int k = 0; k <= L_; ++k) {
+    const T a = (k == 0 || k == L_) ? T(0.5) * eps_ : eps_;
+    const bool drift = k < L_;
     T part[TM];
 #pragma unroll
     for (int r = 0; r < TM; ++r) part[r] = T(0);
@@ -591,10 +599,10 @@ __global__ void __launch_bounds__(MAXT) k_side_half(SideParams<T> P) {
     if (drift) {
       for (int idx = tm.tid; idx < rows_valid * d; idx += tm.nthreads) {
         const int r = idx / d;
-        Q[idx] = Q[idx] + P.eps * (p_rows[r] * D[idx]);                                 // hmc_side.py:115,124
+        Q[idx] = Q[idx] + eps_ * (p_rows[r] * D[idx]);                                 // hmc_side.py:115,124
       }
       __syncthreads();
-      if (!frozen) eval_target<T, BM, TM>(P.tg, tm, Q, G, As, red, lp_rows, rows_valid, k == P.L - 1);
+      if (!frozen) eval_target<T, BM, TM>(P.tg, tm, Q, G, As, red, lp_rows, rows_valid, k == L_ - 1);
     }
   }
   if (frozen) eval_target<T, BM, TM>(P.tg, tm, Q, G, As, red, lp_rows, rows_valid, true);

@@ -30,6 +30,21 @@ class hx_target(C.Structure):
     ]
 
 
+class hx_adapt_params(C.Structure):
+    _fields_ = [("use_da", C.c_int32), ("use_chees", C.c_int32), ("agg_harmonic", C.c_int32), ("pass_L", C.c_int32),
+                ("da_target_accept", C.c_double), ("da_t0", C.c_double), ("da_gamma", C.c_double), ("da_kappa", C.c_double),
+                ("da_init_step", C.c_double),
+                ("ch_T_min", C.c_double), ("ch_T_max", C.c_double), ("ch_T_interp", C.c_double), ("ch_jitter", C.c_double),
+                ("ch_lr", C.c_double), ("ch_beta1", C.c_double), ("ch_beta2", C.c_double), ("ch_reg", C.c_double),
+                ("pass_step", C.c_double)]
+
+
+class hx_adapt_state(C.Structure):
+    _fields_ = [("da_iteration", C.c_int64), ("da_log_step", C.c_double), ("da_log_step_bar", C.c_double), ("da_H_bar", C.c_double),
+                ("ch_log_T", C.c_double), ("ch_log_T_bar", C.c_double), ("ch_m1", C.c_double), ("ch_m2", C.c_double),
+                ("ch_iteration", C.c_double), ("ch_halton", C.c_double)]
+
+
 _P = C.c_void_p
 _KEY = C.POINTER(C.c_uint32)
 _PROTOS = {
@@ -64,6 +79,8 @@ _PROTOS = {
                             _P, _P]),
     "hx_run_iterations": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.c_double,
                                     C.c_int32, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    "hx_run_warmup": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.POINTER(hx_adapt_params),
+                                C.POINTER(hx_adapt_state), _P, C.c_int64, _P, _P, _P, _P, _P]),
     "hx_dist_init": (C.c_int, [_P, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "hx_dist_connect": (C.c_int, [_P, _P]),
     "hx_dist_buffers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),

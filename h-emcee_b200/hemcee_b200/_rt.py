@@ -34,6 +34,7 @@ class _Config:
         self.rng_impl = "partitionable"
         self.precision = "auto"
         self.leapfrog_form = "auto"
+        self.device_adaptation = True     # warm-up adapters resident on the device (hx_run_warmup) when applicable
 
     def update(self, name, value):
         if name in ("enable_x64", "jax_enable_x64"):
@@ -54,6 +55,8 @@ class _Config:
             self.leapfrog_form = value
             for h in _ctx.values():
                 _lib.check(_lib.load().hx_ctx_set_leapfrog_form(h, self.LEAPFROG_FORMS[value]), "hx_ctx_set_leapfrog_form")
+        elif name == "device_adaptation":
+            self.device_adaptation = bool(value)
         elif name == "jax_threefry_partitionable":
             self.rng_impl = "partitionable" if value else "legacy"
         else:

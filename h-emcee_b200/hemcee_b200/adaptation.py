@@ -315,3 +315,59 @@ def find_reasonable_step_size(key, group1, group2, log_prob, grad_log_prob, init
         last_dir, direction = direction, new_dir
         it += 1
     return step
+
+
+# ---- device-resident warm-up (include/hx.h section 4b): adapter objects <-> the C structs ------------------------------
+def device_params(adapter):
+    """hx_adapt_params for a DualAveraging / ChEES / Composite adapter, or None if the adapter has no device form."""
+    from . import _lib
+    da = ch = None
+    if isinstance(adapter, CompositeAdapter):
+        da, ch = adapter.da_adapter, adapter.chees_adapter
+    elif isinstance(adapter, DualAveragingAdapter):
+        da = adapter
+    elif isinstance(adapter, ChEESAdapter):
+        ch = adapter
+    else:
+        return None
+    if ch is not None and ch.move_type == "hmc_move":
+        return None
+    p = _lib.hx_adapt_params()
+    p.use_da, p.use_chees = int(da is not None), int(ch is not None)
+    if da is not None:
+        P = da.parameters
+        p.agg_harmonic = int(P.agg == "harmonic")
+        p.da_target_accept, p.da_t0, p.da_gamma, p.da_kappa = P.target_accept, P.t0, P.gamma, P.kappa
+        p.da_init_step = float(da.dt(da.initial_step_size))
+        p.pass_L = int(da.passthrough_L)
+    if ch is not None:
+        P = ch.parameters
+        p.ch_T_min, p.ch_T_max, p.ch_T_interp, p.ch_jitter = P.T_min, P.T_max, P.T_interpolation, P.jitter
+        p.ch_lr, p.ch_beta1, p.ch_beta2, p.ch_reg = P.lr_T, P.beta1, P.beta2, P.regularization
+        p.pass_step = float(ch.dt(ch.passthrough_step_size))
+    return p
+
+
+def state_to_device(adapter, state):
+    from . import _lib
+    s = _lib.hx_adapt_state()
+    da = state.da_state if isinstance(state, CompositeState) else (state if isinstance(state, DAState) else None)
+    ch = state.chees_state if isinstance(state, CompositeState) else (state if isinstance(state, ChEESState) else None)
+    if da is not None:
+        s.da_iteration, s.da_log_step, s.da_log_step_bar, s.da_H_bar = int(da.iteration), float(da.log_stepsize), \
+            float(da.log_stepsize_bar), float(da.H_bar)
+    if ch is not None:
+        s.ch_log_T, s.ch_log_T_bar, s.ch_m1, s.ch_m2 = float(ch.log_T), float(ch.log_T_bar), float(ch.first_moment), \
+            float(ch.second_moment)
+        s.ch_iteration, s.ch_halton = float(ch.iteration), float(ch.halton)
+    return s
+
+
+def state_from_device(adapter, state, s):
+    """Rebuild the adapter's NamedTuple state from the C struct (values already are in the run's float type)."""
+    dt = adapter.da_adapter.dt if isinstance(adapter, CompositeAdapter) else adapter.dt
+    da = DAState(int(s.da_iteration), dt(s.da_log_step), dt(s.da_log_step_bar), dt(s.da_H_bar))
+    ch = ChEESState(dt(s.ch_log_T), dt(s.ch_log_T_bar), dt(s.ch_m1), dt(s.ch_m2), dt(s.ch_iteration), np.float32(s.ch_halton))
+    if isinstance(state, CompositeState):
+        return CompositeState(da, ch)
+    return da if isinstance(state, DAState) else ch

@@ -135,6 +135,20 @@ class HamiltonianEnsembleSampler(BaseSampler):
         import torch.distributed as dist
         dist.all_gather_into_tensor(full, local, group=self.group)
 
+    def _device_adapt_ok(self):
+        """Device-resident adaptation (hx_run_warmup) runs the exact SIMT kernels; problems that the precision policy sends to
+        the tensor-core path (whose launch sequence depends on L on the host) and ChEES beyond dim 128 keep the host loop."""
+        if adaptation.device_params(self.adapter) is None or not _rt.config.device_adaptation:
+            return False
+        ch_on = isinstance(self.adapter, (adaptation.ChEESAdapter, adaptation.CompositeAdapter))
+        if ch_on and self.dim > 128:
+            return False
+        from .targets import GaussianFull
+        n = self.total_chains // 2
+        tc = (_rt.config.precision != "exact" and self.dtype == torch.float32 and isinstance(self.target, GaussianFull)
+              and ((self.dim >= 256 and n >= 2048) if _rt.config.precision == "auto" else (self.dim >= 16 and n >= 64)))
+        return not tc
+
     @property
     def _peer_ok(self):
         """Peer-memory exchange needs a rank's rows and log-probs to be multiples of 16 bytes (vector stores)."""
@@ -180,9 +194,10 @@ class HamiltonianEnsembleSampler(BaseSampler):
         return self.get_chain(discard=warmup, thin=thin_by)                         # :139
 
     # -- batch-level engine (single GPU): T iterations per libhx call ----------------------------------
-    def _run_batches(self, key, X, lp, T, step_size, L, batch_size, offset, key_order, show_progress):
+    def _run_batches(self, key, X, lp, T, step_size, L, batch_size, offset, key_order, show_progress, adapt=None):
         """Runs T iterations in batches; streams (chain, log-prob) batches to pinned host memory on a
-        side stream while the next batch computes.  Returns per-walker accept counts (numpy)."""
+        side stream while the next batch computes.  Returns per-walker accept counts (numpy).
+        `adapt` = (hx_adapt_params, hx_adapt_state): warm-up with the adapter resident on the device (hx_run_warmup)."""
         dev, W, d = self.device, self.total_chains, self.dim
         n = W // 2
         lib = _lib.load()
@@ -210,11 +225,19 @@ class HamiltonianEnsembleSampler(BaseSampler):
             cbuf, lbuf = bufs[b % 2]
             if done[b % 2] is not None:
                 main.wait_event(done[b % 2])          # the copy out of this buffer must be finished
-            st = lib.hx_run_iterations(_rt.ctx(dev), _rt.dtype_code(self.dtype), _rt.impl_code(self.impl),
-                                       self._move_kind, key_order, desc, _rt.ptr(X), _rt.ptr(lp), n, float(step_size),
-                                       int(L), _rt.ptr(keys_dev[4 * start:]), stop - start, _rt.ptr(cbuf), _rt.ptr(lbuf),
+            if adapt is None:
+                st = lib.hx_run_iterations(_rt.ctx(dev), _rt.dtype_code(self.dtype), _rt.impl_code(self.impl),
+                                           self._move_kind, key_order, desc, _rt.ptr(X), _rt.ptr(lp), n, float(step_size),
+                                           int(L), _rt.ptr(keys_dev[4 * start:]), stop - start, _rt.ptr(cbuf), _rt.ptr(lbuf),
+                                           _rt.ptr(accepts), _rt.ptr(flag), _rt.stream(dev))
+                _lib.check(st, "hx_run_iterations")
+            else:
+                import ctypes as C
+                st = lib.hx_run_warmup(_rt.ctx(dev), _rt.dtype_code(self.dtype), _rt.impl_code(self.impl), self._move_kind, desc,
+                                       _rt.ptr(X), _rt.ptr(lp), n, C.byref(adapt[0]), C.byref(adapt[1]),
+                                       _rt.ptr(keys_dev[4 * start:]), stop - start, _rt.ptr(cbuf), _rt.ptr(lbuf),
                                        _rt.ptr(accepts), _rt.ptr(flag), _rt.stream(dev))
-            _lib.check(st, "hx_run_iterations")
+                _lib.check(st, "hx_run_warmup")
             ev = torch.cuda.Event()
             ev.record(main)
             copy_stream.wait_event(ev)
@@ -431,6 +454,15 @@ class HamiltonianEnsembleSampler(BaseSampler):
             X = torch.cat([group1, group2]).contiguous()
             lp = self.log_prob(X)
             acc = self._run_batches(key, X, lp, warmup, step, L, batch_size, 0, 1, show_progress)
+            group1, group2 = X[: self.total_chains // 2].clone(), X[self.total_chains // 2:].clone()
+        elif not noop and self.world == 1 and self._device_adapt_ok():
+            # adapter resident on the device: (step, L) read by the move kernels, update kernels between move and accept
+            params = adaptation.device_params(adapter)
+            dstate = adaptation.state_to_device(adapter, self.adapter_state)
+            X = torch.cat([group1, group2]).contiguous()
+            lp = self.log_prob(X)
+            acc = self._run_batches(key, X, lp, warmup, None, None, batch_size, 0, 1, show_progress, adapt=(params, dstate))
+            self.adapter_state = adaptation.state_from_device(adapter, self.adapter_state, dstate)
             group1, group2 = X[: self.total_chains // 2].clone(), X[self.total_chains // 2:].clone()
         elif noop and self._peer_ok:
             step, L = adapter.value(self.adapter_state)

@@ -223,6 +223,30 @@ HX_API int hx_run_iterations(hx_ctx* ctx, int dtype, int impl, int move_kind, in
                       const uint32_t* keys_dev, int64_t T, void* chain_out_dev, void* lp_out_dev,
                       int32_t* accepts_inout_dev, int32_t* nonfinite_flag_dev, void* stream);
 
+/* ---- (4b) batch level: the WARM-UP scan with live adapters (device-resident adaptation) ---------------------
+ * Replaces the warm-up scan body of samplers/hamiltonian_ensemble.py:165-217 for the dual-averaging step-size adapter
+ * (adaptation/dual_averaging.py:16-96), the ChEES trajectory-length adapter (adaptation/chees.py:18-219) and their
+ * composite (adaptation/adapter.py:44-78): per half-move (step, L) = adapter.value(state) is read by the move kernel from
+ * device memory, adapter.update runs on the device after the move and before the accept, keys are used in the warm-up
+ * order (keys[t,0] move1, [t,1] accept1, [t,2] move2, [t,3] accept2).  `state_inout` is a HOST struct (doubles hold the
+ * run dtype's values exactly); the call synchronises the stream once at the end to return it.  Exact SIMT kernels only;
+ * ChEES needs dim <= 128 (HX_E_UNSUPPORTED otherwise: the caller keeps its host-driven loop).                       */
+typedef struct hx_adapt_params {
+  int32_t use_da, use_chees, agg_harmonic, pass_L;
+  double da_target_accept, da_t0, da_gamma, da_kappa, da_init_step;
+  double ch_T_min, ch_T_max, ch_T_interp, ch_jitter, ch_lr, ch_beta1, ch_beta2, ch_reg;
+  double pass_step;
+} hx_adapt_params;
+typedef struct hx_adapt_state {
+  int64_t da_iteration;
+  double da_log_step, da_log_step_bar, da_H_bar;
+  double ch_log_T, ch_log_T_bar, ch_m1, ch_m2, ch_iteration, ch_halton;
+} hx_adapt_state;
+HX_API int hx_run_warmup(hx_ctx* ctx, int dtype, int impl, int move_kind, const hx_target* tgt, void* X_inout_dev,
+                  void* lp_inout_dev, int32_t n, const hx_adapt_params* params, hx_adapt_state* state_inout,
+                  const uint32_t* keys_dev, int64_t T, void* chain_out_dev, void* lp_out_dev,
+                  int32_t* accepts_inout_dev, int32_t* nonfinite_flag_dev, void* stream);
+
 /* ---- (5) row-sharded multi-GPU batch loop (the reference is single-device) ---------------------------
  * One process per GPU.  Rows of BOTH halves are split over `world` ranks (rank r owns rows [r n/world, (r+1) n/world) of each
  * half); every rank keeps a full copy [2n, dim] + log-probs [2n] in a library-owned region that its peers map with CUDA

@@ -100,6 +100,48 @@ def test_warmup_adaptation_parity_x64(x64, move):
     assert s.backend.iteration == 50 and chain.shape == (10, W, d)
 
 
+@pytest.mark.parametrize("move", ["walk", "side"])
+@pytest.mark.parametrize("adapt", [(True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("target", ["iso", "rosenbrock"])
+def test_device_adaptation_equals_host_loop_x64(x64, move, adapt, target):
+    """hx_run_warmup (adapter state, value() and update() on the device) against the host-driven warm-up loop: same adapter
+    trajectory (step to 1e-10, same L) and chain, for DA, ChEES and both, walk and side moves."""
+    hx = x64
+    W, d = 24, 4
+    tgt = hx.targets.GaussianIso(d) if target == "iso" else hx.targets.Rosenbrock(d)
+    keys = R.split(R.PRNGKey(4), 2)
+    x0 = R.normal(keys[0], (W, d), np.float64) * (1.0 if target == "iso" else 0.3) + (0.0 if target == "iso" else 1.0)
+    pm = hx.hmc_walk_move if move == "walk" else hx.hmc_side_move
+    out = {}
+    try:
+        for dev_adapt in (True, False):
+            hx.config.update("device_adaptation", dev_adapt)
+            s = hx.HamiltonianEnsembleSampler(W, d, tgt, step_size=0.05, L=5, move=pm, adapt_inital_step_size=False,
+                                              adapt_step_size=adapt[0], adapt_length=adapt[1], verbose=False)
+            chain = s.run_mcmc(keys[1], x0, 6, warmup=30, batch_size=7)
+            out[dev_adapt] = (chain, s.found, s.get_chain(), s.diagnostics_warmup["accepts"])
+    finally:
+        hx.config.update("device_adaptation", True)
+    assert int(out[True][1][1]) == int(out[False][1][1])
+    np.testing.assert_allclose(float(out[True][1][0]), float(out[False][1][0]), rtol=1e-10)
+    np.testing.assert_allclose(out[True][2], out[False][2], rtol=1e-8, atol=1e-9)        # warm-up + main chain
+    np.testing.assert_array_equal(out[True][3], out[False][3])
+
+
+def test_device_adaptation_f32_runs(hx):
+    """f32 warm-up on the device: finite chain, sane tuned values (draw-level agreement with the host loop is not expected in
+    f32: exp/log/pow differ in the last bit between NumPy and CUDA and one flipped accept decorrelates the trajectories)."""
+    W, d = 64, 8
+    tgt = hx.targets.Rosenbrock(d)
+    keys = R.split(R.PRNGKey(6), 2)
+    x0 = (R.normal(keys[0], (W, d), np.float32) * 0.3 + 1.0).astype(np.float32)
+    s = hx.HamiltonianEnsembleSampler(W, d, tgt, step_size=0.01, L=5, adapt_inital_step_size=False, verbose=False)
+    chain = s.run_mcmc(keys[1], x0, 20, warmup=100)
+    assert np.all(np.isfinite(chain)) and chain.shape == (20, W, d)
+    assert 1e-4 < float(s.found[0]) < 1.0 and 1 <= int(s.found[1]) <= 10000
+    assert s.backend.iteration == 120
+
+
 def test_quickstart_initial_step(x64):
     """docs/tutorials/quickstart.ipynb cell 8 prints 'Using inital step size of 1.6'."""
     hx = x64
