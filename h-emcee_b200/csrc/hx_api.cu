@@ -463,8 +463,19 @@ static int walk_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1,
   }
   ctx->last_path = 0;
   T *C, *M;
-  if (int e = center_complement<T>(ctx, X2, n, d, ldd, &C, s)) return e;
-  if (int e = gram_matrix<T>(ctx, C, n, ldd, &M, s)) return e;
+  if ((size_t)n * ldd <= (size_t)kPrepSmall && ldd <= 64) {
+    void *pC, *pMean, *pM;
+    if (int e = ws_get(ctx, WS_C, (size_t)n * ldd * sizeof(T), &pC)) return e;
+    if (int e = ws_get(ctx, WS_MEAN, (size_t)d * sizeof(T), &pMean)) return e;
+    if (int e = ws_get(ctx, WS_M, (size_t)ldd * ldd * sizeof(T), &pM)) return e;
+    k_prep_small<T><<<1, 256, 0, s>>>(X2, n, d, ldd, (T*)pMean, (T*)pC, (T*)pM);
+    HX_LAUNCH_CHECK("k_prep_small");
+    C = (T*)pC; M = (T*)pM;
+    ctx->last_gram_slices = 1;
+  } else {
+    if (int e = center_complement<T>(ctx, X2, n, d, ldd, &C, s)) return e;
+    if (int e = gram_matrix<T>(ctx, C, n, ldd, &M, s)) return e;
+  }
   void* pG;
   if (int e = ws_get(ctx, WS_G, (size_t)rows * d * sizeof(T), &pG)) return e;
   if (!pproj) {

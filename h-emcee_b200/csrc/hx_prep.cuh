@@ -100,6 +100,32 @@ __global__ void __launch_bounds__(256) k_gram(const T* __restrict__ C, int n, in
   }
 }
 
+// Small ensembles (n * ldd <= kPrepSmall): mean, centred complement and Gram matrix by ONE CTA in one launch instead of
+// 4-5 launch-latency-bound ones (the whole iteration of a 32-walker problem is ~10 launches).  Fixed summation order.
+constexpr int kPrepSmall = 8192;
+template <typename T>
+__global__ void __launch_bounds__(256) k_prep_small(const T* __restrict__ X, int n, int d, int ldd, T* __restrict__ mean,
+                                                    T* __restrict__ C, T* __restrict__ M) {
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    T s = T(0);
+    for (int r = 0; r < n; ++r) s += X[(size_t)r * d + c];
+    mean[c] = s / T(n);
+  }
+  __syncthreads();
+  const T sc = sqrt_t(T(n));
+  for (int i = threadIdx.x; i < n * ldd; i += blockDim.x) {
+    const int r = i / ldd, c = i - r * ldd;
+    C[i] = (c < d) ? (X[(size_t)r * d + c] - mean[c]) / sc : T(0);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ldd * ldd; i += blockDim.x) {
+    const int a = i / ldd, b = i - a * ldd;
+    T s = T(0);
+    for (int r = 0; r < n; ++r) s = fma_t(C[(size_t)r * ldd + a], C[(size_t)r * ldd + b], s);
+    M[i] = s;
+  }
+}
+
 template <typename T>
 __global__ void k_sum_slices(const T* __restrict__ part, int nslices, size_t count, T* __restrict__ out) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
