@@ -16,6 +16,7 @@
 #include "hx_tc_walk.h"
 #include "hx_dist.cuh"
 #include "hx_adapt.cuh"
+#include "hx_vanilla.cuh"
 #include <type_traits>
 
 using namespace hx;
@@ -766,6 +767,98 @@ extern "C" HX_API int hx_run_iterations(hx_ctx* ctx, int dtype, int impl, int mo
                                    (float*)chain_out, (float*)lp_out, accepts, nonfinite, s);
   return run_iterations_t<double>(ctx, impl, move_kind, key_order, tgt, (double*)X, (double*)lp, n, step_size, L, keys_dev, T,
                                   (double*)chain_out, (double*)lp_out, accepts, nonfinite, s);
+}
+
+// ---- (6) derivative-free ensemble moves (hx_vanilla.cuh) -----------------------------------------------------------------
+template <typename T>
+static int vanilla_half_t(hx_ctx* ctx, int impl, int kind, const hx_target* tgt, T* X1, const T* X2, int n, int row0, int rows,
+                          double stretch, Key key, const uint32_t* key_ptr, T* lp1, T* Q, T* logacc, T* lp_out, int do_accept,
+                          int32_t* accepts, T* chain_out, T* chain_lp, int32_t* nonfinite, cudaStream_t s) {
+  const int d = tgt->dim;
+  const int legacy = impl == HX_RNG_LEGACY ? 1 : 0;
+  void *pIdx = nullptr, *pExtra, *pShift = nullptr;
+  if (int e = ws_get(ctx, WS_LA, (size_t)2 * rows * sizeof(T), &pExtra)) return e;      // [extra | (unused)]
+  if (kind == kVanillaStretch || kind == kVanillaSide) {
+    if (int e = ws_get(ctx, WS_IDX, (size_t)rows * 2 * sizeof(int32_t), &pIdx)) return e;
+    // keys[0:n] of split(key, n + 2) drive the per-walker choices (stretch.py:35-46, side.py:30-39)
+    if (int e = launch_choice2(nullptr, key, key_ptr, (uint64_t)n + 2, row0, rows, impl, n, (int32_t*)pIdx, s)) return e;
+  } else {
+    T* mean;
+    if (int e = complement_mean<T>(ctx, X2, n, d, &mean, s)) return e;
+    if (int e = ws_get(ctx, WS_AD_MEAN, (size_t)2 * d * sizeof(T), &pShift)) return e;
+    k_vanilla_walk_shift<T><<<(d + 255) / 256, 256, 0, s>>>(X2, mean, n, d, key, key_ptr, legacy, (T*)pShift);
+    HX_LAUNCH_CHECK("k_vanilla_walk_shift");
+  }
+  k_vanilla_propose<T><<<(rows + 7) / 8, 256, 0, s>>>(kind, X1, X2, (const int32_t*)pIdx, key, key_ptr, legacy, n, row0, rows, d,
+                                                      (T)stretch, (const T*)pShift, Q, (T*)pExtra);
+  HX_LAUNCH_CHECK("k_vanilla_propose");
+  if (int e = log_prob_t<T>(ctx, tgt, Q, rows, lp_out, nullptr, s)) return e;
+  k_vanilla_finish<T><<<(rows + 7) / 8, 256, 0, s>>>(X1, Q, lp1, lp_out, (const T*)pExtra, logacc, do_accept, key, key_ptr, legacy, n,
+                                                     row0, rows, d, accepts, chain_out, chain_lp, nonfinite);
+  HX_LAUNCH_CHECK("k_vanilla_finish");
+  ctx->launches += 5;
+  return 0;
+}
+
+extern "C" HX_API int hx_vanilla_move(hx_ctx* ctx, int dtype, int impl, int kind, const hx_target* tgt, const void* X1, const void* X2,
+                               int32_t n, int32_t row0, int32_t rows, double stretch, const uint32_t key[2], const void* lp1,
+                               void* Q, void* logacc, void* lp_out, void* stream) {
+  if (!ctx || !tgt || !key || !X1 || !X2 || !lp1 || !Q || !logacc || !lp_out) return fail(HX_E_NULL, "hx_vanilla_move: NULL argument");
+  if (int e = check_dtype_impl(dtype, impl, "hx_vanilla_move")) return e;
+  if (kind < kVanillaStretch || kind > kVanillaWalk) return fail(HX_E_DTYPE, "hx_vanilla_move: kind must be 0 (stretch), 1 (side) or 2 (walk)");
+  if (n < 2 || row0 < 0 || rows < 1 || row0 + rows > n) return fail(HX_E_SHAPE, "hx_vanilla_move: bad row shard [%d, %d) of %d", row0, row0 + rows, n);
+  if (kind == kVanillaStretch && !(stretch >= 1.0)) return fail(HX_E_SHAPE, "hx_vanilla_move: stretch must be >= 1");
+  HX_CUDA(cudaSetDevice(ctx->device));
+  const Key k{key[0], key[1]};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == HX_F32)
+    return vanilla_half_t<float>(ctx, impl, kind, tgt, (float*)const_cast<void*>(X1), (const float*)X2, n, row0, rows, stretch, k, nullptr,
+                                 (float*)const_cast<void*>(lp1), (float*)Q, (float*)logacc, (float*)lp_out, 0, nullptr, nullptr, nullptr,
+                                 nullptr, s);
+  return vanilla_half_t<double>(ctx, impl, kind, tgt, (double*)const_cast<void*>(X1), (const double*)X2, n, row0, rows, stretch, k, nullptr,
+                                (double*)const_cast<void*>(lp1), (double*)Q, (double*)logacc, (double*)lp_out, 0, nullptr, nullptr,
+                                nullptr, nullptr, s);
+}
+
+template <typename T>
+static int run_vanilla_t(hx_ctx* ctx, int impl, int kind, const hx_target* tgt, T* X, T* lp, int n, double stretch, const uint32_t* keys,
+                         int64_t Tn, T* chain, T* chain_lp, int32_t* accepts, int32_t* nonfinite, cudaStream_t s) {
+  const int d = tgt->dim;
+  void *pQ, *pLa, *pLp;
+  if (int e = ws_get(ctx, WS_Q, (size_t)n * d * sizeof(T), &pQ)) return e;
+  if (int e = ws_get(ctx, WS_AD_STAT, (size_t)n * sizeof(T), &pLa)) return e;
+  if (int e = ws_get(ctx, WS_LP, (size_t)n * sizeof(T), &pLp)) return e;
+  const size_t W2 = (size_t)2 * n;
+  for (int64_t t = 0; t < Tn; ++t) {
+    for (int half = 0; half < 2; ++half) {
+      const uint32_t* k = keys + (size_t)t * 4 + 2 * half;      // keys[t, half]: move AND accept (ensemble.py:100-109)
+      T* Xa = X + (size_t)half * n * d;
+      T* Xb = X + (size_t)(1 - half) * n * d;
+      if (int e = vanilla_half_t<T>(ctx, impl, kind, tgt, Xa, Xb, n, 0, n, stretch, Key{0, 0}, k, lp + (size_t)half * n, (T*)pQ, (T*)pLa,
+                                    (T*)pLp, 1, accepts + (size_t)half * n,
+                                    chain ? chain + ((size_t)t * W2 + (size_t)half * n) * d : nullptr,
+                                    chain_lp ? chain_lp + (size_t)t * W2 + (size_t)half * n : nullptr, nonfinite, s))
+        return e;
+    }
+  }
+  return 0;
+}
+
+extern "C" HX_API int hx_run_vanilla_iterations(hx_ctx* ctx, int dtype, int impl, int kind, const hx_target* tgt, void* X, void* lp,
+                                         int32_t n, double stretch, const uint32_t* keys_dev, int64_t T, void* chain_out,
+                                         void* lp_out, int32_t* accepts, int32_t* nonfinite, void* stream) {
+  if (!ctx || !tgt || !X || !lp || !keys_dev || !accepts || !nonfinite) return fail(HX_E_NULL, "hx_run_vanilla_iterations: NULL argument");
+  if (int e = check_dtype_impl(dtype, impl, "hx_run_vanilla_iterations")) return e;
+  if (kind < kVanillaStretch || kind > kVanillaWalk) return fail(HX_E_DTYPE, "hx_run_vanilla_iterations: kind must be 0, 1 or 2");
+  if (n < 2 || T < 0) return fail(HX_E_SHAPE, "hx_run_vanilla_iterations: need n >= 2, T >= 0");
+  if (kind == kVanillaStretch && !(stretch >= 1.0)) return fail(HX_E_SHAPE, "hx_run_vanilla_iterations: stretch must be >= 1");
+  HX_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == HX_F32)
+    return run_vanilla_t<float>(ctx, impl, kind, tgt, (float*)X, (float*)lp, n, stretch, keys_dev, T, (float*)chain_out, (float*)lp_out,
+                                accepts, nonfinite, s);
+  return run_vanilla_t<double>(ctx, impl, kind, tgt, (double*)X, (double*)lp, n, stretch, keys_dev, T, (double*)chain_out, (double*)lp_out,
+                               accepts, nonfinite, s);
 }
 
 // ---- (4b) warm-up scan with live adapters: adapter state, value() and update() on the device (hx_adapt.cuh) ---------------------

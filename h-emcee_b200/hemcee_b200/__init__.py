@@ -13,8 +13,9 @@ from .adaptation import ChEESParameters, DAParameters
 from .backend import Backend
 from .moves import hmc_side_move, hmc_walk_move
 from .sampler import HamiltonianEnsembleSampler
+from .ensemble import EnsembleSampler, side_move, stretch_move, walk_move
 
 __version__ = "0.1.0"
 
-__all__ = ["HamiltonianEnsembleSampler", "hmc_walk_move", "hmc_side_move", "DAParameters", "ChEESParameters",
+__all__ = ["HamiltonianEnsembleSampler", "EnsembleSampler", "stretch_move", "side_move", "walk_move", "hmc_walk_move", "hmc_side_move", "DAParameters", "ChEESParameters",
            "Backend", "autocorr", "random", "targets", "config", "HxError"]

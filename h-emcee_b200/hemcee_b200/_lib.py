@@ -81,6 +81,10 @@ _PROTOS = {
                                     C.c_int32, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "hx_run_warmup": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.POINTER(hx_adapt_params),
                                 C.POINTER(hx_adapt_state), _P, C.c_int64, _P, _P, _P, _P, _P]),
+    "hx_vanilla_move": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_double, _KEY, _P, _P, _P, _P, _P]),
+    "hx_run_vanilla_iterations": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.c_double, _P,
+                                            C.c_int64, _P, _P, _P, _P, _P]),
     "hx_dist_init": (C.c_int, [_P, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "hx_dist_connect": (C.c_int, [_P, _P]),
     "hx_dist_buffers": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),

@@ -247,6 +247,19 @@ HX_API int hx_run_warmup(hx_ctx* ctx, int dtype, int impl, int move_kind, const 
                   const uint32_t* keys_dev, int64_t T, void* chain_out_dev, void* lp_out_dev,
                   int32_t* accepts_inout_dev, int32_t* nonfinite_flag_dev, void* stream);
 
+/* ---- (6) derivative-free ensemble moves and their scan --------------------------------------
+ * kind 0 = stretch_move (moves/vanilla/stretch.py:5-76), 1 = side_move (moves/vanilla/side.py:5-56), 2 = walk_move
+ * (moves/vanilla/walk.py:5-42).  hx_vanilla_move mirrors move(group1, group2, key, log_prob, log_prob_group1, stretch)
+ * -> (proposed, log_accept_prob, proposed_log_prob); hx_run_vanilla_iterations replaces the scan of
+ * samplers/ensemble.py:97-129 (keys_dev uint32 [T,2,2] = split(key, 2T); keys[t,h] drives move AND accept of half h).  */
+HX_API int hx_vanilla_move(hx_ctx* ctx, int dtype, int impl, int kind, const hx_target* tgt, const void* X1_dev,
+                    const void* X2_dev, int32_t n, int32_t row0, int32_t rows, double stretch, const uint32_t key[2],
+                    const void* lp1_dev, void* Q_out_dev, void* logacc_out_dev, void* lp_out_dev, void* stream);
+HX_API int hx_run_vanilla_iterations(hx_ctx* ctx, int dtype, int impl, int kind, const hx_target* tgt, void* X_inout_dev,
+                              void* lp_inout_dev, int32_t n, double stretch, const uint32_t* keys_dev, int64_t T,
+                              void* chain_out_dev, void* lp_out_dev, int32_t* accepts_inout_dev,
+                              int32_t* nonfinite_flag_dev, void* stream);
+
 /* ---- (5) row-sharded multi-GPU batch loop (the reference is single-device) ---------------------------
  * One process per GPU.  Rows of BOTH halves are split over `world` ranks (rank r owns rows [r n/world, (r+1) n/world) of each
  * half); every rank keeps a full copy [2n, dim] + log-probs [2n] in a library-owned region that its peers map with CUDA

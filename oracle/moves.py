@@ -143,3 +143,58 @@ def accept_proposal(current, proposed, log_accept_prob, key, impl=jaxrng.DEFAULT
 
 hmc_walk_move.__name__ = "hmc_walk_move"
 hmc_side_move.__name__ = "hmc_side_move"
+
+
+# ---- derivative-free ensemble moves -----------------------------------------------------------------
+def sample_inv_sqrt_density(key, a, shape, dt, impl=jaxrng.DEFAULT_IMPL):
+    """moves/vanilla/stretch.py:58-76: z ~ z^{-1/2} on [1/a, a] by inversion, in the default float type."""
+    a = dt(a)
+    u = jaxrng.uniform(key, shape, dt, 0.0, 1.0, impl)
+    sqrt_a = np.sqrt(a)
+    inv_sqrt_a = dt(1.0) / sqrt_a
+    t = inv_sqrt_a + u * (sqrt_a - inv_sqrt_a)
+    return (t * t).astype(dt)
+
+
+def stretch_move(group1, group2, key, log_prob, log_prob_group1, stretch=2.0, impl=jaxrng.DEFAULT_IMPL):
+    """moves/vanilla/stretch.py:5-56 (Goodman-Weare stretch move, Alg. 1 of arXiv:2505.02987)."""
+    dt = _dt(group1)
+    n, dim = group1.shape
+    keys = jaxrng.split(key, n + 2, impl)                                       # :35-38
+    idx = np.array([jaxrng.choice_no_replace(k, n, 1, impl)[0] for k in keys[:n]])   # :40-46
+    z = sample_inv_sqrt_density(keys[-1], stretch, (n,), dt, impl)              # :48
+    xj = group2[idx]
+    prop = (xj + z[:, None] * (group1 - xj)).astype(dt)                         # :49
+    lpp = log_prob(prop)
+    la = (dt(dim - 1) * np.log(z) + lpp - log_prob_group1).astype(dt)           # :53
+    return prop, la, lpp
+
+
+def side_move(group1, group2, key, log_prob, log_prob_group1, stretch=2.0, impl=jaxrng.DEFAULT_IMPL):
+    """moves/vanilla/side.py:5-56 (Alg. 2)."""
+    dt = _dt(group1)
+    n = group1.shape[0]
+    keys = jaxrng.split(key, n + 2, impl)                                       # :30-33
+    ch = side_choices(keys[:n], n, impl)                                        # :35-39
+    z = jaxrng.normal(keys[-2], (n, 1), dt, impl)                               # :44
+    prop = (group1 + (dt(stretch) * z) * (group2[ch[:, 0]] - group2[ch[:, 1]])).astype(dt)   # :49
+    lpp = log_prob(prop)
+    return prop, (lpp - log_prob_group1).astype(dt), lpp                        # :52
+
+
+def walk_move(group1, group2, key, log_prob, log_prob_group1, impl=jaxrng.DEFAULT_IMPL, **_):
+    """moves/vanilla/walk.py:5-42 (Alg. 4): ONE shared random combination of the centred complement shifts every walker."""
+    dt = _dt(group1)
+    n = group1.shape[0]
+    key_noise = jaxrng.split(key, 2, impl)[0]                                   # :29
+    m = np.mean(group2, axis=0, dtype=dt)                                       # :32
+    xi = jaxrng.normal(key_noise, (n,), dt, impl)                               # :33
+    shift = (np.einsum("bi,b->i", group2 - m, xi) / np.sqrt(dt(n))).astype(dt)  # :35
+    prop = (group1 + shift[None, :]).astype(dt)                                 # :36
+    lpp = log_prob(prop)
+    return prop, (lpp - log_prob_group1).astype(dt), lpp                        # :39
+
+
+stretch_move.__name__ = "stretch_move"
+side_move.__name__ = "side_move"
+walk_move.__name__ = "walk_move"

@@ -223,3 +223,52 @@ class HamiltonianEnsembleSampler:
             return
         *_, accepts = self._scan(body, carry, keys, batch_size, warmup_offset)
         self.diagnostics_main = {"accepts": accepts, "acceptance_rate": accepts / total}
+
+
+class EnsembleSampler:
+    """reference src/hemcee/samplers/ensemble.py:9-140 (derivative-free affine-invariant ensemble sampler)."""
+
+    def __init__(self, total_chains, dim, log_prob, move=moves.stretch_move, backend=None, dtype=np.float32,
+                 impl=None):
+        from . import jaxrng
+        if total_chains < 4:
+            raise ValueError("`total_chains` must be at least 4 to form meaningful ensemble groups")
+        self.total_chains, self.dim = int(total_chains), int(dim)
+        self.log_prob = log_prob[0] if isinstance(log_prob, tuple) else log_prob
+        self.move = move
+        self.dtype = dtype
+        self.impl = impl or jaxrng.DEFAULT_IMPL
+        self.backend = Backend() if backend is None else backend
+        self.backend.reset(total_chains, dim)
+        self.diagnostics_main = None
+
+    def get_chain(self, discard=0, thin=1, flat=False):
+        return self.backend.get_chain(discard=discard, thin=thin, flat=flat)
+
+    def run_mcmc(self, key, initial_state, num_samples, warmup=1000, thin_by=1, batch_size=None, **kwargs):
+        from . import jaxrng
+        total = warmup + num_samples * thin_by                                  # :66
+        x = np.asarray(initial_state, dtype=self.dtype)
+        n1 = self.total_chains // 2
+        keys = jaxrng.split(key, total * 2, self.impl).reshape(total, 2, 2)     # :79-81
+        g1, g2 = x[:n1].copy(), x[n1:].copy()
+        lp1, lp2 = self.log_prob(g1), self.log_prob(g2)
+        accepts = np.zeros(self.total_chains)
+        chain = np.empty((total, self.total_chains, self.dim), self.dtype)
+        lps = np.empty((total, self.total_chains), self.dtype)
+        for t in range(total):                                                  # body :97-122
+            k = keys[t]
+            prop, la, lpp = self.move(g1, g2, k[0], self.log_prob, lp1, impl=self.impl, **kwargs)
+            g1, a1 = moves.accept_proposal(g1, prop, la, k[0], self.impl)
+            lp1, _ = moves.accept_proposal(lp1, lpp, la, k[0], self.impl)
+            prop, la, lpp = self.move(g2, g1, k[1], self.log_prob, lp2, impl=self.impl, **kwargs)
+            g2, a2 = moves.accept_proposal(g2, prop, la, k[1], self.impl)
+            lp2, _ = moves.accept_proposal(lp2, lpp, la, k[1], self.impl)
+            accepts += np.concatenate([a1, a2])
+            chain[t] = np.concatenate([g1, g2])
+            lps[t] = np.concatenate([lp1, lp2])
+            if not np.all(np.isfinite(lps[t])):
+                raise ValueError("Log probability returned NaN or inf value, please check your log probability function")
+        self.backend.save_slice(chain, lps, accepts, 0)
+        self.diagnostics_main = {"accepts": accepts, "acceptance_rate": accepts / total if total else accepts}
+        return self.get_chain(discard=warmup, thin=thin_by)

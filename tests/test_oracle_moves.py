@@ -163,3 +163,28 @@ def test_halton_and_da_quirks():
     # notebook ends at 0.1016 after 2e5 updates with 99.9 % acceptance
     assert abs(float(da.finalize(st)[0]) - 0.1016) < 5e-4
     assert da.average_over_rate(np.array([0.0, -np.inf])) == 0.0  # harmonic mean: any zero accept prob -> 0
+
+
+# ---- derivative-free moves: affine invariance (reference tests/affine_invariance/test_proposal_vanilla.py:17-90) ------------
+@pytest.mark.parametrize("name", ["stretch_move", "side_move", "walk_move"])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_vanilla_moves_affine_invariant_oracle(name, seed):
+    """R(A X + b; phi_# pi) = A R(X; pi) + b for the same key, and identical log-accept ratios."""
+    from oracle import jaxrng as R, moves as OM
+    d, n = 5, 20
+    ks = R.split(R.PRNGKey(seed), 7)
+    A = R.normal(ks[0], (d, d), np.float64) + 3.0 * np.eye(d)
+    b = R.normal(ks[1], (d,), np.float64)
+    Sig = np.cov(R.normal(ks[2], (4 * d, d), np.float64).T) + np.eye(d)
+    P = np.linalg.inv(Sig)
+    Ainv = np.linalg.inv(A)
+    lp = lambda x: -0.5 * np.einsum("bi,ij,bj->b", x, P, x)
+    lp_push = lambda y: lp((y - b) @ Ainv.T)          # density of A x + b up to a constant
+    g1 = R.normal(ks[4], (n, d), np.float64)
+    g2 = R.normal(ks[5], (n, d), np.float64)
+    t1, t2 = g1 @ A.T + b, g2 @ A.T + b
+    mv = getattr(OM, name)
+    q, la, _ = mv(g1, g2, ks[6], lp, lp(g1))
+    qt, lat, _ = mv(t1, t2, ks[6], lp_push, lp_push(t1))
+    np.testing.assert_allclose(qt, q @ A.T + b, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(lat, la, rtol=1e-8, atol=1e-8)
