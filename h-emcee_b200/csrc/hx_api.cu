@@ -703,6 +703,22 @@ extern "C" HX_API int hx_accept(hx_ctx* ctx, int dtype, int impl, void* cur, con
   return 0;
 }
 
+// thinned chain emit: iteration t of a batch call is stored iff (t + phase) % every == 0, into consecutive slots
+static inline int64_t chain_slot(const hx_ctx* ctx, int64_t t) {
+  const int every = ctx->chain_every > 1 ? ctx->chain_every : 1;
+  if (every == 1) return t;
+  const int64_t g = t + ctx->chain_phase;
+  return (g % every == 0) ? (g / every - (ctx->chain_phase + every - 1) / every) : -1;
+}
+
+extern "C" HX_API int hx_ctx_set_chain_thinning(hx_ctx* ctx, int32_t every, int32_t phase) {
+  if (!ctx) return fail(HX_E_NULL, "hx_ctx_set_chain_thinning: NULL ctx");
+  if (every < 1 || phase < 0 || phase >= every) return fail(HX_E_SHAPE, "hx_ctx_set_chain_thinning: need every >= 1 and 0 <= phase < every");
+  ctx->chain_every = every;
+  ctx->chain_phase = phase;
+  return 0;
+}
+
 // ---- batch level: T iterations of the main phase ----------------------------------------------------------------------
 template <typename T>
 static int run_iterations_t(hx_ctx* ctx, int impl, int move_kind, int key_order, const hx_target* tgt, T* X, T* lp, int n, double eps,
@@ -729,8 +745,9 @@ static int run_iterations_t(hx_ctx* ctx, int impl, int move_kind, int key_order,
       T* lpa = lp + (size_t)half * n;
       Fuse<T> f;
       f.akey_ptr = kacc; f.lp1w = lpa; f.accepts = accepts + (size_t)half * n;
-      f.chain_out = chain ? chain + ((size_t)t * W2 + (size_t)half * n) * d : nullptr;
-      f.chain_lp = chain_lp ? chain_lp + (size_t)t * W2 + (size_t)half * n : nullptr;
+      const int64_t slot = chain_slot(ctx, t);     // -1: this iteration is not stored (thinned emit)
+      f.chain_out = (chain && slot >= 0) ? chain + ((size_t)slot * W2 + (size_t)half * n) * d : nullptr;
+      f.chain_lp = (chain_lp && slot >= 0) ? chain_lp + (size_t)slot * W2 + (size_t)half * n : nullptr;
       f.nonfinite = nonfinite;
       f.push = nullptr;
       int e;
@@ -1083,8 +1100,9 @@ static int run_iterations_sharded_t(hx_ctx* ctx, int impl, int move_kind, int ke
       T* lpa = lpf + (size_t)half * n + row0;
       Fuse<T> f;
       f.akey_ptr = kt + 2 * ia; f.lp1w = lpa; f.accepts = accepts + (size_t)half * rows;
-      f.chain_out = chain ? chain + ((size_t)t * 2 * rows + (size_t)half * rows) * d : nullptr;
-      f.chain_lp = chain_lp ? chain_lp + (size_t)t * 2 * rows + (size_t)half * rows : nullptr;
+      const int64_t slot = chain_slot(ctx, t);
+      f.chain_out = (chain && slot >= 0) ? chain + ((size_t)slot * 2 * rows + (size_t)half * rows) * d : nullptr;
+      f.chain_lp = (chain_lp && slot >= 0) ? chain_lp + (size_t)slot * 2 * rows + (size_t)half * rows : nullptr;
       f.nonfinite = nonfinite;
       // exchange: the rank's updated rows (+ log-probs) are stored into every peer's copy and the epoch is published, either by
       // the tensor-core path's finish kernel itself or by k_dist_push after the SIMT half-move

@@ -59,6 +59,7 @@ struct hx_ctx {
   P0Job hint; int hint_valid;              // hx_walk_prefetch: the walk half-move after the next one
   int leap_form;                           // HX_LEAP_*
   HxDist dist;
+  int chain_every, chain_phase;            // thinned chain emit of the batch loops (hx_ctx_set_chain_thinning); 0/1 = every iteration
   const void* ctl_eps; const int* ctl_L;   // device-resident (step, L) the SIMT move kernels read during adaptive warm-up
   int energy_bf16;                         // 1: propagator-form energy products from bf16 hi/lo operands (default tf32 hi/lo)
   int gram_tf32;                           // 1: Gram from tf32 hi/lo operands instead of bf16 hi/lo

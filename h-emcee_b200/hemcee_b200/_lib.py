@@ -79,6 +79,7 @@ _PROTOS = {
                             _P, _P]),
     "hx_run_iterations": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.c_double,
                                     C.c_int32, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    "hx_ctx_set_chain_thinning": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "hx_run_warmup": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.POINTER(hx_adapt_params),
                                 C.POINTER(hx_adapt_state), _P, C.c_int64, _P, _P, _P, _P, _P]),
     "hx_vanilla_move": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.c_int32, C.c_int32,

@@ -87,7 +87,7 @@ class BaseSampler:
 class HamiltonianEnsembleSampler(BaseSampler):
     def __init__(self, total_chains, dim, log_prob, step_size=0.1, L=10, move=hmc_walk_move, backend=None,
                  adapt_inital_step_size=True, adapt_step_size=True, adapt_length=True, *, device=None, group=None,
-                 chain_store="full", exchange="peer", verbose=True):
+                 chain_store="full", exchange="peer", store="full", verbose=True):
         super().__init__(total_chains, dim, log_prob, move, backend)
         if getattr(move, "__name__", None) not in ("hmc_walk_move", "hmc_side_move"):
             raise ValueError("HamiltonianEnsembleSampler on B200 supports move=hmc_walk_move or hmc_side_move")
@@ -102,6 +102,10 @@ class HamiltonianEnsembleSampler(BaseSampler):
         self.verbose = verbose
         self.group = group
         self.chain_store = chain_store
+        if store not in ("full", "thinned"):
+            raise ValueError("store must be 'full' (every iteration, like the reference) or 'thinned' (only the iterations "
+                             "run_mcmc returns: no warm-up, every thin_by-th main iteration)")
+        self.store = store
         if exchange not in ("peer", "nccl"):
             raise ValueError("exchange must be 'peer' (NVLink peer-memory stores from the kernels) or 'nccl' (all-gather)")
         self.exchange = exchange
@@ -157,6 +161,10 @@ class HamiltonianEnsembleSampler(BaseSampler):
         return self.exchange == "peer" and (rows * self.dim * esz) % 16 == 0 and (rows * esz) % 16 == 0
 
     @property
+    def _thinned(self):
+        return self.store == "thinned" and self.world == 1
+
+    @property
     def _move_kind(self):
         return 0 if self.move.__name__ == "hmc_walk_move" else 1
 
@@ -191,13 +199,21 @@ class HamiltonianEnsembleSampler(BaseSampler):
         self._mcmc_main(keys[2], group1, group2, num_samples, thin_by, step_size, L, main_bs, show_progress,
                         warmup_offset=warmup)
         self._say("Main sampling complete.")
+        if self._thinned:
+            # only the returned iterations were stored; the backend counts the iterations that were RUN
+            self.backend.iteration = warmup + num_samples * thin_by
+            self.backend.iteration_main = num_samples * thin_by
+            return self.backend.get_chain()[-num_samples:] if num_samples > 0 else self.backend.get_chain()[:0]
         return self.get_chain(discard=warmup, thin=thin_by)                         # :139
 
     # -- batch-level engine (single GPU): T iterations per libhx call ----------------------------------
-    def _run_batches(self, key, X, lp, T, step_size, L, batch_size, offset, key_order, show_progress, adapt=None):
+    def _run_batches(self, key, X, lp, T, step_size, L, batch_size, offset, key_order, show_progress, adapt=None,
+                     thin_store=1):
         """Runs T iterations in batches; streams (chain, log-prob) batches to pinned host memory on a
         side stream while the next batch computes.  Returns per-walker accept counts (numpy).
-        `adapt` = (hx_adapt_params, hx_adapt_state): warm-up with the adapter resident on the device (hx_run_warmup)."""
+        `adapt` = (hx_adapt_params, hx_adapt_state): warm-up with the adapter resident on the device (hx_run_warmup).
+        `thin_store` = k > 1: only iterations 0, k, 2k, ... of this phase are emitted and stored (hx_ctx_set_chain_thinning);
+        0: nothing is stored."""
         dev, W, d = self.device, self.total_chains, self.dim
         n = W // 2
         lib = _lib.load()
@@ -207,11 +223,15 @@ class HamiltonianEnsembleSampler(BaseSampler):
             return accepts.cpu().numpy()
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
         nb = (T + batch_size - 1) // batch_size
-        host_chain = torch.empty((T, W, d), dtype=self.dtype, pin_memory=True)
-        host_lp = torch.empty((T, W), dtype=self.dtype, pin_memory=True)
+        k = int(thin_store)
+        nstore = lambda a, b: (b - a) if k == 1 else (0 if k == 0 else (-(-b // k)) - (-(-a // k)))   # stored iterations in [a, b)
+        Ts = nstore(0, T)
+        host_chain = torch.empty((Ts, W, d), dtype=self.dtype, pin_memory=Ts > 0)
+        host_lp = torch.empty((Ts, W), dtype=self.dtype, pin_memory=Ts > 0)
         host_flag = torch.zeros(nb, dtype=torch.int32, pin_memory=True)
-        bufs = [(torch.empty((min(batch_size, T), W, d), dtype=self.dtype, device=dev),
-                 torch.empty((min(batch_size, T), W), dtype=self.dtype, device=dev)) for _ in range(min(2, nb))]
+        bmax = max(nstore(b * batch_size, min((b + 1) * batch_size, T)) for b in range(nb))
+        bufs = [(torch.empty((max(bmax, 1), W, d), dtype=self.dtype, device=dev),
+                 torch.empty((max(bmax, 1), W), dtype=self.dtype, device=dev)) for _ in range(min(2, nb))]
         copy_stream = torch.cuda.Stream(dev)
         done = [None, None]
         main = torch.cuda.current_stream(dev)
@@ -220,42 +240,56 @@ class HamiltonianEnsembleSampler(BaseSampler):
         if show_progress:
             from tqdm import tqdm
             it = tqdm(it)
-        for b in it:
-            start, stop = b * batch_size, min((b + 1) * batch_size, T)
-            cbuf, lbuf = bufs[b % 2]
-            if done[b % 2] is not None:
-                main.wait_event(done[b % 2])          # the copy out of this buffer must be finished
-            if adapt is None:
-                st = lib.hx_run_iterations(_rt.ctx(dev), _rt.dtype_code(self.dtype), _rt.impl_code(self.impl),
-                                           self._move_kind, key_order, desc, _rt.ptr(X), _rt.ptr(lp), n, float(step_size),
-                                           int(L), _rt.ptr(keys_dev[4 * start:]), stop - start, _rt.ptr(cbuf), _rt.ptr(lbuf),
+        pos = 0
+        try:
+            for b in it:
+                start, stop = b * batch_size, min((b + 1) * batch_size, T)
+                cbuf, lbuf = bufs[b % 2]
+                ns = nstore(start, stop)
+                if done[b % 2] is not None:
+                    main.wait_event(done[b % 2])          # the copy out of this buffer must be finished
+                if k > 1:
+                    _lib.check(lib.hx_ctx_set_chain_thinning(_rt.ctx(dev), k, start % k), "hx_ctx_set_chain_thinning")
+                cptr, lptr = (_rt.ptr(cbuf), _rt.ptr(lbuf)) if k != 0 else (None, None)
+                if adapt is None:
+                    st = lib.hx_run_iterations(_rt.ctx(dev), _rt.dtype_code(self.dtype), _rt.impl_code(self.impl),
+                                               self._move_kind, key_order, desc, _rt.ptr(X), _rt.ptr(lp), n, float(step_size),
+                                               int(L), _rt.ptr(keys_dev[4 * start:]), stop - start, cptr, lptr,
+                                               _rt.ptr(accepts), _rt.ptr(flag), _rt.stream(dev))
+                    _lib.check(st, "hx_run_iterations")
+                else:
+                    import ctypes as C
+                    st = lib.hx_run_warmup(_rt.ctx(dev), _rt.dtype_code(self.dtype), _rt.impl_code(self.impl), self._move_kind, desc,
+                                           _rt.ptr(X), _rt.ptr(lp), n, C.byref(adapt[0]), C.byref(adapt[1]),
+                                           _rt.ptr(keys_dev[4 * start:]), stop - start, cptr, lptr,
                                            _rt.ptr(accepts), _rt.ptr(flag), _rt.stream(dev))
-                _lib.check(st, "hx_run_iterations")
-            else:
-                import ctypes as C
-                st = lib.hx_run_warmup(_rt.ctx(dev), _rt.dtype_code(self.dtype), _rt.impl_code(self.impl), self._move_kind, desc,
-                                       _rt.ptr(X), _rt.ptr(lp), n, C.byref(adapt[0]), C.byref(adapt[1]),
-                                       _rt.ptr(keys_dev[4 * start:]), stop - start, _rt.ptr(cbuf), _rt.ptr(lbuf),
-                                       _rt.ptr(accepts), _rt.ptr(flag), _rt.stream(dev))
-                _lib.check(st, "hx_run_warmup")
-            ev = torch.cuda.Event()
-            ev.record(main)
-            copy_stream.wait_event(ev)
-            with torch.cuda.stream(copy_stream):
-                host_chain[start:stop].copy_(cbuf[: stop - start], non_blocking=True)
-                host_lp[start:stop].copy_(lbuf[: stop - start], non_blocking=True)
-                host_flag[b:b + 1].copy_(flag, non_blocking=True)
-                done[b % 2] = torch.cuda.Event()
-                done[b % 2].record(copy_stream)
-            if b >= 1 and int(host_flag[b - 1]) != 0 and done[(b - 1) % 2].query():
-                raise ValueError(_NONFINITE_MSG)                                     # sampler_utils.py:74-75
+                    _lib.check(st, "hx_run_warmup")
+                ev = torch.cuda.Event()
+                ev.record(main)
+                copy_stream.wait_event(ev)
+                with torch.cuda.stream(copy_stream):
+                    if ns > 0:
+                        host_chain[pos:pos + ns].copy_(cbuf[:ns], non_blocking=True)
+                        host_lp[pos:pos + ns].copy_(lbuf[:ns], non_blocking=True)
+                    host_flag[b:b + 1].copy_(flag, non_blocking=True)
+                    done[b % 2] = torch.cuda.Event()
+                    done[b % 2].record(copy_stream)
+                pos += ns
+                if b >= 1 and int(host_flag[b - 1]) != 0 and done[(b - 1) % 2].query():
+                    raise ValueError(_NONFINITE_MSG)                                     # sampler_utils.py:74-75
+        finally:
+            if k > 1:
+                lib.hx_ctx_set_chain_thinning(_rt.ctx(dev), 1, 0)
         copy_stream.synchronize()
         main.synchronize()
         if int(host_flag.max()) != 0:
             raise ValueError(_NONFINITE_MSG)
         acc = accepts.cpu().numpy()
         # one slice for the whole phase: the pinned host buffer becomes the stored chain without another copy
-        self.backend.save_slice(host_chain.numpy(), host_lp.numpy(), acc, offset)
+        if Ts > 0:
+            self.backend.save_slice(host_chain.numpy(), host_lp.numpy(), acc, offset)
+        else:
+            self.backend.accepted = self.backend.accepted + acc
         self.kernel_launch_count += T * 2 * (6 if self._move_kind == 0 else 2)
         return acc
 
@@ -453,7 +487,8 @@ class HamiltonianEnsembleSampler(BaseSampler):
             step, L = adapter.value(self.adapter_state)
             X = torch.cat([group1, group2]).contiguous()
             lp = self.log_prob(X)
-            acc = self._run_batches(key, X, lp, warmup, step, L, batch_size, 0, 1, show_progress)
+            acc = self._run_batches(key, X, lp, warmup, step, L, batch_size, 0, 1, show_progress,
+                                    thin_store=0 if self._thinned else 1)
             group1, group2 = X[: self.total_chains // 2].clone(), X[self.total_chains // 2:].clone()
         elif not noop and self.world == 1 and self._device_adapt_ok():
             # adapter resident on the device: (step, L) read by the move kernels, update kernels between move and accept
@@ -461,7 +496,8 @@ class HamiltonianEnsembleSampler(BaseSampler):
             dstate = adaptation.state_to_device(adapter, self.adapter_state)
             X = torch.cat([group1, group2]).contiguous()
             lp = self.log_prob(X)
-            acc = self._run_batches(key, X, lp, warmup, None, None, batch_size, 0, 1, show_progress, adapt=(params, dstate))
+            acc = self._run_batches(key, X, lp, warmup, None, None, batch_size, 0, 1, show_progress, adapt=(params, dstate),
+                                    thin_store=0 if self._thinned else 1)
             self.adapter_state = adaptation.state_from_device(adapter, self.adapter_state, dstate)
             group1, group2 = X[: self.total_chains // 2].clone(), X[self.total_chains // 2:].clone()
         elif noop and self._peer_ok:
@@ -484,7 +520,8 @@ class HamiltonianEnsembleSampler(BaseSampler):
         if self.world == 1:
             X = torch.cat([group1, group2]).contiguous()
             lp = self.log_prob(X)                                                    # :325-326
-            acc = self._run_batches(key, X, lp, total, step_size, L, batch_size, warmup_offset, 0, show_progress)
+            acc = self._run_batches(key, X, lp, total, step_size, L, batch_size, 0 if self._thinned else warmup_offset, 0,
+                                    show_progress, thin_store=thin_by if self._thinned else 1)
             self.last_state = X
         elif self._peer_ok:
             acc = self._run_batches_sharded(key, group1, group2, total, step_size, L, batch_size, warmup_offset, 0, show_progress)

@@ -223,6 +223,12 @@ HX_API int hx_run_iterations(hx_ctx* ctx, int dtype, int impl, int move_kind, in
                       const uint32_t* keys_dev, int64_t T, void* chain_out_dev, void* lp_out_dev,
                       int32_t* accepts_inout_dev, int32_t* nonfinite_flag_dev, void* stream);
 
+/* Thinned chain emit for hx_run_iterations / hx_run_iterations_sharded: iteration t of a call is written
+ * to chain_out / lp_out iff (t + phase) % every == 0, into consecutive slots (chain_out then holds
+ * ceil((T + phase) / every) - ceil(phase / every) slices).  The reference stores every iteration and thins on read
+ * (backend/backend.py:63-66), which is 262 MB per iteration at c5.  every = 1 restores the default.               */
+HX_API int hx_ctx_set_chain_thinning(hx_ctx* ctx, int32_t every, int32_t phase);
+
 /* ---- (4b) batch level: the WARM-UP scan with live adapters (device-resident adaptation) ---------------------
  * Replaces the warm-up scan body of samplers/hamiltonian_ensemble.py:165-217 for the dual-averaging step-size adapter
  * (adaptation/dual_averaging.py:16-96), the ChEES trajectory-length adapter (adaptation/chees.py:18-219) and their

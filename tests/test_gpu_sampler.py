@@ -142,6 +142,26 @@ def test_device_adaptation_f32_runs(hx):
     assert s.backend.iteration == 120
 
 
+@pytest.mark.parametrize("move", ["walk", "side"])
+@pytest.mark.parametrize("warm,adapt", [(0, False), (5, False), (6, True)])
+def test_thinned_store_equals_full_store(hx, move, warm, adapt):
+    """store='thinned' (hx_ctx_set_chain_thinning: only the iterations run_mcmc returns leave the device) returns bit for bit
+    what the reference-style full store + get_chain(discard=warmup, thin=thin_by) returns."""
+    W, d = 32, 6
+    tgt = hx.targets.Rosenbrock(d)
+    keys = R.split(R.PRNGKey(9), 2)
+    x0 = (R.normal(keys[0], (W, d), np.float32) * 0.3 + 1.0).astype(np.float32)
+    pm = hx.hmc_walk_move if move == "walk" else hx.hmc_side_move
+    out = {}
+    for store in ("full", "thinned"):
+        s = hx.HamiltonianEnsembleSampler(W, d, tgt, step_size=0.01, L=4, move=pm, adapt_inital_step_size=False,
+                                          adapt_step_size=adapt, adapt_length=adapt, store=store, verbose=False)
+        out[store] = s.run_mcmc(keys[1], x0, 7, warmup=warm, thin_by=3, batch_size=4)
+        assert s.backend.iteration == warm + 21
+    assert out["thinned"].shape == (7, W, d)
+    np.testing.assert_array_equal(out["thinned"], out["full"])
+
+
 def test_quickstart_initial_step(x64):
     """docs/tutorials/quickstart.ipynb cell 8 prints 'Using inital step size of 1.6'."""
     hx = x64
