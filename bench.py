@@ -224,7 +224,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb, per_iter = cpu_reference(args.workload, args.steps, max(args.warmup, 0))
+        cb, per_iter = cpu_reference(args.workload, args.steps, max(args.warmup, 0), budget_s=150.0)   # bounded: a few minutes at most
         line = dict(impl="reference", metric="leapfrog_walker_steps_per_sec", value=cb["value"], unit="walker-steps/s",
                     n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=per_iter * 1e3,
                     higher_is_better=True, scaling="strong", vs_baseline=None,
@@ -281,14 +281,18 @@ def main():
     desc = tgt.descriptor(tdt, dev)
     mk = 0 if cfg["move"] == "walk" else 1
 
+    # the device chain buffer holds CB iterations and is reused cyclically (every iteration still writes its 262 MB slice at c5),
+    # so memory does not grow with --steps
+    CB = max(1, min(max(K, Wu), 16))
     if world == 1:
-        chain = torch.empty((max(K, Wu), W, d), dtype=tdt, device=dev)
-        clp = torch.empty((max(K, Wu), W), dtype=tdt, device=dev)
+        chain = torch.empty((CB, W, d), dtype=tdt, device=dev)
+        clp = torch.empty((CB, W), dtype=tdt, device=dev)
 
         def run(t0, T):
-            _lib.check(lib.hx_run_iterations(ctx, _rt.dtype_code(tdt), _rt.impl_code(), mk, 0, desc, _rt.ptr(X),
-                                             _rt.ptr(lp), n, eps, L, _rt.ptr(keys_dev[4 * t0:]), T, _rt.ptr(chain),
-                                             _rt.ptr(clp), _rt.ptr(accepts), _rt.ptr(flag), _rt.stream(dev)), "run")
+            for c0 in range(0, T, CB):
+                _lib.check(lib.hx_run_iterations(ctx, _rt.dtype_code(tdt), _rt.impl_code(), mk, 0, desc, _rt.ptr(X),
+                                                 _rt.ptr(lp), n, eps, L, _rt.ptr(keys_dev[4 * (t0 + c0):]), min(CB, T - c0),
+                                                 _rt.ptr(chain), _rt.ptr(clp), _rt.ptr(accepts), _rt.ptr(flag), _rt.stream(dev)), "run")
     else:
         # row-sharded: every rank holds the full state in its peer-mapped exchange region and updates its own rows; the kernels
         # store the updated rows into the peers' copies over NVLink (include/hx.h section 5)
@@ -297,13 +301,14 @@ def main():
         torch.cuda.synchronize(dev)
         dist.barrier()
         accepts = torch.zeros(2 * rows, dtype=torch.int32, device=dev)
-        chain = torch.empty((max(K, Wu), 2 * rows, d), dtype=tdt, device=dev)
-        clp = torch.empty((max(K, Wu), 2 * rows), dtype=tdt, device=dev)
+        chain = torch.empty((CB, 2 * rows, d), dtype=tdt, device=dev)
+        clp = torch.empty((CB, 2 * rows), dtype=tdt, device=dev)
 
         def run(t0, T):
-            _lib.check(lib.hx_run_iterations_sharded(ctx, _rt.dtype_code(tdt), _rt.impl_code(), mk, 0, desc, eps, L,
-                                                     _rt.ptr(keys_dev[4 * t0:]), T, _rt.ptr(chain), _rt.ptr(clp), _rt.ptr(accepts),
-                                                     _rt.ptr(flag), _rt.stream(dev)), "run_sharded")
+            for c0 in range(0, T, CB):
+                _lib.check(lib.hx_run_iterations_sharded(ctx, _rt.dtype_code(tdt), _rt.impl_code(), mk, 0, desc, eps, L,
+                                                         _rt.ptr(keys_dev[4 * (t0 + c0):]), min(CB, T - c0), _rt.ptr(chain),
+                                                         _rt.ptr(clp), _rt.ptr(accepts), _rt.ptr(flag), _rt.stream(dev)), "run_sharded")
 
     def barrier():
         if world > 1:
@@ -404,6 +409,9 @@ def main():
 
     # ---- end-to-end through the public API with host buffers (`e2e`) -----------------------------------
     e2e = None
+    # e2e keeps the reference's store-everything semantics, so the host chain is K x W x d: cap K by ~8 GB of pinned host memory
+    isz_ = 8 if cfg["x64"] else 4
+    Ke = max(1, min(K, int(8e9 // (W * d * isz_ / max(world, 1)))))
     if world == 1 and not args.no_e2e:
         x0_host = x0.cpu().pin_memory()
         s = hx.HamiltonianEnsembleSampler(W, d, tgt, step_size=eps, L=L, move=move, adapt_inital_step_size=False,
@@ -411,7 +419,7 @@ def main():
         # untimed warm-up run of the same size: page-locking the host chain buffer costs ~0.64 ms/MB the first time
         # (0.84 s for 5 slices of c5); afterwards torch's caching host allocator reuses the block, which is the
         # steady state of a user who samples repeatedly
-        w = s.run_mcmc(k_run, x0_host, K, warmup=0, batch_size=1)
+        w = s.run_mcmc(k_run, x0_host, Ke, warmup=0, batch_size=1)
         del w, s
         import gc
         gc.collect()
@@ -419,16 +427,16 @@ def main():
         s = hx.HamiltonianEnsembleSampler(W, d, tgt, step_size=eps, L=L, move=move, adapt_inital_step_size=False,
                                           adapt_step_size=False, adapt_length=False, verbose=False)
         t0 = time.perf_counter()
-        out = s.run_mcmc(k_run, x0_host, K, warmup=0, batch_size=1)
+        out = s.run_mcmc(k_run, x0_host, Ke, warmup=0, batch_size=1)
         torch.cuda.synchronize(dev)
         el = time.perf_counter() - t0
         isz = 8 if cfg["x64"] else 4
-        e2e = dict(value=W * L * K / el, unit="walker-steps/s",
-                   h2d_bytes_per_step=int(W * d * isz / K + 32), d2h_bytes_per_step=int(W * d * isz + W * isz),
-                   seconds=el, api="HamiltonianEnsembleSampler.run_mcmc (host initial_state -> host chain)",
+        e2e = dict(value=W * L * Ke / el, unit="walker-steps/s",
+                   h2d_bytes_per_step=int(W * d * isz / Ke + 32), d2h_bytes_per_step=int(W * d * isz + W * isz),
+                   seconds=el, steps=Ke, api="HamiltonianEnsembleSampler.run_mcmc (host initial_state -> host chain)",
                    note="h2d = initial ensemble amortised over the steps + 4 keys; d2h = the step's chain slice and log-probs; "
                         "pinned host chain buffer reused from an untimed warm-up run of the same size")
-        assert out.shape == (K, W, d)
+        assert out.shape == (Ke, W, d)
     elif world > 1 and not args.no_e2e:
         # every rank streams the chain of ITS rows to its own pinned host buffer (chain_store='local'); max over ranks
         x0_host = x0.cpu().pin_memory()
@@ -436,25 +444,25 @@ def main():
                                                     adapt_step_size=False, adapt_length=False, verbose=False,
                                                     group=dist.group.WORLD, chain_store="local", exchange="peer")
         s = mkS()
-        w = s.run_mcmc(k_run, x0_host, K, warmup=0, batch_size=1)
+        w = s.run_mcmc(k_run, x0_host, Ke, warmup=0, batch_size=1)
         del w, s
         import gc
         gc.collect()
         s = mkS()
         barrier()
         t0 = time.perf_counter()
-        out = s.run_mcmc(k_run, x0_host, K, warmup=0, batch_size=1)
+        out = s.run_mcmc(k_run, x0_host, Ke, warmup=0, batch_size=1)
         torch.cuda.synchronize(dev)
         el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
         el = float(el[0])
         isz = 8 if cfg["x64"] else 4
-        e2e = dict(value=W * L * K / el, unit="walker-steps/s", h2d_bytes_per_step=int(W * d * isz / K + 32),
-                   d2h_bytes_per_step=int((W * d * isz + W * isz) / world), seconds=el,
+        e2e = dict(value=W * L * Ke / el, unit="walker-steps/s", h2d_bytes_per_step=int(W * d * isz / Ke + 32),
+                   d2h_bytes_per_step=int((W * d * isz + W * isz) / world), seconds=el, steps=Ke,
                    api="HamiltonianEnsembleSampler.run_mcmc(group=..., chain_store='local') (host initial_state -> per-rank host chain)",
                    note="per rank: h2d = the initial ensemble amortised over the steps + keys, d2h = the chain slice and log-probs of "
                         "the rank's own rows; time = max over ranks")
-        assert out.shape == (K, 2 * rows, d)
+        assert out.shape == (Ke, 2 * rows, d)
 
     # ---- ESS/s leg (BASELINE metric): tau_int via the reference's estimator (autocorr.py:44-118, c=5, tol=50,
     #      quiet) on a fixed subset of <= 16 dims x <= 1024 walkers, after a burn-in; device-resident state, untimed by `value`
