@@ -91,6 +91,7 @@ extern "C" HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value) {
   else if (what == 1) ctx->proj_slices = value;
   else if (what == 2) ctx->gram_tf32 = value;
   else if (what == 3) ctx->energy_bf16 = value;
+  else if (what == 4) ctx->graphs_off = value ? 0 : 1;
   else return hx_fail(HX_E_DTYPE, "hx_ctx_set_tuning: unknown knob %d", what);
   return 0;
 }
@@ -179,6 +180,14 @@ extern "C" HX_API int hx_ctx_destroy(hx_ctx* ctx) {
     for (cudaEvent_t e : *ctx->ev) cudaEventDestroy(e);
     delete ctx->ev;
     delete ctx->ev_tag;
+  }
+  if (ctx->graphs) {
+    for (GraphEntry& g : *ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    delete ctx->graphs;
+  }
+  if (ctx->gstream) cudaStreamDestroy(ctx->gstream);
+  if (ctx->key_stage) cudaFree(ctx->key_stage);
+  {
   }
   if (ctx->side_ready) {
     cudaStreamDestroy(ctx->side);
@@ -703,6 +712,76 @@ extern "C" HX_API int hx_accept(hx_ctx* ctx, int dtype, int impl, void* cur, con
   return 0;
 }
 
+// ---- CUDA graphs for launch-bound batch loops -----------------------------------------------------------------------------------
+// Small ensembles spend their time in launch latency (a 32-walker iteration is ~4 launches of a few microseconds each).  A batch
+// call whose argument set was seen before is captured once into a CUDA graph (on a private stream; the caller's stream may be
+// the legacy default stream, which cannot be captured) and replayed afterwards; the per-batch keys are first copied to a fixed
+// staging address so the replays are argument-identical.  First use of an argument set runs eagerly and primes the workspaces
+// (no allocation may happen during capture).  Not used while the timing hooks are on, nor on the tensor-core path (side streams).
+static uint64_t fnv1a(const void* p, size_t nbytes, uint64_t h = 1469598103934665603ull) {
+  const unsigned char* b = (const unsigned char*)p;
+  for (size_t i = 0; i < nbytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+static int stage_keys(hx_ctx* ctx, const uint32_t* keys, size_t nwords, const uint32_t** staged, cudaStream_t s) {
+  const size_t bytes = nwords * sizeof(uint32_t);
+  if (ctx->key_stage_cap < bytes) {
+    if (ctx->key_stage) HX_CUDA(cudaFree(ctx->key_stage));
+    ctx->key_stage = nullptr; ctx->key_stage_cap = 0;
+    HX_CUDA(cudaMalloc(&ctx->key_stage, bytes * 2));
+    ctx->key_stage_cap = bytes * 2;
+    if (ctx->graphs) {                       // cached graphs read the old staging address
+      for (GraphEntry& g : *ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+      ctx->graphs->clear();
+    }
+  }
+  HX_CUDA(cudaMemcpyAsync(ctx->key_stage, keys, bytes, cudaMemcpyDeviceToDevice, s));
+  *staged = (const uint32_t*)ctx->key_stage;
+  return 0;
+}
+
+template <class F>
+static int run_maybe_graphed(hx_ctx* ctx, cudaStream_t s, uint64_t key, F&& enqueue) {
+  if (ctx->timing || ctx->graphs_off) return enqueue(s);
+  if (!ctx->graphs) ctx->graphs = new (std::nothrow) std::vector<GraphEntry>();
+  if (!ctx->graphs) return enqueue(s);
+  ctx->graph_tick += 1;
+  GraphEntry* ent = nullptr;
+  for (GraphEntry& g : *ctx->graphs) if (g.key == key) ent = &g;
+  if (!ent) {
+    if (ctx->graphs->size() >= 16) {         // evict the least recently used entry
+      size_t lru = 0;
+      for (size_t i = 1; i < ctx->graphs->size(); ++i) if ((*ctx->graphs)[i].last_use < (*ctx->graphs)[lru].last_use) lru = i;
+      if ((*ctx->graphs)[lru].exec) cudaGraphExecDestroy((*ctx->graphs)[lru].exec);
+      ctx->graphs->erase(ctx->graphs->begin() + lru);
+    }
+    ctx->graphs->push_back(GraphEntry{key, nullptr, ctx->graph_tick});
+    return enqueue(s);                       // first use: eager (primes workspaces and function attributes)
+  }
+  ent->last_use = ctx->graph_tick;
+  if (!ent->exec) {
+    if (!ctx->gstream) HX_CUDA(cudaStreamCreateWithFlags(&ctx->gstream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(ctx->gstream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); ctx->graphs_off = 1; return enqueue(s); }
+    const int e = enqueue(ctx->gstream);
+    const cudaError_t ce = cudaStreamEndCapture(ctx->gstream, &graph);
+    if (e || ce != cudaSuccess || !graph) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      ctx->graphs_off = 1;                   // fall back to eager launches for good
+      return e ? e : enqueue(s);
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ci = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ci != cudaSuccess || !exec) { cudaGetLastError(); ctx->graphs_off = 1; return enqueue(s); }
+    ent->exec = exec;
+  }
+  HX_CUDA(cudaGraphLaunch(ent->exec, s));
+  return 0;
+}
+
 // thinned chain emit: iteration t of a batch call is stored iff (t + phase) % every == 0, into consecutive slots
 static inline int64_t chain_slot(const hx_ctx* ctx, int64_t t) {
   const int every = ctx->chain_every > 1 ? ctx->chain_every : 1;
@@ -721,7 +800,7 @@ extern "C" HX_API int hx_ctx_set_chain_thinning(hx_ctx* ctx, int32_t every, int3
 
 // ---- batch level: T iterations of the main phase ----------------------------------------------------------------------
 template <typename T>
-static int run_iterations_t(hx_ctx* ctx, int impl, int move_kind, int key_order, const hx_target* tgt, T* X, T* lp, int n, double eps,
+static int run_iterations_body(hx_ctx* ctx, int impl, int move_kind, int key_order, const hx_target* tgt, T* X, T* lp, int n, double eps,
                             int L, const uint32_t* keys, int64_t Tn, T* chain, T* chain_lp, int32_t* accepts,
                             int32_t* nonfinite, cudaStream_t s) {
   const int d = tgt->dim;
@@ -767,6 +846,29 @@ static int run_iterations_t(hx_ctx* ctx, int impl, int move_kind, int key_order,
     }
   }
   return 0;
+}
+
+template <typename T>
+static int run_iterations_t(hx_ctx* ctx, int impl, int move_kind, int key_order, const hx_target* tgt, T* X, T* lp, int n, double eps,
+                            int L, const uint32_t* keys, int64_t Tn, T* chain, T* chain_lp, int32_t* accepts,
+                            int32_t* nonfinite, cudaStream_t s) {
+  bool tc_path = false;
+  if constexpr (std::is_same<T, float>::value) tc_path = move_kind == 0 && tc::walk_eligible(ctx, HX_F32, tgt, n, n, 0);
+  // launch-bound sizes only: a graph node per launch is not worth it once the kernels run for hundreds of microseconds
+  const bool small = (size_t)n * tgt->dim <= 65536 && Tn >= 1 && Tn <= 4096;
+  if (tc_path || !small || ctx->timing || ctx->graphs_off)
+    return run_iterations_body<T>(ctx, impl, move_kind, key_order, tgt, X, lp, n, eps, L, keys, Tn, chain, chain_lp, accepts, nonfinite, s);
+  const uint32_t* staged = nullptr;
+  if (int e = stage_keys(ctx, keys, (size_t)Tn * 8, &staged, s)) return e;
+  struct { int impl, move_kind, key_order, n, L, every, phase, dt; double eps; int64_t Tn; const void *X, *lp, *chain, *clp, *acc, *nf; hx_target tg; } K;
+  memset(&K, 0, sizeof(K));
+  K.impl = impl; K.move_kind = move_kind; K.key_order = key_order; K.n = n; K.L = L; K.every = ctx->chain_every; K.phase = ctx->chain_phase;
+  K.dt = (int)sizeof(T); K.eps = eps; K.Tn = Tn; K.X = X; K.lp = lp; K.chain = chain; K.clp = chain_lp; K.acc = accepts; K.nf = nonfinite;
+  K.tg = *tgt;
+  const uint64_t key = fnv1a(&K, sizeof(K), 0x9e3779b97f4a7c15ull ^ (uint64_t)ctx->precision);
+  return run_maybe_graphed(ctx, s, key, [&](cudaStream_t cs) {
+    return run_iterations_body<T>(ctx, impl, move_kind, key_order, tgt, X, lp, n, eps, L, staged, Tn, chain, chain_lp, accepts, nonfinite, cs);
+  });
 }
 
 extern "C" HX_API int hx_run_iterations(hx_ctx* ctx, int dtype, int impl, int move_kind, int key_order, const hx_target* tgt, void* X,

@@ -33,6 +33,13 @@ struct HxDist {
   uint32_t epoch;         // half-moves pushed so far
 };
 
+// cached CUDA graphs of launch-bound batch loops (small ensembles): one entry per distinct argument set
+struct GraphEntry {
+  uint64_t key;
+  cudaGraphExec_t exec;      // nullptr: the argument set was seen once (run eagerly, workspaces primed), capture on the next use
+  uint64_t last_use;
+};
+
 struct hx_ctx {
   int device;
   void* buf[WS_NSLOT];
@@ -59,6 +66,8 @@ struct hx_ctx {
   P0Job hint; int hint_valid;              // hx_walk_prefetch: the walk half-move after the next one
   int leap_form;                           // HX_LEAP_*
   HxDist dist;
+  std::vector<GraphEntry>* graphs; cudaStream_t gstream; uint64_t graph_tick; int graphs_off;
+  void* key_stage; size_t key_stage_cap;    // fixed-address copy of a batch's keys (graph replays read the keys from here)
   int chain_every, chain_phase;            // thinned chain emit of the batch loops (hx_ctx_set_chain_thinning); 0/1 = every iteration
   const void* ctl_eps; const int* ctl_L;   // device-resident (step, L) the SIMT move kernels read during adaptive warm-up
   int energy_bf16;                         // 1: propagator-form energy products from bf16 hi/lo operands (default tf32 hi/lo)

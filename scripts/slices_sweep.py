@@ -36,9 +36,10 @@ def rep(name, a):
           f"dla rms {(la-la_t).pow(2).mean().sqrt().item():.3e} mean {(la-la_t).mean().item():+.3e}", flush=True)
 hx.config.update("precision", "exact")
 rep("exact fp32 SIMT", hx.hmc_walk_move(G1, G2, eps, keys[0], tgt, tgt, L, LP1))
-hx.config.update("precision", "bf16x3")
 for form in ("stepwise", "propagator"):
     hx.config.update("leapfrog_form", form)
-    for eb in (0, 1):
-        lib.hx_ctx_set_tuning(ctx, 3, eb)
-        rep(f"bf16x3 {form} energy={'bf16' if eb else 'tf32'}", hx.hmc_walk_move(G1, G2, eps, keys[0], tgt, tgt, L, LP1))
+    for mode in ("bf16x3", "tf32x3"):
+        hx.config.update("precision", mode)
+        for g32 in (0, 1):
+            lib.hx_ctx_set_tuning(ctx, 2, g32)
+            rep(f"{mode} {form} gram={'tf32' if g32 else 'bf16'}", hx.hmc_walk_move(G1, G2, eps, keys[0], tgt, tgt, L, LP1))
