@@ -37,11 +37,12 @@ WORKLOADS = {
     "c1": dict(target="gauss", d=10, kappa=1e3, W=32, L=10, eps=0.1, x64=True, move="walk"),
     "c2": dict(target="gauss", d=100, kappa=1e4, W=1024, L=10, eps=0.1, x64=False, move="walk"),
     "c2s": dict(target="gauss", d=100, kappa=1e4, W=1024, L=10, eps=0.1, x64=False, move="side"),
+    "c3a": dict(target="rosenbrock", d=2, kappa=0, W=8192, L=10, eps=0.01, x64=False, move="walk"),
     "c3": dict(target="rosenbrock", d=50, kappa=0, W=8192, L=10, eps=0.01, x64=False, move="walk"),
     "c4": dict(target="funnel", d=25, kappa=0, W=16384, L=10, eps=0.05, x64=False, move="walk"),
     "c5": dict(target="gauss", d=1000, kappa=1e4, W=65536, L=10, eps=0.1, x64=False, move="walk"),
 }
-CPU_SAMPLE_W = {"c1": 32, "c2": 1024, "c2s": 1024, "c3": 1024, "c4": 2048, "c5": 4096}
+CPU_SAMPLE_W = {"c3a": 1024, "c1": 32, "c2": 1024, "c2s": 1024, "c3": 1024, "c4": 2048, "c5": 4096}
 
 
 def make_cov(d, kappa, seed=1):

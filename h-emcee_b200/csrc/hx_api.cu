@@ -92,6 +92,7 @@ extern "C" HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value) {
   else if (what == 2) ctx->gram_tf32 = value;
   else if (what == 3) ctx->energy_bf16 = value;
   else if (what == 4) ctx->graphs_off = value ? 0 : 1;
+  else if (what == 5) ctx->narrow_off = value ? 0 : 1;
   else return hx_fail(HX_E_DTYPE, "hx_ctx_set_tuning: unknown knob %d", what);
   return 0;
 }
@@ -497,6 +498,15 @@ static int walk_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1,
   W.P.logacc = logacc; W.P.lp_out = lp_out; W.P.dK_out = nullptr;
   W.P.n = n; W.P.d = d; W.P.ldd = ldd; W.P.row0 = row0; W.P.rows = rows; W.P.L = L;
   W.P.flags = (flags & HX_MOVE_FROZEN_GRAD) ? kFlagFrozen : 0;
+  // narrow targets with many complement walkers: the RNG-bound projection runs in its own kernel (lanes split the complement
+  // index, no barrier per draw) and the half-move kernel starts from the given S0.  The choice depends on (n, dim) only, so
+  // row shards reproduce the single-GPU chain.
+  if (ldd <= 40 && n >= 1024 && !ctx->narrow_off) {       // beyond ~40 columns the per-lane partial sums crowd out occupancy
+    if (int e = launch_project_narrow<T>(key, key_ptr, (impl == HX_RNG_LEGACY) ? 1 : 0, C, n, ldd, d, row0, rows, pproj, ctx->sm_count, s))
+      return e;
+    W.P.flags |= kFlagGivenMomentum;
+    ctx->launches += 1;
+  }
   W.P.eps = (T)eps; W.P.key = key; W.P.key_ptr = key_ptr;
   W.P.eps_ptr = (const T*)ctx->ctl_eps; W.P.L_ptr = ctx->ctl_L;
   if (fuse) {

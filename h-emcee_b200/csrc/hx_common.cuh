@@ -22,6 +22,13 @@ __device__ __forceinline__ void ld4(const double* p, double (&o)[4]) {
   const double2 b = reinterpret_cast<const double2*>(p)[1];
   o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
 }
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(double* p, const double (&v)[4]) {
+  reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]);
+  reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
+}
 __device__ __forceinline__ void ld4_ro(const float* p, float (&o)[4]) {
   const float4 t = __ldg(reinterpret_cast<const float4*>(p));
   o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;

@@ -70,6 +70,7 @@ struct hx_ctx {
   void* key_stage; size_t key_stage_cap;    // fixed-address copy of a batch's keys (graph replays read the keys from here)
   int chain_every, chain_phase;            // thinned chain emit of the batch loops (hx_ctx_set_chain_thinning); 0/1 = every iteration
   const void* ctl_eps; const int* ctl_L;   // device-resident (step, L) the SIMT move kernels read during adaptive warm-up
+  int narrow_off;                          // 1: keep the momentum projection of narrow targets inside the half-move kernel
   int energy_bf16;                         // 1: propagator-form energy products from bf16 hi/lo operands (default tf32 hi/lo)
   int gram_tf32;                           // 1: Gram from tf32 hi/lo operands instead of bf16 hi/lo
   int proj_slices;                         // split-K slices of the projection GEMM (0: default)

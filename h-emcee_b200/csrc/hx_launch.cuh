@@ -38,6 +38,9 @@ static int dispatch_tile(int ldd, int rows, int sm_count, F&& f) {
   return f.template run<32, 4, 256>();
 }
 
+// narrow-target momentum projection (hx_move.cuh k_project_narrow); returns HX_E_UNSUPPORTED if ldd > 64
+template <typename T> int launch_project_narrow(Key key, const uint32_t* key_ptr, int legacy, const T* C, int n, int ldd, int d, int row0,
+                                               int rows, T* S0, int sm_count, cudaStream_t s);
 template <typename T> int launch_walk(const WalkParams<T>& P, int sm_count, cudaStream_t s);
 template <typename T> int launch_side(const SideParams<T>& P, int sm_count, cudaStream_t s);
 template <typename T> int launch_log_prob(const LogProbParams<T>& P, int sm_count, cudaStream_t s);

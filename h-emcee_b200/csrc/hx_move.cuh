@@ -373,6 +373,70 @@ __device__ __forceinline__ void accept_and_emit(bool legacy, T* Q, T* X1w, T* lp
   }
 }
 
+
+// ---- momentum projection for narrow targets (dim <= 64): S0[i][:] = sum_j normal(key,(n,n))[row0+i][j] * C[j][:] ------------------
+// RNG-bound (119 instructions per draw vs dim FMAs).  A CTA of 8 warps owns 8*WPW walkers; the centred complement streams through
+// shared memory in tiles of TJ rows (each tile is read once per 8*WPW walkers).  Inside a warp the LANES split the complement
+// index j and every lane keeps WPW x dim partial sums in registers, so there is no barrier per draw and WPW independent
+// hash/erf_inv chains per lane; a butterfly adds the 32 partials at the end (fixed order: results depend only on n).
+template <typename T, int DV /* float4/double4 groups per row: ldd/4 <= 16 */, int WPW>
+__global__ void __launch_bounds__(256) k_project_narrow(Key key, const uint32_t* key_ptr, int legacy, const T* __restrict__ C, int n,
+                                                        int ldd, int d, int row0, int rows, T* __restrict__ S0) {
+  constexpr int TJ = 64;                       // complement rows per shared tile
+  extern __shared__ __align__(16) unsigned char smem_raw_pn[];
+  T* tile = reinterpret_cast<T*>(smem_raw_pn);  // [TJ][sld]
+  const int sld = (DV | 1) * 4;                 // row stride: an odd number of 16-byte groups => conflict-free vector reads
+  if (key_ptr) { key.k0 = key_ptr[0]; key.k1 = key_ptr[1]; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w0 = (blockIdx.x * 8 + warp) * WPW;            // first local walker of this warp
+  T acc[WPW][DV * 4];
+#pragma unroll
+  for (int w = 0; w < WPW; ++w)
+#pragma unroll
+    for (int c = 0; c < DV * 4; ++c) acc[w][c] = T(0);
+  const uint64_t nn = (uint64_t)n * (uint64_t)n;
+  for (int j0 = 0; j0 < n; j0 += TJ) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TJ * DV; idx += 256) {
+      const int jj = idx / DV, g = idx - jj * DV;
+      T v[4] = {T(0), T(0), T(0), T(0)};
+      if (j0 + jj < n && 4 * g < ldd) ld4_ro(C + (size_t)(j0 + jj) * ldd + 4 * g, v);
+      st4(tile + jj * sld + 4 * g, v);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < TJ / 32; ++h) {
+      const int jj = h * 32 + lane, j = j0 + jj;
+      T x[WPW];
+#pragma unroll
+      for (int w = 0; w < WPW; ++w) {
+        const int i = w0 + w;
+        x[w] = (i < rows && j < n) ? normal_rt<T>(key, (uint64_t)(row0 + i) * (uint64_t)n + (uint64_t)j, nn, legacy != 0) : T(0);
+      }
+#pragma unroll
+      for (int g = 0; g < DV; ++g) {
+        T v[4];
+        ld4(tile + jj * sld + 4 * g, v);
+#pragma unroll
+        for (int w = 0; w < WPW; ++w)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[w][4 * g + k] = fma_t(x[w], v[k], acc[w][4 * g + k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < WPW; ++w) {
+    const int i = w0 + w;
+#pragma unroll
+    for (int c = 0; c < DV * 4; ++c) {
+      T v = acc[w][c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == (c & 31) && i < rows && c < d) S0[(size_t)i * d + c] = v;
+    }
+  }
+}
+
 template <typename T, int BM, int TM, int MAXT>
 __global__ void __launch_bounds__(MAXT) k_walk_half(WalkParams<T> P) {
   using TM_t = TileMap<T, BM, TM>;

@@ -122,7 +122,8 @@ HX_API int hx_tc_microbench(hx_ctx* ctx, int mode, int32_t n, int32_t rows, int3
  * projection GEMM, summed in fp32 in a fixed order (default 1 = accumulate all of K = n inside the tensor core; measured:
  * no accuracy gain from more); what = 2: 1 = Gram matrix from tf32 hi/lo operands instead of bf16 hi/lo (default 0);
  * what = 3: 1 = propagator-form energy products from bf16 hi/lo operands (default 0 = tf32 hi/lo); what = 4: 0 disables the CUDA-graph
- * replay of launch-bound batch loops (default 1)                                                                      */
+ * replay of launch-bound batch loops (default 1); what = 5: 0 keeps the momentum projection of narrow targets (dim <= 40, n >= 1024)
+ * inside the half-move kernel instead of the lane-split projection kernel (default 1)                                                                      */
 HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value);
 /* which kernel the timing hooks bracketed last: 0 = fused SIMT half-move, 1 = tcgen05 projection GEMM */
 HX_API int hx_ctx_last_path(const hx_ctx* ctx);

@@ -16,7 +16,7 @@ def sample(stop, out):
         line = p.stdout.readline()
         if line: out.append(line.strip().split(", "))
     p.terminate()
-runs = [(1, 4, "gemm alone"), (2, 2, "both, draw 2 CTA/SM"), (2, 3, "both, draw 3 CTA/SM"), (2, 4, "both, draw 4 CTA/SM"), (2, 5, "both, draw 5 CTA/SM"), (2, 6, "both, draw 6 CTA/SM")]
+runs = [(0, 4, "draw alone 4"), (1, 4, "gemm alone"), (2, 3, "both, draw 3 CTA/SM"), (2, 4, "both, draw 4 CTA/SM"), (2, 5, "both, draw 5 CTA/SM"), (2, 6, "both, draw 6 CTA/SM"), (2, 8, "both, draw 8 CTA/SM")]
 for mode, cps, name in runs:
     lib.hx_ctx_set_tuning(ctx, 0, cps)
     ms = (C.c_double * 3)()
