@@ -40,9 +40,16 @@ WORKLOADS = {
     "c3a": dict(target="rosenbrock", d=2, kappa=0, W=8192, L=10, eps=0.01, x64=False, move="walk"),
     "c3": dict(target="rosenbrock", d=50, kappa=0, W=8192, L=10, eps=0.01, x64=False, move="walk"),
     "c4": dict(target="funnel", d=25, kappa=0, W=16384, L=10, eps=0.05, x64=False, move="walk"),
+    # mid-size probes of the precision policy (not BASELINE configs)
+    "m4": dict(target="gauss", d=128, kappa=1e3, W=2048, L=10, eps=0.1, x64=False, move="walk"),
+    "m5": dict(target="gauss", d=64, kappa=1e3, W=8192, L=10, eps=0.1, x64=False, move="walk"),
+    "m6": dict(target="gauss", d=128, kappa=1e3, W=8192, L=10, eps=0.1, x64=False, move="walk"),
+    "m1": dict(target="gauss", d=256, kappa=1e3, W=4096, L=10, eps=0.1, x64=False, move="walk"),
+    "m2": dict(target="gauss", d=256, kappa=1e3, W=16384, L=10, eps=0.1, x64=False, move="walk"),
+    "m3": dict(target="gauss", d=512, kappa=1e3, W=16384, L=10, eps=0.1, x64=False, move="walk"),
     "c5": dict(target="gauss", d=1000, kappa=1e4, W=65536, L=10, eps=0.1, x64=False, move="walk"),
 }
-CPU_SAMPLE_W = {"c3a": 1024, "c1": 32, "c2": 1024, "c2s": 1024, "c3": 1024, "c4": 2048, "c5": 4096}
+CPU_SAMPLE_W = {"m4": 1024, "m5": 1024, "m6": 1024, "m1": 1024, "m2": 1024, "m3": 1024, "c3a": 1024, "c1": 32, "c2": 1024, "c2s": 1024, "c3": 1024, "c4": 2048, "c5": 4096}
 
 
 def make_cov(d, kappa, seed=1):
@@ -367,7 +374,9 @@ def main():
     path = lib.hx_ctx_last_path(ctx)
     form = args.leapfrog_form
     if form == "auto":
-        form = "propagator" if (rows >= 6 * d and L >= 4) else "stepwise"
+        el_ = rows * d * 28.0 / 2.6e12           # same cost model as csrc/hx_tc_walk.cu (HX_LEAP_AUTO)
+        form = ("propagator" if (L + 3) * max(el_, 25e-6) > (L + 1) * (27e-6 + 15e-6 * (d / 1000.0) ** 2) + 60e-6 + max(4 * el_, 80e-6)
+                else "stepwise")
     extra = {}
     if path == 1:
         # tensor-core path: the bracketed section is the momentum projection S0 = P0 C of one half-move: tcgen05 GEMM chunks

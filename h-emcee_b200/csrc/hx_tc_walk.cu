@@ -467,7 +467,9 @@ static int leapfrog_bform(hx_ctx* ctx, const LeapArgs& a, cudaStream_t s) {
 bool walk_eligible(const hx_ctx* ctx, int dtype, const hx_target* tgt, int n, int rows, int flags) {
   if (ctx->precision == HX_PREC_EXACT) return false;
   if (dtype != HX_F32 || tgt->kind != HX_TARGET_GAUSS_FULL || flags != 0) return false;
-  if (ctx->precision == HX_PREC_AUTO) return tgt->dim >= 256 && n >= 2048 && rows >= 128;
+  // measured on B200 (bench.py --workload m1..m6): the tensor-core path overtakes the SIMT kernels from about dim 128 x 2048
+  // walkers per group (its ~30 launches per half-move cost ~0.35 ms whatever the size)
+  if (ctx->precision == HX_PREC_AUTO) return tgt->dim >= 128 && n >= 2048 && rows >= 128;
   return tgt->dim >= 16 && n >= 64;      // forced tensor-core modes (tests)
 }
 
@@ -556,7 +558,17 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   typedef __nv_bfloat16 bf;
   // leapfrog form: step-by-step kicks on every walker, or (Gaussian target => linear dynamics) the L-step propagator
   // built once per half-move from 2d basis trajectories and applied to all walkers in one GEMM
-  bool prop = ctx->leap_form == HX_LEAP_PROPAGATOR || (ctx->leap_form == HX_LEAP_AUTO && rows >= 6 * d && L >= 4);
+  // AUTO: cost model fitted to B200 timings (scripts / DESIGN.md §7).  A kick over `rows` walkers is bound by its epilogue's
+  // HBM traffic (28 bytes per element at ~2.6 TB/s effective) with a ~25 us latency floor; the basis run is (L+1)
+  // latency-bound launches on 2d rows; the apply + energy products cost about four kicks' worth of traffic.
+  bool prop = ctx->leap_form == HX_LEAP_PROPAGATOR;
+  if (ctx->leap_form == HX_LEAP_AUTO) {
+    const double bw = 2.6e12, elems = (double)rows * d * 28.0;
+    const double t_kick = elems / bw > 25e-6 ? elems / bw : 25e-6;
+    const double t_bk = 27e-6 + 15e-6 * (d / 1000.0) * (d / 1000.0);
+    const double t_apply = 4.0 * elems / bw > 80e-6 ? 4.0 * elems / bw : 80e-6;
+    prop = (L + 3) * t_kick > (L + 1) * t_bk + 60e-6 + t_apply;
+  }
   const bool g1_tf32 = ctx->precision == HX_PREC_TF32X3;
   const bool e_bf16 = ctx->energy_bf16 && !g1_tf32;          // propagator form: energy products from bf16 hi/lo operands
   const int rQ = prop ? (rA > bRA ? rA : bRA) : rA;            // rows of the q - mu operand planes (basis run reuses them)

@@ -150,7 +150,7 @@ class HamiltonianEnsembleSampler(BaseSampler):
         from .targets import GaussianFull
         n = self.total_chains // 2
         tc = (_rt.config.precision != "exact" and self.dtype == torch.float32 and isinstance(self.target, GaussianFull)
-              and ((self.dim >= 256 and n >= 2048) if _rt.config.precision == "auto" else (self.dim >= 16 and n >= 64)))
+              and ((self.dim >= 128 and n >= 2048) if _rt.config.precision == "auto" else (self.dim >= 16 and n >= 64)))
         return not tc
 
     @property

@@ -97,7 +97,7 @@ HX_API int hx_ctx_destroy(hx_ctx* ctx);
 HX_API size_t hx_ctx_workspace_bytes(const hx_ctx* ctx);
 /* Precision policy of the walk move's dense contractions:
  *   HX_PREC_AUTO   exact SIMT fp32/fp64 kernels, except fp32 full-covariance Gaussian targets with
- *                  dim >= 256 and >= 2048 walkers per group, which use HX_PREC_BF16X3
+ *                  dim >= 128 and >= 2048 walkers per group, which use HX_PREC_BF16X3
  *   HX_PREC_EXACT  always the exact SIMT kernels (fp32 FMA / fp64)
  *   HX_PREC_BF16X3 tcgen05 tensor cores, operands split into bf16 hi+lo, three products, fp32
  *                  accumulation in TMEM (fp32-class accuracy, ~2^-16 per product)
@@ -111,7 +111,7 @@ HX_API int hx_ctx_set_precision(hx_ctx* ctx, int mode);
  *   HX_LEAP_PROPAGATOR  the dynamics of a Gaussian target are linear, so the L-step map of (q - mean, p C) is a
  *                       2dim x 2dim matrix: integrate 2*dim basis trajectories with the same recurrence, then apply the
  *                       map to all walkers in one GEMM (cost independent of L per walker)
- *   HX_LEAP_AUTO        propagator when rows >= 6*dim and L >= 4                                            */
+ *   HX_LEAP_AUTO        whichever a cost model fitted to B200 timings predicts to be faster (propagator for many rows / long L)                                          */
 enum { HX_LEAP_AUTO = 0, HX_LEAP_STEPWISE = 1, HX_LEAP_PROPAGATOR = 2 };
 HX_API int hx_ctx_set_leapfrog_form(hx_ctx* ctx, int form);
 /* Diagnostics for the roofline discussion: wall time [ms] of `reps` repetitions of (mode 0) the momentum draw

@@ -43,7 +43,10 @@ def test_zero_step_exposes_the_projected_draw(hx, name):
     g1, g2, key = _state(hx, W, d, 1.0 if name.startswith("c3") else 0.0, 0.3 if name.startswith("c3") else 1.0)
     lp1 = tgt.log_prob(g1)
     q, la, pp, lp = hx.hmc_walk_move(g1, g2, 0.0, key, tgt, tgt, 3, lp1)
-    assert torch.equal(q, g1)                                       # no drift
+    if name == "c5":   # propagator form: q_L = [q0 - mu | S0] @ Tq with Tq = [I; 0] through the split-bf16 GEMM, not a copy
+        assert float((q - g1).abs().max()) <= 2e-5 * float(g1.abs().max())
+    else:
+        assert torch.equal(q, g1)                                   # no drift
     assert float(la.abs().max()) <= (2e-2 if name == "c5" else 1e-4)   # dH = lp1 - lp' only (c5: tensor-core log-density)
     # S0 for sampled rows: rows of normal(key, (n, n)) from the RNG entry point, projected in float64
     C = (g2.double() - g2.double().mean(0)) / np.sqrt(n)
