@@ -436,6 +436,7 @@ static int leapfrog_bform(hx_ctx* ctx, const LeapArgs& a, cudaStream_t s) {
   // same row tile (other column tiles) may still be reading the current one (updating in place is a race).
   void* planes[2] = {a.pQC, a.pQC2};
   const bool narrow = ((rows + kBM - 1) / kBM) * ((d + BN - 1) / BN) * 2 <= ctx->sm_count;
+  const bool narrow64 = ((rows + kBM - 1) / kBM) * ((d + 127) / 128) * 2 <= ctx->sm_count;      // still under half the SMs at 128
   for (int k = 0; k <= a.L; ++k) {
     GemmArgs x = gg;
     x.S_in = (k == 0) ? a.S0 : a.S; x.S = a.S; x.Q = a.Q; x.Qs = a.Qs; x.first = (k == 0) ? 1 : 0;
@@ -444,7 +445,9 @@ static int leapfrog_bform(hx_ctx* ctx, const LeapArgs& a, cudaStream_t s) {
     x.drift = k < a.L ? 1 : 0;
     // few rows (the propagator's 2d basis trajectories): 128-wide tiles double the CTAs and halve both the MMA chain and
     // the per-thread epilogue of these latency-bound launches
-    if (narrow) {
+    if (narrow64) {
+      if (int e = launch_gemm<EPI_KICKB, KIND, 64>(ctx, planes[k & 1], rA, a.pBoP, dB, dK, x, s)) return e;
+    } else if (narrow) {
       if (int e = launch_gemm<EPI_KICKB, KIND, 128>(ctx, planes[k & 1], rA, a.pBoP, dB, dK, x, s)) return e;
     } else {
       if (int e = launch_gemm<EPI_KICKB, KIND>(ctx, planes[k & 1], rA, a.pBoP, dB, dK, x, s)) return e;
