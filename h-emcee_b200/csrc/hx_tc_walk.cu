@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(256) k_small_gemm(const float* __restrict__ A,
 
 // Rows [0, rows_chunk) of the P0 planes (hi at `planes`, lo at `planes + plane`): P0[r][j] = normal(key, (n, n))[row0 + r, j],
 // zero for r >= rows or j >= n; 8 consecutive j per thread
-__global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key_ptr, int legacy, int n, int row0, int rows,
+template <bool LEGACY>
+__global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key_ptr, int n, int row0, int rows,
                                                     int rows_chunk, int Kp, size_t plane, __nv_bfloat16* __restrict__ planes) {
   if (key_ptr) { key.k0 = key_ptr[0]; key.k1 = key_ptr[1]; }
   const size_t nvec = (size_t)rows_chunk * Kp / 8;
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key
     for (int t = 0; t < 8; ++t) {
       const int j = j0 + t;
       float x = 0.f;
-      if (r < rows && j < n) x = normal_rt<float>(key, (uint64_t)(row0 + r) * (uint64_t)n + (uint64_t)j, nn, legacy != 0);
+      if (r < rows && j < n) x = normal_at<float, LEGACY>(key, (uint64_t)(row0 + r) * (uint64_t)n + (uint64_t)j, nn);
       split_bf16(x, hi[t], lo[t]);
     }
     *reinterpret_cast<uint4*>(planes + i) = *reinterpret_cast<const uint4*>(hi);
@@ -492,7 +493,8 @@ static int side_init(hx_ctx* ctx) {
     ctx->ev_chunk[b] = new std::vector<cudaEvent_t>();
   }
   // same L1/shared carve-out as the GEMM kernel, otherwise the two kernels cannot share an SM
-  HX_CUDA(cudaFuncSetAttribute(k_rng_planes, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  HX_CUDA(cudaFuncSetAttribute(k_rng_planes<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  HX_CUDA(cudaFuncSetAttribute(k_rng_planes<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   ctx->side_ready = 1;
   return 0;
 }
@@ -533,8 +535,10 @@ static int job_launch(hx_ctx* ctx, int b, __nv_bfloat16* buf, int impl, int n, i
     int rng_grid = grid_for((size_t)rcp * nK / 8, 256);
     const int cap = ctx->sm_count * (ctx->rng_ctas_per_sm > 0 ? ctx->rng_ctas_per_sm : 4);
     if (rng_grid > cap) rng_grid = cap;
-    k_rng_planes<<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, impl == HX_RNG_LEGACY ? 1 : 0, n, row0 + r0, rc, rcp, nK, plane,
-                                                  buf + (size_t)r0 * nK);
+    if (impl == HX_RNG_LEGACY)
+      k_rng_planes<true><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, buf + (size_t)r0 * nK);
+    else
+      k_rng_planes<false><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, buf + (size_t)r0 * nK);
     HX_LAUNCH_CHECK("k_rng_planes");
     HX_CUDA(cudaEventRecord(evs[c], ctx->side));
     ctx->launches += 1;
