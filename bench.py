@@ -217,7 +217,7 @@ def main():
     ap.add_argument("--leapfrog-form", default="auto", choices=["auto", "stepwise", "propagator"])
     ap.add_argument("--tune", action="append", default=[], help="hx_ctx_set_tuning knob as what=value (diagnostics)")
     ap.add_argument("--clock-period", type=float, default=0.01, help="NVML sampling period in s (0 = no clock sampling)")
-    ap.add_argument("--ess-iters", type=int, default=160, help="iterations of the ESS/s leg (0 = skip)")
+    ap.add_argument("--ess-iters", type=int, default=192, help="iterations of the ESS/s leg (0 = skip)")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -509,6 +509,41 @@ def main():
                    note="min over the sampled dims of (iterations * walkers / tau_int) / wall time of those iterations; fixed "
                         "step size and L (no adaptation), chain started from N(0, I)")
         del sub, cbuf
+
+    # ESS/s at N > 1: the sharded loop continues from the timed state; every rank estimates tau_int on a subset of ITS rows
+    if world > 1 and args.ess_iters > 0 and not args.no_e2e:
+        from hemcee_b200 import autocorr as hac
+        Tb, Te = 16, args.ess_iters
+        Xf.copy_(x0); lpf.copy_(tgt.log_prob(Xf))
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        ke = hx.random.split_device(hx.random.PRNGKey(12345), 4 * (Tb + Te))
+        dims = torch.linspace(0, d - 1, min(16, d)).long().to(dev)
+        wsel = torch.linspace(0, 2 * rows - 1, min(max(1024 // world, 64), 2 * rows)).long().to(dev)
+        sub = torch.empty((Te, wsel.numel(), dims.numel()), dtype=tdt, device=dev)
+
+        def run_s(t0, T, store):
+            for c0 in range(0, T, CB):
+                nb_ = min(CB, T - c0)
+                _lib.check(lib.hx_run_iterations_sharded(ctx, _rt.dtype_code(tdt), _rt.impl_code(), mk, 0, desc, eps, L,
+                                                         _rt.ptr(ke[4 * (t0 + c0):]), nb_, _rt.ptr(chain), _rt.ptr(clp), _rt.ptr(accepts),
+                                                         _rt.ptr(flag), _rt.stream(dev)), "run_ess_sharded")
+                if store:
+                    sub[c0:c0 + nb_] = chain[:nb_][:, wsel][:, :, dims]
+        run_s(0, Tb + 32, False)             # burn-in (the ensemble starts from N(0, I))
+        barrier()
+        t0 = time.perf_counter()
+        run_s(Tb + 32, Te - 32, True)
+        barrier()
+        el = time.perf_counter() - t0
+        Tm = Te - 32
+        tau = np.asarray(hac.integrated_time(sub[:Tm], c=5, tol=50, quiet=True))
+        tt = torch.tensor([float(np.nanmax(tau))], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tmax = float(tt[0])
+        ess = dict(value=Tm * W / tmax / el, unit="ESS/s", tau_max=tmax, iterations=Tm, burn_in=Tb + 32, seconds=el,
+                   reliable=bool(50 * tmax <= Tm), dims=int(dims.numel()), walkers_in_estimate=int(wsel.numel()) * world,
+                   note="max tau_int over ranks (each on a subset of its own rows); iterations * walkers / tau / wall time")
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
