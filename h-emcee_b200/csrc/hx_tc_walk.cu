@@ -67,29 +67,44 @@ static int make_tmap(hx_ctx* ctx, CUtensorMap* out, const void* base, uint64_t r
 // ---- elementwise / layout kernels -----------------------------------------------------------------------------
 // CT planes [2, dB_pad, Kp]: CT[c][j] = (X2[j][c] - mean[c]) / sqrt(n); zero outside (c < d, j < n)
 // planes32 (nullable): the same matrix as tf32 hi/lo planes [2, dB_pad, Kp] for the Gram product
-__global__ void k_center_planes_T(const float* __restrict__ X2, const float* __restrict__ mean, int n, int d,
-                                  int dB_pad, int Kp, __nv_bfloat16* __restrict__ planes, float* __restrict__ planes32) {
-  __shared__ float tile[32][33];
-  const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+// One CTA transposes a 256 (walkers j) x 32 (columns c) block through shared memory: coalesced 128-byte reads of X2 rows, and
+// 16-byte stores (8 consecutive j) of the K-major planes.
+__global__ void __launch_bounds__(256) k_center_planes_T(const float* __restrict__ X2, const float* __restrict__ mean, int n, int d,
+                                                         int dB_pad, int Kp, __nv_bfloat16* __restrict__ planes,
+                                                         float* __restrict__ planes32) {
+  constexpr int TJ = 256, TC = 32;
+  __shared__ float tile[TJ][TC + 1];
+  const int j0 = blockIdx.x * TJ, c0 = blockIdx.y * TC;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const float sc = sqrtf((float)n);
-  for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
-    const int j = j0 + jj, c = c0 + threadIdx.x;
-    tile[jj][threadIdx.x] = (j < n && c < d) ? (X2[(size_t)j * d + c] - mean[c]) / sc : 0.f;
+  const int c = c0 + tx;
+  const float m = (c < d) ? mean[c] : 0.f;
+  for (int jj = ty; jj < TJ; jj += 8) {
+    const int j = j0 + jj;
+    tile[jj][tx] = (j < n && c < d) ? (X2[(size_t)j * d + c] - m) / sc : 0.f;
   }
   __syncthreads();
   const size_t plane = (size_t)dB_pad * Kp;
-  for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
-    const int c = c0 + cc, j = j0 + threadIdx.x;
-    if (c < dB_pad && j < Kp) {
-      __nv_bfloat16 hi, lo;
-      split_bf16(tile[threadIdx.x][cc], hi, lo);
-      planes[(size_t)c * Kp + j] = hi;
-      planes[plane + (size_t)c * Kp + j] = lo;
-      if (planes32) {
-        float h32, l32;
-        split_tf32(tile[threadIdx.x][cc], h32, l32);
-        planes32[(size_t)c * Kp + j] = h32;
-        planes32[plane + (size_t)c * Kp + j] = l32;
+  for (int idx = threadIdx.x; idx < TC * (TJ / 8); idx += 256) {
+    const int cc = idx / (TJ / 8), jc = idx - cc * (TJ / 8);       // lanes run over the 8-walker chunks of one column
+    const int crow = c0 + cc, jb = j0 + jc * 8;
+    if (crow >= dB_pad || jb >= Kp) continue;                       // Kp is a multiple of 64: chunks are all-in or all-out
+    __align__(16) __nv_bfloat16 hi[8], lo[8];
+    float h32[8], l32[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float v = tile[jc * 8 + t][cc];
+      split_bf16(v, hi[t], lo[t]);
+      if (planes32) split_tf32(v, h32[t], l32[t]);
+    }
+    const size_t o = (size_t)crow * Kp + jb;
+    *reinterpret_cast<uint4*>(planes + o) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(planes + plane + o) = *reinterpret_cast<const uint4*>(lo);
+    if (planes32) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        reinterpret_cast<float4*>(planes32 + o)[q] = make_float4(h32[4 * q], h32[4 * q + 1], h32[4 * q + 2], h32[4 * q + 3]);
+        reinterpret_cast<float4*>(planes32 + plane + o)[q] = make_float4(l32[4 * q], l32[4 * q + 1], l32[4 * q + 2], l32[4 * q + 3]);
       }
     }
   }
@@ -123,39 +138,49 @@ __global__ void k_split_planes(const float* __restrict__ src, int dim_r, int dim
 // proposed positions (measured against an f64 integration; oracle-side check in tests/test_oracle_moves.py).
 __global__ void __launch_bounds__(256) k_small_gemm(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                     int dim, float* __restrict__ out, int ldo) {
-  constexpr int TB = 64, KB = 16;
-  __shared__ __align__(16) float sa[KB][TB + 4];
-  __shared__ __align__(16) float sb[KB][TB + 4];
-  const int ti = blockIdx.y * TB, tj = blockIdx.x * TB;
+  constexpr int TBI = 128, TBJ = 64, KB = 16;          // 128 x 64 output tile, 8 x 4 per thread, inputs widened once per tile
+  __shared__ __align__(16) double sa[KB][TBI + 2];
+  __shared__ __align__(16) double sb[KB][TBJ + 2];
+  const int ti = blockIdx.y * TBI, tj = blockIdx.x * TBJ;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double acc[4][4];
+  double acc[8][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
   for (int k0 = 0; k0 < dim; k0 += KB) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < KB * TB; idx += 256) {
+    for (int idx = threadIdx.x; idx < KB * TBI; idx += 256) {
       const int i = idx / KB, kk = idx - i * KB;
-      sa[kk][i] = (ti + i < dim && k0 + kk < dim) ? A[(size_t)(ti + i) * lda + k0 + kk] : 0.f;
-      const int k2 = idx / TB, j = idx - k2 * TB;
-      sb[k2][j] = (k0 + k2 < dim && tj + j < dim) ? B[(size_t)(k0 + k2) * ldb + tj + j] : 0.f;
+      sa[kk][i] = (ti + i < dim && k0 + kk < dim) ? (double)A[(size_t)(ti + i) * lda + k0 + kk] : 0.0;
+    }
+    for (int idx = threadIdx.x; idx < KB * TBJ; idx += 256) {
+      const int k2 = idx / TBJ, j = idx - k2 * TBJ;
+      sb[k2][j] = (k0 + k2 < dim && tj + j < dim) ? (double)B[(size_t)(k0 + k2) * ldb + tj + j] : 0.0;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < KB; ++kk) {
-      float a[4], b[4];
-      ld4(&sa[kk][4 * ty], a);
-      ld4(&sb[kk][4 * tx], b);
+      double a[8], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; i += 2) {
+        const double2 t = *reinterpret_cast<const double2*>(&sa[kk][8 * ty + i]);
+        a[i] = t.x; a[i + 1] = t.y;
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma((double)a[i], (double)b[j], acc[i][j]);
+      for (int j = 0; j < 4; j += 2) {
+        const double2 t = *reinterpret_cast<const double2*>(&sb[kk][4 * tx + j]);
+        b[j] = t.x; b[j + 1] = t.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gi = ti + 4 * ty + i;
+  for (int i = 0; i < 8; ++i) {
+    const int gi = ti + 8 * ty + i;
     if (gi >= dim) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -628,8 +653,8 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   if (gram32)
     if (int e = ws_get(ctx, WS_TC_CT32, (size_t)2 * dAB * nK * sizeof(float), &pCT32)) return e;
   {
-    dim3 g((nK + 31) / 32, (dAB + 31) / 32), b(32, 8);
-    k_center_planes_T<<<g, b, 0, s>>>(X2, mean_dev, n, d, dAB, nK, (bf*)pCT, (float*)pCT32);
+    dim3 g((nK + 255) / 256, (dAB + 31) / 32);
+    k_center_planes_T<<<g, 256, 0, s>>>(X2, mean_dev, n, d, dAB, nK, (bf*)pCT, (float*)pCT32);
     HX_LAUNCH_CHECK("k_center_planes_T");
   }
   GemmArgs ga;
@@ -663,7 +688,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     ga.kb_per_slice = 0; ga.slice_stride = 0;
   }
   {
-    dim3 g((d + 63) / 64, (d + 63) / 64);
+    dim3 g((d + 63) / 64, (d + 127) / 128);
     k_small_gemm<<<g, 256, 0, s>>>((const float*)pM, d, (const float*)tgt->precision, tgt->ld, d, (float*)pBo, d);
     HX_LAUNCH_CHECK("k_small_gemm");
   }
