@@ -213,7 +213,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--precision", default="auto", choices=["auto", "exact", "bf16x3", "bf16", "tf32x3"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "exact", "bf16x3", "bf16", "tf32x3", "f16f8"])
     ap.add_argument("--leapfrog-form", default="auto", choices=["auto", "stepwise", "propagator"])
     ap.add_argument("--tune", action="append", default=[], help="hx_ctx_set_tuning knob as what=value (diagnostics)")
     ap.add_argument("--clock-period", type=float, default=0.01, help="NVML sampling period in s (0 = no clock sampling)")

@@ -66,7 +66,7 @@ int timing_mark(hx_ctx* ctx, cudaStream_t s, int phase) {
 
 extern "C" HX_API int hx_ctx_set_precision(hx_ctx* ctx, int mode) {
   if (!ctx) return hx_fail(HX_E_NULL, "hx_ctx_set_precision: NULL ctx");
-  if (mode < HX_PREC_AUTO || mode > HX_PREC_TF32X3) return hx_fail(HX_E_DTYPE, "hx_ctx_set_precision: unknown mode %d", mode);
+  if (mode < HX_PREC_AUTO || mode > HX_PREC_F16F8) return hx_fail(HX_E_DTYPE, "hx_ctx_set_precision: unknown mode %d", mode);
   ctx->precision = mode;
   return 0;
 }
@@ -93,6 +93,9 @@ extern "C" HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value) {
   else if (what == 3) ctx->energy_bf16 = value;
   else if (what == 4) ctx->graphs_off = value ? 0 : 1;
   else if (what == 5) ctx->narrow_off = value ? 0 : 1;
+  else if (what == 6) ctx->draw_fork = value;
+  else if (what == 7) ctx->mp_dfma = value ? 1 : 0;
+  else if (what == 8) ctx->proj_pair = value ? 1 : 0;
   else return hx_fail(HX_E_DTYPE, "hx_ctx_set_tuning: unknown knob %d", what);
   return 0;
 }

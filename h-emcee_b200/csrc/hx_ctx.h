@@ -12,7 +12,7 @@ enum Slot {
   // tensor-core path
   WS_TC_CT, WS_TC_MP, WS_TC_PP, WS_TC_P0, WS_TC_QC, WS_TC_GP, WS_TC_LPP, WS_TC_DKP, WS_TC_MASK, WS_TC_BO, WS_TC_S0,
   // propagator form of the Gaussian leapfrog
-  WS_TC_BX, WS_TC_BS, WS_TC_TQ, WS_TC_TS, WS_TC_TW, WS_TC_WP, WS_TC_B1, WS_TC_B2, WS_TC_ZB, WS_TC_ZT, WS_TC_QC2, WS_TC_PP32, WS_TC_S0P, WS_TC_CT32,
+  WS_TC_BX, WS_TC_BS, WS_TC_TQ, WS_TC_TS, WS_TC_TW, WS_TC_WP, WS_TC_B1, WS_TC_B2, WS_TC_ZB, WS_TC_ZT, WS_TC_QC2, WS_TC_PP32, WS_TC_S0P, WS_TC_CT32, WS_TC_CT8, WS_TC_SC8,
   // device-resident adaptation
   WS_AD_STATE, WS_AD_MEAN, WS_AD_PART, WS_AD_CHOL, WS_AD_STAT, WS_AD_PROP,
   WS_NSLOT
@@ -20,7 +20,7 @@ enum Slot {
 
 // one momentum draw P0 = normal(key, (n, n))[row0 : row0 + rows] held (or being written) in a draw buffer
 struct P0Job {
-  int valid, impl, n, row0, rows;
+  int valid, fmt, impl, n, row0, rows;       // fmt: 0 bf16 hi/lo planes, 1 fp16 + e4m3 planes
   uint32_t k0, k1;
   const uint32_t* key_ptr;       // device-resident key (batch loop) or NULL (key by value)
 };
@@ -75,6 +75,9 @@ struct hx_ctx {
   int gram_tf32;                           // 1: Gram from tf32 hi/lo operands instead of bf16 hi/lo
   int proj_slices;                         // split-K slices of the projection GEMM (0: default)
   int rng_ctas_per_sm;                     // resident CTAs/SM of the draw kernel (0: default 4)
+  int draw_fork;                           // next half-move's draw is queued after this many projection chunks (0: at the start)
+  int proj_pair;                           // 1: momentum projection by the CTA-pair (cta_group::2) GEMM kernel
+  int mp_dfma;                             // 1: B = M P by the DFMA tile kernel instead of the DMMA kernel
 };
 
 // grow-only scratch slot

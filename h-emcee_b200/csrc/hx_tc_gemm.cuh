@@ -23,7 +23,7 @@ namespace tc {
 constexpr int kBM = 128;      // UMMA M
 constexpr int kThreads = 192;
 
-enum : int { KIND_BF16 = 0, KIND_TF32 = 1 };
+enum : int { KIND_BF16 = 0, KIND_TF32 = 1, KIND_F16F8 = 2 };
 enum : int { EPI_STORE = 0, EPI_KICKB = 1, EPI_DOT = 2, EPI_PROP = 3 };
 
 template <int KIND> struct Kind;
@@ -32,6 +32,14 @@ template <> struct Kind<KIND_BF16> {
   static constexpr int ROW_ELEMS = 64;   // elements per 128-byte swizzle row = K per stage
   static constexpr int UMMA_K = 16;
 };
+// fp16 main operand + two e4m3 correction operands (EPI_STORE only; see k_tc_gemm): plane 0 = fp16(x), plane 1 = per
+// 64-element K-block 64 bytes of e4m3(x) followed by 64 bytes of e4m3((x - fp16(x)) * 2^11), i.e. the same 128-byte rows
+template <> struct Kind<KIND_F16F8> {
+  typedef uint16_t elem;
+  static constexpr int ROW_ELEMS = 64;
+  static constexpr int UMMA_K = 16;
+};
+constexpr float kF8ResidualScale = 2048.0f;     // 2^11: the fp16 rounding residual of |x| < 64 times this is < 32
 template <> struct Kind<KIND_TF32> {
   typedef float elem;
   static constexpr int ROW_ELEMS = 32;
@@ -64,6 +72,8 @@ struct GemmArgs {
   // split-K (EPI_STORE only): grid.z slices of kb_per_slice K-blocks each, slice z stores to out + z * slice_stride; the
   // caller adds the slices in a fixed order (also shortens the tensor core's truncating accumulation chains).  0 = no split.
   int kb_per_slice; size_t slice_stride;
+  // KIND_F16F8: out = (main + corr / 2^11) * scale_ptr[1]   (scale_ptr = {sc, 1/sc}, the power-of-two scale of the B operand)
+  const float* scale_ptr;
 };
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -144,7 +154,7 @@ struct SmemLayout {
 
 template <int KIND>
 __device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
-  if (KIND == KIND_BF16) {
+  if (KIND != KIND_TF32) {
     umma_bf16(tmem_d, ad, bd, idesc, acc);
   } else {
     asm volatile(
@@ -156,6 +166,109 @@ __device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint64_t ad, uint64_
         "l"(ad), "l"(bd), "r"(idesc), "r"(acc)
         : "memory");
   }
+}
+
+// Epilogue of one 128 x BN accumulator tile held in this CTA's TMEM (main product at columns [0, BN), correction products at
+// [BN, 2 BN)): warp quadrant q owns TMEM lanes [32 q, 32 q + 32), one thread per output row.
+template <int BN, int EPI, int KIND>
+__device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t tmem_base, int m0, int n0, int ntile, int q, int lane) {
+  const int row = m0 + 32 * q + lane;
+  const bool rok = row < g.M;
+  const bool vec = (g.N & 3) == 0 && (EPI == EPI_STORE ? (g.ldo & 3) == 0 : true);
+  float rowacc = 0.f;
+  const int NC = BN / 32;
+  const int blk = (EPI == EPI_PROP) ? n0 / g.blk_cols : 0;
+  const int cn0 = (EPI == EPI_PROP) ? n0 - blk * g.blk_cols : n0;
+#pragma unroll 1
+  for (int cc = 0; cc < NC; ++cc) {
+    const int col0 = cn0 + cc * 32;
+    if (col0 >= g.N) break;           // warp-uniform
+    float v[32];
+    tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cc * 32), v);
+    if (g.nprod == 3) {
+      float vc[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(BN + cc * 32), vc);
+      if (KIND == KIND_F16F8) {
+        const float so = g.scale_ptr[1];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(vc[j], 1.0f / kF8ResidualScale, v[j]) * so;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += vc[j];
+      }
+    }
+    if (!rok) continue;
+    const int nval = min(32, g.N - col0);
+    const bool fast = vec && nval == 32;
+    if (EPI == EPI_STORE) {
+      store32(g.out + (size_t)blockIdx.z * g.slice_stride + (size_t)row * g.ldo + col0, v, nval, fast);
+    } else if (EPI == EPI_PROP) {
+      const size_t base = (size_t)row * g.N + col0;
+      if (blk == 0) {
+        float qv[32];
+        if (g.mu) {
+          load32(g.mu + col0, qv, nval, fast);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) qv[j] += v[j];
+          store32(g.Q + base, qv, nval, fast);
+        } else {
+          store32(g.Q + base, v, nval, fast);
+        }
+        if (g.planes_bf16)
+          store_planes32<KIND_BF16>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, v, nval, fast);
+        else
+          store_planes32<KIND_TF32>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, v, nval, fast);
+      } else {
+        store32(g.S + base, v, nval, fast);
+      }
+    } else {
+      const size_t base = (size_t)row * g.N + col0;
+      float mu[32];
+      if (g.mu) load32(g.mu + col0, mu, nval, fast);
+      else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mu[j] = 0.f;
+      }
+      if (EPI == EPI_DOT) {
+        float x[32];
+        load32(g.X + base, x, nval, fast);
+        if (g.Y) {
+          float y[32];
+          load32(g.Y + base, y, nval, fast);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] += y[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rowacc = fmaf(v[j], x[j] - mu[j], rowacc);   // padded lanes hold acc = 0
+      } else {
+        // EPI_KICKB
+        float sv[32], qv[32], ws[32];
+        load32(g.S_in + base, sv, nval, fast);
+        load32(g.Q + base, qv, nval, fast);
+        if (g.first) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ws[j] = 0.f;
+        } else {
+          load32(g.Qs + base, ws, nval, fast);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          ws[j] = fmaf(g.a, qv[j] - mu[j], ws[j]);        // impulse-weighted position sum (G_total = Qs @ P)
+          sv[j] = sv[j] - g.a * v[j];
+          qv[j] = qv[j] + g.eps * sv[j];
+        }
+        store32(g.S + base, sv, nval, fast);
+        store32(g.Qs + base, ws, nval, fast);
+        if (g.drift) {
+          store32(g.Q + base, qv, nval, fast);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) qv[j] -= mu[j];
+          store_planes32<KIND == KIND_F16F8 ? KIND_BF16 : KIND>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, qv, nval, fast);
+        }
+      }
+    }
+  }
+  if (EPI == EPI_DOT && rok) g.part[(size_t)row * g.NT + ntile] = rowacc;
 }
 
 template <int BN, int EPI, int KIND>
@@ -215,7 +328,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   } else if (warp == 1) {
     if (lane == 0) {
       // kind::f16 / kind::tf32 instruction descriptor: D = F32, A/B format (1 = BF16, 2 = TF32), K-major, N>>3, M>>4
-      constexpr uint32_t fmt = (KIND == KIND_BF16) ? 1u : 2u;
+      constexpr uint32_t fmt = (KIND == KIND_TF32) ? 2u : 1u;
       constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % L::STAGES;
@@ -226,6 +339,22 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t a_lo = a_hi + L::A_PLANE;
         const uint32_t b_hi = a_hi + 2 * L::A_PLANE;
         const uint32_t b_lo = b_hi + L::B_PLANE;
+        if (KIND == KIND_F16F8) {
+          // main: fp16(a) * fp16(b) (kind::f16, 4 x K16); corrections into the second accumulator: e4m3(a) * e4m3(res b) and
+          // e4m3(res a) * e4m3(b) (kind::f8f6f4, 4 x K32 at twice the rate) -- the 128-byte row of the second plane is
+          // [value | residual], so K-step k of A pairs with K-step (k + 2) % 4 of B
+          constexpr uint32_t idesc16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);   // A = B = F16
+          constexpr uint32_t idesc8 = umma_idesc_e4m3(kBM, BN);
+          const uint64_t ad = umma_desc_k128(a_hi), bd = umma_desc_k128(b_hi);
+          const uint64_t ad8 = umma_desc_k128(a_lo), bd8 = umma_desc_k128(b_lo);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc16, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f8(tmem_base + (uint32_t)BN, ad8 + (uint64_t)(2 * k), bd8 + (uint64_t)(2 * ((k + 2) & 3)), idesc8,
+                    (kb | k) != 0 ? 1u : 0u);
+        } else {
         const int np = g.nprod;
 #pragma unroll 1
         for (int p = 0; p < np; ++p) {
@@ -237,112 +366,155 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             umma_issue<KIND>(tmem_base + (p == 0 ? 0u : (uint32_t)BN), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, acc);
           }
         }
+        }
         umma_commit(&empty[s]);     // frees the smem stage when these MMAs have read it
       }
       umma_commit(tmem_full);       // accumulator complete
     }
   } else {
     // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); thread = one output row ----------
-    const int q = warp & 3;
     mbar_wait_backoff(tmem_full, 0, 512);
     tc_fence_after();
-    const int row = m0 + 32 * q + lane;
-    const bool rok = row < g.M;
-    const bool vec = (g.N & 3) == 0 && (EPI == EPI_STORE ? (g.ldo & 3) == 0 : true);
-    float rowacc = 0.f;
-    const int NC = BN / 32;
-    const int blk = (EPI == EPI_PROP) ? n0 / g.blk_cols : 0;
-    const int cn0 = (EPI == EPI_PROP) ? n0 - blk * g.blk_cols : n0;
-#pragma unroll 1
-    for (int cc = 0; cc < NC; ++cc) {
-      const int col0 = cn0 + cc * 32;
-      if (col0 >= g.N) break;           // warp-uniform
-      float v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cc * 32), v);
-      if (g.nprod == 3) {
-        float vc[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(BN + cc * 32), vc);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += vc[j];
-      }
-      if (!rok) continue;
-      const int nval = min(32, g.N - col0);
-      const bool fast = vec && nval == 32;
-      if (EPI == EPI_STORE) {
-        store32(g.out + (size_t)blockIdx.z * g.slice_stride + (size_t)row * g.ldo + col0, v, nval, fast);
-      } else if (EPI == EPI_PROP) {
-        const size_t base = (size_t)row * g.N + col0;
-        if (blk == 0) {
-          float qv[32];
-          if (g.mu) {
-            load32(g.mu + col0, qv, nval, fast);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) qv[j] += v[j];
-            store32(g.Q + base, qv, nval, fast);
-          } else {
-            store32(g.Q + base, v, nval, fast);
-          }
-          if (g.planes_bf16)
-            store_planes32<KIND_BF16>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, v, nval, fast);
-          else
-            store_planes32<KIND_TF32>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, v, nval, fast);
-        } else {
-          store32(g.S + base, v, nval, fast);
-        }
-      } else {
-        const size_t base = (size_t)row * g.N + col0;
-        float mu[32];
-        if (g.mu) load32(g.mu + col0, mu, nval, fast);
-        else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mu[j] = 0.f;
-        }
-        if (EPI == EPI_DOT) {
-          float x[32];
-          load32(g.X + base, x, nval, fast);
-          if (g.Y) {
-            float y[32];
-            load32(g.Y + base, y, nval, fast);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] += y[j];
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) rowacc = fmaf(v[j], x[j] - mu[j], rowacc);   // padded lanes hold acc = 0
-        } else {
-          // EPI_KICKB
-          float sv[32], qv[32], ws[32];
-          load32(g.S_in + base, sv, nval, fast);
-          load32(g.Q + base, qv, nval, fast);
-          if (g.first) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) ws[j] = 0.f;
-          } else {
-            load32(g.Qs + base, ws, nval, fast);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            ws[j] = fmaf(g.a, qv[j] - mu[j], ws[j]);        // impulse-weighted position sum (G_total = Qs @ P)
-            sv[j] = sv[j] - g.a * v[j];
-            qv[j] = qv[j] + g.eps * sv[j];
-          }
-          store32(g.S + base, sv, nval, fast);
-          store32(g.Qs + base, ws, nval, fast);
-          if (g.drift) {
-            store32(g.Q + base, qv, nval, fast);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) qv[j] -= mu[j];
-            store_planes32<KIND>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, qv, nval, fast);
-          }
-        }
-      }
-    }
-    if (EPI == EPI_DOT && rok) g.part[(size_t)row * g.NT + blockIdx.x] = rowacc;
+    epilogue_rows<BN, EPI, KIND>(g, tmem_base, m0, n0, (int)blockIdx.x, warp & 3, lane);
     tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ---- CTA-pair variant (cta_group::2) ----------------------------------------------------------------------------------------
+// Two CTAs of a (2, 1, 1) cluster own two consecutive 128-row tiles of one 256-column block and run ONE MMA of M = 256: each
+// CTA stages its own 128 rows of A and only HALF of the B tile (128 of the 256 rows); the tensor cores read the other half from
+// the peer's shared memory.  Per CTA and K-block that is 64 KB from L2 instead of 96 KB.  The single-CTA kernel is bound by the
+// L2 -> SM operand stream (about 6.7 KB/clk over the chip, the measured TMA ceiling), not by the tensor pipe, so a third less
+// operand traffic is a third more head-room; the smaller stage also buys a third pipeline stage in the same shared memory.
+// Both CTAs issue TMA loads that complete on the LEADER's `full` barrier, the leader's elected thread issues the MMAs and its
+// commits arrive on the `empty` / `tmem_full` barriers of both CTAs; every CTA drains its own 128 TMEM lanes.
+struct SmemLayoutPair {
+  static constexpr int A_PLANE = kBM * 128;          // 16 KB
+  static constexpr int B_PLANE = 128 * 128;          // this CTA's half of the 256-row B tile
+  static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+  static constexpr int STAGES = 3;
+  static constexpr int BYTES = STAGES * STAGE + 256 + 1024;
+};
+
+template <int EPI, int KIND>
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_gemm_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  constexpr int BN = 256;
+  using L = SmemLayoutPair;
+  using KD = Kind<KIND>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint64_t* bars = (uint64_t*)(smem + L::STAGES * L::STAGE);
+  uint64_t* full = bars;                  // [STAGES]  (used in the leader)
+  uint64_t* empty = bars + L::STAGES;     // [STAGES]
+  uint64_t* tmem_full = bars + 2 * L::STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * L::STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // 1-D grid of (2, 1, 1) clusters: pair p = blockIdx.x / 2 owns column tile p % NT of row tiles 2 (p / NT) + {0, 1}, so
+  // consecutive pairs sweep the column tiles of the same rows (A tile reuse in L2)
+  const uint32_t rank = cluster_ctarank();           // 0 = leader
+  const int pair_id = (int)blockIdx.x >> 1, ntiles = (g.N + BN - 1) / BN;
+  const int ntile = pair_id % ntiles;
+  const int m0 = (2 * (pair_id / ntiles) + (int)rank) * kBM, n0 = ntile * BN;
+  const int num_kb_total = g.Kp / KD::ROW_ELEMS;
+  const int kb0 = g.kb_per_slice ? (int)blockIdx.z * g.kb_per_slice : 0;
+  const int num_kb = g.kb_per_slice ? min(g.kb_per_slice, num_kb_total - kb0) : num_kb_total;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < L::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 2 * BN);
+  tc_fence_before();
+  cluster_sync_all();                     // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t planes = g.nprod == 3 ? 2u : 1u;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % L::STAGES;
+        const uint32_t ph = (uint32_t)(kb / L::STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* st = stage_base + s * L::STAGE;
+        if (rank == 0) mbar_expect_tx(&full[s], 2u * planes * (uint32_t)(L::A_PLANE + L::B_PLANE));   // both CTAs' bytes
+        const uint32_t lbar = mapa_shared(smem_u32(&full[s]), 0);
+        const int kc = (kb0 + kb) * KD::ROW_ELEMS;
+        const int nb = n0 + (int)rank * 128;
+        tma_load_2d_pair(st, &tmA, lbar, kc, m0);
+        tma_load_2d_pair(st + 2 * L::A_PLANE, &tmB, lbar, kc, nb);
+        if (g.nprod == 3) {
+          tma_load_2d_pair(st + L::A_PLANE, &tmA, lbar, kc, g.rowsA_pad + m0);
+          tma_load_2d_pair(st + 2 * L::A_PLANE + L::B_PLANE, &tmB, lbar, kc, g.rowsB_pad + nb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t fmt = (KIND == KIND_TF32) ? 2u : (KIND == KIND_F16F8 ? 0u : 1u);
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * kBM) >> 4) << 24);
+      constexpr uint32_t idesc8 = umma_idesc_e4m3(2 * kBM, BN);
+      static_assert(KIND != KIND_TF32, "pair kernel: bf16 hi/lo or fp16 + e4m3 operands");
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % L::STAGES;
+        const uint32_t ph = (uint32_t)(kb / L::STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(stage_base + s * L::STAGE);
+        const uint32_t a_lo = a_hi + L::A_PLANE;
+        const uint32_t b_hi = a_hi + 2 * L::A_PLANE;
+        const uint32_t b_lo = b_hi + L::B_PLANE;
+        if (KIND == KIND_F16F8) {
+          const uint64_t ad = umma_desc_k128(a_hi), bd = umma_desc_k128(b_hi);
+          const uint64_t ad8 = umma_desc_k128(a_lo), bd8 = umma_desc_k128(b_lo);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_pair_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_pair_f8(tmem_base + (uint32_t)BN, ad8 + (uint64_t)(2 * k), bd8 + (uint64_t)(2 * ((k + 2) & 3)), idesc8,
+                         (kb | k) != 0 ? 1u : 0u);
+        } else {
+          const int np = g.nprod;
+#pragma unroll 1
+          for (int p = 0; p < np; ++p) {
+            const uint64_t ad = umma_desc_k128(p == 2 ? a_lo : a_hi);
+            const uint64_t bd = umma_desc_k128(p == 1 ? b_lo : b_hi);
+#pragma unroll
+            for (int k = 0; k < KD::ROW_ELEMS / KD::UMMA_K; ++k) {
+              const uint32_t acc = p == 0 ? ((kb | k) != 0 ? 1u : 0u) : ((kb | (p - 1) | k) != 0 ? 1u : 0u);
+              umma_pair_f16(tmem_base + (p == 0 ? 0u : (uint32_t)BN), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, acc);
+            }
+          }
+        }
+        umma_commit_pair(&empty[s]);      // frees the stage in both CTAs
+      }
+      umma_commit_pair(tmem_full);        // accumulators of both CTAs complete
+    }
+  } else {
+    mbar_wait_backoff(tmem_full, 0, 512);
+    tc_fence_after();
+    epilogue_rows<BN, EPI, KIND>(g, tmem_base, m0, n0, ntile, warp & 3, lane);
+    tc_fence_before();
+  }
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();                     // the peer's shared memory and barriers stay alive until both CTAs are done
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 2 * BN);
   }
 }
 

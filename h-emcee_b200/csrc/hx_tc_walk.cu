@@ -24,6 +24,8 @@
 #include "hx_common.cuh"
 #include "hx_tc_gemm.cuh"
 #include "hx_tc_walk.h"
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 namespace hx {
 namespace tc {
@@ -52,16 +54,76 @@ static int make_tmap(hx_ctx* ctx, CUtensorMap* out, const void* base, uint64_t r
                      int kind) {
   EncodeFn enc;
   if (int e = get_encode(ctx, &enc)) return e;
-  const uint64_t esz = kind == KIND_BF16 ? 2 : 4;
+  const uint64_t esz = kind == KIND_TF32 ? 4 : 2;
   cuuint64_t dims[2] = {Kp, rows_total};
   cuuint64_t strides[1] = {Kp * esz};
   cuuint32_t box[2] = {(cuuint32_t)(128 / esz), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, kind == KIND_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  const CUtensorMapDataType dt = kind == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                               : kind == KIND_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
+  CUresult r = enc(out, dt, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return hx_fail(HX_E_UNSUPPORTED, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
+}
+
+// ---- fp16 + e4m3 operand form (KIND_F16F8, hx_tc_gemm.cuh) ------------------------------------------------------------------
+// x ~= fp16(x) + residual; the tensor core gets fp16(x) for the main product and e4m3(x), e4m3(residual * 2^11) for the two
+// correction products.  8 consecutive K elements at a time: 16 bytes of the fp16 plane, 8 + 8 bytes of the e4m3 plane whose
+// 128-byte rows hold [64 values | 64 residuals] per 64-element K-block.
+__device__ __forceinline__ void store_f16f8_x8(uint16_t* __restrict__ plane16, uint8_t* __restrict__ plane8_row, size_t o16, int j0,
+                                               const float (&x)[8]) {
+  __align__(16) __half h[8];
+  __align__(8) __nv_fp8x2_storage_t v8[4], r8[4];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) h[t] = __float2half_rn(x[t]);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float r0 = (x[2 * t] - __half2float(h[2 * t])) * kF8ResidualScale;
+    const float r1 = (x[2 * t + 1] - __half2float(h[2 * t + 1])) * kF8ResidualScale;
+    v8[t] = __nv_cvt_float2_to_fp8x2(make_float2(x[2 * t], x[2 * t + 1]), __NV_SATFINITE, __NV_E4M3);
+    r8[t] = __nv_cvt_float2_to_fp8x2(make_float2(r0, r1), __NV_SATFINITE, __NV_E4M3);
+  }
+  *reinterpret_cast<uint4*>(plane16 + o16) = *reinterpret_cast<const uint4*>(h);
+  uint8_t* p8 = plane8_row + (size_t)(j0 >> 6) * 128 + (j0 & 63);
+  *reinterpret_cast<uint2*>(p8) = *reinterpret_cast<const uint2*>(v8);
+  *reinterpret_cast<uint2*>(p8 + 64) = *reinterpret_cast<const uint2*>(r8);
+}
+
+// power-of-two scale of the centred complement C = (X2 - mean)/sqrt(n): max |C| * sc lies in [32, 64), inside the fp16 and
+// e4m3 ranges with room for the accumulating sums.  amax_bits = bits of max |X2 - mean| (k_absmax_centred).
+__device__ __forceinline__ float f8_scale_from_amax(uint32_t amax_bits, int n) {
+  const float amax = __uint_as_float(amax_bits) / sqrtf((float)n);
+  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+  int e;
+  frexpf(amax, &e);                       // amax = m * 2^e, m in [0.5, 1)
+  return ldexpf(1.f, 6 - e);              // amax * sc = m * 64 in [32, 64)
+}
+__global__ void __launch_bounds__(256) k_absmax_centred(const float* __restrict__ X2, const float* __restrict__ mean, int n, int d,
+                                                        uint32_t* __restrict__ amax_bits) {
+  float m = 0.f;
+  const size_t tot = (size_t)n * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (size_t)d);
+    m = fmaxf(m, fabsf(X2[i] - mean[c]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float wm[8];
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, wm[w]);
+    atomicMax(amax_bits, __float_as_uint(m));       // non-negative floats order like their bit patterns
+  }
+}
+// scale_out = {sc, 1/sc}
+__global__ void k_f8_scale(const uint32_t* __restrict__ amax_bits, int n, float* __restrict__ scale_out) {
+  const float sc = f8_scale_from_amax(*amax_bits, n);
+  scale_out[0] = sc;
+  scale_out[1] = 1.0f / sc;
 }
 
 // ---- elementwise / layout kernels -----------------------------------------------------------------------------
@@ -71,7 +133,8 @@ static int make_tmap(hx_ctx* ctx, CUtensorMap* out, const void* base, uint64_t r
 // 16-byte stores (8 consecutive j) of the K-major planes.
 __global__ void __launch_bounds__(256) k_center_planes_T(const float* __restrict__ X2, const float* __restrict__ mean, int n, int d,
                                                          int dB_pad, int Kp, __nv_bfloat16* __restrict__ planes,
-                                                         float* __restrict__ planes32) {
+                                                         float* __restrict__ planes32, uint16_t* __restrict__ planes8,
+                                                         const float* __restrict__ scale8) {
   constexpr int TJ = 256, TC = 32;
   __shared__ float tile[TJ][TC + 1];
   const int j0 = blockIdx.x * TJ, c0 = blockIdx.y * TC;
@@ -98,6 +161,13 @@ __global__ void __launch_bounds__(256) k_center_planes_T(const float* __restrict
       if (planes32) split_tf32(v, h32[t], l32[t]);
     }
     const size_t o = (size_t)crow * Kp + jb;
+    if (planes8) {      // scaled copy in fp16 + e4m3 form for the momentum projection (KIND_F16F8)
+      const float sc = scale8[0];
+      float xs[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) xs[t] = tile[jc * 8 + t][cc] * sc;
+      store_f16f8_x8(planes8, reinterpret_cast<uint8_t*>(planes8 + plane + (size_t)crow * Kp), o, jb, xs);
+    }
     *reinterpret_cast<uint4*>(planes + o) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(planes + plane + o) = *reinterpret_cast<const uint4*>(lo);
     if (planes32) {
@@ -190,9 +260,84 @@ __global__ void __launch_bounds__(256) k_small_gemm(const float* __restrict__ A,
   }
 }
 
+
+// B = M P on the fp64 tensor-core path: DMMA m8n8k4 (fp64 operands and accumulators), fp32 inputs widened once when a
+// K-block is staged in shared memory, register-prefetched double buffering.  64 x 64 output tile per CTA, four warps of
+// 32 x 32 (4 x 4 DMMA tiles).  Row strides of the staged tiles are = 4 mod 16 doubles: the 8-byte fragment loads of a
+// half-warp (4 rows x 4 k) then cover the 32 banks exactly once.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(128) k_mp_dmma(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                 int dim, float* __restrict__ out, int ldo) {
+  constexpr int TB = 64, KB = 16, LDA = KB + 4, LDB = TB + 4;
+  __shared__ double sa[2][TB * LDA];      // [m][k]
+  __shared__ double sb[2][KB * LDB];      // [k][n]
+  const int ti = blockIdx.y * TB, tj = blockIdx.x * TB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  float ra[8], rb[8];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int idx = threadIdx.x + r * 128;
+      const int m = idx >> 4, k = idx & 15;
+      ra[r] = (ti + m < dim && k0 + k < dim) ? A[(size_t)(ti + m) * lda + k0 + k] : 0.f;
+      const int k2 = idx >> 6, n = idx & 63;
+      rb[r] = (k0 + k2 < dim && tj + n < dim) ? B[(size_t)(k0 + k2) * ldb + tj + n] : 0.f;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int idx = threadIdx.x + r * 128;
+      sa[buf][(idx >> 4) * LDA + (idx & 15)] = (double)ra[r];
+      sb[buf][(idx >> 6) * LDB + (idx & 63)] = (double)rb[r];
+    }
+  };
+  const int nkb = (dim + KB - 1) / KB;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int buf = kb & 1;
+    if (kb + 1 < nkb) gload((kb + 1) * KB);
+#pragma unroll
+    for (int kk = 0; kk < KB; kk += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sa[buf][(wm + 8 * i + g) * LDA + kk + t];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sb[buf][(kk + t) * LDB + wn + 8 * j + g];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    if (kb + 1 < nkb) sstore(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gi = ti + wm + 8 * i + g;
+    if (gi >= dim) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gj = tj + wn + 8 * j + 2 * t;
+      if (gj < dim) out[(size_t)gi * ldo + gj] = (float)acc[i][j][0];
+      if (gj + 1 < dim) out[(size_t)gi * ldo + gj + 1] = (float)acc[i][j][1];
+    }
+  }
+}
+
 // Rows [0, rows_chunk) of the P0 planes (hi at `planes`, lo at `planes + plane`): P0[r][j] = normal(key, (n, n))[row0 + r, j],
 // zero for r >= rows or j >= n; 8 consecutive j per thread
-template <bool LEGACY>
+template <bool LEGACY, int FMT>      // FMT 0: bf16 hi/lo planes, 1: fp16 + e4m3 planes (KIND_F16F8)
 __global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key_ptr, int n, int row0, int rows,
                                                     int rows_chunk, int Kp, size_t plane, __nv_bfloat16* __restrict__ planes) {
   if (key_ptr) { key.k0 = key_ptr[0]; key.k1 = key_ptr[1]; }
@@ -201,16 +346,23 @@ __global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
     const size_t i = v * 8;
     const int r = (int)(i / Kp), j0 = (int)(i - (size_t)r * Kp);
-    __align__(16) __nv_bfloat16 hi[8], lo[8];
+    float x[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       const int j = j0 + t;
-      float x = 0.f;
-      if (r < rows && j < n) x = normal_at<float, LEGACY>(key, (uint64_t)(row0 + r) * (uint64_t)n + (uint64_t)j, nn);
-      split_bf16(x, hi[t], lo[t]);
+      x[t] = 0.f;
+      if (r < rows && j < n) x[t] = normal_at<float, LEGACY>(key, (uint64_t)(row0 + r) * (uint64_t)n + (uint64_t)j, nn);
     }
-    *reinterpret_cast<uint4*>(planes + i) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(planes + plane + i) = *reinterpret_cast<const uint4*>(lo);
+    if (FMT == 1) {
+      uint16_t* p16 = reinterpret_cast<uint16_t*>(planes);
+      store_f16f8_x8(p16, reinterpret_cast<uint8_t*>(p16 + plane + (size_t)r * Kp), i, j0, x);
+    } else {
+      __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) split_bf16(x[t], hi[t], lo[t]);
+      *reinterpret_cast<uint4*>(planes + i) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(planes + plane + i) = *reinterpret_cast<const uint4*>(lo);
+    }
   }
 }
 
@@ -428,6 +580,41 @@ static int launch_gemm(hx_ctx* ctx, const void* A, int rowsA_pad, const void* B,
   return 0;
 }
 
+// CTA-pair variant (k_tc_gemm_pair): 256-column tiles, grid.y rounded up to whole pairs (the odd tail tile reads zero rows
+// through the tensor map's out-of-bounds fill and stores nothing)
+template <int EPI, int KIND>
+static int launch_gemm_pair(hx_ctx* ctx, const void* A, int rowsA_pad, const void* B, int rowsB_pad, int Kp, GemmArgs g,
+                            cudaStream_t s, uint64_t mapA_rows = 0, int slices = 1) {
+  CUtensorMap tmA, tmB;
+  if (int e = make_tmap(ctx, &tmA, A, mapA_rows ? mapA_rows : 2ull * rowsA_pad, Kp, kBM, KIND)) return e;
+  if (int e = make_tmap(ctx, &tmB, B, 2ull * rowsB_pad, Kp, 128, KIND)) return e;
+  g.Kp = Kp; g.rowsA_pad = rowsA_pad; g.rowsB_pad = rowsB_pad;
+  static bool attr_done = false;
+  if (!attr_done) {
+    HX_CUDA(cudaFuncSetAttribute(k_tc_gemm_pair<EPI, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayoutPair::BYTES));
+    attr_done = true;
+  }
+  const int mt = (g.M + kBM - 1) / kBM;
+  dim3 grid(((g.N + 255) / 256) * ((mt + 1) & ~1), 1, slices);      // 1-D: see the tile mapping in the kernel
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = SmemLayoutPair::BYTES; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, k_tc_gemm_pair<EPI, KIND>, tmA, tmB, g);
+  if (le != cudaSuccess) {
+    int nclusters = -1;
+    cudaError_t oe = cudaOccupancyMaxActiveClusters(&nclusters, k_tc_gemm_pair<EPI, KIND>, &cfg);
+    (void)cudaGetLastError();
+    return hx_fail((int)le, "launch k_tc_gemm_pair grid (%u,%u,%u) smem %d failed: %s (max active clusters %d, query %s)", grid.x, grid.y,
+                   grid.z, (int)SmemLayoutPair::BYTES, cudaGetErrorString(le), nclusters, cudaGetErrorString(oe));
+  }
+  ctx->launches += 1;
+  return 0;
+}
+
 static inline int pad_to(int x, int m) { return ((x + m - 1) / m) * m; }
 static inline int grid_for(size_t n, int block) {
   size_t g = (n + block - 1) / block;
@@ -518,27 +705,31 @@ static int side_init(hx_ctx* ctx) {
     ctx->ev_chunk[b] = new std::vector<cudaEvent_t>();
   }
   // same L1/shared carve-out as the GEMM kernel, otherwise the two kernels cannot share an SM
-  HX_CUDA(cudaFuncSetAttribute(k_rng_planes<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  HX_CUDA(cudaFuncSetAttribute(k_rng_planes<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  HX_CUDA(cudaFuncSetAttribute(k_rng_planes<false, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  HX_CUDA(cudaFuncSetAttribute(k_rng_planes<true, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  HX_CUDA(cudaFuncSetAttribute(k_rng_planes<false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  HX_CUDA(cudaFuncSetAttribute(k_rng_planes<true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   ctx->side_ready = 1;
   return 0;
 }
 
-static bool job_matches(const P0Job& j, int impl, int n, int row0, int rows, Key key, const uint32_t* key_ptr) {
-  if (!j.valid || j.impl != impl || j.n != n || j.row0 != row0 || j.rows != rows) return false;
+static bool job_matches(const P0Job& j, int fmt, int impl, int n, int row0, int rows, Key key, const uint32_t* key_ptr) {
+  if (!j.valid || j.fmt != fmt || j.impl != impl || j.n != n || j.row0 != row0 || j.rows != rows) return false;
   if (key_ptr || j.key_ptr) return key_ptr == j.key_ptr;
   return key.k0 == j.k0 && key.k1 == j.k1;
 }
 
 static int chunk_rows(const hx_ctx* ctx, int rA, int NT) {
-  int chunk = (ctx->sm_count / NT) * kBM;     // projection GEMM of one chunk = one wave of 128 x BN tiles
+  int tiles = ctx->sm_count / NT;             // projection GEMM of one chunk = one wave of 128 x BN tiles
+  if (ctx->proj_pair && tiles > 1) tiles &= ~1;      // CTA pairs own two consecutive row tiles
+  int chunk = tiles * kBM;
   if (chunk < kBM) chunk = kBM;
   if (chunk > rA) chunk = rA;
   return chunk;
 }
 
 // enqueue the draw of (key, row0, rows) into buffer b on the side stream
-static int job_launch(hx_ctx* ctx, int b, __nv_bfloat16* buf, int impl, int n, int row0, int rows, int rA, int nK, int chunk,
+static int job_launch(hx_ctx* ctx, int b, __nv_bfloat16* buf, int fmt, int impl, int n, int row0, int rows, int rA, int nK, int chunk,
                       Key key, const uint32_t* key_ptr, cudaStream_t s) {
   const int nchunks = (rows + chunk - 1) / chunk;
   std::vector<cudaEvent_t>& evs = *ctx->ev_chunk[b];
@@ -560,16 +751,20 @@ static int job_launch(hx_ctx* ctx, int b, __nv_bfloat16* buf, int impl, int n, i
     int rng_grid = grid_for((size_t)rcp * nK / 8, 256);
     const int cap = ctx->sm_count * (ctx->rng_ctas_per_sm > 0 ? ctx->rng_ctas_per_sm : 4);
     if (rng_grid > cap) rng_grid = cap;
-    if (impl == HX_RNG_LEGACY)
-      k_rng_planes<true><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, buf + (size_t)r0 * nK);
-    else
-      k_rng_planes<false><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, buf + (size_t)r0 * nK);
+    __nv_bfloat16* dst = buf + (size_t)r0 * nK;
+    if (impl == HX_RNG_LEGACY) {
+      if (fmt) k_rng_planes<true, 1><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
+      else k_rng_planes<true, 0><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
+    } else {
+      if (fmt) k_rng_planes<false, 1><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
+      else k_rng_planes<false, 0><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
+    }
     HX_LAUNCH_CHECK("k_rng_planes");
     HX_CUDA(cudaEventRecord(evs[c], ctx->side));
     ctx->launches += 1;
   }
   P0Job& j = ctx->job[b];
-  j.valid = 1; j.impl = impl; j.n = n; j.row0 = row0; j.rows = rows; j.k0 = key.k0; j.k1 = key.k1; j.key_ptr = key_ptr;
+  j.valid = 1; j.fmt = fmt; j.impl = impl; j.n = n; j.row0 = row0; j.rows = rows; j.k0 = key.k0; j.k1 = key.k1; j.key_ptr = key_ptr;
   return 0;
 }
 
@@ -578,6 +773,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
               float* logacc, float* S, float* lp_out, const FuseF32* fuse, const NextDraw* next, cudaStream_t s) {
   const int d = tgt->dim;
   const int nprod = (ctx->precision == HX_PREC_BF16) ? 1 : 3;   // momentum projection / Gram only
+  const int f8 = (ctx->precision == HX_PREC_F16F8) ? 1 : 0;      // momentum projection from fp16 + e4m3 operands
   const int dB = pad_to(d, BN);            // rows of B-operand planes (N side)
   const int dK = pad_to(d, 64);            // K padding when dim is the reduction axis
   const int nK = pad_to(n, 64);            // K padding when the walker index is the reduction axis
@@ -636,10 +832,11 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   }
   int cur = -1;
   for (int b = 0; b < 2; ++b)
-    if (job_matches(ctx->job[b], impl, n, row0, rows, key, key_ptr)) cur = b;
+    if (job_matches(ctx->job[b], f8, impl, n, row0, rows, key, key_ptr)) cur = b;
+  const bool prefetched = cur >= 0;
   if (cur < 0) {
     cur = ctx->job[0].valid ? (ctx->job[1].valid ? 0 : 1) : 0;
-    if (int e = job_launch(ctx, cur, Pbuf[cur], impl, n, row0, rows, rA, nK, chunk, key, key_ptr, s)) return e;
+    if (int e = job_launch(ctx, cur, Pbuf[cur], f8, impl, n, row0, rows, rA, nK, chunk, key, key_ptr, s)) return e;
   }
   ctx->job[cur].valid = 0;       // consumed by this half-move
 
@@ -652,9 +849,22 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   void* pCT32 = nullptr;
   if (gram32)
     if (int e = ws_get(ctx, WS_TC_CT32, (size_t)2 * dAB * nK * sizeof(float), &pCT32)) return e;
+  void *pCT8 = nullptr, *pSc8 = nullptr;
+  if (f8) {
+    // power-of-two scale of C from max |X2 - mean| (order-independent reduction: bit-reproducible)
+    if (int e = ws_get(ctx, WS_TC_CT8, (size_t)2 * dAB * nK * sizeof(uint16_t), &pCT8)) return e;
+    if (int e = ws_get(ctx, WS_TC_SC8, 16, &pSc8)) return e;
+    uint32_t* amax = reinterpret_cast<uint32_t*>(pSc8) + 2;
+    HX_CUDA(cudaMemsetAsync(amax, 0, sizeof(uint32_t), s));
+    k_absmax_centred<<<grid_for((size_t)n * d / 4, 256), 256, 0, s>>>(X2, mean_dev, n, d, amax);
+    HX_LAUNCH_CHECK("k_absmax_centred");
+    k_f8_scale<<<1, 1, 0, s>>>(amax, n, (float*)pSc8);
+    HX_LAUNCH_CHECK("k_f8_scale");
+    ctx->launches += 2;
+  }
   {
     dim3 g((nK + 255) / 256, (dAB + 31) / 32);
-    k_center_planes_T<<<g, 256, 0, s>>>(X2, mean_dev, n, d, dAB, nK, (bf*)pCT, (float*)pCT32);
+    k_center_planes_T<<<g, 256, 0, s>>>(X2, mean_dev, n, d, dAB, nK, (bf*)pCT, (float*)pCT32, (uint16_t*)pCT8, (const float*)pSc8);
     HX_LAUNCH_CHECK("k_center_planes_T");
   }
   GemmArgs ga;
@@ -688,9 +898,15 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     ga.kb_per_slice = 0; ga.slice_stride = 0;
   }
   {
-    dim3 g((d + 63) / 64, (d + 127) / 128);
-    k_small_gemm<<<g, 256, 0, s>>>((const float*)pM, d, (const float*)tgt->precision, tgt->ld, d, (float*)pBo, d);
-    HX_LAUNCH_CHECK("k_small_gemm");
+    if (ctx->mp_dfma) {
+      dim3 g((d + 63) / 64, (d + 127) / 128);
+      k_small_gemm<<<g, 256, 0, s>>>((const float*)pM, d, (const float*)tgt->precision, tgt->ld, d, (float*)pBo, d);
+      HX_LAUNCH_CHECK("k_small_gemm");
+    } else {
+      dim3 g((d + 63) / 64, (d + 63) / 64);
+      k_mp_dmma<<<g, 128, 0, s>>>((const float*)pM, d, (const float*)tgt->precision, tgt->ld, d, (float*)pBo, d);
+      HX_LAUNCH_CHECK("k_mp_dmma");
+    }
   }
   ctx->launches += 2;
 
@@ -751,8 +967,10 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   // (3) projection S0 = P0 C, chunk by chunk as the draw completes.  The NEXT half-move's draw is queued here: it then runs
   //     under the throughput-bound projection / apply GEMMs (measured to overlap fully, scripts/overlap_bench.py) and stays
   //     out of the way of the small latency-bound launches above, which it would slow 3-4x.
-  if (next && next->rows == rows) {
-    if (int e = job_launch(ctx, 1 - cur, Pbuf[1 - cur], impl, n, next->row0, next->rows, rA, nK, chunk, next->key, next->key_ptr, s))
+  const bool draw_next = next && next->rows == rows;
+  const int fork_at = ctx->draw_fork < 0 ? 0 : (ctx->draw_fork > nchunks ? nchunks : ctx->draw_fork);   // after that many projection chunks
+  if (draw_next && fork_at == 0) {
+    if (int e = job_launch(ctx, 1 - cur, Pbuf[1 - cur], f8, impl, n, next->row0, next->rows, rA, nK, chunk, next->key, next->key_ptr, s))
       return e;
   }
   {
@@ -768,20 +986,37 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     void* pS0P = nullptr;
     if (slices > 1)
       if (int e = ws_get(ctx, WS_TC_S0P, (size_t)slices * chunk * d * sizeof(float), &pS0P)) return e;
-    for (int c = 0; c < nchunks; ++c) {
+    // CTA-pair kernel (hx_ctx_set_tuning(8, 1)): when the whole draw was queued ahead of time (the steady state of a batch
+    // loop) the projection is ONE launch over all rows -- back-to-back waves without a tail per chunk; otherwise chunk by
+    // chunk behind the draw like the single-CTA kernel
+    const bool pair = ctx->proj_pair && slices == 1 && d > 128;
+    const int group = (pair && prefetched) ? nchunks : 1;          // chunks per launch
+    for (int c = 0; c < nchunks; c += group) {
       const int r0 = c * chunk;
-      const int rc = (rows - r0) < chunk ? (rows - r0) : chunk;
-      HX_CUDA(cudaStreamWaitEvent(s, evs[c], 0));
+      const int cl = (c + group < nchunks ? c + group : nchunks) - 1;      // last chunk of this launch
+      const int rend = (cl + 1) * chunk < rows ? (cl + 1) * chunk : rows;
+      const int rc = rend - r0;
+      HX_CUDA(cudaStreamWaitEvent(s, evs[cl], 0));
       ga.M = rc; ga.N = d; ga.ldo = d;
       ga.out = slices > 1 ? (float*)pS0P : S0 + (size_t)r0 * d;
       ga.kb_per_slice = slices > 1 ? kbs : 0; ga.slice_stride = (size_t)rc * d;
-      if (int e = launch_gemm<EPI_STORE, KIND_BF16>(ctx, Pbuf[cur] + (size_t)r0 * nK, rA, pCT, dAB, nK, ga, s,
-                                                    (uint64_t)rA + pad_to(rc, kBM), 0, slices))
-        return e;
+      const uint64_t map_rows = (uint64_t)rA + pad_to(rc, kBM);
+      const bf* Ac = Pbuf[cur] + (size_t)r0 * nK;
+      if (f8) ga.scale_ptr = (const float*)pSc8;
+      int e;
+      if (pair) e = f8 ? launch_gemm_pair<EPI_STORE, KIND_F16F8>(ctx, Ac, rA, pCT8, dAB, nK, ga, s, map_rows, slices)
+                       : launch_gemm_pair<EPI_STORE, KIND_BF16>(ctx, Ac, rA, pCT, dAB, nK, ga, s, map_rows, slices);
+      else e = f8 ? launch_gemm<EPI_STORE, KIND_F16F8>(ctx, Ac, rA, pCT8, dAB, nK, ga, s, map_rows, 0, slices)
+                  : launch_gemm<EPI_STORE, KIND_BF16>(ctx, Ac, rA, pCT, dAB, nK, ga, s, map_rows, 0, slices);
+      if (e) return e;
       if (slices > 1) {
         k_sum_slices_f<<<grid_for((size_t)rc * d, 256), 256, 0, s>>>((const float*)pS0P, slices, (size_t)rc * d, S0 + (size_t)r0 * d);
         HX_LAUNCH_CHECK("k_sum_slices_f");
         ctx->launches += 1;
+      }
+      if (draw_next && fork_at > c && fork_at <= cl + 1 && fork_at > 0) {
+        if (int e2 = job_launch(ctx, 1 - cur, Pbuf[1 - cur], f8, impl, n, next->row0, next->rows, rA, nK, chunk, next->key, next->key_ptr, s))
+          return e2;
       }
     }
     ga.kb_per_slice = 0; ga.slice_stride = 0;
@@ -854,26 +1089,29 @@ int microbench(hx_ctx* ctx, int mode, int n, int rows, int d, int reps, double* 
   const int dB = pad_to(d, BN), nK = pad_to(n, 64), rA = pad_to(rows, kBM), dA = pad_to(d, kBM);
   const int dAB = dB > dA ? dB : dA, NT = (d + BN - 1) / BN;
   typedef __nv_bfloat16 bf;
-  void *pCT, *pP0, *pS0;
+  void *pCT, *pP0, *pS0, *pSc8;
+  const int f8 = ctx->precision == HX_PREC_F16F8 ? 1 : 0;
   const size_t buf_elems = (size_t)2 * rA * nK;
   if (int e = ws_get(ctx, WS_TC_CT, (size_t)2 * dAB * nK * sizeof(bf), &pCT)) return e;
   if (int e = ws_get(ctx, WS_TC_P0, 2 * buf_elems * sizeof(bf), &pP0)) return e;
   if (int e = ws_get(ctx, WS_TC_S0, (size_t)rows * d * sizeof(float), &pS0)) return e;
+  if (int e = ws_get(ctx, WS_TC_SC8, 16, &pSc8)) return e;
   if (int e = side_init(ctx)) return e;
   ctx->job[0].valid = ctx->job[1].valid = 0;
   ctx->p0_base = nullptr;
-  HX_CUDA(cudaMemsetAsync(pCT, 0x3c, (size_t)2 * dAB * nK * sizeof(bf), s));     // finite bf16 pattern
+  HX_CUDA(cudaMemsetAsync(pCT, 0x3c, (size_t)2 * dAB * nK * sizeof(bf), s));     // finite bf16 / fp16 / e4m3 pattern
+  HX_CUDA(cudaMemsetAsync(pSc8, 0x3c, 16, s));
   bf* Pbuf[2] = {(bf*)pP0, (bf*)pP0 + buf_elems};
   const int chunk = chunk_rows(ctx, rA, NT);
   Key key{1u, 2u};
-  if (int e = job_launch(ctx, 0, Pbuf[0], 0, n, 0, rows, rA, nK, chunk, key, nullptr, s)) return e;   // valid operand for the GEMM
+  if (int e = job_launch(ctx, 0, Pbuf[0], f8, 0, n, 0, rows, rA, nK, chunk, key, nullptr, s)) return e;   // valid operand for the GEMM
   HX_CUDA(cudaStreamSynchronize(ctx->side));
   cudaEvent_t e0, e1, eside, eg;
   HX_CUDA(cudaEventCreate(&e0)); HX_CUDA(cudaEventCreate(&e1)); HX_CUDA(cudaEventCreate(&eside)); HX_CUDA(cudaEventCreate(&eg));
   HX_CUDA(cudaEventRecord(e0, s));
   for (int r = 0; r < reps; ++r) {
     if (mode == 0 || mode == 2)
-      if (int e = job_launch(ctx, 1, Pbuf[1], 0, n, 0, rows, rA, nK, chunk, key, nullptr, s)) return e;
+      if (int e = job_launch(ctx, 1, Pbuf[1], f8, 0, n, 0, rows, rA, nK, chunk, key, nullptr, s)) return e;
     if (mode == 1 || mode == 2) {
       GemmArgs ga;
       memset(&ga, 0, sizeof(ga));
@@ -882,7 +1120,11 @@ int microbench(hx_ctx* ctx, int mode, int n, int rows, int d, int reps, double* 
       for (int c = 0; c < nchunks; ++c) {
         const int r0 = c * chunk, rc = (rows - r0) < chunk ? (rows - r0) : chunk;
         ga.M = rc; ga.N = d; ga.out = (float*)pS0 + (size_t)r0 * d; ga.ldo = d;
-        if (int e = launch_gemm<EPI_STORE, KIND_BF16>(ctx, Pbuf[0] + (size_t)r0 * nK, rA, pCT, dAB, nK, ga, s, (uint64_t)rA + pad_to(rc, kBM)))
+        if (f8) {
+          ga.scale_ptr = (const float*)pSc8;
+          if (int e = launch_gemm<EPI_STORE, KIND_F16F8>(ctx, Pbuf[0] + (size_t)r0 * nK, rA, pCT, dAB, nK, ga, s, (uint64_t)rA + pad_to(rc, kBM)))
+            return e;
+        } else if (int e = launch_gemm<EPI_STORE, KIND_BF16>(ctx, Pbuf[0] + (size_t)r0 * nK, rA, pCT, dAB, nK, ga, s, (uint64_t)rA + pad_to(rc, kBM)))
           return e;
       }
     }

@@ -26,7 +26,7 @@ class _Config:
                  "propagator" (L-step linear map of a Gaussian target applied in one GEMM), or "auto".
     """
 
-    PRECISIONS = {"auto": 0, "exact": 1, "bf16x3": 2, "bf16": 3, "tf32x3": 4}
+    PRECISIONS = {"auto": 0, "exact": 1, "bf16x3": 2, "bf16": 3, "tf32x3": 4, "f16f8": 5}
     LEAPFROG_FORMS = {"auto": 0, "stepwise": 1, "propagator": 2}
 
     def __init__(self):

@@ -104,7 +104,7 @@ HX_API size_t hx_ctx_workspace_bytes(const hx_ctx* ctx);
  *   HX_PREC_BF16   tcgen05, single bf16 product for the momentum projection (statistical parity only)
  *   HX_PREC_TF32X3 like BF16X3 but the leapfrog kicks / energy products use tf32 hi+lo operands
  *                  (~2^-21 per product) — for targets conditioned worse than ~1e6                  */
-enum { HX_PREC_AUTO = 0, HX_PREC_EXACT = 1, HX_PREC_BF16X3 = 2, HX_PREC_BF16 = 3, HX_PREC_TF32X3 = 4 };
+enum { HX_PREC_AUTO = 0, HX_PREC_EXACT = 1, HX_PREC_BF16X3 = 2, HX_PREC_BF16 = 3, HX_PREC_TF32X3 = 4, HX_PREC_F16F8 = 5 };
 HX_API int hx_ctx_set_precision(hx_ctx* ctx, int mode);
 /* Form of the walk move's leapfrog on the tensor-core path (full-covariance Gaussian targets):
  *   HX_LEAP_STEPWISE    one kick GEMM per leapfrog step on every walker (hmc_walk.py:85-102 as written)

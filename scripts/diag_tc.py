@@ -23,7 +23,7 @@ for regime in ("N(0,I)", "burned"):
         G1, G2 = X[:n].contiguous(), X[n:].contiguous()
     LP1 = tgt.log_prob(G1)
     res = {}
-    for mode, form in (("exact", "auto"), ("bf16x3", "stepwise"), ("bf16x3", "propagator"), ("tf32x3", "stepwise"), ("tf32x3", "propagator")):
+    for mode, form in (("exact", "auto"), ("bf16x3", "stepwise"), ("bf16x3", "propagator"), ("f16f8", "stepwise"), ("f16f8", "propagator"), ("tf32x3", "stepwise"), ("tf32x3", "propagator")):
         hx.config.update("precision", mode); hx.config.update("leapfrog_form", form)
         a = hx.hmc_walk_move(G1, G2, eps, keys[0], tgt, tgt, L, LP1)
         b = hx.hmc_walk_move(G1, G2, eps, keys[0], tgt, tgt, L, LP1)

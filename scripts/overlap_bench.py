@@ -16,8 +16,13 @@ def sample(stop, out):
         line = p.stdout.readline()
         if line: out.append(line.strip().split(", "))
     p.terminate()
-runs = [(0, 4, "draw alone 4"), (1, 4, "gemm alone"), (2, 3, "both, draw 3 CTA/SM"), (2, 4, "both, draw 4 CTA/SM"), (2, 5, "both, draw 5 CTA/SM"), (2, 6, "both, draw 6 CTA/SM"), (2, 8, "both, draw 8 CTA/SM")]
-for mode, cps, name in runs:
+PRECS = os.environ.get("PRECS", "bf16x3,f16f8").split(",")
+CPS = [int(c) for c in os.environ.get("CPS", "2,3,4,6").split(",")]
+runs = []
+for pr in PRECS:
+    runs += [(pr, 0, 4, f"{pr}: draw alone 4"), (pr, 1, 4, f"{pr}: gemm alone")] + [(pr, 2, c, f"{pr}: both, draw {c} CTA/SM") for c in CPS]
+for pr, mode, cps, name in runs:
+    lib.hx_ctx_set_precision(ctx, hx.config.PRECISIONS[pr])
     lib.hx_ctx_set_tuning(ctx, 0, cps)
     ms = (C.c_double * 3)()
     with torch.cuda.stream(user):
@@ -32,5 +37,5 @@ for mode, cps, name in runs:
     clk = np.median([float(r[0]) for r in busy]) if busy else float("nan")
     pw = np.max([float(r[1]) for r in busy]) if busy else float("nan")
     cap = sum(r[2].lower().startswith("active") for r in busy)
-    print(f"{name:22s} total {ms[0] / reps:7.3f} ms/rep  gemm-stream {ms[1] / reps:7.3f}  draw-stream {ms[2] / reps:7.3f}   sm clock {clk:.0f} MHz  max power {pw:.0f} W  power-cap {cap}/{len(busy)}", flush=True)
+    print(f"{name:30s} total {ms[0] / reps:7.3f} ms/rep  gemm-stream {ms[1] / reps:7.3f}  draw-stream {ms[2] / reps:7.3f}   sm clock {clk:.0f} MHz  max power {pw:.0f} W  power-cap {cap}/{len(busy)}", flush=True)
     time.sleep(0.5)

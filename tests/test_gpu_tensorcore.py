@@ -41,14 +41,15 @@ def _problem(hx, n, d, seed=0, kappa=100.0):
 @pytest.mark.parametrize("n,d", [(128, 64), (256, 200), (640, 256), (384, 300)])
 @pytest.mark.parametrize("L", [1, 4])
 @pytest.mark.parametrize("lf", ["stepwise", "propagator"])
-def test_bf16x3_matches_exact_and_oracle(hx, prec, form, n, d, L, lf):
+@pytest.mark.parametrize("mode", ["bf16x3", "f16f8"])
+def test_bf16x3_matches_exact_and_oracle(hx, prec, form, n, d, L, lf, mode):
     form(lf)
     tgt, (olp, og), g1, g2, key = _problem(hx, n, d)
     G1, G2 = torch.from_numpy(g1).cuda(), torch.from_numpy(g2).cuda()
     LP1 = tgt.log_prob(G1)
     prec("exact")
     qe, lae, ppe, lpe = hx.hmc_walk_move(G1, G2, 0.03, key, tgt, tgt, L, LP1)
-    prec("bf16x3")
+    prec(mode)
     qt, lat, ppt, lpt = hx.hmc_walk_move(G1, G2, 0.03, key, tgt, tgt, L, LP1)
     a64, b64 = g1.astype(np.float64), g2.astype(np.float64)
     q64, la64, pp64, lp64 = OM.hmc_walk_move(a64, b64, 0.03, key, olp, og, L, olp(a64), rng_dtype=np.float32)
@@ -73,8 +74,9 @@ def test_bf16_single_pass_statistical(hx, prec):
     assert np.all(np.isfinite(lat.cpu().numpy()))
 
 
-def test_tc_shard_invariance_and_determinism(hx, prec):
-    prec("bf16x3")
+@pytest.mark.parametrize("mode", ["bf16x3", "f16f8"])
+def test_tc_shard_invariance_and_determinism(hx, prec, mode):
+    prec(mode)
     tgt, _, g1, g2, key = _problem(hx, 512, 96)
     G1, G2 = torch.from_numpy(g1).cuda(), torch.from_numpy(g2).cuda()
     LP1 = tgt.log_prob(G1)
