@@ -77,6 +77,9 @@ struct hx_ctx {
   int rng_ctas_per_sm;                     // resident CTAs/SM of the draw kernel (0: default 4)
   int draw_fork;                           // next half-move's draw is queued after this many projection chunks (0: at the start)
   int proj_pair;                           // 1: momentum projection by the CTA-pair (cta_group::2) GEMM kernel
+  int pair_chunked;                        // 1: CTA-pair projection launched one wave at a time even when the draw is complete
+  int draw_nostore;                        // diagnostics: momentum draw without its stores (results are garbage)
+  int l2_hints;                            // 1: momentum planes stored / loaded evict-first, complement planes loaded evict-last
   int mp_dfma;                             // 1: B = M P by the DFMA tile kernel instead of the DMMA kernel
 };
 

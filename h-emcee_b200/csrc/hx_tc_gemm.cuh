@@ -74,6 +74,7 @@ struct GemmArgs {
   int kb_per_slice; size_t slice_stride;
   // KIND_F16F8: out = (main + corr / 2^11) * scale_ptr[1]   (scale_ptr = {sc, 1/sc}, the power-of-two scale of the B operand)
   const float* scale_ptr;
+  int l2_hints;      // 1: A tiles loaded evict-first, B tiles evict-last (momentum projection)
 };
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -317,11 +318,20 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         uint8_t* st = stage_base + s * L::STAGE;
         mbar_expect_tx(&full[s], bytes);
         const int kc = (kb0 + kb) * KD::ROW_ELEMS;
-        tma_load_2d(st, &tmA, &full[s], kc, m0);
-        tma_load_2d(st + 2 * L::A_PLANE, &tmB, &full[s], kc, n0);
-        if (g.nprod == 3) {
-          tma_load_2d(st + L::A_PLANE, &tmA, &full[s], kc, g.rowsA_pad + m0);
-          tma_load_2d(st + 2 * L::A_PLANE + L::B_PLANE, &tmB, &full[s], kc, g.rowsB_pad + n0);
+        if (g.l2_hints) {     // A streamed once (momentum draw), B re-read by every row tile (centred complement)
+          tma_load_2d_hint(st, &tmA, &full[s], kc, m0, kL2EvictFirst);
+          tma_load_2d_hint(st + 2 * L::A_PLANE, &tmB, &full[s], kc, n0, kL2EvictLast);
+          if (g.nprod == 3) {
+            tma_load_2d_hint(st + L::A_PLANE, &tmA, &full[s], kc, g.rowsA_pad + m0, kL2EvictFirst);
+            tma_load_2d_hint(st + 2 * L::A_PLANE + L::B_PLANE, &tmB, &full[s], kc, g.rowsB_pad + n0, kL2EvictLast);
+          }
+        } else {
+          tma_load_2d(st, &tmA, &full[s], kc, m0);
+          tma_load_2d(st + 2 * L::A_PLANE, &tmB, &full[s], kc, n0);
+          if (g.nprod == 3) {
+            tma_load_2d(st + L::A_PLANE, &tmA, &full[s], kc, g.rowsA_pad + m0);
+            tma_load_2d(st + 2 * L::A_PLANE + L::B_PLANE, &tmB, &full[s], kc, g.rowsB_pad + n0);
+          }
         }
       }
     }

@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(128) k_mp_dmma(const float* __restrict__ A, in
 
 // Rows [0, rows_chunk) of the P0 planes (hi at `planes`, lo at `planes + plane`): P0[r][j] = normal(key, (n, n))[row0 + r, j],
 // zero for r >= rows or j >= n; 8 consecutive j per thread
-template <bool LEGACY, int FMT>      // FMT 0: bf16 hi/lo planes, 1: fp16 + e4m3 planes (KIND_F16F8)
+template <bool LEGACY, int FMT, bool STREAM = false>      // FMT 0: bf16 hi/lo planes, 1: fp16 + e4m3 planes (KIND_F16F8)
 __global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key_ptr, int n, int row0, int rows,
                                                     int rows_chunk, int Kp, size_t plane, __nv_bfloat16* __restrict__ planes) {
   if (key_ptr) { key.k0 = key_ptr[0]; key.k1 = key_ptr[1]; }
@@ -353,15 +353,25 @@ __global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key
       x[t] = 0.f;
       if (r < rows && j < n) x[t] = normal_at<float, LEGACY>(key, (uint64_t)(row0 + r) * (uint64_t)n + (uint64_t)j, nn);
     }
-    if (FMT == 1) {
+    if (FMT == 2) {        // diagnostics (hx_ctx_set_tuning(10, 1)): the draw's arithmetic without its stores
+      float t = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t += x[u];
+      if (t == 12345.678f) planes[i] = __float2bfloat16_rn(t);
+    } else if (FMT == 1) {
       uint16_t* p16 = reinterpret_cast<uint16_t*>(planes);
       store_f16f8_x8(p16, reinterpret_cast<uint8_t*>(p16 + plane + (size_t)r * Kp), i, j0, x);
     } else {
       __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
       for (int t = 0; t < 8; ++t) split_bf16(x[t], hi[t], lo[t]);
-      *reinterpret_cast<uint4*>(planes + i) = *reinterpret_cast<const uint4*>(hi);
-      *reinterpret_cast<uint4*>(planes + plane + i) = *reinterpret_cast<const uint4*>(lo);
+      if (STREAM) {       // consumed once, half a move later: keep the planes out of the way of the GEMM's L2-resident operand
+        __stcs(reinterpret_cast<uint4*>(planes + i), *reinterpret_cast<const uint4*>(hi));
+        __stcs(reinterpret_cast<uint4*>(planes + plane + i), *reinterpret_cast<const uint4*>(lo));
+      } else {
+        *reinterpret_cast<uint4*>(planes + i) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(planes + plane + i) = *reinterpret_cast<const uint4*>(lo);
+      }
     }
   }
 }
@@ -709,6 +719,8 @@ static int side_init(hx_ctx* ctx) {
   HX_CUDA(cudaFuncSetAttribute(k_rng_planes<true, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   HX_CUDA(cudaFuncSetAttribute(k_rng_planes<false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   HX_CUDA(cudaFuncSetAttribute(k_rng_planes<true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  HX_CUDA(cudaFuncSetAttribute(k_rng_planes<false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  HX_CUDA(cudaFuncSetAttribute(k_rng_planes<false, 0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   ctx->side_ready = 1;
   return 0;
 }
@@ -752,7 +764,11 @@ static int job_launch(hx_ctx* ctx, int b, __nv_bfloat16* buf, int fmt, int impl,
     const int cap = ctx->sm_count * (ctx->rng_ctas_per_sm > 0 ? ctx->rng_ctas_per_sm : 4);
     if (rng_grid > cap) rng_grid = cap;
     __nv_bfloat16* dst = buf + (size_t)r0 * nK;
-    if (impl == HX_RNG_LEGACY) {
+    if (ctx->draw_nostore) {
+      k_rng_planes<false, 2><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
+    } else if (ctx->l2_hints && !fmt && impl != HX_RNG_LEGACY) {
+      k_rng_planes<false, 0, true><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
+    } else if (impl == HX_RNG_LEGACY) {
       if (fmt) k_rng_planes<true, 1><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
       else k_rng_planes<true, 0><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
     } else {
@@ -990,7 +1006,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     // loop) the projection is ONE launch over all rows -- back-to-back waves without a tail per chunk; otherwise chunk by
     // chunk behind the draw like the single-CTA kernel
     const bool pair = ctx->proj_pair && slices == 1 && d > 128;
-    const int group = (pair && prefetched) ? nchunks : 1;          // chunks per launch
+    const int group = (pair && prefetched && !ctx->pair_chunked) ? nchunks : 1;          // chunks per launch
     for (int c = 0; c < nchunks; c += group) {
       const int r0 = c * chunk;
       const int cl = (c + group < nchunks ? c + group : nchunks) - 1;      // last chunk of this launch
@@ -1003,6 +1019,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
       const uint64_t map_rows = (uint64_t)rA + pad_to(rc, kBM);
       const bf* Ac = Pbuf[cur] + (size_t)r0 * nK;
       if (f8) ga.scale_ptr = (const float*)pSc8;
+      ga.l2_hints = ctx->l2_hints;
       int e;
       if (pair) e = f8 ? launch_gemm_pair<EPI_STORE, KIND_F16F8>(ctx, Ac, rA, pCT8, dAB, nK, ga, s, map_rows, slices)
                        : launch_gemm_pair<EPI_STORE, KIND_BF16>(ctx, Ac, rA, pCT, dAB, nK, ga, s, map_rows, slices);
@@ -1103,6 +1120,7 @@ int microbench(hx_ctx* ctx, int mode, int n, int rows, int d, int reps, double* 
   HX_CUDA(cudaMemsetAsync(pSc8, 0x3c, 16, s));
   bf* Pbuf[2] = {(bf*)pP0, (bf*)pP0 + buf_elems};
   const int chunk = chunk_rows(ctx, rA, NT);
+  const int gchunk = (ctx->proj_pair && !ctx->pair_chunked) ? rA : chunk;        // pair kernel: one launch over all rows (steady state of a batch loop)
   Key key{1u, 2u};
   if (int e = job_launch(ctx, 0, Pbuf[0], f8, 0, n, 0, rows, rA, nK, chunk, key, nullptr, s)) return e;   // valid operand for the GEMM
   HX_CUDA(cudaStreamSynchronize(ctx->side));
@@ -1116,16 +1134,20 @@ int microbench(hx_ctx* ctx, int mode, int n, int rows, int d, int reps, double* 
       GemmArgs ga;
       memset(&ga, 0, sizeof(ga));
       ga.nprod = 3;
-      const int nchunks = (rows + chunk - 1) / chunk;
+      const int nchunks = (rows + gchunk - 1) / gchunk;
       for (int c = 0; c < nchunks; ++c) {
-        const int r0 = c * chunk, rc = (rows - r0) < chunk ? (rows - r0) : chunk;
+        const int r0 = c * gchunk, rc = (rows - r0) < gchunk ? (rows - r0) : gchunk;
         ga.M = rc; ga.N = d; ga.out = (float*)pS0 + (size_t)r0 * d; ga.ldo = d;
-        if (f8) {
-          ga.scale_ptr = (const float*)pSc8;
-          if (int e = launch_gemm<EPI_STORE, KIND_F16F8>(ctx, Pbuf[0] + (size_t)r0 * nK, rA, pCT, dAB, nK, ga, s, (uint64_t)rA + pad_to(rc, kBM)))
-            return e;
-        } else if (int e = launch_gemm<EPI_STORE, KIND_BF16>(ctx, Pbuf[0] + (size_t)r0 * nK, rA, pCT, dAB, nK, ga, s, (uint64_t)rA + pad_to(rc, kBM)))
-          return e;
+        ga.scale_ptr = (const float*)pSc8;
+        ga.l2_hints = ctx->l2_hints;
+        const uint64_t mr = (uint64_t)rA + pad_to(rc, kBM);
+        const bf* Ac = Pbuf[0] + (size_t)r0 * nK;
+        int e;
+        if (ctx->proj_pair) e = f8 ? launch_gemm_pair<EPI_STORE, KIND_F16F8>(ctx, Ac, rA, pCT, dAB, nK, ga, s, mr)
+                                   : launch_gemm_pair<EPI_STORE, KIND_BF16>(ctx, Ac, rA, pCT, dAB, nK, ga, s, mr);
+        else e = f8 ? launch_gemm<EPI_STORE, KIND_F16F8>(ctx, Ac, rA, pCT, dAB, nK, ga, s, mr)
+                    : launch_gemm<EPI_STORE, KIND_BF16>(ctx, Ac, rA, pCT, dAB, nK, ga, s, mr);
+        if (e) return e;
       }
     }
   }

@@ -103,7 +103,11 @@ HX_API size_t hx_ctx_workspace_bytes(const hx_ctx* ctx);
  *                  accumulation in TMEM (fp32-class accuracy, ~2^-16 per product)
  *   HX_PREC_BF16   tcgen05, single bf16 product for the momentum projection (statistical parity only)
  *   HX_PREC_TF32X3 like BF16X3 but the leapfrog kicks / energy products use tf32 hi+lo operands
- *                  (~2^-21 per product) — for targets conditioned worse than ~1e6                  */
+ *                  (~2^-21 per product) — for targets conditioned worse than ~1e6
+ *   HX_PREC_F16F8  like BF16X3 but the momentum projection takes fp16(x) for the main product and e4m3(x),
+ *                  e4m3((x - fp16(x)) 2^11) for the two correction products (kind::f8f6f4 at twice the rate;
+ *                  the complement is scaled by a power of two into the fp16 / e4m3 range): 8 instead of 12
+ *                  MMA slots per K-block at ~2^-15 per product (measured |dS0| 1.2e-5 vs 0.7e-5 relative)  */
 enum { HX_PREC_AUTO = 0, HX_PREC_EXACT = 1, HX_PREC_BF16X3 = 2, HX_PREC_BF16 = 3, HX_PREC_TF32X3 = 4, HX_PREC_F16F8 = 5 };
 HX_API int hx_ctx_set_precision(hx_ctx* ctx, int mode);
 /* Form of the walk move's leapfrog on the tensor-core path (full-covariance Gaussian targets):
@@ -123,7 +127,16 @@ HX_API int hx_tc_microbench(hx_ctx* ctx, int mode, int32_t n, int32_t rows, int3
  * no accuracy gain from more); what = 2: 1 = Gram matrix from tf32 hi/lo operands instead of bf16 hi/lo (default 0);
  * what = 3: 1 = propagator-form energy products from bf16 hi/lo operands (default 0 = tf32 hi/lo); what = 4: 0 disables the CUDA-graph
  * replay of launch-bound batch loops (default 1); what = 5: 0 keeps the momentum projection of narrow targets (dim <= 40, n >= 1024)
- * inside the half-move kernel instead of the lane-split projection kernel (default 1)                                                                      */
+ * inside the half-move kernel instead of the lane-split projection kernel (default 1);
+ * what = 6: the next half-move's momentum draw is queued after that many projection chunks instead of at the projection's start
+ * (default 0; measured: any later start runs into the latency-bound launches and costs more than it saves);
+ * what = 7: 1 = B = M P by the DFMA tile kernel instead of the DMMA (fp64 tensor core) kernel (default 0);
+ * what = 8: 1 = momentum projection by the CTA-pair kernel (tcgen05 cta_group::2: M = 256 per pair, each CTA stages half of the
+ * B tile; 3.15 instead of 3.98 ms alone at c5, bit-identical output), default 0 because it runs WORSE next to the concurrent
+ * momentum draw; what = 9: 1 = CTA-pair projection launched one wave at a time even when the draw is
+ * complete (default 0 = one launch); what = 10: 1 = draw kernel without its stores (garbage results; overlap diagnostics only);
+ * what = 11: 1 = L2 eviction hints (draw stored streaming, P0 tiles loaded evict-first, complement tiles evict-last; measured:
+ * no effect, default 0)                                                                                                        */
 HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value);
 /* which kernel the timing hooks bracketed last: 0 = fused SIMT half-move, 1 = tcgen05 projection GEMM */
 HX_API int hx_ctx_last_path(const hx_ctx* ctx);

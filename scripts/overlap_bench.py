@@ -19,10 +19,18 @@ def sample(stop, out):
 PRECS = os.environ.get("PRECS", "bf16x3,f16f8").split(",")
 CPS = [int(c) for c in os.environ.get("CPS", "2,3,4,6").split(",")]
 runs = []
+PAIRS = [int(c) for c in os.environ.get("PAIRS", "0,1").split(",")]
 for pr in PRECS:
-    runs += [(pr, 0, 4, f"{pr}: draw alone 4"), (pr, 1, 4, f"{pr}: gemm alone")] + [(pr, 2, c, f"{pr}: both, draw {c} CTA/SM") for c in CPS]
-for pr, mode, cps, name in runs:
+    runs += [(pr, 0, 0, 4, f"{pr}: draw alone 4")]
+    for pair in PAIRS:
+        runs += [(pr, pair, 1, 4, f"{pr} pair={pair}: gemm alone")] + [(pr, pair, 2, c, f"{pr} pair={pair}: both, draw {c} CTA/SM") for c in CPS]
+NOSTORE = int(os.environ.get("NOSTORE", 0))
+lib.hx_ctx_set_tuning(ctx, 10, NOSTORE)
+lib.hx_ctx_set_tuning(ctx, 11, int(os.environ.get("L2HINTS", 0)))
+for pr, pair, mode, cps, name in runs:
     lib.hx_ctx_set_precision(ctx, hx.config.PRECISIONS[pr])
+    lib.hx_ctx_set_tuning(ctx, 8, 1 if pair else 0)
+    lib.hx_ctx_set_tuning(ctx, 9, 1 if pair == 2 else 0)        # pair = 2: CTA-pair kernel launched wave by wave
     lib.hx_ctx_set_tuning(ctx, 0, cps)
     ms = (C.c_double * 3)()
     with torch.cuda.stream(user):
@@ -37,5 +45,5 @@ for pr, mode, cps, name in runs:
     clk = np.median([float(r[0]) for r in busy]) if busy else float("nan")
     pw = np.max([float(r[1]) for r in busy]) if busy else float("nan")
     cap = sum(r[2].lower().startswith("active") for r in busy)
-    print(f"{name:30s} total {ms[0] / reps:7.3f} ms/rep  gemm-stream {ms[1] / reps:7.3f}  draw-stream {ms[2] / reps:7.3f}   sm clock {clk:.0f} MHz  max power {pw:.0f} W  power-cap {cap}/{len(busy)}", flush=True)
+    print(f"{name:40s} total {ms[0] / reps:7.3f} ms/rep  gemm-stream {ms[1] / reps:7.3f}  draw-stream {ms[2] / reps:7.3f}   sm clock {clk:.0f} MHz  max power {pw:.0f} W  power-cap {cap}/{len(busy)}", flush=True)
     time.sleep(0.5)
