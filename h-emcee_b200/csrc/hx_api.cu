@@ -98,7 +98,7 @@ extern "C" HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value) {
   else if (what == 8) ctx->proj_pair = value ? 1 : 0;
   else if (what == 9) ctx->pair_chunked = value ? 1 : 0;
   else if (what == 10) ctx->draw_nostore = value ? 1 : 0;
-  else if (what == 11) ctx->l2_hints = value ? 1 : 0;
+  else if (what == 12) ctx->aux_pair = value ? 1 : 0;
   else return hx_fail(HX_E_DTYPE, "hx_ctx_set_tuning: unknown knob %d", what);
   return 0;
 }
@@ -165,6 +165,7 @@ extern "C" HX_API int hx_ctx_create(hx_ctx** out, int device) {
   if (!c) return fail(HX_E_NULL, "hx_ctx_create: out of host memory");
   memset(c, 0, sizeof(*c));
   c->device = device;
+  c->aux_pair = 1;
   cudaDeviceProp prop;
   HX_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;

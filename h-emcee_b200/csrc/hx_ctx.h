@@ -79,7 +79,7 @@ struct hx_ctx {
   int proj_pair;                           // 1: momentum projection by the CTA-pair (cta_group::2) GEMM kernel
   int pair_chunked;                        // 1: CTA-pair projection launched one wave at a time even when the draw is complete
   int draw_nostore;                        // diagnostics: momentum draw without its stores (results are garbage)
-  int l2_hints;                            // 1: momentum planes stored / loaded evict-first, complement planes loaded evict-last
+  int aux_pair;                            // 1: Gram and propagator-apply GEMMs by the CTA-pair kernel
   int mp_dfma;                             // 1: B = M P by the DFMA tile kernel instead of the DMMA kernel
 };
 

@@ -69,18 +69,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
-// L2 eviction-priority hints for TMA loads (the encodings CUTLASS passes as `cache_hint`): operand tiles that every CTA of a wave
-// re-reads (the centred complement) are kept, tiles that are streamed once (the momentum draw) are evicted first
-constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
-constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
-__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1, uint64_t hint) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
-      : "memory");
-}
-
 // ---- TMEM ----------------------------------------------------------------------------------------------------
 // allocate `ncols` (power of two >= 32) TMEM columns; one full warp executes this
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {

@@ -74,7 +74,7 @@ struct GemmArgs {
   int kb_per_slice; size_t slice_stride;
   // KIND_F16F8: out = (main + corr / 2^11) * scale_ptr[1]   (scale_ptr = {sc, 1/sc}, the power-of-two scale of the B operand)
   const float* scale_ptr;
-  int l2_hints;      // 1: A tiles loaded evict-first, B tiles evict-last (momentum projection)
+  int n_cover;       // pair kernel: padded N the grid covers (0: N); EPI_PROP covers two column blocks
 };
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -318,20 +318,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         uint8_t* st = stage_base + s * L::STAGE;
         mbar_expect_tx(&full[s], bytes);
         const int kc = (kb0 + kb) * KD::ROW_ELEMS;
-        if (g.l2_hints) {     // A streamed once (momentum draw), B re-read by every row tile (centred complement)
-          tma_load_2d_hint(st, &tmA, &full[s], kc, m0, kL2EvictFirst);
-          tma_load_2d_hint(st + 2 * L::A_PLANE, &tmB, &full[s], kc, n0, kL2EvictLast);
-          if (g.nprod == 3) {
-            tma_load_2d_hint(st + L::A_PLANE, &tmA, &full[s], kc, g.rowsA_pad + m0, kL2EvictFirst);
-            tma_load_2d_hint(st + 2 * L::A_PLANE + L::B_PLANE, &tmB, &full[s], kc, g.rowsB_pad + n0, kL2EvictLast);
-          }
-        } else {
-          tma_load_2d(st, &tmA, &full[s], kc, m0);
-          tma_load_2d(st + 2 * L::A_PLANE, &tmB, &full[s], kc, n0);
-          if (g.nprod == 3) {
-            tma_load_2d(st + L::A_PLANE, &tmA, &full[s], kc, g.rowsA_pad + m0);
-            tma_load_2d(st + 2 * L::A_PLANE + L::B_PLANE, &tmB, &full[s], kc, g.rowsB_pad + n0);
-          }
+        tma_load_2d(st, &tmA, &full[s], kc, m0);
+        tma_load_2d(st + 2 * L::A_PLANE, &tmB, &full[s], kc, n0);
+        if (g.nprod == 3) {
+          tma_load_2d(st + L::A_PLANE, &tmA, &full[s], kc, g.rowsA_pad + m0);
+          tma_load_2d(st + 2 * L::A_PLANE + L::B_PLANE, &tmB, &full[s], kc, g.rowsB_pad + n0);
         }
       }
     }
@@ -430,7 +421,7 @@ k_tc_gemm_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // 1-D grid of (2, 1, 1) clusters: pair p = blockIdx.x / 2 owns column tile p % NT of row tiles 2 (p / NT) + {0, 1}, so
   // consecutive pairs sweep the column tiles of the same rows (A tile reuse in L2)
   const uint32_t rank = cluster_ctarank();           // 0 = leader
-  const int pair_id = (int)blockIdx.x >> 1, ntiles = (g.N + BN - 1) / BN;
+  const int pair_id = (int)blockIdx.x >> 1, ntiles = ((g.n_cover ? g.n_cover : g.N) + BN - 1) / BN;
   const int ntile = pair_id % ntiles;
   const int m0 = (2 * (pair_id / ntiles) + (int)rank) * kBM, n0 = ntile * BN;
   const int num_kb_total = g.Kp / KD::ROW_ELEMS;

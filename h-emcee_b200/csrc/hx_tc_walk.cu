@@ -142,14 +142,25 @@ __global__ void __launch_bounds__(256) k_center_planes_T(const float* __restrict
   const float sc = sqrtf((float)n);
   const int c = c0 + tx;
   const float m = (c < d) ? mean[c] : 0.f;
-  for (int jj = ty; jj < TJ; jj += 8) {
-    const int j = j0 + jj;
-    tile[jj][tx] = (j < n && c < d) ? (X2[(size_t)j * d + c] - m) / sc : 0.f;
+  // 8 independent row loads in flight per thread (the rows are 4 d bytes apart: every load is a separate DRAM burst)
+#pragma unroll 1
+  for (int g0 = 0; g0 < TJ; g0 += 64) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + g0 + ty + 8 * u;
+      v[u] = (j < n && c < d) ? X2[(size_t)j * d + c] : m;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) tile[g0 + ty + 8 * u][tx] = (v[u] - m) / sc;
   }
   __syncthreads();
   const size_t plane = (size_t)dB_pad * Kp;
-  for (int idx = threadIdx.x; idx < TC * (TJ / 8); idx += 256) {
-    const int cc = idx / (TJ / 8), jc = idx - cc * (TJ / 8);       // lanes run over the 8-walker chunks of one column
+  // lane = 4 consecutive 8-walker chunks x 8 columns: the shared-memory reads (row pitch 33 words, rows 8 apart per chunk)
+  // hit 32 distinct banks, and the four lanes of one column store 64 contiguous bytes
+  const int jcl = threadIdx.x & 3, ccl = (threadIdx.x >> 2) & 7, wq = threadIdx.x >> 5;
+  for (int it = 0; it < TC / 8; ++it) {
+    const int cc = it * 8 + ccl, jc = wq * 4 + jcl;
     const int crow = c0 + cc, jb = j0 + jc * 8;
     if (crow >= dB_pad || jb >= Kp) continue;                       // Kp is a multiple of 64: chunks are all-in or all-out
     __align__(16) __nv_bfloat16 hi[8], lo[8];
@@ -337,7 +348,7 @@ __global__ void __launch_bounds__(128) k_mp_dmma(const float* __restrict__ A, in
 
 // Rows [0, rows_chunk) of the P0 planes (hi at `planes`, lo at `planes + plane`): P0[r][j] = normal(key, (n, n))[row0 + r, j],
 // zero for r >= rows or j >= n; 8 consecutive j per thread
-template <bool LEGACY, int FMT, bool STREAM = false>      // FMT 0: bf16 hi/lo planes, 1: fp16 + e4m3 planes (KIND_F16F8)
+template <bool LEGACY, int FMT>      // FMT 0: bf16 hi/lo planes, 1: fp16 + e4m3 planes (KIND_F16F8)
 __global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key_ptr, int n, int row0, int rows,
                                                     int rows_chunk, int Kp, size_t plane, __nv_bfloat16* __restrict__ planes) {
   if (key_ptr) { key.k0 = key_ptr[0]; key.k1 = key_ptr[1]; }
@@ -365,13 +376,8 @@ __global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key
       __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
       for (int t = 0; t < 8; ++t) split_bf16(x[t], hi[t], lo[t]);
-      if (STREAM) {       // consumed once, half a move later: keep the planes out of the way of the GEMM's L2-resident operand
-        __stcs(reinterpret_cast<uint4*>(planes + i), *reinterpret_cast<const uint4*>(hi));
-        __stcs(reinterpret_cast<uint4*>(planes + plane + i), *reinterpret_cast<const uint4*>(lo));
-      } else {
-        *reinterpret_cast<uint4*>(planes + i) = *reinterpret_cast<const uint4*>(hi);
-        *reinterpret_cast<uint4*>(planes + plane + i) = *reinterpret_cast<const uint4*>(lo);
-      }
+      *reinterpret_cast<uint4*>(planes + i) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(planes + plane + i) = *reinterpret_cast<const uint4*>(lo);
     }
   }
 }
@@ -594,18 +600,18 @@ static int launch_gemm(hx_ctx* ctx, const void* A, int rowsA_pad, const void* B,
 // through the tensor map's out-of-bounds fill and stores nothing)
 template <int EPI, int KIND>
 static int launch_gemm_pair(hx_ctx* ctx, const void* A, int rowsA_pad, const void* B, int rowsB_pad, int Kp, GemmArgs g,
-                            cudaStream_t s, uint64_t mapA_rows = 0, int slices = 1) {
+                            cudaStream_t s, uint64_t mapA_rows = 0, int slices = 1, int n_grid = 0) {
   CUtensorMap tmA, tmB;
   if (int e = make_tmap(ctx, &tmA, A, mapA_rows ? mapA_rows : 2ull * rowsA_pad, Kp, kBM, KIND)) return e;
   if (int e = make_tmap(ctx, &tmB, B, 2ull * rowsB_pad, Kp, 128, KIND)) return e;
-  g.Kp = Kp; g.rowsA_pad = rowsA_pad; g.rowsB_pad = rowsB_pad;
+  g.Kp = Kp; g.rowsA_pad = rowsA_pad; g.rowsB_pad = rowsB_pad; g.n_cover = n_grid;
   static bool attr_done = false;
   if (!attr_done) {
     HX_CUDA(cudaFuncSetAttribute(k_tc_gemm_pair<EPI, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayoutPair::BYTES));
     attr_done = true;
   }
   const int mt = (g.M + kBM - 1) / kBM;
-  dim3 grid(((g.N + 255) / 256) * ((mt + 1) & ~1), 1, slices);      // 1-D: see the tile mapping in the kernel
+  dim3 grid((((n_grid ? n_grid : g.N) + 255) / 256) * ((mt + 1) & ~1), 1, slices);      // 1-D: see the tile mapping in the kernel
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = SmemLayoutPair::BYTES; cfg.stream = s;
@@ -720,7 +726,6 @@ static int side_init(hx_ctx* ctx) {
   HX_CUDA(cudaFuncSetAttribute(k_rng_planes<false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   HX_CUDA(cudaFuncSetAttribute(k_rng_planes<true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   HX_CUDA(cudaFuncSetAttribute(k_rng_planes<false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  HX_CUDA(cudaFuncSetAttribute(k_rng_planes<false, 0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   ctx->side_ready = 1;
   return 0;
 }
@@ -766,8 +771,6 @@ static int job_launch(hx_ctx* ctx, int b, __nv_bfloat16* buf, int fmt, int impl,
     __nv_bfloat16* dst = buf + (size_t)r0 * nK;
     if (ctx->draw_nostore) {
       k_rng_planes<false, 2><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
-    } else if (ctx->l2_hints && !fmt && impl != HX_RNG_LEGACY) {
-      k_rng_planes<false, 0, true><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
     } else if (impl == HX_RNG_LEGACY) {
       if (fmt) k_rng_planes<true, 1><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
       else k_rng_planes<true, 0><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
@@ -903,6 +906,8 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     ga.kb_per_slice = slices > 1 ? kbs : 0; ga.slice_stride = (size_t)d * d;
     if (gram32) {
       if (int e = launch_gemm<EPI_STORE, KIND_TF32>(ctx, pCT32, dAB, pCT32, dAB, nK, ga, s, 0, 0, slices)) return e;
+    } else if (ctx->aux_pair && d > 128) {
+      if (int e = launch_gemm_pair<EPI_STORE, KIND_BF16>(ctx, pCT, dAB, pCT, dAB, nK, ga, s, 0, slices)) return e;
     } else {
       if (int e = launch_gemm<EPI_STORE, KIND_BF16>(ctx, pCT, dAB, pCT, dAB, nK, ga, s, 0, 0, slices)) return e;
     }
@@ -1019,7 +1024,6 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
       const uint64_t map_rows = (uint64_t)rA + pad_to(rc, kBM);
       const bf* Ac = Pbuf[cur] + (size_t)r0 * nK;
       if (f8) ga.scale_ptr = (const float*)pSc8;
-      ga.l2_hints = ctx->l2_hints;
       int e;
       if (pair) e = f8 ? launch_gemm_pair<EPI_STORE, KIND_F16F8>(ctx, Ac, rA, pCT8, dAB, nK, ga, s, map_rows, slices)
                        : launch_gemm_pair<EPI_STORE, KIND_BF16>(ctx, Ac, rA, pCT, dAB, nK, ga, s, map_rows, slices);
@@ -1052,6 +1056,8 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     g1.planes_out = pQC; g1.rows_out_pad = rQ; g1.Kout_p = dK; g1.planes_bf16 = e_bf16 ? 1 : 0;
     if (g1_tf32) {
       if (int e = launch_gemm<EPI_PROP, KIND_TF32>(ctx, pZT, rA, pB1, 2 * dB, K2, g1, s, 0, 2 * dB)) return e;
+    } else if (ctx->aux_pair) {
+      if (int e = launch_gemm_pair<EPI_PROP, KIND_BF16>(ctx, pZB, rA, pB1, 2 * dB, K2, g1, s, 0, 1, 2 * dB)) return e;
     } else {
       if (int e = launch_gemm<EPI_PROP, KIND_BF16>(ctx, pZB, rA, pB1, 2 * dB, K2, g1, s, 0, 2 * dB)) return e;
     }
@@ -1139,8 +1145,7 @@ int microbench(hx_ctx* ctx, int mode, int n, int rows, int d, int reps, double* 
         const int r0 = c * gchunk, rc = (rows - r0) < gchunk ? (rows - r0) : gchunk;
         ga.M = rc; ga.N = d; ga.out = (float*)pS0 + (size_t)r0 * d; ga.ldo = d;
         ga.scale_ptr = (const float*)pSc8;
-        ga.l2_hints = ctx->l2_hints;
-        const uint64_t mr = (uint64_t)rA + pad_to(rc, kBM);
+          const uint64_t mr = (uint64_t)rA + pad_to(rc, kBM);
         const bf* Ac = Pbuf[0] + (size_t)r0 * nK;
         int e;
         if (ctx->proj_pair) e = f8 ? launch_gemm_pair<EPI_STORE, KIND_F16F8>(ctx, Ac, rA, pCT, dAB, nK, ga, s, mr)

@@ -135,8 +135,8 @@ HX_API int hx_tc_microbench(hx_ctx* ctx, int mode, int32_t n, int32_t rows, int3
  * B tile; 3.15 instead of 3.98 ms alone at c5, bit-identical output), default 0 because it runs WORSE next to the concurrent
  * momentum draw; what = 9: 1 = CTA-pair projection launched one wave at a time even when the draw is
  * complete (default 0 = one launch); what = 10: 1 = draw kernel without its stores (garbage results; overlap diagnostics only);
- * what = 11: 1 = L2 eviction hints (draw stored streaming, P0 tiles loaded evict-first, complement tiles evict-last; measured:
- * no effect, default 0)                                                                                                        */
+ * what = 12: 0 = Gram and propagator-apply GEMMs by the single-CTA kernel instead of the CTA-pair kernel
+ * (default 1: bit-identical, ~0.1 ms per half-move faster at c5; these launches do not overlap the draw)                       */
 HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value);
 /* which kernel the timing hooks bracketed last: 0 = fused SIMT half-move, 1 = tcgen05 projection GEMM */
 HX_API int hx_ctx_last_path(const hx_ctx* ctx);

@@ -26,7 +26,6 @@ for pr in PRECS:
         runs += [(pr, pair, 1, 4, f"{pr} pair={pair}: gemm alone")] + [(pr, pair, 2, c, f"{pr} pair={pair}: both, draw {c} CTA/SM") for c in CPS]
 NOSTORE = int(os.environ.get("NOSTORE", 0))
 lib.hx_ctx_set_tuning(ctx, 10, NOSTORE)
-lib.hx_ctx_set_tuning(ctx, 11, int(os.environ.get("L2HINTS", 0)))
 for pr, pair, mode, cps, name in runs:
     lib.hx_ctx_set_precision(ctx, hx.config.PRECISIONS[pr])
     lib.hx_ctx_set_tuning(ctx, 8, 1 if pair else 0)
