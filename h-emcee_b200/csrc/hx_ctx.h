@@ -12,7 +12,7 @@ enum Slot {
   // tensor-core path
   WS_TC_CT, WS_TC_MP, WS_TC_PP, WS_TC_P0, WS_TC_QC, WS_TC_GP, WS_TC_LPP, WS_TC_DKP, WS_TC_MASK, WS_TC_BO, WS_TC_S0,
   // propagator form of the Gaussian leapfrog
-  WS_TC_BX, WS_TC_BS, WS_TC_TQ, WS_TC_TS, WS_TC_TW, WS_TC_WP, WS_TC_B1, WS_TC_B2, WS_TC_ZB, WS_TC_ZT, WS_TC_QC2, WS_TC_PP32, WS_TC_S0P, WS_TC_CT32, WS_TC_CT8, WS_TC_SC8,
+  WS_TC_BX, WS_TC_BS, WS_TC_TQ, WS_TC_TS, WS_TC_TW, WS_TC_WP, WS_TC_B1, WS_TC_B2, WS_TC_ZB, WS_TC_ZT, WS_TC_QC2, WS_TC_PP32, WS_TC_S0P, WS_TC_CT32, WS_TC_CT8, WS_TC_SC8, WS_TC_AM, WS_TC_RSC,
   // device-resident adaptation
   WS_AD_STATE, WS_AD_MEAN, WS_AD_PART, WS_AD_CHOL, WS_AD_STAT, WS_AD_PROP,
   WS_NSLOT
@@ -71,7 +71,7 @@ struct hx_ctx {
   int chain_every, chain_phase;            // thinned chain emit of the batch loops (hx_ctx_set_chain_thinning); 0/1 = every iteration
   const void* ctl_eps; const int* ctl_L;   // device-resident (step, L) the SIMT move kernels read during adaptive warm-up
   int narrow_off;                          // 1: keep the momentum projection of narrow targets inside the half-move kernel
-  int energy_bf16;                         // 1: propagator-form energy products from bf16 hi/lo operands (default tf32 hi/lo)
+  int energy_bf16;                         // propagator-form energy products: 0 tf32 hi/lo (default), 1 bf16 hi/lo, 2 fp16 hi/lo (scaled)
   int gram_tf32;                           // 1: Gram from tf32 hi/lo operands instead of bf16 hi/lo
   int proj_slices;                         // split-K slices of the projection GEMM (0: default)
   int rng_ctas_per_sm;                     // resident CTAs/SM of the draw kernel (0: default 4)

@@ -16,6 +16,7 @@
 #include "hx_tc.cuh"
 #include "hx_common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace hx {
 namespace tc {
@@ -23,7 +24,7 @@ namespace tc {
 constexpr int kBM = 128;      // UMMA M
 constexpr int kThreads = 192;
 
-enum : int { KIND_BF16 = 0, KIND_TF32 = 1, KIND_F16F8 = 2 };
+enum : int { KIND_BF16 = 0, KIND_TF32 = 1, KIND_F16F8 = 2, KIND_F16 = 3 };
 enum : int { EPI_STORE = 0, EPI_KICKB = 1, EPI_DOT = 2, EPI_PROP = 3 };
 
 template <int KIND> struct Kind;
@@ -36,6 +37,14 @@ template <> struct Kind<KIND_BF16> {
 // 64-element K-block 64 bytes of e4m3(x) followed by 64 bytes of e4m3((x - fp16(x)) * 2^11), i.e. the same 128-byte rows
 template <> struct Kind<KIND_F16F8> {
   typedef uint16_t elem;
+  static constexpr int ROW_ELEMS = 64;
+  static constexpr int UMMA_K = 16;
+};
+// fp16 hi/lo (22 significand bits, 2^-22 per product at the kind::f16 rate, twice the tf32 rate): hi = fp16(x s), lo = fp16(x s - hi)
+// with a power-of-two scale s per operand from its max-abs (f16_scale) so that the pair stays in fp16's normal range; the
+// epilogues divide the scales out again.  Used for the propagator-form energy products.
+template <> struct Kind<KIND_F16> {
+  typedef __half elem;
   static constexpr int ROW_ELEMS = 64;
   static constexpr int UMMA_K = 16;
 };
@@ -68,12 +77,16 @@ struct GemmArgs {
   // two column blocks of blk_cols (padded) columns each; block 0: Q = acc + mu, planes_out (tf32 hi/lo) <- split(acc);
   // block 1: S = acc.  blk_cols = 0 for the other epilogues (one block).
   int blk_cols;
-  int planes_bf16;   // EPI_PROP: kind of planes_out (1 bf16 hi/lo, 0 tf32 hi/lo)
+  int planes_bf16;   // EPI_PROP: kind of planes_out (0 tf32 hi/lo, 1 bf16 hi/lo, 2 fp16 hi/lo scaled by row_scale)
   // split-K (EPI_STORE only): grid.z slices of kb_per_slice K-blocks each, slice z stores to out + z * slice_stride; the
   // caller adds the slices in a fixed order (also shortens the tensor core's truncating accumulation chains).  0 = no split.
   int kb_per_slice; size_t slice_stride;
   // KIND_F16F8: out = (main + corr / 2^11) * scale_ptr[1]   (scale_ptr = {sc, 1/sc}, the power-of-two scale of the B operand)
   const float* scale_ptr;
+  // fp16 energy operands.  EPI_STORE with amax_out: atomicMax of |out| into it (max-abs of W P);
+  // EPI_DOT with dot_pair = 1 / 2: partial sums are divided by row_scale[row] * f16_scale(amax[1] / amax[0]) (operands Z x WP / Z x P);
+  // EPI_PROP with planes_bf16 = 2: planes_out = fp16 hi/lo of acc * row_scale[row]
+  uint32_t* amax_out; const uint32_t* amax; const float* row_scale; int dot_pair;
   int n_cover;       // pair kernel: padded N the grid covers (0: N); EPI_PROP covers two column blocks
 };
 
@@ -93,6 +106,23 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = rn_tf32(x);
   lo = rn_tf32(x - hi);
 }
+
+__device__ __forceinline__ void split_f16(float xs, __half& hi, __half& lo) {
+  hi = __float2half_rn(xs);
+  lo = __float2half_rn(xs - __half2float(hi));
+}
+// power-of-two scale that puts a max-abs value (given by its bit pattern) into [2^(top-1), 2^top)
+__device__ __forceinline__ float f16_scale(uint32_t amax_bits, int top) {
+  const float amax = __uint_as_float(amax_bits);
+  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+  int e;
+  frexpf(amax, &e);
+  return ldexpf(1.f, top - e);
+}
+// A operands (z0 = [q0 - mu | S0] and q_L - mu) are scaled per ROW (walker) from the row's own max-abs -- row-local, so a
+// row-sharded run reproduces the unsharded one bit for bit; q_L - mu reuses its walker's z0 scale, which leaves 16x head-room.
+// B operands (P, W P) are replicated on every rank and use one scale each from max-abs words [0] P, [1] W P.
+constexpr int kF16TopZ = 12, kF16TopB = 15;
 
 // 32 contiguous floats of one row: vector path when `fast`, predicated scalar path otherwise
 __device__ __forceinline__ void load32(const float* p, float (&v)[32], int nval, bool fast) {
@@ -118,8 +148,24 @@ __device__ __forceinline__ void store32(float* p, const float (&v)[32], int nval
 }
 // split 32 values into the hi/lo planes of the given kind (plane stride in elements)
 template <int KIND>
-__device__ __forceinline__ void store_planes32(void* planes, size_t pbase, size_t plane, const float (&v)[32], int nval, bool fast) {
-  if (KIND == KIND_BF16) {
+__device__ __forceinline__ void store_planes32(void* planes, size_t pbase, size_t plane, const float (&v)[32], int nval, bool fast,
+                                               float scale = 1.f) {
+  if (KIND == KIND_F16) {
+    __half* P = reinterpret_cast<__half*>(planes);
+    __align__(16) __half hi[32], lo[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) split_f16(j < nval ? v[j] * scale : 0.f, hi[j], lo[j]);
+    if (fast) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        reinterpret_cast<uint4*>(P + pbase)[j] = reinterpret_cast<const uint4*>(hi)[j];
+        reinterpret_cast<uint4*>(P + plane + pbase)[j] = reinterpret_cast<const uint4*>(lo)[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { P[pbase + j] = hi[j]; P[plane + pbase + j] = lo[j]; }
+    }
+  } else if (KIND == KIND_BF16) {
     __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(planes);
     __align__(16) __nv_bfloat16 hi[32], lo[32];
 #pragma unroll
@@ -203,6 +249,10 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t tmem_b
     const bool fast = vec && nval == 32;
     if (EPI == EPI_STORE) {
       store32(g.out + (size_t)blockIdx.z * g.slice_stride + (size_t)row * g.ldo + col0, v, nval, fast);
+      if (g.amax_out) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < nval) rowacc = fmaxf(rowacc, fabsf(v[j]));
+      }
     } else if (EPI == EPI_PROP) {
       const size_t base = (size_t)row * g.N + col0;
       if (blk == 0) {
@@ -215,7 +265,10 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t tmem_b
         } else {
           store32(g.Q + base, v, nval, fast);
         }
-        if (g.planes_bf16)
+        if (g.planes_bf16 == 2)
+          store_planes32<KIND_F16>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, v, nval, fast,
+                                   g.row_scale[row]);
+        else if (g.planes_bf16)
           store_planes32<KIND_BF16>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, v, nval, fast);
         else
           store_planes32<KIND_TF32>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, v, nval, fast);
@@ -264,12 +317,21 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t tmem_b
           store32(g.Q + base, qv, nval, fast);
 #pragma unroll
           for (int j = 0; j < 32; ++j) qv[j] -= mu[j];
-          store_planes32<KIND == KIND_F16F8 ? KIND_BF16 : KIND>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, qv, nval, fast);
+          store_planes32<(KIND == KIND_F16F8 || KIND == KIND_F16) ? KIND_BF16 : KIND>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, qv, nval, fast);
         }
       }
     }
   }
-  if (EPI == EPI_DOT && rok) g.part[(size_t)row * g.NT + ntile] = rowacc;
+  if (EPI == EPI_DOT && rok) {
+    float sc = 1.f;
+    if (g.dot_pair) sc = 1.f / (g.row_scale[row] * f16_scale(g.amax[g.dot_pair == 1 ? 1 : 0], kF16TopB));
+    g.part[(size_t)row * g.NT + ntile] = rowacc * sc;
+  }
+  if (EPI == EPI_STORE && g.amax_out) {      // rows beyond M hold rowacc = 0: the max over the warp is the tile's max-abs
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rowacc = fmaxf(rowacc, __shfl_xor_sync(0xffffffffu, rowacc, o));
+    if (lane == 0 && rowacc > 0.f) atomicMax(g.amax_out, __float_as_uint(rowacc));
+  }
 }
 
 template <int BN, int EPI, int KIND>
@@ -329,7 +391,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   } else if (warp == 1) {
     if (lane == 0) {
       // kind::f16 / kind::tf32 instruction descriptor: D = F32, A/B format (1 = BF16, 2 = TF32), K-major, N>>3, M>>4
-      constexpr uint32_t fmt = (KIND == KIND_TF32) ? 2u : 1u;
+      constexpr uint32_t fmt = (KIND == KIND_TF32) ? 2u : (KIND == KIND_F16 ? 0u : 1u);
       constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % L::STAGES;
@@ -464,7 +526,7 @@ k_tc_gemm_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t fmt = (KIND == KIND_TF32) ? 2u : (KIND == KIND_F16F8 ? 0u : 1u);
+      constexpr uint32_t fmt = (KIND == KIND_TF32) ? 2u : ((KIND == KIND_F16F8 || KIND == KIND_F16) ? 0u : 1u);
       constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * kBM) >> 4) << 24);
       constexpr uint32_t idesc8 = umma_idesc_e4m3(2 * kBM, BN);
       static_assert(KIND != KIND_TF32, "pair kernel: bf16 hi/lo or fp16 + e4m3 operands");

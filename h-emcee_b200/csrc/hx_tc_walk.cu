@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) k_absmax_centred(const float* __restrict_
   const size_t tot = (size_t)n * d;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % (size_t)d);
-    m = fmaxf(m, fabsf(X2[i] - mean[c]));
+    m = fmaxf(m, fabsf(X2[i] - (mean ? mean[c] : 0.f)));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -118,6 +118,18 @@ __global__ void __launch_bounds__(256) k_absmax_centred(const float* __restrict_
     for (int w = 1; w < 8; ++w) m = fmaxf(m, wm[w]);
     atomicMax(amax_bits, __float_as_uint(m));       // non-negative floats order like their bit patterns
   }
+}
+// max |src[r * ld + c]| over r < rows, c < cols
+__global__ void __launch_bounds__(256) k_absmax_ld(const float* __restrict__ src, int rows, int cols, int ld, uint32_t* __restrict__ amax_bits) {
+  float m = 0.f;
+  const size_t tot = (size_t)rows * cols;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (size_t)cols), c = (int)(i - (size_t)r * cols);
+    m = fmaxf(m, fabsf(src[(size_t)r * ld + c]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
 }
 // scale_out = {sc, 1/sc}
 __global__ void k_f8_scale(const uint32_t* __restrict__ amax_bits, int n, float* __restrict__ scale_out) {
@@ -194,12 +206,18 @@ __global__ void __launch_bounds__(256) k_center_planes_T(const float* __restrict
 // planes [2, rows_pad, Kp] <- split(src[r*ld + k]) for r < dim_r, k < dim_k, zero elsewhere
 template <int KIND>
 __global__ void k_split_planes(const float* __restrict__ src, int dim_r, int dim_k, int ld, int rows_pad, int Kp,
-                               typename Kind<KIND>::elem* __restrict__ planes) {
+                               typename Kind<KIND>::elem* __restrict__ planes, const uint32_t* __restrict__ amax = nullptr) {
   const size_t tot = (size_t)rows_pad * Kp, plane = tot;
+  const float sc16 = (KIND == KIND_F16) ? f16_scale(*amax, kF16TopB) : 1.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / Kp), k = (int)(i - (size_t)r * Kp);
     const float v = (r < dim_r && k < dim_k) ? src[(size_t)r * ld + k] : 0.f;
-    if (KIND == KIND_BF16) {
+    if (KIND == KIND_F16) {
+      __half hi, lo;
+      split_f16(v * sc16, hi, lo);
+      reinterpret_cast<__half*>(planes)[i] = hi;
+      reinterpret_cast<__half*>(planes)[plane + i] = lo;
+    } else if (KIND == KIND_BF16) {
       __nv_bfloat16 hi, lo;
       split_bf16(v, hi, lo);
       reinterpret_cast<__nv_bfloat16*>(planes)[i] = hi;
@@ -454,13 +472,68 @@ __global__ void k_z0_planes(const float* __restrict__ X1, const float* __restric
   }
 }
 
+// The same z0 with the energy operand in fp16 hi/lo form: one warp per row (walker), which first finds the row's max-abs and
+// scales the row by a power of two (row_scale[r], read back by the epilogues).  zB = bf16 hi/lo [2, rA, K2] (unscaled, apply
+// GEMM), zH = fp16 hi/lo [2, rA, K2].  Rows >= `rows` and columns >= d are zero.  dK <= 32 * 4 * kZ0Chunks.
+constexpr int kZ0Chunks = 8;      // float4 chunks per lane and half: dK <= 1024
+__global__ void __launch_bounds__(256) k_z0_planes_f16(const float* __restrict__ X1, const float* __restrict__ mu,
+                                                       const float* __restrict__ S0, int rows, int d, int rA, int dK,
+                                                       __nv_bfloat16* __restrict__ zB, __half* __restrict__ zH,
+                                                       float* __restrict__ row_scale) {
+  const int lane = threadIdx.x & 31;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rA) return;
+  const int K2 = 2 * dK;
+  const size_t plane = (size_t)rA * K2;
+  float v[2][kZ0Chunks][4];
+  float m = 0.f;
+#pragma unroll
+  for (int part = 0; part < 2; ++part)
+#pragma unroll
+    for (int t = 0; t < kZ0Chunks; ++t) {
+      const int c0 = 4 * lane + 128 * t;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u;
+        float x = 0.f;
+        if (r < rows && c < d) x = part ? S0[(size_t)r * d + c] : X1[(size_t)r * d + c] - (mu ? mu[c] : 0.f);
+        v[part][t][u] = x;
+        m = fmaxf(m, fabsf(x));
+      }
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const float sc = f16_scale(__float_as_uint(m), kF16TopZ);
+  if (lane == 0 && r < rows) row_scale[r] = sc;
+#pragma unroll
+  for (int part = 0; part < 2; ++part)
+#pragma unroll
+    for (int t = 0; t < kZ0Chunks; ++t) {
+      const int c0 = 4 * lane + 128 * t;
+      if (c0 >= dK) continue;
+      const size_t i = (size_t)r * K2 + (size_t)part * dK + c0;
+      __align__(8) __nv_bfloat16 bh[4], bl[4];
+      __align__(8) __half hh[4], hl[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        split_bf16(v[part][t][u], bh[u], bl[u]);
+        split_f16(v[part][t][u] * sc, hh[u], hl[u]);
+      }
+      *reinterpret_cast<uint2*>(zB + i) = *reinterpret_cast<const uint2*>(bh);
+      *reinterpret_cast<uint2*>(zB + plane + i) = *reinterpret_cast<const uint2*>(bl);
+      *reinterpret_cast<uint2*>(zH + i) = *reinterpret_cast<const uint2*>(hh);
+      *reinterpret_cast<uint2*>(zH + plane + i) = *reinterpret_cast<const uint2*>(hl);
+    }
+}
+
 // B-operand planes of a propagator block: planes[row_off + c][kk] = split(src[k(kk)][c]) for c < d, where src is
 // [2d, d] (basis index k major) and kk -> k maps the z0 column layout (kk < dK: k = kk; else k = d + kk - dK);
 // zero outside.  Covers rows [row_off, row_off + rows_blk) of both planes ([2, rows_pad, K2]).
 template <int KIND>
 __global__ void k_transpose_planes(const float* __restrict__ src, int d, int dK, int rows_blk, int rows_pad, int row_off,
-                                   typename Kind<KIND>::elem* __restrict__ planes) {
+                                   typename Kind<KIND>::elem* __restrict__ planes, const uint32_t* __restrict__ amax = nullptr) {
   __shared__ float tile[32][33];
+  const float sc16 = (KIND == KIND_F16) ? f16_scale(*amax, kF16TopB) : 1.f;
   const int K2 = 2 * dK;
   const int kk0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {       // i: kk index, threadIdx.x: c index (coalesced over c)
@@ -475,7 +548,12 @@ __global__ void k_transpose_planes(const float* __restrict__ src, int d, int dK,
     if (c < rows_blk && kk < K2) {
       const size_t o = (size_t)(row_off + c) * K2 + kk;
       const float v = tile[threadIdx.x][i];
-      if (KIND == KIND_BF16) {
+      if (KIND == KIND_F16) {
+        __half hi, lo;
+        split_f16(v * sc16, hi, lo);
+        reinterpret_cast<__half*>(planes)[o] = hi;
+        reinterpret_cast<__half*>(planes)[plane + o] = lo;
+      } else if (KIND == KIND_BF16) {
         __nv_bfloat16 hi, lo;
         split_bf16(v, hi, lo);
         reinterpret_cast<__nv_bfloat16*>(planes)[o] = hi;
@@ -817,7 +895,9 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     prop = (L + 3) * t_kick > (L + 1) * t_bk + 60e-6 + t_apply;
   }
   const bool g1_tf32 = ctx->precision == HX_PREC_TF32X3;
-  const bool e_bf16 = ctx->energy_bf16 && !g1_tf32;          // propagator form: energy products from bf16 hi/lo operands
+  // propagator form: operand kind of the energy products -- tf32 hi/lo (0), bf16 hi/lo (1), fp16 hi/lo with row / matrix scales (2)
+  const int ekind = g1_tf32 ? 0 : ((ctx->energy_bf16 == 2 && dK > 128 * kZ0Chunks) ? 0 : ctx->energy_bf16);
+  const bool e_bf16 = ekind == 1, e_f16 = ekind == 2;
   const int rQ = prop ? (rA > bRA ? rA : bRA) : rA;            // rows of the q - mu operand planes (basis run reuses them)
 
   void *pCT, *pM, *pBo, *pBoP, *pPP, *pP0, *pQC, *pQC2, *pQsP, *pS0, *pQs, *pLPP, *pDKP;
@@ -935,7 +1015,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   //     trajectories with the same kick/drift recurrence (tf32 hi/lo operands), giving q_L - mu = z0 Tq, S_L = z0 Ts
   //     and the impulse-weighted position sum Qs = z0 W; fold the precision into W for the kinetic-energy product.
   void *pBX = nullptr, *pBS = nullptr, *pTQ = nullptr, *pTS = nullptr, *pTW = nullptr, *pWP = nullptr, *pB1 = nullptr,
-       *pB2 = nullptr, *pZB = nullptr, *pZT = nullptr, *pPP32 = nullptr;
+       *pB2 = nullptr, *pZB = nullptr, *pZT = nullptr, *pPP32 = nullptr, *pAM = nullptr, *pRS = nullptr;
   if (prop) {
     if (int e = timing_mark(ctx, s, HX_PH_BASIS)) return e;
     const size_t bsz = (size_t)bR * d * sizeof(float);
@@ -948,7 +1028,12 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     if (int e = ws_get(ctx, WS_TC_B1, (size_t)2 * (2 * dB) * K2 * sizeof(float), &pB1)) return e;
     if (int e = ws_get(ctx, WS_TC_B2, (size_t)2 * dB * K2 * sizeof(float), &pB2)) return e;
     if (int e = ws_get(ctx, WS_TC_ZB, g1_tf32 ? 16 : (size_t)2 * rA * K2 * sizeof(bf), &pZB)) return e;
-    if (int e = ws_get(ctx, WS_TC_ZT, e_bf16 ? 16 : (size_t)2 * rA * K2 * sizeof(float), &pZT)) return e;
+    if (int e = ws_get(ctx, WS_TC_ZT, e_bf16 ? 16 : (size_t)2 * rA * K2 * (e_f16 ? sizeof(__half) : sizeof(float)), &pZT)) return e;
+    if (e_f16) {
+      if (int e = ws_get(ctx, WS_TC_AM, 16, &pAM)) return e;
+      if (int e = ws_get(ctx, WS_TC_RSC, (size_t)rA * sizeof(float), &pRS)) return e;
+      HX_CUDA(cudaMemsetAsync(pAM, 0, 16, s));
+    }
     k_basis_init<<<grid_for((size_t)bR * d, 256), 256, 0, s>>>((float*)pBX, (float*)pBS, d);
     HX_LAUNCH_CHECK("k_basis_init");
     LeapArgs la;
@@ -969,7 +1054,17 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     GemmArgs gw;
     memset(&gw, 0, sizeof(gw));
     gw.nprod = 3; gw.M = bR; gw.N = d; gw.out = (float*)pWP; gw.ldo = d;
+    if (e_f16) gw.amax_out = (uint32_t*)pAM + 1;              // max |W P| for the scale of its fp16 planes
     if (int e = launch_gemm<EPI_STORE, KIND_TF32>(ctx, pQsP, bRA, pPP32, dB, dK, gw, s)) return e;
+    if (e_f16) {
+      // fp16 hi/lo planes of P (over the bf16 planes the basis run no longer needs), scaled from max |P|
+      k_absmax_ld<<<grid_for((size_t)d * d / 4, 256), 256, 0, s>>>((const float*)tgt->precision, d, d, tgt->ld, (uint32_t*)pAM);
+      HX_LAUNCH_CHECK("k_absmax_ld(P)");
+      k_split_planes<KIND_F16><<<grid_for((size_t)dB * dK, 256), 256, 0, s>>>((const float*)tgt->precision, d, d, tgt->ld, dB, dK,
+                                                                             (__half*)pPP, (const uint32_t*)pAM);
+      HX_LAUNCH_CHECK("k_split_planes(P, f16)");
+      ctx->launches += 2;
+    }
     // B operands: [Tq ; Ts]^T for the apply GEMM, (W P)^T for the kinetic-energy product
     dim3 tg((K2 + 31) / 32, (dB + 31) / 32), tb(32, 8);
     if (g1_tf32) {
@@ -979,7 +1074,8 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
       k_transpose_planes<KIND_BF16><<<tg, tb, 0, s>>>((const float*)pTQ, d, dK, dB, 2 * dB, 0, (bf*)pB1);
       k_transpose_planes<KIND_BF16><<<tg, tb, 0, s>>>((const float*)pTS, d, dK, dB, 2 * dB, dB, (bf*)pB1);
     }
-    if (e_bf16) k_transpose_planes<KIND_BF16><<<tg, tb, 0, s>>>((const float*)pWP, d, dK, dB, dB, 0, (bf*)pB2);
+    if (e_f16) k_transpose_planes<KIND_F16><<<tg, tb, 0, s>>>((const float*)pWP, d, dK, dB, dB, 0, (__half*)pB2, (const uint32_t*)pAM + 1);
+    else if (e_bf16) k_transpose_planes<KIND_BF16><<<tg, tb, 0, s>>>((const float*)pWP, d, dK, dB, dB, 0, (bf*)pB2);
     else k_transpose_planes<KIND_TF32><<<tg, tb, 0, s>>>((const float*)pWP, d, dK, dB, dB, 0, (float*)pB2);
     HX_LAUNCH_CHECK("k_transpose_planes");
     ctx->launches += 5;
@@ -1046,14 +1142,18 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
 
   // (4) leapfrog + energy products
   if (prop) {
-    k_z0_planes<<<grid_for((size_t)rA * K2 / 4, 256), 256, 0, s>>>(X1, mu, S0, rows, d, rA, dK, g1_tf32 ? nullptr : (bf*)pZB,
-                                                                   e_bf16 ? nullptr : (float*)pZT);
+    if (e_f16)
+      k_z0_planes_f16<<<(rA + 7) / 8, 256, 0, s>>>(X1, mu, S0, rows, d, rA, dK, (bf*)pZB, (__half*)pZT, (float*)pRS);
+    else
+      k_z0_planes<<<grid_for((size_t)rA * K2 / 4, 256), 256, 0, s>>>(X1, mu, S0, rows, d, rA, dK, g1_tf32 ? nullptr : (bf*)pZB,
+                                                                     e_bf16 ? nullptr : (float*)pZT);
     HX_LAUNCH_CHECK("k_z0_planes");
     ctx->launches += 1;
     GemmArgs g1;
     memset(&g1, 0, sizeof(g1));
     g1.nprod = 3; g1.M = rows; g1.N = d; g1.mu = mu; g1.Q = Q; g1.S = S; g1.blk_cols = dB;
-    g1.planes_out = pQC; g1.rows_out_pad = rQ; g1.Kout_p = dK; g1.planes_bf16 = e_bf16 ? 1 : 0;
+    g1.planes_out = pQC; g1.rows_out_pad = rQ; g1.Kout_p = dK; g1.planes_bf16 = ekind;
+    g1.row_scale = (const float*)pRS;
     if (g1_tf32) {
       if (int e = launch_gemm<EPI_PROP, KIND_TF32>(ctx, pZT, rA, pB1, 2 * dB, K2, g1, s, 0, 2 * dB)) return e;
     } else if (ctx->aux_pair) {
@@ -1064,7 +1164,10 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     GemmArgs g2;
     memset(&g2, 0, sizeof(g2));
     g2.nprod = 3; g2.M = rows; g2.N = d; g2.NT = NT; g2.X = S0; g2.Y = S; g2.part = (float*)pDKP;
-    if (e_bf16) {
+    if (e_f16) {
+      g2.amax = (const uint32_t*)pAM; g2.row_scale = (const float*)pRS; g2.dot_pair = 1;
+      if (int e = launch_gemm<EPI_DOT, KIND_F16>(ctx, pZT, rA, pB2, dB, K2, g2, s)) return e;
+    } else if (e_bf16) {
       if (int e = launch_gemm<EPI_DOT, KIND_BF16>(ctx, pZB, rA, pB2, dB, K2, g2, s)) return e;
     } else {
       if (int e = launch_gemm<EPI_DOT, KIND_TF32>(ctx, pZT, rA, pB2, dB, K2, g2, s)) return e;
@@ -1072,7 +1175,10 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     GemmArgs g3;
     memset(&g3, 0, sizeof(g3));
     g3.nprod = 3; g3.M = rows; g3.N = d; g3.NT = NT; g3.mu = mu; g3.X = Q; g3.part = (float*)pLPP;
-    if (e_bf16) {
+    if (e_f16) {
+      g3.amax = (const uint32_t*)pAM; g3.row_scale = (const float*)pRS; g3.dot_pair = 2;
+      if (int e = launch_gemm<EPI_DOT, KIND_F16>(ctx, pQC, rQ, pPP, dB, dK, g3, s)) return e;       // pPP: fp16 planes of P
+    } else if (e_bf16) {
       if (int e = launch_gemm<EPI_DOT, KIND_BF16>(ctx, pQC, rQ, pPP, dB, dK, g3, s)) return e;      // pPP: bf16 planes from the basis run
     } else {
       if (int e = launch_gemm<EPI_DOT, KIND_TF32>(ctx, pQC, rQ, pPP32, dB, dK, g3, s)) return e;

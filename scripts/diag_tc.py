@@ -6,6 +6,9 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "h-emcee_b200")]
 import hemcee_b200 as hx
 from bench import make_cov
 
+from hemcee_b200 import _lib as _l0, _rt as _r0
+import torch as _t0
+_l0.load().hx_ctx_set_tuning(_r0.ctx(_t0.device("cuda", 0)), 3, int(os.environ.get("EKIND", 0)))   # energy operand kind
 d = int(os.environ.get("D", 1000)); n = int(os.environ.get("N", 8192)); L = 10; eps = 0.1
 _, prec = make_cov(d, 1e4)
 tgt = hx.targets.GaussianFull(precision=prec)

@@ -230,3 +230,35 @@ def test_f16f8_projection_accuracy(hx, prec):
     for mode in ("bf16x3", "f16f8"):
         assert (res[mode][2] - res["exact"][2]).abs().max().item() <= 1e-4 * ps
         assert (res[mode][1] - res["exact"][1]).abs().max().item() <= 5e-3
+
+
+def test_fp16_energy_products_match_tf32(hx, prec, form):
+    """hx_ctx_set_tuning(3, 2): propagator-form energy products (kinetic-energy change and lp') from fp16 hi/lo operands with a
+    power-of-two scale per walker row instead of tf32 hi/lo.  Positions / momenta do not depend on the energy operands (bit
+    equal); log-accept and lp' agree with the tf32 form and the f64 oracle within the tensor-core tolerance, and -- the row
+    scales being row-local -- a row shard reproduces the unsharded result bit for bit."""
+    from hemcee_b200 import _lib, _rt
+    lib, ctx = _lib.load(), _rt.ctx(torch.device("cuda", 0))
+    n, d, L, eps = 512, 256, 6, 0.05
+    tgt, (olp, og), g1, g2, key = _problem(hx, n, d, seed=5, kappa=1000.0)
+    G1, G2 = torch.from_numpy(g1).cuda(), torch.from_numpy(g2).cuda()
+    LP1 = tgt.log_prob(G1)
+    prec("bf16x3")
+    form("propagator")
+    out = {}
+    try:
+        for kind in (0, 2):
+            _lib.check(lib.hx_ctx_set_tuning(ctx, 3, kind), "hx_ctx_set_tuning")
+            out[kind] = hx.hmc_walk_move(G1, G2, eps, key, tgt, tgt, L, LP1)
+        parts = [hx.hmc_walk_move(G1[r * 128:(r + 1) * 128], G2, eps, key, tgt, tgt, L, LP1[r * 128:(r + 1) * 128],
+                                  row0=r * 128, n=n) for r in range(4)]
+    finally:
+        lib.hx_ctx_set_tuning(ctx, 3, 0)
+    assert torch.equal(out[0][0], out[2][0]) and torch.equal(out[0][2], out[2][2])
+    a64, b64 = g1.astype(np.float64), g2.astype(np.float64)
+    _, la64, _, lp64 = OM.hmc_walk_move(a64, b64, eps, key, olp, og, L, olp(a64), rng_dtype=np.float32)
+    for kind in (0, 2):
+        np.testing.assert_allclose(out[kind][1].cpu().numpy(), la64, rtol=0, atol=5e-3)
+        np.testing.assert_allclose(out[kind][3].cpu().numpy(), lp64, rtol=2e-4, atol=2e-3)
+    for i in range(4):
+        assert torch.equal(torch.cat([p[i] for p in parts]), out[2][i])
