@@ -98,7 +98,7 @@ extern "C" HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value) {
   else if (what == 8) ctx->proj_pair = value ? 1 : 0;
   else if (what == 9) ctx->pair_chunked = value ? 1 : 0;
   else if (what == 10) ctx->draw_nostore = value ? 1 : 0;
-  else if (what == 12) ctx->aux_pair = value ? 1 : 0;
+  else if (what == 12) ctx->aux_pair = value;
   else return hx_fail(HX_E_DTYPE, "hx_ctx_set_tuning: unknown knob %d", what);
   return 0;
 }
@@ -166,6 +166,7 @@ extern "C" HX_API int hx_ctx_create(hx_ctx** out, int device) {
   memset(c, 0, sizeof(*c));
   c->device = device;
   c->aux_pair = 1;
+  c->energy_bf16 = 2;
   cudaDeviceProp prop;
   HX_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;

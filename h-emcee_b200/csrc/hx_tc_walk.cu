@@ -1166,7 +1166,9 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     g2.nprod = 3; g2.M = rows; g2.N = d; g2.NT = NT; g2.X = S0; g2.Y = S; g2.part = (float*)pDKP;
     if (e_f16) {
       g2.amax = (const uint32_t*)pAM; g2.row_scale = (const float*)pRS; g2.dot_pair = 1;
-      if (int e = launch_gemm<EPI_DOT, KIND_F16>(ctx, pZT, rA, pB2, dB, K2, g2, s)) return e;
+      if (ctx->aux_pair == 2) {
+        if (int e = launch_gemm_pair<EPI_DOT, KIND_F16>(ctx, pZT, rA, pB2, dB, K2, g2, s)) return e;
+      } else if (int e = launch_gemm<EPI_DOT, KIND_F16>(ctx, pZT, rA, pB2, dB, K2, g2, s)) return e;
     } else if (e_bf16) {
       if (int e = launch_gemm<EPI_DOT, KIND_BF16>(ctx, pZB, rA, pB2, dB, K2, g2, s)) return e;
     } else {
@@ -1177,7 +1179,9 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     g3.nprod = 3; g3.M = rows; g3.N = d; g3.NT = NT; g3.mu = mu; g3.X = Q; g3.part = (float*)pLPP;
     if (e_f16) {
       g3.amax = (const uint32_t*)pAM; g3.row_scale = (const float*)pRS; g3.dot_pair = 2;
-      if (int e = launch_gemm<EPI_DOT, KIND_F16>(ctx, pQC, rQ, pPP, dB, dK, g3, s)) return e;       // pPP: fp16 planes of P
+      if (ctx->aux_pair == 2) {
+        if (int e = launch_gemm_pair<EPI_DOT, KIND_F16>(ctx, pQC, rQ, pPP, dB, dK, g3, s)) return e;
+      } else if (int e = launch_gemm<EPI_DOT, KIND_F16>(ctx, pQC, rQ, pPP, dB, dK, g3, s)) return e;       // pPP: fp16 planes of P
     } else if (e_bf16) {
       if (int e = launch_gemm<EPI_DOT, KIND_BF16>(ctx, pQC, rQ, pPP, dB, dK, g3, s)) return e;      // pPP: bf16 planes from the basis run
     } else {

@@ -126,8 +126,8 @@ HX_API int hx_tc_microbench(hx_ctx* ctx, int mode, int32_t n, int32_t rows, int3
  * projection GEMM, summed in fp32 in a fixed order (default 1 = accumulate all of K = n inside the tensor core; measured:
  * no accuracy gain from more); what = 2: 1 = Gram matrix from tf32 hi/lo operands instead of bf16 hi/lo (default 0);
  * what = 3: operand kind of the propagator-form energy products: 0 = tf32 hi/lo (2^-21 per product, tf32 rate), 1 = bf16 hi/lo
- * (2^-16: too coarse for kappa = 1e4), 2 = fp16 hi/lo with power-of-two scales per walker row / per matrix (2^-22 at the
- * kind::f16 rate, twice the tf32 rate); what = 4: 0 disables the CUDA-graph
+ * (2^-16: too coarse for kappa = 1e4), 2 (default) = fp16 hi/lo with power-of-two scales per walker row / per matrix (2^-22 at
+ * the kind::f16 rate, twice the tf32 rate; dim <= 1024, tf32 beyond); what = 4: 0 disables the CUDA-graph
  * replay of launch-bound batch loops (default 1); what = 5: 0 keeps the momentum projection of narrow targets (dim <= 40, n >= 1024)
  * inside the half-move kernel instead of the lane-split projection kernel (default 1);
  * what = 6: the next half-move's momentum draw is queued after that many projection chunks instead of at the projection's start
