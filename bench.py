@@ -381,27 +381,38 @@ def main():
     if path == 1:
         # tensor-core path: the bracketed section is the momentum projection S0 = P0 C of one half-move: tcgen05 GEMM chunks
         # (128 x 256 tiles, K = n) while the counter-based draw of the NEXT half-move's P0 runs concurrently on the ALU pipes
-        kname = ("tc::k_tc_gemm<256,EPI_STORE,bf16 hi/lo> projection S0 = P0 C (all row chunks of a half-move), "
-                 "tc::k_rng_planes of the next half-move concurrent")
+        tune = dict(kv.split("=") for kv in args.tune)
+        f8 = args.precision in ("auto", "f16f8")                      # projection operands: fp16 + 2 x e4m3 (default) or bf16 hi/lo
+        ekind = int(tune.get("3", 2)) if args.precision != "tf32x3" else 0   # propagator energy operands: 2 fp16 hi/lo, 0 tf32 hi/lo
+        kname = ("tc::k_tc_gemm<256,EPI_STORE,%s> projection S0 = P0 C (all row chunks of a half-move), "
+                 "tc::k_rng_planes of the next half-move concurrent" % ("fp16 + e4m3" if f8 else "bf16 hi/lo"))
         flops = 2.0 * rows * n * d
         nK, dpad = -(-n // 64) * 64, -(-d // 256) * 256
-        executed = 3.0 * 2.0 * (-(-rows // 128) * 128) * nK * dpad
+        # tensor work actually issued, in units of one bf16-rate product: bf16 hi/lo = 3 products; fp16 + e4m3 = one fp16 product
+        # + two e4m3 products at twice the rate = 2 units; single bf16 = 1
+        units = 1.0 if args.precision == "bf16" else (2.0 if f8 else 3.0)
+        executed = units * 2.0 * (-(-rows // 128) * 128) * nK * dpad
         dB, dK = dpad, -(-d // 64) * 64
         # executed tensor flops of the whole half-move in bf16 units (tf32 products count double: half the MMA rate)
+        ef = 2.0 if ekind == 0 else 1.0
+        kf = 2.0 if args.precision == "tf32x3" else 1.0
         if form == "propagator":
-            lf = 3 * 2.0 * rows * (2 * dK) * (2 * dB) + 2 * 3 * (2.0 * rows * (2 * dK) * dB + 2.0 * rows * dK * dB)
-            lf += 2 * 3 * (L + 1) * 2.0 * (2 * d) * dK * dB + 2 * 3 * 2.0 * (2 * d) * dK * dB
+            lf = kf * 3 * 2.0 * rows * (2 * dK) * (2 * dB) + ef * 3 * (2.0 * rows * (2 * dK) * dB + 2.0 * rows * dK * dB)
+            lf += kf * 3 * (L + 1) * 2.0 * (2 * d) * dK * dB + 2 * 3 * 2.0 * (2 * d) * dK * dB
         else:
-            lf = 3 * (L + 3) * 2.0 * rows * dK * dB
+            lf = kf * 3 * (L + 3) * 2.0 * rows * dK * dB
         gram = 3 * 2.0 * dB * dB * nK
         step_exec = executed + lf + gram
         extra = dict(executed_tflops=executed / (k_ms * 1e-3) / 1e12, executed_frac=executed / (k_ms * 1e-3) / 1e12 / peak_tf,
                      step_executed_tflops=step_exec * 2 * K / (ms * 1e-3) / 1e12,
                      step_executed_frac=step_exec * 2 * K / (ms * 1e-3) / 1e12 / peak_tf)
         note = ("achieved/frac = ALGORITHMIC flops 2*rows*n*d of the projection (SURVEY §8d first term) / section time. fp32-class "
-                "accuracy on bf16 tensor cores takes 3 products per algorithmic product (hi*hi + hi*lo + lo*hi), so frac <= 1/3 by "
-                "construction; executed_* counts the products actually issued (incl. d padded to 256); step_executed_* is the whole "
-                "iteration (projection + leapfrog/energy GEMMs + Gram; tf32 products counted double) against the same peak")
+                "accuracy on 16-bit tensor-core operands takes 3 products per algorithmic product (hi*hi + hi*lo + lo*hi; by default "
+                "the two correction products run in e4m3 at twice the rate, i.e. 2 bf16-rate units, so frac <= 1/2 by construction, "
+                "1/3 with --precision bf16x3); executed_* counts the bf16-rate units actually issued (incl. d padded to 256); "
+                "step_executed_* is the whole iteration (projection + leapfrog/energy GEMMs + Gram; tf32 products counted double) "
+                "against the same peak.  The section is co-bound by the concurrent momentum draw (ALU: 4.55 ms alone per half-move "
+                "at c5 on one GPU, DESIGN.md section 4), not by the tensor pipe")
         if args.workload == "c5" and world == 1:
             extra["traffic_source"] = ("profiles/r01c_c5_ncu_full_summary.txt: dram bytes read+write of the 7 chunk launches of one "
                                        "half-move (6 x 758.9 MB + 709.6 MB) = the P0 planes + C^T planes, i.e. no re-reads")

@@ -870,7 +870,9 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
               float* logacc, float* S, float* lp_out, const FuseF32* fuse, const NextDraw* next, cudaStream_t s) {
   const int d = tgt->dim;
   const int nprod = (ctx->precision == HX_PREC_BF16) ? 1 : 3;   // momentum projection / Gram only
-  const int f8 = (ctx->precision == HX_PREC_F16F8) ? 1 : 0;      // momentum projection from fp16 + e4m3 operands
+  // momentum projection from fp16 + e4m3 operands: explicit mode, and what AUTO picks (measured 0.25 ms per half-move faster at
+  // c5 than bf16 hi/lo next to the concurrent draw, S0 within 1.7e-5 instead of 1.3e-5 of an f64 product)
+  const int f8 = (ctx->precision == HX_PREC_F16F8 || ctx->precision == HX_PREC_AUTO) ? 1 : 0;
   const int dB = pad_to(d, BN);            // rows of B-operand planes (N side)
   const int dK = pad_to(d, 64);            // K padding when dim is the reduction axis
   const int nK = pad_to(n, 64);            // K padding when the walker index is the reduction axis
@@ -1223,7 +1225,7 @@ int microbench(hx_ctx* ctx, int mode, int n, int rows, int d, int reps, double* 
   const int dAB = dB > dA ? dB : dA, NT = (d + BN - 1) / BN;
   typedef __nv_bfloat16 bf;
   void *pCT, *pP0, *pS0, *pSc8;
-  const int f8 = ctx->precision == HX_PREC_F16F8 ? 1 : 0;
+  const int f8 = (ctx->precision == HX_PREC_F16F8 || ctx->precision == HX_PREC_AUTO) ? 1 : 0;
   const size_t buf_elems = (size_t)2 * rA * nK;
   if (int e = ws_get(ctx, WS_TC_CT, (size_t)2 * dAB * nK * sizeof(bf), &pCT)) return e;
   if (int e = ws_get(ctx, WS_TC_P0, 2 * buf_elems * sizeof(bf), &pP0)) return e;

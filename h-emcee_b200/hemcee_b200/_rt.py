@@ -20,8 +20,8 @@ class _Config:
     rng_impl   : "partitionable" (JAX >= 0.5 default, the mode the reference authors ran)
                  or "legacy" (`jax_threefry_partitionable=False`).
     precision  : how the walk move's dense contractions are evaluated (include/hx.h HX_PREC_*):
-                 "auto" (exact fp32/fp64 SIMT kernels; split-bf16 tensor cores for large fp32
-                 full-covariance Gaussian problems), "exact", "bf16x3", "bf16", "tf32x3".
+                 "auto" (exact fp32/fp64 SIMT kernels; split-operand tensor cores ("f16f8") for large fp32
+                 full-covariance Gaussian problems), "exact", "bf16x3", "bf16", "tf32x3", "f16f8".
     leapfrog_form : tensor-core walk path only (include/hx.h HX_LEAP_*): "stepwise" kicks on every walker,
                  "propagator" (L-step linear map of a Gaussian target applied in one GEMM), or "auto".
     """

@@ -97,7 +97,7 @@ HX_API int hx_ctx_destroy(hx_ctx* ctx);
 HX_API size_t hx_ctx_workspace_bytes(const hx_ctx* ctx);
 /* Precision policy of the walk move's dense contractions:
  *   HX_PREC_AUTO   exact SIMT fp32/fp64 kernels, except fp32 full-covariance Gaussian targets with
- *                  dim >= 128 and >= 2048 walkers per group, which use HX_PREC_BF16X3
+ *                  dim >= 128 and >= 2048 walkers per group, which use HX_PREC_F16F8
  *   HX_PREC_EXACT  always the exact SIMT kernels (fp32 FMA / fp64)
  *   HX_PREC_BF16X3 tcgen05 tensor cores, operands split into bf16 hi+lo, three products, fp32
  *                  accumulation in TMEM (fp32-class accuracy, ~2^-16 per product)
