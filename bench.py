@@ -414,8 +414,9 @@ def main():
                 "against the same peak.  The section is co-bound by the concurrent momentum draw (ALU: 4.55 ms alone per half-move "
                 "at c5 on one GPU, DESIGN.md section 4), not by the tensor pipe")
         if args.workload == "c5" and world == 1:
-            extra["traffic_source"] = ("profiles/r01c_c5_ncu_full_summary.txt: dram bytes read+write of the 7 chunk launches of one "
-                                       "half-move (6 x 758.9 MB + 709.6 MB) = the P0 planes + C^T planes, i.e. no re-reads")
+            extra["traffic_source"] = ("profiles/r01e_c5_ncu_full_summary.txt: dram bytes read+write of the 7 chunk launches of one "
+                                       "half-move (6 x 755.0 MB + 704.7 MB read, 28 MB written) = the P0 planes + C^T planes, "
+                                       "i.e. no re-reads (same plane sizes for bf16 hi/lo: profiles/r01c)")
     else:
         kname = "k_walk_half" if mk == 0 else "k_side_half"
         flops = algorithmic_flops_half_move(rows, n, d, L, cfg["target"])
