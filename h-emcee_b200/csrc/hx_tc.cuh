@@ -25,12 +25,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity);
 // Spin on try_wait (which itself suspends for a hardware time slice).  No legitimate wait in these kernels lasts longer than a
-// few milliseconds; a pipeline that never completes (a descriptor / byte-count bug) traps after ~2^26 polls instead of hanging
+// few milliseconds; a pipeline that never completes (a descriptor / byte-count bug) traps after 2^28 polls (seconds) instead of hanging
 // the device.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity))
-    if (++polls > (1u << 26)) __trap();
+    if (++polls > (1u << 28)) __trap();
 }
 
 // polling wait with back-off: for warps that wait for a whole main loop (epilogue warps) so their polling does not take

@@ -117,7 +117,7 @@ __device__ __forceinline__ float f16_scale(uint32_t amax_bits, int top) {
   if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
   int e;
   frexpf(amax, &e);
-  return ldexpf(1.f, top - e);
+  return ldexpf(1.f, min(top - e, 100));      // (nearly) all-zero operands: keep the scale and its reciprocal finite
 }
 // A operands (z0 = [q0 - mu | S0] and q_L - mu) are scaled per ROW (walker) from the row's own max-abs -- row-local, so a
 // row-sharded run reproduces the unsharded one bit for bit; q_L - mu reuses its walker's z0 scale, which leaves 16x head-room.

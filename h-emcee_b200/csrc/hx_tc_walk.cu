@@ -98,7 +98,7 @@ __device__ __forceinline__ float f8_scale_from_amax(uint32_t amax_bits, int n) {
   if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
   int e;
   frexpf(amax, &e);                       // amax = m * 2^e, m in [0.5, 1)
-  return ldexpf(1.f, 6 - e);              // amax * sc = m * 64 in [32, 64)
+  return ldexpf(1.f, min(6 - e, 100));    // amax * sc = m * 64 in [32, 64); (nearly) all-zero complement: finite scale
 }
 __global__ void __launch_bounds__(256) k_absmax_centred(const float* __restrict__ X2, const float* __restrict__ mean, int n, int d,
                                                         uint32_t* __restrict__ amax_bits) {
