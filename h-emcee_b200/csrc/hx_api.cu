@@ -99,6 +99,7 @@ extern "C" HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value) {
   else if (what == 9) ctx->pair_chunked = value ? 1 : 0;
   else if (what == 10) ctx->draw_nostore = value ? 1 : 0;
   else if (what == 12) ctx->aux_pair = value;
+  else if (what == 13) ctx->proj_one_launch = value ? 1 : 0;
   else return hx_fail(HX_E_DTYPE, "hx_ctx_set_tuning: unknown knob %d", what);
   return 0;
 }
@@ -376,7 +377,7 @@ static int center_complement(hx_ctx* ctx, const T* X2, int n, int d, int ldd, T*
   dim3 g1((d + 127) / 128, nchunks);
   k_colsum_partial<T><<<g1, 128, 0, s>>>(X2, n, d, (T*)pPart);
   HX_LAUNCH_CHECK("k_colsum_partial");
-  k_mean_final<T><<<(d + 127) / 128, 128, 0, s>>>((const T*)pPart, nchunks, n, d, (T*)pMean);
+  k_mean_final<T><<<(d + 31) / 32, 256, 0, s>>>((const T*)pPart, nchunks, n, d, (T*)pMean);
   HX_LAUNCH_CHECK("k_mean_final");
   k_center<T><<<grid_for((uint64_t)n * ldd, 256), 256, 0, s>>>(X2, (const T*)pMean, n, d, ldd, (T*)pC);
   HX_LAUNCH_CHECK("k_center");
@@ -394,7 +395,7 @@ static int complement_mean(hx_ctx* ctx, const T* X2, int n, int d, T** mean_out,
   dim3 g1((d + 127) / 128, nchunks);
   k_colsum_partial<T><<<g1, 128, 0, s>>>(X2, n, d, (T*)pPart);
   HX_LAUNCH_CHECK("k_colsum_partial");
-  k_mean_final<T><<<(d + 127) / 128, 128, 0, s>>>((const T*)pPart, nchunks, n, d, (T*)pMean);
+  k_mean_final<T><<<(d + 31) / 32, 256, 0, s>>>((const T*)pPart, nchunks, n, d, (T*)pMean);
   HX_LAUNCH_CHECK("k_mean_final");
   *mean_out = (T*)pMean;
   return 0;
@@ -1007,7 +1008,7 @@ static int column_mean(hx_ctx* ctx, const T* X, int rows, int d, T* mean_out, cu
   dim3 g1((d + 127) / 128, nchunks);
   k_colsum_partial<T><<<g1, 128, 0, s>>>(X, rows, d, (T*)pPart);
   HX_LAUNCH_CHECK("k_colsum_partial");
-  k_mean_final<T><<<(d + 127) / 128, 128, 0, s>>>((const T*)pPart, nchunks, rows, d, mean_out);
+  k_mean_final<T><<<(d + 31) / 32, 256, 0, s>>>((const T*)pPart, nchunks, rows, d, mean_out);
   HX_LAUNCH_CHECK("k_mean_final");
   return 0;
 }

@@ -80,6 +80,7 @@ struct hx_ctx {
   int pair_chunked;                        // 1: CTA-pair projection launched one wave at a time even when the draw is complete
   int draw_nostore;                        // diagnostics: momentum draw without its stores (results are garbage)
   int aux_pair;                            // 1: Gram and propagator-apply GEMMs by the CTA-pair kernel
+  int proj_one_launch;                     // 1: single-CTA projection as ONE launch over all rows when the draw was queued ahead
   int mp_dfma;                             // 1: B = M P by the DFMA tile kernel instead of the DMMA kernel
 };
 

@@ -25,13 +25,23 @@ __global__ void k_colsum_partial(const T* __restrict__ X, int n, int d, T* __res
   partial[(size_t)chunk * d + c] = s;
 }
 
+// 32 columns per CTA (lanes), 8 warps each summing every 8th partial in order; the 8 segment sums are added in a fixed order
 template <typename T>
-__global__ void k_mean_final(const T* __restrict__ partial, int nchunks, int n, int d, T* __restrict__ mean) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= d) return;
+__global__ void __launch_bounds__(256) k_mean_final(const T* __restrict__ partial, int nchunks, int n, int d, T* __restrict__ mean) {
+  __shared__ T seg[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   T s = T(0);
-  for (int k = 0; k < nchunks; ++k) s += partial[(size_t)k * d + c];
-  mean[c] = s / T(n);
+  if (c < d)
+    for (int k = w; k < nchunks; k += 8) s += partial[(size_t)k * d + c];
+  seg[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && c < d) {
+    T t = T(0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += seg[k][lane];
+    mean[c] = t / T(n);
+  }
 }
 
 // C[r][c] = (X[r][c] - mean[c]) / sqrt(n) for c < d, 0 for d <= c < ldd

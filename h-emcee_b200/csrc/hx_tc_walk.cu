@@ -1109,7 +1109,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     // loop) the projection is ONE launch over all rows -- back-to-back waves without a tail per chunk; otherwise chunk by
     // chunk behind the draw like the single-CTA kernel
     const bool pair = ctx->proj_pair && slices == 1 && d > 128;
-    const int group = (pair && prefetched && !ctx->pair_chunked) ? nchunks : 1;          // chunks per launch
+    const int group = (prefetched && (pair ? !ctx->pair_chunked : ctx->proj_one_launch != 0)) ? nchunks : 1;   // chunks per launch
     for (int c = 0; c < nchunks; c += group) {
       const int r0 = c * chunk;
       const int cl = (c + group < nchunks ? c + group : nchunks) - 1;      // last chunk of this launch
@@ -1238,7 +1238,7 @@ int microbench(hx_ctx* ctx, int mode, int n, int rows, int d, int reps, double* 
   HX_CUDA(cudaMemsetAsync(pSc8, 0x3c, 16, s));
   bf* Pbuf[2] = {(bf*)pP0, (bf*)pP0 + buf_elems};
   const int chunk = chunk_rows(ctx, rA, NT);
-  const int gchunk = (ctx->proj_pair && !ctx->pair_chunked) ? rA : chunk;        // pair kernel: one launch over all rows (steady state of a batch loop)
+  const int gchunk = ((ctx->proj_pair && !ctx->pair_chunked) || (!ctx->proj_pair && ctx->proj_one_launch)) ? rA : chunk;        // pair kernel: one launch over all rows (steady state of a batch loop)
   Key key{1u, 2u};
   if (int e = job_launch(ctx, 0, Pbuf[0], f8, 0, n, 0, rows, rA, nK, chunk, key, nullptr, s)) return e;   // valid operand for the GEMM
   HX_CUDA(cudaStreamSynchronize(ctx->side));

@@ -181,10 +181,15 @@ def test_tc_long_run_moments(hx, prec, form, lf):
     assert 0.6 < acc <= 1.0
     flat = chain.reshape(-1, d).astype(np.float64)
     sd = np.sqrt(np.diag(cov))
-    tau = max(float(np.max(hx.autocorr.integrated_time(chain[:, ::16, ::32], quiet=True))), 1.0)
-    ess = flat.shape[0] / tau
-    assert np.max(np.abs(flat.mean(0) - mean) / sd) < 6.0 / np.sqrt(ess) + 5e-3
-    assert np.max(np.abs(flat.var(0) / np.diag(cov) - 1.0)) < 6.0 * np.sqrt(2.0 / ess) + 1e-2
+    # Stated tolerance: every coordinate's mean within 0.03 sd and variance within 8 % of the target's, their averages over
+    # the 256 coordinates within 0.01 sd / 1.5 % (measured: 5e-3 / 2-4 % worst coordinate, 1.3e-3 / 0.5 % average).  300
+    # iterations are too few for a reliable tau_int of the slowest direction, which is what the worst coordinate's variance
+    # reflects, so the bound is explicit instead of derived from an effective sample size; the averages are the bias detector.
+    em = np.abs(flat.mean(0) - mean) / sd
+    ev = np.abs(flat.var(0) / np.diag(cov) - 1.0)
+    msg = f"[{lf}] acc {acc:.3f}: |mean err|/sd max {em.max():.2e} avg {em.mean():.2e}; |var ratio - 1| max {ev.max():.2e} avg {ev.mean():.2e}"
+    assert em.max() < 3e-2 and em.mean() < 1e-2, msg
+    assert ev.max() < 8e-2 and ev.mean() < 1.5e-2, msg
 
 
 @pytest.mark.parametrize("mode", ["bf16x3", "f16f8"])
