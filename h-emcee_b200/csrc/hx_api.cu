@@ -100,6 +100,7 @@ extern "C" HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value) {
   else if (what == 10) ctx->draw_nostore = value ? 1 : 0;
   else if (what == 12) ctx->aux_pair = value;
   else if (what == 13) ctx->proj_one_launch = value ? 1 : 0;
+  else if (what == 14) ctx->kick_f16 = value;
   else return hx_fail(HX_E_DTYPE, "hx_ctx_set_tuning: unknown knob %d", what);
   return 0;
 }

@@ -12,7 +12,7 @@ enum Slot {
   // tensor-core path
   WS_TC_CT, WS_TC_MP, WS_TC_PP, WS_TC_P0, WS_TC_QC, WS_TC_GP, WS_TC_LPP, WS_TC_DKP, WS_TC_MASK, WS_TC_BO, WS_TC_S0,
   // propagator form of the Gaussian leapfrog
-  WS_TC_BX, WS_TC_BS, WS_TC_TQ, WS_TC_TS, WS_TC_TW, WS_TC_WP, WS_TC_B1, WS_TC_B2, WS_TC_ZB, WS_TC_ZT, WS_TC_QC2, WS_TC_PP32, WS_TC_S0P, WS_TC_CT32, WS_TC_CT8, WS_TC_SC8, WS_TC_AM, WS_TC_RSC,
+  WS_TC_BX, WS_TC_BS, WS_TC_TQ, WS_TC_TS, WS_TC_TW, WS_TC_WP, WS_TC_B1, WS_TC_B2, WS_TC_ZB, WS_TC_ZT, WS_TC_QC2, WS_TC_PP32, WS_TC_S0P, WS_TC_CT32, WS_TC_CT8, WS_TC_SC8, WS_TC_AM, WS_TC_RSC, WS_TC_RSB, WS_TC_CTR,
   // device-resident adaptation
   WS_AD_STATE, WS_AD_MEAN, WS_AD_PART, WS_AD_CHOL, WS_AD_STAT, WS_AD_PROP,
   WS_NSLOT
@@ -81,6 +81,7 @@ struct hx_ctx {
   int draw_nostore;                        // diagnostics: momentum draw without its stores (results are garbage)
   int aux_pair;                            // 1: Gram and propagator-apply GEMMs by the CTA-pair kernel
   int proj_one_launch;                     // 1: single-CTA projection as ONE launch over all rows when the draw was queued ahead
+  int kick_f16;                            // kicks / propagator apply from fp16 hi/lo operands: 0 auto (stepwise form only), 1 always, 2 never
   int mp_dfma;                             // 1: B = M P by the DFMA tile kernel instead of the DMMA kernel
 };
 

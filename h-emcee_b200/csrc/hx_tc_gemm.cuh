@@ -87,6 +87,8 @@ struct GemmArgs {
   // EPI_DOT with dot_pair = 1 / 2: partial sums are divided by row_scale[row] * f16_scale(amax[1] / amax[0]) (operands Z x WP / Z x P);
   // EPI_PROP with planes_bf16 = 2: planes_out = fp16 hi/lo of acc * row_scale[row]
   uint32_t* amax_out; const uint32_t* amax; const float* row_scale; int dot_pair;
+  // KIND_F16 with EPI_KICKB / EPI_PROP: acc is divided by row_scale[row] * f16_scale(amax[unscale_idx]) before use
+  int unscale_idx;
   int n_cover;       // pair kernel: padded N the grid covers (0: N); EPI_PROP covers two column blocks
 };
 
@@ -223,6 +225,9 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t tmem_b
   const bool rok = row < g.M;
   const bool vec = (g.N & 3) == 0 && (EPI == EPI_STORE ? (g.ldo & 3) == 0 : true);
   float rowacc = 0.f;
+  float f16_inv = 1.f;
+  if (KIND == KIND_F16 && (EPI == EPI_KICKB || EPI == EPI_PROP) && rok)
+    f16_inv = 1.f / (g.row_scale[row] * f16_scale(g.amax[g.unscale_idx], kF16TopB));
   const int NC = BN / 32;
   const int blk = (EPI == EPI_PROP) ? n0 / g.blk_cols : 0;
   const int cn0 = (EPI == EPI_PROP) ? n0 - blk * g.blk_cols : n0;
@@ -245,6 +250,10 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t tmem_b
       }
     }
     if (!rok) continue;
+    if (KIND == KIND_F16 && (EPI == EPI_KICKB || EPI == EPI_PROP)) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= f16_inv;
+    }
     const int nval = min(32, g.N - col0);
     const bool fast = vec && nval == 32;
     if (EPI == EPI_STORE) {
@@ -317,7 +326,12 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t tmem_b
           store32(g.Q + base, qv, nval, fast);
 #pragma unroll
           for (int j = 0; j < 32; ++j) qv[j] -= mu[j];
-          store_planes32<(KIND == KIND_F16F8 || KIND == KIND_F16) ? KIND_BF16 : KIND>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, qv, nval, fast);
+          if (KIND == KIND_F16)
+            store_planes32<KIND_F16>(g.planes_out, (size_t)row * g.Kout_p + col0, (size_t)g.rows_out_pad * g.Kout_p, qv, nval, fast,
+                                     g.row_scale[row]);
+          else
+            store_planes32<KIND == KIND_F16F8 ? KIND_BF16 : KIND>(g.planes_out, (size_t)row * g.Kout_p + col0,
+                                                                   (size_t)g.rows_out_pad * g.Kout_p, qv, nval, fast);
         }
       }
     }

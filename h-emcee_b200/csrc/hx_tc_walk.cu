@@ -206,15 +206,16 @@ __global__ void __launch_bounds__(256) k_center_planes_T(const float* __restrict
 // planes [2, rows_pad, Kp] <- split(src[r*ld + k]) for r < dim_r, k < dim_k, zero elsewhere
 template <int KIND>
 __global__ void k_split_planes(const float* __restrict__ src, int dim_r, int dim_k, int ld, int rows_pad, int Kp,
-                               typename Kind<KIND>::elem* __restrict__ planes, const uint32_t* __restrict__ amax = nullptr) {
+                               typename Kind<KIND>::elem* __restrict__ planes, const uint32_t* __restrict__ amax = nullptr,
+                               const float* __restrict__ row_scale = nullptr) {
   const size_t tot = (size_t)rows_pad * Kp, plane = tot;
-  const float sc16 = (KIND == KIND_F16) ? f16_scale(*amax, kF16TopB) : 1.f;
+  const float sc16 = (KIND == KIND_F16 && amax) ? f16_scale(*amax, kF16TopB) : 1.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / Kp), k = (int)(i - (size_t)r * Kp);
     const float v = (r < dim_r && k < dim_k) ? src[(size_t)r * ld + k] : 0.f;
     if (KIND == KIND_F16) {
       __half hi, lo;
-      split_f16(v * sc16, hi, lo);
+      split_f16(v * ((row_scale && r < dim_r) ? row_scale[r] : sc16), hi, lo);
       reinterpret_cast<__half*>(planes)[i] = hi;
       reinterpret_cast<__half*>(planes)[plane + i] = lo;
     } else if (KIND == KIND_BF16) {
@@ -368,11 +369,26 @@ __global__ void __launch_bounds__(128) k_mp_dmma(const float* __restrict__ A, in
 // zero for r >= rows or j >= n; 8 consecutive j per thread
 template <bool LEGACY, int FMT>      // FMT 0: bf16 hi/lo planes, 1: fp16 + e4m3 planes (KIND_F16F8)
 __global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key_ptr, int n, int row0, int rows,
-                                                    int rows_chunk, int Kp, size_t plane, __nv_bfloat16* __restrict__ planes) {
+                                                    int rows_chunk, int Kp, size_t plane, __nv_bfloat16* __restrict__ planes,
+                                                    unsigned int* __restrict__ work_ctr) {
   if (key_ptr) { key.k0 = key_ptr[0]; key.k1 = key_ptr[1]; }
   const size_t nvec = (size_t)rows_chunk * Kp / 8;
   const uint64_t nn = (uint64_t)n * (uint64_t)n;
-  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+  // Work items of 256 x 4 vectors are handed out through an atomic counter instead of a static grid-stride split: the kernel
+  // shares the SMs with GEMM CTAs of another stream, so its resident CTAs progress at very different rates (and may be placed
+  // unevenly), and a static split makes the whole draw wait for the slowest one (measured: a bimodal 18.3 / 22 ms per iteration)
+  __shared__ unsigned int s_item;
+  const unsigned int nitems = (unsigned int)((nvec + 1023) / 1024);
+  for (;;) {
+    if (threadIdx.x == 0) s_item = atomicAdd(work_ctr, 1u);
+    __syncthreads();
+    const unsigned int item = s_item;
+    __syncthreads();
+    if (item >= nitems) break;
+#pragma unroll 1
+  for (int u4 = 0; u4 < 4; ++u4) {
+    const size_t v = (size_t)item * 1024 + (size_t)u4 * 256 + threadIdx.x;
+    if (v >= nvec) break;
     const size_t i = v * 8;
     const int r = (int)(i / Kp), j0 = (int)(i - (size_t)r * Kp);
     float x[8];
@@ -397,6 +413,7 @@ __global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key
       *reinterpret_cast<uint4*>(planes + i) = *reinterpret_cast<const uint4*>(hi);
       *reinterpret_cast<uint4*>(planes + plane + i) = *reinterpret_cast<const uint4*>(lo);
     }
+  }
   }
 }
 
@@ -519,11 +536,58 @@ __global__ void __launch_bounds__(256) k_z0_planes_f16(const float* __restrict__
         split_bf16(v[part][t][u], bh[u], bl[u]);
         split_f16(v[part][t][u] * sc, hh[u], hl[u]);
       }
-      *reinterpret_cast<uint2*>(zB + i) = *reinterpret_cast<const uint2*>(bh);
-      *reinterpret_cast<uint2*>(zB + plane + i) = *reinterpret_cast<const uint2*>(bl);
+      if (zB) {
+        *reinterpret_cast<uint2*>(zB + i) = *reinterpret_cast<const uint2*>(bh);
+        *reinterpret_cast<uint2*>(zB + plane + i) = *reinterpret_cast<const uint2*>(bl);
+      }
       *reinterpret_cast<uint2*>(zH + i) = *reinterpret_cast<const uint2*>(hh);
       *reinterpret_cast<uint2*>(zH + plane + i) = *reinterpret_cast<const uint2*>(hl);
     }
+}
+
+// Start of a kick sequence with fp16 hi/lo operands: Q <- X1, planes <- fp16 hi/lo of (X1 - mu) * row_scale[r], where the
+// power-of-two row scale comes from max(|X1 - mu|, trajectory length * |S0|) of the row (what q - mu can grow to along the
+// trajectory, with 16x head-room on top).  One warp per row; dK <= 128 * kZ0Chunks.
+__global__ void __launch_bounds__(256) k_tc_init_f16(const float* __restrict__ X1, const float* __restrict__ mu,
+                                                     const float* __restrict__ S0, float traj, int rows, int d, int rows_pad, int Kp,
+                                                     float* __restrict__ Q, __half* __restrict__ planes, float* __restrict__ row_scale) {
+  const int lane = threadIdx.x & 31;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows_pad) return;
+  const size_t plane = (size_t)rows_pad * Kp;
+  float v[kZ0Chunks][4];
+  float m = 0.f;
+#pragma unroll
+  for (int t = 0; t < kZ0Chunks; ++t) {
+    const int c0 = 4 * lane + 128 * t;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u;
+      float x = 0.f;
+      if (r < rows && c < d) {
+        const float xr = X1[(size_t)r * d + c];
+        Q[(size_t)r * d + c] = xr;
+        x = xr - (mu ? mu[c] : 0.f);
+        m = fmaxf(m, fmaxf(fabsf(x), traj * fabsf(S0[(size_t)r * d + c])));
+      }
+      v[t][u] = x;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const float sc = f16_scale(__float_as_uint(m), kF16TopZ);
+  if (lane == 0 && r < rows) row_scale[r] = sc;
+#pragma unroll
+  for (int t = 0; t < kZ0Chunks; ++t) {
+    const int c0 = 4 * lane + 128 * t;
+    if (c0 >= Kp) continue;
+    const size_t i = (size_t)r * Kp + c0;
+    __align__(8) __half hh[4], hl[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) split_f16(v[t][u] * sc, hh[u], hl[u]);
+    *reinterpret_cast<uint2*>(planes + i) = *reinterpret_cast<const uint2*>(hh);
+    *reinterpret_cast<uint2*>(planes + plane + i) = *reinterpret_cast<const uint2*>(hl);
+  }
 }
 
 // B-operand planes of a propagator block: planes[row_off + c][kk] = split(src[k(kk)][c]) for c < d, where src is
@@ -722,6 +786,8 @@ struct LeapArgs {
   float* Q; float* S; float* S0; float* Qs; const float* Bo; const float* prec; int ld_prec;
   void* pBoP; void* pPP; void* pQC; void* pQC2; void* pQsP; float* lpp; float* dkp;
   int energies;     // 0: integrate only (propagator basis run)
+  // KIND_F16: max-abs words ([0] P, [2] Bop), per-row scales of the q - mu operand (written by k_tc_init_f16)
+  uint32_t* am; float* rs;
 };
 
 // L+1 kicks in B-form (every kick but the last followed by a drift; hmc_walk.py:85-102), then the two energy products.
@@ -729,16 +795,35 @@ template <int KIND>
 static int leapfrog_bform(hx_ctx* ctx, const LeapArgs& a, cudaStream_t s) {
   typedef typename Kind<KIND>::elem E;
   const int rows = a.rows, d = a.d, rA = a.rA, dK = a.dK, dB = a.dB;
-  k_split_planes<KIND><<<grid_for((size_t)dB * dK, 256), 256, 0, s>>>(a.Bo, d, d, d, dB, dK, (E*)a.pBoP);
-  HX_LAUNCH_CHECK("k_split_planes(Bop)");
-  k_split_planes<KIND><<<grid_for((size_t)dB * dK, 256), 256, 0, s>>>(a.prec, d, d, a.ld_prec, dB, dK, (E*)a.pPP);
-  HX_LAUNCH_CHECK("k_split_planes(P)");
-  k_tc_init<KIND><<<grid_for((size_t)rA * dK, 256), 256, 0, s>>>(a.X1, a.mu, rows, d, rA, dK, a.Q, (E*)a.pQC);
-  HX_LAUNCH_CHECK("k_tc_init");
-  ctx->launches += 3;
+  if (KIND == KIND_F16) {
+    // fp16 hi/lo operands: Bop (and P for the energies) scaled by one power of two each from their max-abs, q - mu per row
+    k_absmax_ld<<<grid_for((size_t)d * d / 4, 256), 256, 0, s>>>(a.Bo, d, d, d, a.am + 2);
+    HX_LAUNCH_CHECK("k_absmax_ld(Bop)");
+    k_split_planes<KIND_F16><<<grid_for((size_t)dB * dK, 256), 256, 0, s>>>(a.Bo, d, d, d, dB, dK, (__half*)a.pBoP, a.am + 2);
+    HX_LAUNCH_CHECK("k_split_planes(Bop, f16)");
+    if (a.energies) {
+      k_absmax_ld<<<grid_for((size_t)d * d / 4, 256), 256, 0, s>>>(a.prec, d, d, a.ld_prec, a.am);
+      HX_LAUNCH_CHECK("k_absmax_ld(P)");
+      k_split_planes<KIND_F16><<<grid_for((size_t)dB * dK, 256), 256, 0, s>>>(a.prec, d, d, a.ld_prec, dB, dK, (__half*)a.pPP, a.am);
+      HX_LAUNCH_CHECK("k_split_planes(P, f16)");
+      ctx->launches += 2;
+    }
+    k_tc_init_f16<<<(rA + 7) / 8, 256, 0, s>>>(a.X1, a.mu, a.S0, (float)(a.eps * a.L), rows, d, rA, dK, a.Q, (__half*)a.pQC, a.rs);
+    HX_LAUNCH_CHECK("k_tc_init_f16");
+    ctx->launches += 3;
+  } else {
+    k_split_planes<KIND><<<grid_for((size_t)dB * dK, 256), 256, 0, s>>>(a.Bo, d, d, d, dB, dK, (E*)a.pBoP);
+    HX_LAUNCH_CHECK("k_split_planes(Bop)");
+    k_split_planes<KIND><<<grid_for((size_t)dB * dK, 256), 256, 0, s>>>(a.prec, d, d, a.ld_prec, dB, dK, (E*)a.pPP);
+    HX_LAUNCH_CHECK("k_split_planes(P)");
+    k_tc_init<KIND><<<grid_for((size_t)rA * dK, 256), 256, 0, s>>>(a.X1, a.mu, rows, d, rA, dK, a.Q, (E*)a.pQC);
+    HX_LAUNCH_CHECK("k_tc_init");
+    ctx->launches += 3;
+  }
   GemmArgs gg;
   memset(&gg, 0, sizeof(gg));
   gg.nprod = 3; gg.M = rows; gg.N = d; gg.mu = a.mu; gg.NT = a.NT; gg.eps = (float)a.eps;
+  if (KIND == KIND_F16) { gg.amax = a.am; gg.row_scale = a.rs; gg.unscale_idx = 2; }
   // The q - mu operand planes ping-pong between two buffers: a kick's epilogue writes the NEXT operand while sibling CTAs of the
   // same row tile (other column tiles) may still be reading the current one (updating in place is a race).
   void* planes[2] = {a.pQC, a.pQC2};
@@ -763,9 +848,13 @@ static int leapfrog_bform(hx_ctx* ctx, const LeapArgs& a, cudaStream_t s) {
   void* planes_L = planes[a.L & 1];      // q_L - mu (written by the last drift, kick L-1)
   if (!a.energies) return 0;
   // energies: dK = -1/2 <Qs P, S0 + S_L> ; lp' = -1/2 <(q_L - mu) P, q_L - mu>
-  k_split_planes<KIND><<<grid_for((size_t)rA * dK, 256), 256, 0, s>>>(a.Qs, rows, d, d, rA, dK, (E*)a.pQsP);
+  if (KIND == KIND_F16)
+    k_split_planes<KIND_F16><<<grid_for((size_t)rA * dK, 256), 256, 0, s>>>(a.Qs, rows, d, d, rA, dK, (__half*)a.pQsP, nullptr, a.rs);
+  else
+    k_split_planes<KIND><<<grid_for((size_t)rA * dK, 256), 256, 0, s>>>(a.Qs, rows, d, d, rA, dK, (E*)a.pQsP);
   HX_LAUNCH_CHECK("k_split_planes(Qs)");
   ctx->launches += 1;
+  if (KIND == KIND_F16) gg.dot_pair = 2;      // both energy products are (row-scaled operand) x P
   GemmArgs x = gg;
   x.mu = nullptr; x.X = a.S0; x.Y = a.S; x.part = a.dkp;
   if (int e = launch_gemm<EPI_DOT, KIND>(ctx, a.pQsP, rA, a.pPP, dB, dK, x, s)) return e;
@@ -837,6 +926,11 @@ static int job_launch(hx_ctx* ctx, int b, __nv_bfloat16* buf, int fmt, int impl,
   HX_CUDA(cudaEventRecord(ctx->ev_fork, s));
   HX_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
   const size_t plane = (size_t)rA * nK;
+  void* pCtr;
+  if (int e = ws_get(ctx, WS_TC_CTR, 2 * 512 * sizeof(unsigned int), &pCtr)) return e;
+  if (nchunks > 512) return hx_fail(HX_E_SHAPE, "momentum draw: %d row chunks (max 512)", nchunks);
+  unsigned int* ctr = reinterpret_cast<unsigned int*>(pCtr) + (size_t)b * 512;
+  HX_CUDA(cudaMemsetAsync(ctr, 0, (size_t)nchunks * sizeof(unsigned int), ctx->side));
   for (int c = 0; c < nchunks; ++c) {
     const int r0 = c * chunk;
     const int rc = (rows - r0) < chunk ? (rows - r0) : chunk;
@@ -848,13 +942,13 @@ static int job_launch(hx_ctx* ctx, int b, __nv_bfloat16* buf, int fmt, int impl,
     if (rng_grid > cap) rng_grid = cap;
     __nv_bfloat16* dst = buf + (size_t)r0 * nK;
     if (ctx->draw_nostore) {
-      k_rng_planes<false, 2><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
+      k_rng_planes<false, 2><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst, ctr + c);
     } else if (impl == HX_RNG_LEGACY) {
-      if (fmt) k_rng_planes<true, 1><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
-      else k_rng_planes<true, 0><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
+      if (fmt) k_rng_planes<true, 1><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst, ctr + c);
+      else k_rng_planes<true, 0><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst, ctr + c);
     } else {
-      if (fmt) k_rng_planes<false, 1><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
-      else k_rng_planes<false, 0><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst);
+      if (fmt) k_rng_planes<false, 1><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst, ctr + c);
+      else k_rng_planes<false, 0><<<rng_grid, 256, 0, ctx->side>>>(key, key_ptr, n, row0 + r0, rc, rcp, nK, plane, dst, ctr + c);
     }
     HX_LAUNCH_CHECK("k_rng_planes");
     HX_CUDA(cudaEventRecord(evs[c], ctx->side));
@@ -898,7 +992,12 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   }
   const bool g1_tf32 = ctx->precision == HX_PREC_TF32X3;
   // propagator form: operand kind of the energy products -- tf32 hi/lo (0), bf16 hi/lo (1), fp16 hi/lo with row / matrix scales (2)
-  const int ekind = g1_tf32 ? 0 : ((ctx->energy_bf16 == 2 && dK > 128 * kZ0Chunks) ? 0 : ctx->energy_bf16);
+  // kicks / apply: bf16 hi/lo, or fp16 hi/lo with row / matrix scales (same MMA rate, 2^-22 instead of 2^-16 per product).
+  // hx_ctx_set_tuning(14, v): 0 = auto: fp16 for the stepwise form, whose log-accept error against f64 drops from 1.1e-2 to
+  // 7.7e-4 rms at c5 scale; bf16 for the propagator form, whose error (2.9e-3, set by the apply's long accumulation) does not
+  // change while the extra max-abs launches cost 0.2 ms; 1 = fp16 for both; 2 = bf16 for both.  fp16 kicks imply fp16 energies.
+  const bool kf16 = !g1_tf32 && dK <= 128 * kZ0Chunks && (ctx->kick_f16 == 1 || (ctx->kick_f16 == 0 && !prop));
+  const int ekind = g1_tf32 ? 0 : (kf16 ? 2 : ((ctx->energy_bf16 == 2 && dK > 128 * kZ0Chunks) ? 0 : ctx->energy_bf16));
   const bool e_bf16 = ekind == 1, e_f16 = ekind == 2;
   const int rQ = prop ? (rA > bRA ? rA : bRA) : rA;            // rows of the q - mu operand planes (basis run reuses them)
 
@@ -941,6 +1040,13 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   }
   ctx->job[cur].valid = 0;       // consumed by this half-move
 
+  // hx_ctx_set_tuning(6, -2 / -1): queue the next half-move's draw already at the start of the complement statistics / of the
+  // propagator basis run (a head start over the projection GEMM, at the price of slowing those latency-bound launches)
+  const bool draw_next_early = next && next->rows == rows && ctx->draw_fork < 0;
+  if (draw_next_early && ctx->draw_fork <= -2) {
+    if (int e = job_launch(ctx, 1 - cur, Pbuf[1 - cur], f8, impl, n, next->row0, next->rows, rA, nK, chunk, next->key, next->key_ptr, s))
+      return e;
+  }
   // (1) complement statistics: mean_dev already holds mean_0(X2) (hx_api.cu); C^T planes, M = C^T C, Bop = M P
   if (int e = timing_mark(ctx, s, HX_PH_PREP)) return e;
   // The Gram matrix enters every kick through B = P M, where the ill-conditioning of the target amplifies its error.
@@ -1013,11 +1119,24 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   }
   ctx->launches += 2;
 
+  void *pAM = nullptr, *pRS = nullptr, *pRSB = nullptr;
+  if (kf16 || (prop && e_f16)) {
+    // max-abs words [0] P, [1] W P, [2] Bop, [3] [Tq ; Ts] and the per-row scales of the fp16 operands
+    if (int e = ws_get(ctx, WS_TC_AM, 16, &pAM)) return e;
+    if (int e = ws_get(ctx, WS_TC_RSC, (size_t)rA * sizeof(float), &pRS)) return e;
+    if (int e = ws_get(ctx, WS_TC_RSB, (size_t)bRA * sizeof(float), &pRSB)) return e;
+    HX_CUDA(cudaMemsetAsync(pAM, 0, 16, s));
+  }
+
   // (2) propagator (Gaussian target: the leapfrog is a linear map of z0 = [q0 - mu | S0]).  Integrate the 2d basis
   //     trajectories with the same kick/drift recurrence (tf32 hi/lo operands), giving q_L - mu = z0 Tq, S_L = z0 Ts
   //     and the impulse-weighted position sum Qs = z0 W; fold the precision into W for the kinetic-energy product.
   void *pBX = nullptr, *pBS = nullptr, *pTQ = nullptr, *pTS = nullptr, *pTW = nullptr, *pWP = nullptr, *pB1 = nullptr,
-       *pB2 = nullptr, *pZB = nullptr, *pZT = nullptr, *pPP32 = nullptr, *pAM = nullptr, *pRS = nullptr;
+       *pB2 = nullptr, *pZB = nullptr, *pZT = nullptr, *pPP32 = nullptr;
+  if (draw_next_early && ctx->draw_fork == -1) {
+    if (int e = job_launch(ctx, 1 - cur, Pbuf[1 - cur], f8, impl, n, next->row0, next->rows, rA, nK, chunk, next->key, next->key_ptr, s))
+      return e;
+  }
   if (prop) {
     if (int e = timing_mark(ctx, s, HX_PH_BASIS)) return e;
     const size_t bsz = (size_t)bR * d * sizeof(float);
@@ -1031,21 +1150,19 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     if (int e = ws_get(ctx, WS_TC_B2, (size_t)2 * dB * K2 * sizeof(float), &pB2)) return e;
     if (int e = ws_get(ctx, WS_TC_ZB, g1_tf32 ? 16 : (size_t)2 * rA * K2 * sizeof(bf), &pZB)) return e;
     if (int e = ws_get(ctx, WS_TC_ZT, e_bf16 ? 16 : (size_t)2 * rA * K2 * (e_f16 ? sizeof(__half) : sizeof(float)), &pZT)) return e;
-    if (e_f16) {
-      if (int e = ws_get(ctx, WS_TC_AM, 16, &pAM)) return e;
-      if (int e = ws_get(ctx, WS_TC_RSC, (size_t)rA * sizeof(float), &pRS)) return e;
-      HX_CUDA(cudaMemsetAsync(pAM, 0, 16, s));
-    }
+
     k_basis_init<<<grid_for((size_t)bR * d, 256), 256, 0, s>>>((float*)pBX, (float*)pBS, d);
     HX_LAUNCH_CHECK("k_basis_init");
     LeapArgs la;
     la.X1 = (const float*)pBX; la.mu = nullptr; la.rows = bR; la.d = d; la.rA = bRA; la.dK = dK; la.dB = dB; la.NT = NT; la.L = L;
     la.eps = eps; la.Q = (float*)pTQ; la.S = (float*)pTS; la.S0 = (float*)pBS; la.Qs = (float*)pTW; la.Bo = (const float*)pBo;
     la.prec = (const float*)tgt->precision; la.ld_prec = tgt->ld; la.pBoP = pBoP; la.pPP = pPP; la.pQC = pQC; la.pQC2 = pQC2; la.pQsP = pQsP;
-    la.lpp = nullptr; la.dkp = nullptr; la.energies = 0;
+    la.lpp = nullptr; la.dkp = nullptr; la.energies = 0; la.am = (uint32_t*)pAM; la.rs = (float*)pRSB;
     // the basis run uses the operand kind of the apply GEMM: its rounding (2^-16 per bf16x3 product) is of the same order
     // as the apply's, and bf16 halves both the MMA time and the number of TMA round trips of these latency-bound launches
-    if (int e = g1_tf32 ? leapfrog_bform<KIND_TF32>(ctx, la, s) : leapfrog_bform<KIND_BF16>(ctx, la, s)) return e;
+    if (int e = g1_tf32 ? leapfrog_bform<KIND_TF32>(ctx, la, s)
+                        : (kf16 ? leapfrog_bform<KIND_F16>(ctx, la, s) : leapfrog_bform<KIND_BF16>(ctx, la, s)))
+      return e;
     // tf32 hi/lo planes of the precision matrix for the energy products
     if (int e = ws_get(ctx, WS_TC_PP32, (size_t)2 * dB * dK * sizeof(float), &pPP32)) return e;
     k_split_planes<KIND_TF32><<<grid_for((size_t)dB * dK, 256), 256, 0, s>>>((const float*)tgt->precision, d, d, tgt->ld, dB, dK, (float*)pPP32);
@@ -1069,7 +1186,14 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     }
     // B operands: [Tq ; Ts]^T for the apply GEMM, (W P)^T for the kinetic-energy product
     dim3 tg((K2 + 31) / 32, (dB + 31) / 32), tb(32, 8);
-    if (g1_tf32) {
+    if (kf16) {
+      k_absmax_ld<<<grid_for((size_t)bR * d / 4, 256), 256, 0, s>>>((const float*)pTQ, bR, d, d, (uint32_t*)pAM + 3);
+      k_absmax_ld<<<grid_for((size_t)bR * d / 4, 256), 256, 0, s>>>((const float*)pTS, bR, d, d, (uint32_t*)pAM + 3);
+      HX_LAUNCH_CHECK("k_absmax_ld(Tq, Ts)");
+      k_transpose_planes<KIND_F16><<<tg, tb, 0, s>>>((const float*)pTQ, d, dK, dB, 2 * dB, 0, (__half*)pB1, (const uint32_t*)pAM + 3);
+      k_transpose_planes<KIND_F16><<<tg, tb, 0, s>>>((const float*)pTS, d, dK, dB, 2 * dB, dB, (__half*)pB1, (const uint32_t*)pAM + 3);
+      ctx->launches += 2;
+    } else if (g1_tf32) {
       k_transpose_planes<KIND_TF32><<<tg, tb, 0, s>>>((const float*)pTQ, d, dK, dB, 2 * dB, 0, (float*)pB1);
       k_transpose_planes<KIND_TF32><<<tg, tb, 0, s>>>((const float*)pTS, d, dK, dB, 2 * dB, dB, (float*)pB1);
     } else {
@@ -1086,7 +1210,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   // (3) projection S0 = P0 C, chunk by chunk as the draw completes.  The NEXT half-move's draw is queued here: it then runs
   //     under the throughput-bound projection / apply GEMMs (measured to overlap fully, scripts/overlap_bench.py) and stays
   //     out of the way of the small latency-bound launches above, which it would slow 3-4x.
-  const bool draw_next = next && next->rows == rows;
+  const bool draw_next = next && next->rows == rows && !draw_next_early;
   const int fork_at = ctx->draw_fork < 0 ? 0 : (ctx->draw_fork > nchunks ? nchunks : ctx->draw_fork);   // after that many projection chunks
   if (draw_next && fork_at == 0) {
     if (int e = job_launch(ctx, 1 - cur, Pbuf[1 - cur], f8, impl, n, next->row0, next->rows, rA, nK, chunk, next->key, next->key_ptr, s))
@@ -1145,7 +1269,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   // (4) leapfrog + energy products
   if (prop) {
     if (e_f16)
-      k_z0_planes_f16<<<(rA + 7) / 8, 256, 0, s>>>(X1, mu, S0, rows, d, rA, dK, (bf*)pZB, (__half*)pZT, (float*)pRS);
+      k_z0_planes_f16<<<(rA + 7) / 8, 256, 0, s>>>(X1, mu, S0, rows, d, rA, dK, kf16 ? nullptr : (bf*)pZB, (__half*)pZT, (float*)pRS);
     else
       k_z0_planes<<<grid_for((size_t)rA * K2 / 4, 256), 256, 0, s>>>(X1, mu, S0, rows, d, rA, dK, g1_tf32 ? nullptr : (bf*)pZB,
                                                                      e_bf16 ? nullptr : (float*)pZT);
@@ -1156,7 +1280,10 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     g1.nprod = 3; g1.M = rows; g1.N = d; g1.mu = mu; g1.Q = Q; g1.S = S; g1.blk_cols = dB;
     g1.planes_out = pQC; g1.rows_out_pad = rQ; g1.Kout_p = dK; g1.planes_bf16 = ekind;
     g1.row_scale = (const float*)pRS;
-    if (g1_tf32) {
+    g1.amax = (const uint32_t*)pAM; g1.unscale_idx = 3;
+    if (kf16) {
+      if (int e = launch_gemm_pair<EPI_PROP, KIND_F16>(ctx, pZT, rA, pB1, 2 * dB, K2, g1, s, 0, 1, 2 * dB)) return e;
+    } else if (g1_tf32) {
       if (int e = launch_gemm<EPI_PROP, KIND_TF32>(ctx, pZT, rA, pB1, 2 * dB, K2, g1, s, 0, 2 * dB)) return e;
     } else if (ctx->aux_pair) {
       if (int e = launch_gemm_pair<EPI_PROP, KIND_BF16>(ctx, pZB, rA, pB1, 2 * dB, K2, g1, s, 0, 1, 2 * dB)) return e;
@@ -1194,8 +1321,9 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     la.X1 = X1; la.mu = mu; la.rows = rows; la.d = d; la.rA = rA; la.dK = dK; la.dB = dB; la.NT = NT; la.L = L; la.eps = eps;
     la.Q = Q; la.S = S; la.S0 = S0; la.Qs = Qs; la.Bo = (const float*)pBo; la.prec = (const float*)tgt->precision;
     la.ld_prec = tgt->ld; la.pBoP = pBoP; la.pPP = pPP; la.pQC = pQC; la.pQC2 = pQC2; la.pQsP = pQsP; la.lpp = (float*)pLPP; la.dkp = (float*)pDKP;
-    la.energies = 1;
-    const int e = g1_tf32 ? leapfrog_bform<KIND_TF32>(ctx, la, s) : leapfrog_bform<KIND_BF16>(ctx, la, s);
+    la.energies = 1; la.am = (uint32_t*)pAM; la.rs = (float*)pRS;
+    const int e = g1_tf32 ? leapfrog_bform<KIND_TF32>(ctx, la, s)
+                          : (kf16 ? leapfrog_bform<KIND_F16>(ctx, la, s) : leapfrog_bform<KIND_BF16>(ctx, la, s));
     if (e) return e;
   }
 

@@ -137,6 +137,11 @@ HX_API int hx_tc_microbench(hx_ctx* ctx, int mode, int32_t n, int32_t rows, int3
  * B tile; 3.15 instead of 3.98 ms alone at c5, bit-identical output), default 0 because it runs WORSE next to the concurrent
  * momentum draw; what = 9: 1 = CTA-pair projection launched one wave at a time even when the draw is
  * complete (default 0 = one launch); what = 10: 1 = draw kernel without its stores (garbage results; overlap diagnostics only);
+ * what = 13: 1 = single-CTA projection as ONE launch over all rows when the draw was queued ahead (default 0: one wave per
+ * launch; measured: the GEMM ends earlier but the starved draw then runs into the next phases); what = 14: operand kind of the
+ * kicks / propagator apply: 0 (default) = fp16 hi/lo with power-of-two row / matrix scales for the stepwise form (log-accept
+ * error vs f64 1.1e-2 -> 7.7e-4 rms at c5 scale, same MMA rate) and bf16 hi/lo for the propagator form, 1 = fp16 for both,
+ * 2 = bf16 for both;
  * what = 12: 0 = Gram and propagator-apply GEMMs by the single-CTA kernel instead of the CTA-pair kernel
  * (default 1: bit-identical, ~0.1 ms per half-move faster at c5; these launches do not overlap the draw)                       */
 HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value);

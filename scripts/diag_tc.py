@@ -8,7 +8,8 @@ from bench import make_cov
 
 from hemcee_b200 import _lib as _l0, _rt as _r0
 import torch as _t0
-_l0.load().hx_ctx_set_tuning(_r0.ctx(_t0.device("cuda", 0)), 3, int(os.environ.get("EKIND", 0)))   # energy operand kind
+_l0.load().hx_ctx_set_tuning(_r0.ctx(_t0.device("cuda", 0)), 3, int(os.environ.get("EKIND", 2)))   # energy operand kind
+_l0.load().hx_ctx_set_tuning(_r0.ctx(_t0.device("cuda", 0)), 14, int(os.environ.get("KF16", 0)))   # fp16 hi/lo kicks / apply
 d = int(os.environ.get("D", 1000)); n = int(os.environ.get("N", 8192)); L = 10; eps = 0.1
 _, prec = make_cov(d, 1e4)
 tgt = hx.targets.GaussianFull(precision=prec)

@@ -267,3 +267,43 @@ def test_fp16_energy_products_match_tf32(hx, prec, form):
         np.testing.assert_allclose(out[kind][3].cpu().numpy(), lp64, rtol=2e-4, atol=2e-3)
     for i in range(4):
         assert torch.equal(torch.cat([p[i] for p in parts]), out[2][i])
+
+
+@pytest.mark.parametrize("lf", ["stepwise", "propagator"])
+def test_fp16_kicks_match_oracle_and_shards(hx, prec, form, lf):
+    """hx_ctx_set_tuning(14, 1): kicks / propagator apply (and energies) from fp16 hi/lo operands with power-of-two scales per
+    walker row and per matrix, instead of bf16 hi/lo: same tolerances against the f64 oracle as the bf16 form, closer to the
+    exact path, and row shards bit-identical (the row scales are row-local)."""
+    from hemcee_b200 import _lib, _rt
+    lib, ctx = _lib.load(), _rt.ctx(torch.device("cuda", 0))
+    n, d, L, eps = 512, 256, 6, 0.05
+    tgt, (olp, og), g1, g2, key = _problem(hx, n, d, seed=5, kappa=1000.0)
+    G1, G2 = torch.from_numpy(g1).cuda(), torch.from_numpy(g2).cuda()
+    LP1 = tgt.log_prob(G1)
+    prec("exact")
+    qe, lae, ppe, lpe = hx.hmc_walk_move(G1, G2, eps, key, tgt, tgt, L, LP1)
+    prec("bf16x3")
+    form(lf)
+    out = {}
+    try:
+        for kf in (0, 1):
+            _lib.check(lib.hx_ctx_set_tuning(ctx, 14, 1 if kf else 2), "hx_ctx_set_tuning")     # 1 = fp16 always, 2 = bf16 always
+            out[kf] = hx.hmc_walk_move(G1, G2, eps, key, tgt, tgt, L, LP1)
+        parts = [hx.hmc_walk_move(G1[r * 128:(r + 1) * 128], G2, eps, key, tgt, tgt, L, LP1[r * 128:(r + 1) * 128],
+                                  row0=r * 128, n=n) for r in range(4)]
+    finally:
+        lib.hx_ctx_set_tuning(ctx, 14, 0)
+    a64, b64 = g1.astype(np.float64), g2.astype(np.float64)
+    q64, la64, pp64, lp64 = OM.hmc_walk_move(a64, b64, eps, key, olp, og, L, olp(a64), rng_dtype=np.float32)
+    scale = np.abs(q64).max()
+    q, la, pp, lp = [t.cpu().numpy() for t in out[1]]
+    np.testing.assert_allclose(q, q64, rtol=0, atol=2e-4 * scale)
+    np.testing.assert_allclose(pp, pp64, rtol=0, atol=2e-4 * np.abs(pp64).max())
+    np.testing.assert_allclose(lp, lp64, rtol=2e-4, atol=2e-3)
+    np.testing.assert_allclose(la, la64, rtol=0, atol=5e-3)
+    # not worse than the bf16 hi/lo form against the exact fp32 path (positions)
+    e16 = (out[1][0] - qe).abs().max().item()
+    eb = (out[0][0] - qe).abs().max().item()
+    assert e16 <= 1.5 * eb + 1e-6 * scale, (e16, eb)
+    for i in range(4):
+        assert torch.equal(torch.cat([p[i] for p in parts]), out[1][i])
