@@ -94,7 +94,6 @@ extern "C" HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value) {
   else if (what == 4) ctx->graphs_off = value ? 0 : 1;
   else if (what == 5) ctx->narrow_off = value ? 0 : 1;
   else if (what == 6) ctx->draw_fork = value;
-  else if (what == 7) ctx->mp_dfma = value ? 1 : 0;
   else if (what == 8) ctx->proj_pair = value ? 1 : 0;
   else if (what == 9) ctx->pair_chunked = value ? 1 : 0;
   else if (what == 10) ctx->draw_nostore = value ? 1 : 0;

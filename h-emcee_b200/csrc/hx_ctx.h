@@ -82,7 +82,6 @@ struct hx_ctx {
   int aux_pair;                            // 1: Gram and propagator-apply GEMMs by the CTA-pair kernel
   int proj_one_launch;                     // 1: single-CTA projection as ONE launch over all rows when the draw was queued ahead
   int kick_f16;                            // kicks / propagator apply from fp16 hi/lo operands: 0 auto (stepwise form only), 1 always, 2 never
-  int mp_dfma;                             // 1: B = M P by the DFMA tile kernel instead of the DMMA kernel
 };
 
 // grow-only scratch slot

@@ -6,7 +6,7 @@
 // one ("B-form"): for a Gaussian target grad U = (q - mu) P, so  g @ M = (q - mu) @ (P M).
 //   C^T planes    <- ((X2 - mean)/sqrt(n))^T                      (hmc_walk.py:35)            bf16 hi/lo
 //   M             <- C^T C                                         tc_gemm(CT, CT)             bf16 x3
-//   Bop           <- M P  (exact fp32 SIMT, d^3 flops)            k_small_gemm
+//   Bop           <- M P  (fp64 tensor cores, d^3 flops)            k_mp_dmma
 //   P0 planes     <- normal(key, (n, n))[row shard]                (hmc_walk.py:36)            bf16 hi/lo
 //   S0            <- P0 C                                          tc_gemm(P0, CT)             bf16 x3
 //   per kick:  S  <- S - a (q - mu) Bop^T ; Qs += a (q - mu) ; q += eps S    tc_gemm(QC, Bop)   tf32 x3
@@ -232,65 +232,9 @@ __global__ void k_split_planes(const float* __restrict__ src, int dim_r, int dim
   }
 }
 
-// out[i][j] = sum_k A[i][k] * B[k][j]  (dim x dim; fp32 inputs, fp64 products and accumulation, result rounded to fp32 once;
-// 64x64 tile, 4x4 per thread).  Used for B = M P: the product of the Gram matrix (eigenvalues up to ~1e3 at kappa = 1e4) and
-// the precision (up to ~10) is O(1) by cancellation, and accumulating it in fp32 costs ~1e-4 of the ensemble scale in the
-// proposed positions (measured against an f64 integration; oracle-side check in tests/test_oracle_moves.py).
-__global__ void __launch_bounds__(256) k_small_gemm(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                                                    int dim, float* __restrict__ out, int ldo) {
-  constexpr int TBI = 128, TBJ = 64, KB = 16;          // 128 x 64 output tile, 8 x 4 per thread, inputs widened once per tile
-  __shared__ __align__(16) double sa[KB][TBI + 2];
-  __shared__ __align__(16) double sb[KB][TBJ + 2];
-  const int ti = blockIdx.y * TBI, tj = blockIdx.x * TBJ;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double acc[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int k0 = 0; k0 < dim; k0 += KB) {
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < KB * TBI; idx += 256) {
-      const int i = idx / KB, kk = idx - i * KB;
-      sa[kk][i] = (ti + i < dim && k0 + kk < dim) ? (double)A[(size_t)(ti + i) * lda + k0 + kk] : 0.0;
-    }
-    for (int idx = threadIdx.x; idx < KB * TBJ; idx += 256) {
-      const int k2 = idx / TBJ, j = idx - k2 * TBJ;
-      sb[k2][j] = (k0 + k2 < dim && tj + j < dim) ? (double)B[(size_t)(k0 + k2) * ldb + tj + j] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < KB; ++kk) {
-      double a[8], b[4];
-#pragma unroll
-      for (int i = 0; i < 8; i += 2) {
-        const double2 t = *reinterpret_cast<const double2*>(&sa[kk][8 * ty + i]);
-        a[i] = t.x; a[i + 1] = t.y;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; j += 2) {
-        const double2 t = *reinterpret_cast<const double2*>(&sb[kk][4 * tx + j]);
-        b[j] = t.x; b[j + 1] = t.y;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int gi = ti + 8 * ty + i;
-    if (gi >= dim) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gj = tj + 4 * tx + j;
-      if (gj < dim) out[(size_t)gi * ldo + gj] = (float)acc[i][j];
-    }
-  }
-}
-
-
+// B = M P: the product of the Gram matrix (eigenvalues up to ~1e3 at kappa = 1e4) and the precision (up to ~10) is O(1) by
+// cancellation, and accumulating it in fp32 costs ~1e-4 of the ensemble scale in the proposed positions (measured against an f64
+// integration; oracle-side check in tests/test_oracle_moves.py), so it is formed with fp64 products and accumulation.
 // B = M P on the fp64 tensor-core path: DMMA m8n8k4 (fp64 operands and accumulators), fp32 inputs widened once when a
 // K-block is staged in shared memory, register-prefetched double buffering.  64 x 64 output tile per CTA, four warps of
 // 32 x 32 (4 x 4 DMMA tiles).  Row strides of the staged tiles are = 4 mod 16 doubles: the 8-byte fragment loads of a
@@ -1107,11 +1051,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     ga.kb_per_slice = 0; ga.slice_stride = 0;
   }
   {
-    if (ctx->mp_dfma) {
-      dim3 g((d + 63) / 64, (d + 127) / 128);
-      k_small_gemm<<<g, 256, 0, s>>>((const float*)pM, d, (const float*)tgt->precision, tgt->ld, d, (float*)pBo, d);
-      HX_LAUNCH_CHECK("k_small_gemm");
-    } else {
+    {
       dim3 g((d + 63) / 64, (d + 63) / 64);
       k_mp_dmma<<<g, 128, 0, s>>>((const float*)pM, d, (const float*)tgt->precision, tgt->ld, d, (float*)pBo, d);
       HX_LAUNCH_CHECK("k_mp_dmma");

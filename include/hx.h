@@ -132,7 +132,6 @@ HX_API int hx_tc_microbench(hx_ctx* ctx, int mode, int32_t n, int32_t rows, int3
  * inside the half-move kernel instead of the lane-split projection kernel (default 1);
  * what = 6: the next half-move's momentum draw is queued after that many projection chunks instead of at the projection's start
  * (default 0; measured: any later start runs into the latency-bound launches and costs more than it saves);
- * what = 7: 1 = B = M P by the DFMA tile kernel instead of the DMMA (fp64 tensor core) kernel (default 0);
  * what = 8: 1 = momentum projection by the CTA-pair kernel (tcgen05 cta_group::2: M = 256 per pair, each CTA stages half of the
  * B tile; 3.15 instead of 3.98 ms alone at c5, bit-identical output), default 0 because it runs WORSE next to the concurrent
  * momentum draw; what = 9: 1 = CTA-pair projection launched one wave at a time even when the draw is
