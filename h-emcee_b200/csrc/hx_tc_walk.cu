@@ -1,19 +1,21 @@
 // hx_tc_walk.cu — tensor-core path of the walk half-move for full-covariance Gaussian targets at large
-// dim / walker counts (fp32 state, split-bf16 operands on tcgen05, fp32 accumulation in TMEM).
+// dim / walker counts (fp32 state, split 16-bit / 8-bit operands on tcgen05, fp32 accumulation in TMEM).
 //
 // Same projected-form algorithm as the exact SIMT kernel (hx_move.cuh; reference
 // moves/hamiltonian/hmc_walk.py:6-107), expressed as GEMMs, with the two per-kick products folded into
 // one ("B-form"): for a Gaussian target grad U = (q - mu) P, so  g @ M = (q - mu) @ (P M).
-//   C^T planes    <- ((X2 - mean)/sqrt(n))^T                      (hmc_walk.py:35)            bf16 hi/lo
-//   M             <- C^T C                                         tc_gemm(CT, CT)             bf16 x3
-//   Bop           <- M P  (fp64 tensor cores, d^3 flops)            k_mp_dmma
-//   P0 planes     <- normal(key, (n, n))[row shard]                (hmc_walk.py:36)            bf16 hi/lo
-//   S0            <- P0 C                                          tc_gemm(P0, CT)             bf16 x3
-//   per kick:  S  <- S - a (q - mu) Bop^T ; Qs += a (q - mu) ; q += eps S    tc_gemm(QC, Bop)   tf32 x3
-//   energies:  G = Qs P ; dK = -1/2 <G, S0 + S_L> ; g_L = (q_L - mu) P ; lp' = -1/2 <g_L, q_L - mu>   tf32 x3
-//   finish:    dH = (lp1 - lp') + dK ; log_acc ; optional Metropolis accept + chain emit
-// The kicks and energy products use tf32 hi/lo operands (2^-21 per product): with bf16 hi/lo (2^-16) the
-// energy error of an ill-conditioned target (kappa 1e4) is ~0.3 and visibly lowers the acceptance rate.
+//   C^T planes    <- ((X2 - mean)/sqrt(n))^T                      (hmc_walk.py:35)   bf16 hi/lo (Gram) and fp16 + 2 x e4m3 (projection)
+//   M             <- C^T C                                         k_tc_gemm_pair(CT, CT), split-K          bf16 x3
+//   Bop           <- M P  (fp64 tensor cores, d^3 flops)           k_mp_dmma
+//   P0 planes     <- normal(key, (n, n))[row shard]                (hmc_walk.py:36)   k_rng_planes, one half-move ahead on a side stream
+//   S0            <- P0 C                                          k_tc_gemm(P0, CT)  fp16 main + 2 x e4m3 correction products
+//   stepwise form, per kick:  S <- S - a (q - mu) Bop^T ; Qs += a (q - mu) ; q += eps S      k_tc_gemm<EPI_KICKB>   fp16 hi/lo
+//   propagator form: 2 dim basis trajectories with the same kicks (bf16 x3), then [q_L - mu | S_L] = z0 [Tq | Ts] in ONE GEMM
+//   energies:  dK = -1/2 <Qs P, S0 + S_L> ; lp' = -1/2 <(q_L - mu) P, q_L - mu>            k_tc_gemm<EPI_DOT>     fp16 hi/lo
+//   finish:    dH = (lp1 - lp') + dK ; log_acc ; optional Metropolis accept + chain emit (+ row push to the peers)
+// Operand kinds and what each costs in accuracy are in hx_tc_gemm.cuh and DESIGN.md sections 2 and 4: with bf16 hi/lo (2^-16
+// per product) the energy error of an ill-conditioned target (kappa 1e4) is ~1e-2 and visibly lowers the acceptance rate, so
+// the kicks of the stepwise form and all energy products use fp16 hi/lo operands with power-of-two scales (2^-22).
 #include <cstring>
 #include <cstdio>
 #include <cstdlib>
