@@ -104,11 +104,19 @@ __device__ __forceinline__ float f8_scale_from_amax(uint32_t amax_bits, int n) {
 }
 __global__ void __launch_bounds__(256) k_absmax_centred(const float* __restrict__ X2, const float* __restrict__ mean, int n, int d,
                                                         uint32_t* __restrict__ amax_bits) {
+  // threads over columns (coalesced rows, mean[c] read once), blockIdx.y over chunks of 64 rows; 4 independent loads in flight
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r_lo = blockIdx.y * 64, r_hi = min(n, r_lo + 64);
   float m = 0.f;
-  const size_t tot = (size_t)n * d;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % (size_t)d);
-    m = fmaxf(m, fabsf(X2[i] - (mean ? mean[c] : 0.f)));
+  if (c < d) {
+    const float mc = mean ? mean[c] : 0.f;
+    int r = r_lo;
+    for (; r + 4 <= r_hi; r += 4) {
+      const float a0 = X2[(size_t)r * d + c], a1 = X2[(size_t)(r + 1) * d + c];
+      const float a2 = X2[(size_t)(r + 2) * d + c], a3 = X2[(size_t)(r + 3) * d + c];
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(a0 - mc), fabsf(a1 - mc))), fmaxf(fabsf(a2 - mc), fabsf(a3 - mc)));
+    }
+    for (; r < r_hi; ++r) m = fmaxf(m, fabsf(X2[(size_t)r * d + c] - mc));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -118,7 +126,7 @@ __global__ void __launch_bounds__(256) k_absmax_centred(const float* __restrict_
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int w = 1; w < 8; ++w) m = fmaxf(m, wm[w]);
-    atomicMax(amax_bits, __float_as_uint(m));       // non-negative floats order like their bit patterns
+    if (m > 0.f) atomicMax(amax_bits, __float_as_uint(m));       // non-negative floats order like their bit patterns
   }
 }
 // max |src[r * ld + c]| over r < rows, c < cols
@@ -1009,7 +1017,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     if (int e = ws_get(ctx, WS_TC_SC8, 16, &pSc8)) return e;
     uint32_t* amax = reinterpret_cast<uint32_t*>(pSc8) + 2;
     HX_CUDA(cudaMemsetAsync(amax, 0, sizeof(uint32_t), s));
-    k_absmax_centred<<<grid_for((size_t)n * d / 4, 256), 256, 0, s>>>(X2, mean_dev, n, d, amax);
+    k_absmax_centred<<<dim3((d + 255) / 256, (n + 63) / 64), 256, 0, s>>>(X2, mean_dev, n, d, amax);
     HX_LAUNCH_CHECK("k_absmax_centred");
     k_f8_scale<<<1, 1, 0, s>>>(amax, n, (float*)pSc8);
     HX_LAUNCH_CHECK("k_f8_scale");
