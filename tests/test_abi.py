@@ -47,3 +47,14 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in re.sub(r'"""[\s\S]*?"""', "", src), fn
+
+
+def test_precision_and_leapfrog_enums_match_the_python_mirror():
+    """hemcee_b200.config's precision / leapfrog-form names carry the values of the HX_PREC_* / HX_LEAP_* enums of the header."""
+    from hemcee_b200 import _rt
+    src = open(os.path.join(ROOT, "include", "hx.h")).read()
+    enums = dict((k, int(v)) for k, v in re.findall(r"\b(HX_(?:PREC|LEAP)_\w+)\s*=\s*(\d+)", src))
+    prec = {k[len("HX_PREC_"):].lower(): v for k, v in enums.items() if k.startswith("HX_PREC_")}
+    leap = {k[len("HX_LEAP_"):].lower(): v for k, v in enums.items() if k.startswith("HX_LEAP_")}
+    assert prec == _rt.config.PRECISIONS
+    assert leap == _rt.config.LEAPFROG_FORMS
