@@ -328,11 +328,11 @@ __global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key
   if (key_ptr) { key.k0 = key_ptr[0]; key.k1 = key_ptr[1]; }
   const size_t nvec = (size_t)rows_chunk * Kp / 8;
   const uint64_t nn = (uint64_t)n * (uint64_t)n;
-  // Work items of 256 x 4 vectors are handed out through an atomic counter instead of a static grid-stride split: the kernel
+  // Work items of 256 x 2 vectors are handed out through an atomic counter instead of a static grid-stride split: the kernel
   // shares the SMs with GEMM CTAs of another stream, so its resident CTAs progress at very different rates (and may be placed
   // unevenly), and a static split makes the whole draw wait for the slowest one (measured: a bimodal 18.3 / 22 ms per iteration)
   __shared__ unsigned int s_item;
-  const unsigned int nitems = (unsigned int)((nvec + 1023) / 1024);
+  const unsigned int nitems = (unsigned int)((nvec + 511) / 512);      // short items: the kernel's tail is at most one item long
   for (;;) {
     if (threadIdx.x == 0) s_item = atomicAdd(work_ctr, 1u);
     __syncthreads();
@@ -340,8 +340,8 @@ __global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key
     __syncthreads();
     if (item >= nitems) break;
 #pragma unroll 1
-  for (int u4 = 0; u4 < 4; ++u4) {
-    const size_t v = (size_t)item * 1024 + (size_t)u4 * 256 + threadIdx.x;
+  for (int u4 = 0; u4 < 2; ++u4) {
+    const size_t v = (size_t)item * 512 + (size_t)u4 * 256 + threadIdx.x;
     if (v >= nvec) break;
     const size_t i = v * 8;
     const int r = (int)(i / Kp), j0 = (int)(i - (size_t)r * Kp);
