@@ -10,7 +10,7 @@ from . import autocorr, random, targets
 from ._lib import HxError
 from ._rt import config
 from .adaptation import ChEESParameters, DAParameters
-from .backend import Backend
+from .backend import Backend, FileBackend
 from .moves import hmc_side_move, hmc_walk_move
 from .sampler import HamiltonianEnsembleSampler
 from .ensemble import EnsembleSampler, side_move, stretch_move, walk_move
@@ -18,4 +18,4 @@ from .ensemble import EnsembleSampler, side_move, stretch_move, walk_move
 __version__ = "0.1.0"
 
 __all__ = ["HamiltonianEnsembleSampler", "EnsembleSampler", "stretch_move", "side_move", "walk_move", "hmc_walk_move", "hmc_side_move", "DAParameters", "ChEESParameters",
-           "Backend", "autocorr", "random", "targets", "config", "HxError"]
+           "Backend", "FileBackend", "autocorr", "random", "targets", "config", "HxError"]

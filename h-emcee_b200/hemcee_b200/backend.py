@@ -7,7 +7,7 @@ import numpy as np
 
 from . import autocorr
 
-__all__ = ["Backend"]
+__all__ = ["Backend", "FileBackend"]
 
 
 class Backend:
@@ -77,3 +77,50 @@ class Backend:
 
     def __exit__(self, *exc):
         pass
+
+
+class FileBackend(Backend):
+    """Backend that can be written to / restored from ONE file with the dataset and attribute names of the reference's
+    HDFBackend group (reference src/hemcee/backend/hdf.py:99-128: datasets `chain[T, W, d]`, `log_prob[T, W]`, `accepted[W]`;
+    attributes `version`, `nwalkers`, `ndim`, `iteration`, `iteration_warmup`, `iteration_main`, `warmup_end_index` with -1 for
+    "warm-up not complete").  h5py is not a dependency here, so the container is NumPy's .npz; a maintainer with h5py can copy
+    the arrays into an HDF5 group one to one.  During sampling it behaves like the in-memory Backend (the chain batches arrive
+    from pinned host buffers); `save()` writes what has been stored so far."""
+
+    VERSION = 0
+
+    def __init__(self, filename: str, name: str = "mcmc", read_only: bool = False, dtype=None):
+        super().__init__(dtype)
+        self.filename, self.name, self.read_only = filename, name, read_only
+
+    def save(self):
+        if self.read_only:
+            raise RuntimeError("The backend has been loaded in read-only mode. Set `read_only = False` to make changes.")
+        if not self.initialized:
+            raise AttributeError("nothing to save: the backend has not been reset()")
+        n = self.name
+        empty_c = np.zeros((0, self.nwalkers, self.ndim), dtype=np.float32)
+        chain = self.get_value("chain") if self.iteration > 0 and len(self.chain) else empty_c
+        lp = self.get_value("log_prob") if self.iteration > 0 and len(self.log_prob) else empty_c[:, :, 0]
+        attrs = dict(version=self.VERSION, nwalkers=self.nwalkers, ndim=self.ndim, iteration=self.iteration,
+                     iteration_warmup=self.iteration_warmup, iteration_main=self.iteration_main,
+                     warmup_end_index=-1 if self._warmup_end_index is None else self._warmup_end_index)
+        arrays = {f"{n}/chain": np.asarray(chain), f"{n}/log_prob": np.asarray(lp), f"{n}/accepted": self.accepted}
+        arrays.update({f"{n}/attrs/{k}": np.asarray(v) for k, v in attrs.items()})
+        with open(self.filename, "wb") as f:
+            np.savez(f, **arrays)
+
+    @classmethod
+    def load(cls, filename: str, name: str = "mcmc", read_only: bool = True):
+        b = cls(filename, name, read_only)
+        with np.load(filename) as z:
+            if f"{name}/chain" not in z:
+                raise KeyError(f"no group {name!r} in {filename}")
+            a = {k.split("/")[-1]: z[k].item() for k in z.files if k.startswith(f"{name}/attrs/")}
+            b.reset(a["nwalkers"], a["ndim"])
+            b.dtype = z[f"{name}/accepted"].dtype
+            b.accepted = z[f"{name}/accepted"].copy()
+            b.chain, b.log_prob = [z[f"{name}/chain"].copy()], [z[f"{name}/log_prob"].copy()]
+            b.iteration, b.iteration_warmup, b.iteration_main = a["iteration"], a["iteration_warmup"], a["iteration_main"]
+            b._warmup_end_index = None if a["warmup_end_index"] < 0 else a["warmup_end_index"]
+        return b

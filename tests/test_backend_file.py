@@ -1,0 +1,56 @@
+"""FileBackend: the in-memory chain store written to / restored from one file with the dataset and attribute names of the
+reference's HDF group (reference src/hemcee/backend/hdf.py:99-128); slicing semantics of backend/backend.py:52-71."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "h-emcee_b200"))
+
+
+def test_file_backend_round_trip(tmp_path):
+    from hemcee_b200.backend import Backend, FileBackend
+    rng = np.random.default_rng(0)
+    W, d = 6, 3
+    fn = str(tmp_path / "chain.npz")
+    b = FileBackend(fn)
+    b.reset(W, d)
+    warm = rng.standard_normal((4, W, d)).astype(np.float32)
+    b.save_slice(warm, warm.sum(-1), np.arange(W), 0)
+    b.mark_warmup_end()
+    main = rng.standard_normal((5, W, d)).astype(np.float32)
+    b.save_slice(main, main.sum(-1), np.ones(W), 4)
+    b.save()
+    r = FileBackend.load(fn)
+    assert (r.nwalkers, r.ndim, r.iteration, r.iteration_warmup, r.iteration_main) == (W, d, 9, 4, 5)
+    np.testing.assert_array_equal(r.get_chain(), np.concatenate([warm, main]))
+    np.testing.assert_array_equal(r.get_chain(discard=4, thin=2), main[::2])
+    np.testing.assert_array_equal(r.get_chain(discard=4, flat=True), main.reshape(-1, d))
+    np.testing.assert_array_equal(r.get_log_prob(discard=4), main.sum(-1))
+    np.testing.assert_array_equal(r.accepted, np.arange(W) + 1.0)
+    last, last_lp = r.get_last_sample()
+    np.testing.assert_array_equal(last, main[-1])
+    # same dataset / attribute names as the reference's HDF group
+    with np.load(fn) as z:
+        names = set(z.files)
+    for k in ("chain", "log_prob", "accepted", "attrs/version", "attrs/nwalkers", "attrs/ndim", "attrs/iteration",
+              "attrs/iteration_warmup", "attrs/iteration_main", "attrs/warmup_end_index"):
+        assert f"mcmc/{k}" in names
+    with pytest.raises(RuntimeError):
+        r.save()                                   # loaded read-only, like HDFBackend.open
+
+
+def test_file_backend_before_warmup_end(tmp_path):
+    from hemcee_b200.backend import FileBackend
+    fn = str(tmp_path / "c.npz")
+    b = FileBackend(fn, name="run1")
+    b.reset(4, 2)
+    x = np.zeros((3, 4, 2), np.float32)
+    b.save_slice(x, x.sum(-1), np.zeros(4), 0)
+    b.save()
+    r = FileBackend.load(fn, name="run1")
+    assert r._warmup_end_index is None and r.iteration_warmup == 3 and r.iteration_main == 0
+    with pytest.raises(KeyError):
+        FileBackend.load(fn, name="mcmc")
