@@ -43,8 +43,18 @@ int ws_get(hx_ctx* ctx, int slot, size_t bytes, void** out) {
     size_t want = bytes + bytes / 4;
     HX_CUDA(cudaMalloc(&ctx->buf[slot], want));
     ctx->cap[slot] = want;
+    ctx->ws_generation += 1;        // cached CUDA graphs hold the old address (run_maybe_graphed re-captures)
   }
   *out = ctx->buf[slot];
+  return 0;
+}
+
+int ensure_smem_attr(hx_ctx* ctx, const void* func, int bytes) {
+  if (!ctx->attr_done) ctx->attr_done = new (std::nothrow) std::vector<const void*>();
+  if (ctx->attr_done)
+    for (const void* f : *ctx->attr_done) if (f == func) return 0;
+  HX_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (ctx->attr_done) ctx->attr_done->push_back(func);
   return 0;
 }
 
@@ -100,12 +110,17 @@ extern "C" HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value) {
   else if (what == 12) ctx->aux_pair = value;
   else if (what == 13) ctx->proj_one_launch = value ? 1 : 0;
   else if (what == 14) ctx->kick_f16 = value;
+  else if (what == 15) ctx->proj_fused = value ? 1 : 0;
+  else if (what == 16) ctx->fused_nw = value;
+  else if (what == 17) ctx->fused_slices = value;
+  else if (what == 18) ctx->one_acc = value ? 1 : 0;
+  else if (what == 19) ctx->fused_diag = value;
   else return hx_fail(HX_E_DTYPE, "hx_ctx_set_tuning: unknown knob %d", what);
   return 0;
 }
 extern "C" HX_API int hx_tc_microbench(hx_ctx* ctx, int mode, int32_t n, int32_t rows, int32_t dim, int32_t reps, double* ms_out, void* stream) {
   if (!ctx || !ms_out) return hx_fail(HX_E_NULL, "hx_tc_microbench: NULL argument");
-  if (mode < 0 || mode > 2 || n < 64 || rows < 1 || dim < 16 || reps < 1) return hx_fail(HX_E_SHAPE, "hx_tc_microbench: bad argument");
+  if (mode < 0 || mode > 3 || n < 64 || rows < 1 || dim < 16 || reps < 1) return hx_fail(HX_E_SHAPE, "hx_tc_microbench: bad argument");
   HX_CUDA(cudaSetDevice(ctx->device));
   return tc::microbench(ctx, mode, n, rows, dim, reps, ms_out, (cudaStream_t)stream);
 }
@@ -168,6 +183,7 @@ extern "C" HX_API int hx_ctx_create(hx_ctx** out, int device) {
   c->device = device;
   c->aux_pair = 1;
   c->energy_bf16 = 2;
+  c->proj_fused = 1;
   cudaDeviceProp prop;
   HX_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -195,6 +211,7 @@ extern "C" HX_API int hx_ctx_destroy(hx_ctx* ctx) {
     for (GraphEntry& g : *ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     delete ctx->graphs;
   }
+  delete ctx->attr_done;
   if (ctx->gstream) cudaStreamDestroy(ctx->gstream);
   if (ctx->key_stage) cudaFree(ctx->key_stage);
   {
@@ -775,10 +792,17 @@ static int run_maybe_graphed(hx_ctx* ctx, cudaStream_t s, uint64_t key, F&& enqu
       if ((*ctx->graphs)[lru].exec) cudaGraphExecDestroy((*ctx->graphs)[lru].exec);
       ctx->graphs->erase(ctx->graphs->begin() + lru);
     }
-    ctx->graphs->push_back(GraphEntry{key, nullptr, ctx->graph_tick});
+    ctx->graphs->push_back(GraphEntry{key, 0, nullptr, ctx->graph_tick});
     return enqueue(s);                       // first use: eager (primes workspaces and function attributes)
   }
   ent->last_use = ctx->graph_tick;
+  if (ent->exec && ent->ws_gen != ctx->ws_generation) {
+    // a workspace slot was reallocated since the capture (a larger problem ran on this ctx): the graph's kernel arguments
+    // point into freed memory.  Drop it, run eagerly now (re-primes the slots for this size), capture again on the next use.
+    cudaGraphExecDestroy(ent->exec);
+    ent->exec = nullptr;
+    return enqueue(s);
+  }
   if (!ent->exec) {
     if (!ctx->gstream) HX_CUDA(cudaStreamCreateWithFlags(&ctx->gstream, cudaStreamNonBlocking));
     cudaGraph_t graph = nullptr;
@@ -796,6 +820,7 @@ static int run_maybe_graphed(hx_ctx* ctx, cudaStream_t s, uint64_t key, F&& enqu
     cudaGraphDestroy(graph);
     if (ci != cudaSuccess || !exec) { cudaGetLastError(); ctx->graphs_off = 1; return enqueue(s); }
     ent->exec = exec;
+    ent->ws_gen = ctx->ws_generation;
   }
   HX_CUDA(cudaGraphLaunch(ent->exec, s));
   return 0;
@@ -879,10 +904,10 @@ static int run_iterations_t(hx_ctx* ctx, int impl, int move_kind, int key_order,
     return run_iterations_body<T>(ctx, impl, move_kind, key_order, tgt, X, lp, n, eps, L, keys, Tn, chain, chain_lp, accepts, nonfinite, s);
   const uint32_t* staged = nullptr;
   if (int e = stage_keys(ctx, keys, (size_t)Tn * 8, &staged, s)) return e;
-  struct { int impl, move_kind, key_order, n, L, every, phase, dt; double eps; int64_t Tn; const void *X, *lp, *chain, *clp, *acc, *nf; hx_target tg; } K;
+  struct { int impl, move_kind, key_order, n, L, every, phase, dt, narrow_off, leap_form; double eps; int64_t Tn; const void *X, *lp, *chain, *clp, *acc, *nf; hx_target tg; } K;
   memset(&K, 0, sizeof(K));
   K.impl = impl; K.move_kind = move_kind; K.key_order = key_order; K.n = n; K.L = L; K.every = ctx->chain_every; K.phase = ctx->chain_phase;
-  K.dt = (int)sizeof(T); K.eps = eps; K.Tn = Tn; K.X = X; K.lp = lp; K.chain = chain; K.clp = chain_lp; K.acc = accepts; K.nf = nonfinite;
+  K.dt = (int)sizeof(T); K.narrow_off = ctx->narrow_off; K.leap_form = ctx->leap_form; K.eps = eps; K.Tn = Tn; K.X = X; K.lp = lp; K.chain = chain; K.clp = chain_lp; K.acc = accepts; K.nf = nonfinite;
   K.tg = *tgt;
   const uint64_t key = fnv1a(&K, sizeof(K), 0x9e3779b97f4a7c15ull ^ (uint64_t)ctx->precision);
   return run_maybe_graphed(ctx, s, key, [&](cudaStream_t cs) {

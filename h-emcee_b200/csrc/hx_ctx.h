@@ -36,6 +36,7 @@ struct HxDist {
 // cached CUDA graphs of launch-bound batch loops (small ensembles): one entry per distinct argument set
 struct GraphEntry {
   uint64_t key;
+  uint64_t ws_gen;           // ctx->ws_generation when the graph was captured (it bakes in workspace addresses)
   cudaGraphExec_t exec;      // nullptr: the argument set was seen once (run eagerly, workspaces primed), capture on the next use
   uint64_t last_use;
 };
@@ -67,6 +68,7 @@ struct hx_ctx {
   int leap_form;                           // HX_LEAP_*
   HxDist dist;
   std::vector<GraphEntry>* graphs; cudaStream_t gstream; uint64_t graph_tick; int graphs_off;
+  uint64_t ws_generation;                  // bumped whenever ws_get moves a workspace slot: captured graphs from before are stale
   void* key_stage; size_t key_stage_cap;    // fixed-address copy of a batch's keys (graph replays read the keys from here)
   int chain_every, chain_phase;            // thinned chain emit of the batch loops (hx_ctx_set_chain_thinning); 0/1 = every iteration
   const void* ctl_eps; const int* ctl_L;   // device-resident (step, L) the SIMT move kernels read during adaptive warm-up
@@ -82,8 +84,17 @@ struct hx_ctx {
   int aux_pair;                            // 1: Gram and propagator-apply GEMMs by the CTA-pair kernel
   int proj_one_launch;                     // 1: single-CTA projection as ONE launch over all rows when the draw was queued ahead
   int kick_f16;                            // kicks / propagator apply from fp16 hi/lo operands: 0 auto (stepwise form only), 1 always, 2 never
+  // fused draw + projection kernel (hx_tc_fused.cuh)
+  int proj_fused;                          // 1 (default): P0 is drawn inside the projection GEMM when eligible; 0: staged draw + GEMM
+  int fused_nw;                            // RNG warps per CTA: 8 or 16 (0: default)
+  int fused_slices;                        // split-K slices of the fused projection (0: default = 2 from 4096 walkers per group)
+  int fused_diag;                          // diagnostics: 1 no draw, 2 no MMA (results are garbage)
+  int one_acc;                             // staged bf16 hi/lo projection accumulates all three products in one accumulator (bit-compare with the fused kernel)
+  std::vector<const void*>* attr_done;     // kernels whose dynamic-shared-memory attribute was set on THIS ctx's device (attributes are per device)
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per (ctx = device, kernel)
+int ensure_smem_attr(hx_ctx* ctx, const void* func, int bytes);
 // grow-only scratch slot
 int ws_get(hx_ctx* ctx, int slot, size_t bytes, void** out);
 // phases of a half-move for the timing hooks (hx_ctx_timing_read / hx_ctx_timing_phases)

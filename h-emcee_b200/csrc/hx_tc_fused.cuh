@@ -1,0 +1,349 @@
+// hx_tc_fused.cuh — momentum projection S0 = P0 C with P0 = normal(key, (n, n)) generated INSIDE the GEMM
+// (reference: moves/hamiltonian/hmc_walk.py:36 draws P0, :105 / the first kick consume it only through P0 @ C).
+//
+// The staged path (k_rng_planes + k_tc_gemm) writes the 4.3 GB operand planes of P0 to HBM and reads them back, and
+// its ALU-bound draw and tensor-bound GEMM fight for SMs from two streams.  Here P0 never leaves the SM:
+//
+//   * one CTA owns a 128-row x 512-column tile of S0 (ONE fp32 accumulator = all 512 TMEM columns), so a 128-row
+//     tile of P0 is shared by at most two CTAs (dim <= 1024) -- a CTA PAIR (cluster (2,1,1); pairs pack all 148 SMs,
+//     clusters of four strand 16 of them).  Each CTA of the pair draws HALF of every 128 x 64 K-block of P0
+//     (threefry2x32 + XLA erf_inv in registers), splits it into bf16 hi/lo and stores the 16-byte chunks, already in
+//     the 128-byte-swizzled K-major layout the UMMA descriptor expects, into its own shared memory AND into the
+//     peer's (st.shared::cluster, DSMEM), then arrives on the `fullA` mbarrier of both CTAs;
+//   * warp 0 streams the B operand (C^T planes, bf16 hi/lo) with TMA in units of 256 columns x 64 K;
+//   * warp 1 issues, per unit and K-block, the 12 tcgen05.mma of the three-product split (hi*hi, hi*lo, lo*hi) into
+//     the single accumulator; its commit frees the B stage locally and the A stage in BOTH CTAs (multicast commit);
+//   * the RNG warps drain TMEM at the end (one thread per output row, 128-byte runs).
+//
+// Counters: element (i, j) of the (n, n) draw is counter i * n + j of the partitionable threefry layout (one hash per
+// 32-bit word), so any row range reproduces the rows of the full draw (row shards, App. B of SURVEY.md).  The legacy
+// layout pairs element e with e + n^2/2 in one hash and stays on the staged path.
+#pragma once
+#include "hx_tc_gemm.cuh"
+#include "hx_rng.cuh"
+
+namespace hx {
+namespace tc {
+
+__constant__ uint32_t c_shr9mul = 1u << 23;      // hi32(bits * 2^23) = bits >> 9 as one IMAD.HI (constant bank: no strength reduction)
+
+// y0 ^ y1 of threefry2x32-20(key, (x0, x1)) with x0 = hi + ks0, x1 = lo + ks1 already injected.  70 instructions per hash:
+// 20 x (IADD/IMAD, SHF.L.W, LOP3) + 5 key injections folded into three-input adds.  (Routing rotations through the fma pipe as
+// IMAD.WIDE by 2^r with the OR folded into the round's LOP3 was measured on B200: every such rotation made the kernel slower.)
+__device__ __forceinline__ uint32_t tf_bits(uint32_t x0, uint32_t x1, uint32_t ks0, uint32_t ks1, uint32_t ks2) {
+#define HX_R(r) x0 += x1; x1 = __funnelshift_l(x1, x1, r) ^ x0;
+  HX_R(13) HX_R(15) HX_R(26) HX_R(6)
+  x0 += ks1; x1 += ks2 + 1u;
+  HX_R(17) HX_R(29) HX_R(16) HX_R(24)
+  x0 += ks2; x1 += ks0 + 2u;
+  HX_R(13) HX_R(15) HX_R(26) HX_R(6)
+  x0 += ks0; x1 += ks1 + 3u;
+  HX_R(17) HX_R(29) HX_R(16) HX_R(24)
+  x0 += ks1; x1 += ks2 + 4u;
+  HX_R(13) HX_R(15) HX_R(26) HX_R(6)
+  x0 += ks2; x1 += ks0 + 5u;
+#undef HX_R
+  return x0 ^ x1;
+}
+
+// out of line: used only where the low counter word wraps inside a group of eight elements
+__device__ __noinline__ uint32_t tf_bits_at(Key key, uint32_t ks2, uint64_t e) {
+  return tf_bits((uint32_t)(e >> 32) + key.k0, (uint32_t)e + key.k1, key.k0, key.k1, ks2);
+}
+
+// eight consecutive elements of jax.random.normal(key, (n, n), float32) starting at 64-bit counter e (partitionable layout).
+// Same arithmetic, operation by operation, as normal_at<float, false> (hx_rng.cuh) -- the staged path's draw -- with the
+// rare tail branch of erf_inv (|u| > 0.9966, 0.34 % of the draws) hoisted out of the straight-line code of the eight chains.
+__device__ __forceinline__ void normals8(Key key, uint32_t ks2, uint64_t e, float (&x)[8]) {
+  const uint32_t lo0 = (uint32_t)e, hi0 = (uint32_t)(e >> 32);
+  uint32_t b[8];
+  if (lo0 <= 0xFFFFFFF7u) {
+    const uint32_t a0 = hi0 + key.k0, a1 = lo0 + key.k1;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) b[t] = tf_bits(a0, a1 + (uint32_t)t, key.k0, key.k1, ks2);
+  } else {        // the low counter word wraps inside these eight elements (once per 2^32 draws)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) b[t] = tf_bits_at(key, ks2, e + (uint64_t)t);
+  }
+  float u[8], w[8];
+  bool tail = false;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    // (bits >> 9) | 0x3F800000 as one IMAD.HI: hi32(bits * 2^23) + 0x3F800000 (the two fields do not overlap)
+    const uint32_t m = __umulhi(b[t], c_shr9mul) + 0x3F800000u;
+    const float f = __uint_as_float(m) - 1.0f;
+    u[t] = fmaxf(-0.99999994f, fmaf(f, 2.0f, -0.99999994f));      // 2 f is exact: one rounding, like fmul_rn + fadd_rn
+    w[t] = -0.693147182f * fast_lg2(__fsub_rn(1.0f, __fmul_rn(u[t], u[t])));
+    tail = tail || !(w[t] < 5.0f);
+    const float ww = w[t] - 2.5f;
+    float p = 2.81022636e-08f;
+    p = fmaf(p, ww, 3.43273939e-07f);
+    p = fmaf(p, ww, -3.5233877e-06f);
+    p = fmaf(p, ww, -4.39150654e-06f);
+    p = fmaf(p, ww, 0.00021858087f);
+    p = fmaf(p, ww, -0.00125372503f);
+    p = fmaf(p, ww, -0.00417768164f);
+    p = fmaf(p, ww, 0.246640727f);
+    p = fmaf(p, ww, 1.50140941f);
+    x[t] = 1.41421354f * (p * u[t]);
+  }
+  if (tail) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (!(w[t] < 5.0f)) {
+        const float ww = fast_sqrt(w[t]) - 3.0f;
+        float p = -0.000200214257f;
+        p = fmaf(p, ww, 0.000100950558f);
+        p = fmaf(p, ww, 0.00134934322f);
+        p = fmaf(p, ww, -0.00367342844f);
+        p = fmaf(p, ww, 0.00573950773f);
+        p = fmaf(p, ww, -0.0076224613f);
+        p = fmaf(p, ww, 0.00943887047f);
+        p = fmaf(p, ww, 1.00167406f);
+        p = fmaf(p, ww, 2.83297682f);
+        x[t] = 1.41421354f * (p * u[t]);
+      }
+    }
+  }
+}
+
+// bf16 hi/lo split of eight values, packed: hi[0..3], lo[0..3] hold elements (2t, 2t+1) in the low / high half-words.
+// Identical to split_bf16 (hi = rn(x), lo = rn(x - hi)), two elements per F2FP.
+__device__ __forceinline__ void split8_bf16(const float (&x)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const __nv_bfloat162 hp = __floats2bfloat162_rn(x[2 * t], x[2 * t + 1]);
+    h[t] = *reinterpret_cast<const uint32_t*>(&hp);
+    const float h0 = __uint_as_float(h[t] << 16), h1 = __uint_as_float(h[t] & 0xFFFF0000u);
+    const __nv_bfloat162 lp = __floats2bfloat162_rn(x[2 * t] - h0, x[2 * t + 1] - h1);
+    l[t] = *reinterpret_cast<const uint32_t*>(&lp);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// 16-byte asynchronous store into the peer CTA's shared memory; its completion is counted, in bytes, on an mbarrier of the
+// peer (complete_tx).  No fence or release on the writer's side: a cluster-scope release costs MEMBAR.ALL.GPU per warp and
+// K-block (measured: the dominant stall of the first version of this kernel).
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, const uint4& v, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_mbar)
+               : "memory");
+}
+// commit of a single-CTA MMA sequence that arrives on the same barrier offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+struct FusedArgs {
+  Key key; const uint32_t* key_ptr;   // key by value, or device-resident (batch loops / graph replays)
+  int n;            // walkers per group: row length of the (n, n) draw and the K extent
+  int row0;         // global row index of local row 0 (row shard offset)
+  int rows;         // valid rows of this launch
+  int d;            // valid output columns
+  int num_kb;       // padded K / 64
+  int kb_per_slice; // split-K: grid.y slices of this many K-blocks; slice z stores to out + z * slice_stride
+  size_t slice_stride;
+  int units;        // 256-column units per CTA (1 or 2)
+  int rowsB_pad;    // plane stride of the B planes, in rows
+  float* out; int ldo;
+  int diag;         // diagnostics: 1 = no draw (A garbage), 2 = no MMA; results are garbage
+};
+
+struct FusedSmem {
+  static constexpr int A_PLANE = kBM * 128;            // 16 KB: 128 rows x 64 bf16
+  static constexpr int A_STAGE = 2 * A_PLANE;          // hi + lo
+  static constexpr int B_STAGE = 256 * 128;            // 32 KB: ONE plane (hi or lo) of 256 columns x 64 bf16
+  static constexpr int SA = 3, SB = 4;
+  static constexpr int BAR_OFF = SA * A_STAGE + SB * B_STAGE;       // 224 KB
+  static constexpr int BYTES = BAR_OFF + 256 + 1024;                // + barriers + alignment slack
+};
+
+// SHARE: the two CTAs of a (2,1,1) cluster own the two 512-column halves of one 128-row tile and each draws half of the
+// A tile for both; otherwise every CTA is on its own (dim <= 512).  NW = RNG warps per CTA.
+template <int NW, bool SHARE>
+__global__ void __launch_bounds__(64 + 32 * NW, 1)
+k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
+  using L = FusedSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stA = smem;
+  uint8_t* stB = smem + L::SA * L::A_STAGE;
+  uint64_t* bars = (uint64_t*)(smem + L::BAR_OFF);
+  uint64_t* fullA = bars;                          // [SA]  RNG warps (local arrivals + the peer's bytes) -> MMA
+  uint64_t* emptyA = bars + L::SA;                 // [SA]  MMA commits of the sharing CTAs -> RNG warps
+  uint64_t* fullB = bars + 2 * L::SA;              // [SB]  TMA -> MMA
+  uint64_t* emptyB = bars + 2 * L::SA + L::SB;     // [SB]  MMA commit -> TMA
+  uint64_t* tmem_full = bars + 2 * L::SA + 2 * L::SB;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * L::SA + 2 * L::SB + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = SHARE ? cluster_ctarank() : 0u;
+  const int tile = SHARE ? ((int)blockIdx.x >> 1) : (int)blockIdx.x;
+  const int m0 = tile * kBM;
+  const int n0 = SHARE ? (int)rank * 512 : 0;
+  const int kb0 = f.kb_per_slice ? (int)blockIdx.y * f.kb_per_slice : 0;
+  const int num_kb = f.kb_per_slice ? min(f.kb_per_slice, f.num_kb - kb0) : f.num_kb;
+  constexpr int NCTA = SHARE ? 2 : 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < L::SA; ++s) { mbar_init(&fullA[s], NW); mbar_init(&emptyA[s], NCTA); }
+    for (int s = 0; s < L::SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  if (SHARE) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int units = f.units;
+
+  if (warp == 0) {
+    // ---- B producer: C^T planes, one plane of 256 columns x 64 K per stage, in the order the MMA warp releases them:
+    //      per K-block and unit the hi plane (two products), then the lo plane (one product)
+    if (lane == 0) {
+      int it = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        for (int u = 0; u < units; ++u) {
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl, ++it) {
+            const int s = it % L::SB;
+            mbar_wait(&emptyB[s], ((uint32_t)(it / L::SB) & 1u) ^ 1u);
+            mbar_expect_tx(&fullB[s], (uint32_t)L::B_STAGE);
+            tma_load_2d(stB + s * L::B_STAGE, &tmB, &fullB[s], (kb0 + kb) * 64, pl * f.rowsB_pad + n0 + u * 256);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: per K-block and unit  hi*hi, lo*hi (B hi plane), hi*lo (B lo plane) into the single accumulator -----------
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+      int it = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int sa = kb % L::SA;
+        mbar_wait(&fullA[sa], (uint32_t)(kb / L::SA) & 1u);
+        fence_proxy_async();       // the A stage was written through the generic proxy (st.shared / st.async); the MMA reads it through the async proxy
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(stA + sa * L::A_STAGE), a_lo = a_hi + L::A_PLANE;
+        const uint64_t ad_hi = umma_desc_k128(a_hi), ad_lo = umma_desc_k128(a_lo);
+        for (int u = 0; u < units; ++u) {
+          const uint32_t dcol = tmem_base + (uint32_t)(u * 256);
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl, ++it) {
+            const int s = it % L::SB;
+            mbar_wait(&fullB[s], (uint32_t)(it / L::SB) & 1u);
+            tc_fence_after();
+            const uint64_t bd = umma_desc_k128(smem_u32(stB + s * L::B_STAGE));
+            if (f.diag != 2) {
+              if (pl == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(dcol, ad_hi + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(dcol, ad_lo + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(dcol, ad_hi + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
+              }
+            }
+            umma_commit(&emptyB[s]);
+          }
+        }
+        if (SHARE) umma_commit_mcast(&emptyA[sa], 3);
+        else umma_commit(&emptyA[sa]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ---- RNG warps: draw, split, store into the sharing CTAs' A stages -----------------------------------------------------
+    Key key = f.key;
+    if (f.key_ptr) { key.k0 = f.key_ptr[0]; key.k1 = f.key_ptr[1]; }
+    const uint32_t ks2 = key.k0 ^ key.k1 ^ 0x1BD11BDAu;
+    const int tid = (int)threadIdx.x - 64;                       // 0 .. 32 NW - 1
+    constexpr int ROWS_CTA = SHARE ? 64 : 128;                    // rows of the A tile this CTA draws
+    constexpr int ITEMS = ROWS_CTA * 8 / (32 * NW);               // (row, 8-element chunk) items per thread and K-block
+    static_assert(ITEMS >= 1 && ROWS_CTA * 8 % (32 * NW) == 0, "RNG warp count");
+    const int chunk = tid & 7;
+    const int rbase = (int)rank * ROWS_CTA + (tid >> 3);          // row of item 0; item i is 4 NW rows further
+    uint64_t ebase[ITEMS];
+    uint32_t soff[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int r = rbase + i * 4 * NW;
+      ebase[i] = (uint64_t)(uint32_t)(f.row0 + m0 + r) * (uint64_t)(uint32_t)f.n + (uint64_t)(kb0 * 64 + chunk * 8);
+      soff[i] = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));   // 128-byte swizzle: 16-byte chunk index ^ (row mod 8)
+    }
+    const uint32_t stA_local = smem_u32(stA);
+    const uint32_t stA_peer = SHARE ? mapa_shared(stA_local, rank ^ 1u) : 0u;
+    const uint32_t fullA_peer = SHARE ? mapa_shared(smem_u32(fullA), rank ^ 1u) : 0u;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int sa = kb % L::SA;
+      uint4 hi[ITEMS], lo[ITEMS];
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        hi[i] = lo[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (f.diag != 1) {
+          float x[8];
+          normals8(key, ks2, ebase[i] + (uint64_t)(kb * 64), x);
+          split8_bf16(x, hi[i], lo[i]);
+        }
+      }
+      mbar_wait(&emptyA[sa], ((uint32_t)(kb / L::SA) & 1u) ^ 1u);
+      const uint32_t so = (uint32_t)(sa * L::A_STAGE);
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        st_shared_v4(stA_local + so + soff[i], hi[i]);
+        st_shared_v4(stA_local + so + L::A_PLANE + soff[i], lo[i]);
+        if (SHARE) {
+          st_async_v4(stA_peer + so + soff[i], hi[i], fullA_peer + 8u * sa);
+          st_async_v4(stA_peer + so + L::A_PLANE + soff[i], lo[i], fullA_peer + 8u * sa);
+        }
+      }
+      fence_proxy_async();         // local generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
+      __syncwarp();
+      // one arrival per warp; in a pair it also announces the bytes the peer's warp of the same index stores into THIS CTA
+      if (lane == 0) {
+        if (SHARE) mbar_expect_tx(&fullA[sa], (uint32_t)(ITEMS * 32 * 32));
+        else mbar_arrive(&fullA[sa]);
+      }
+    }
+    // ---- epilogue: TMEM -> registers -> S0 (one thread per output row) ---------------------------------------------------------
+    mbar_wait_backoff(tmem_full, 0, 256);
+    tc_fence_after();
+    const int q = warp & 3, grp = (warp - 2) >> 2;               // TMEM lane quadrant of this warp; column-chunk group
+    const int row = m0 + 32 * q + lane;
+    const bool vec = (f.d & 3) == 0 && (f.ldo & 3) == 0;
+    float* out = f.out + (size_t)blockIdx.y * f.slice_stride;
+#pragma unroll 1
+    for (int cc = grp; cc < units * 8; cc += NW / 4) {
+      const int col0 = n0 + cc * 32;
+      if (col0 >= f.d) break;             // warp-uniform
+      float v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cc * 32), v);
+      if (row < f.rows) {
+        const int nval = min(32, f.d - col0);
+        store32(out + (size_t)row * f.ldo + col0, v, nval, vec && nval == 32);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncwarp();
+  tc_fence_before();
+  if (SHARE) cluster_sync_all(); else __syncthreads();      // the peer's stages and barriers stay alive until both CTAs are done
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace tc
+}  // namespace hx

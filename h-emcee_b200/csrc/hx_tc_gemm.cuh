@@ -90,6 +90,9 @@ struct GemmArgs {
   // KIND_F16 with EPI_KICKB / EPI_PROP: acc is divided by row_scale[row] * f16_scale(amax[unscale_idx]) before use
   int unscale_idx;
   int n_cover;       // pair kernel: padded N the grid covers (0: N); EPI_PROP covers two column blocks
+  int one_acc;       // single-CTA kernel, bf16 hi/lo: all three products into ONE accumulator in the order (hi hi, lo hi, hi lo) per
+                     // K-block -- the accumulation structure of the fused draw + projection kernel (hx_tc_fused.cuh), kept here
+                     // so that the two can be compared bit for bit (hx_ctx_set_tuning(18, 1))
 };
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -237,7 +240,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t tmem_b
     if (col0 >= g.N) break;           // warp-uniform
     float v[32];
     tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cc * 32), v);
-    if (g.nprod == 3) {
+    if (g.nprod == 3 && !g.one_acc) {
       float vc[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(BN + cc * 32), vc);
       if (KIND == KIND_F16F8) {
@@ -434,13 +437,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         } else {
         const int np = g.nprod;
 #pragma unroll 1
-        for (int p = 0; p < np; ++p) {
+        for (int p0 = 0; p0 < np; ++p0) {
+          const int p = g.one_acc ? (p0 == 0 ? 0 : 3 - p0) : p0;      // one accumulator: hi hi, lo hi, hi lo (the fused kernel's order)
           const uint64_t ad = umma_desc_k128(p == 2 ? a_lo : a_hi);
           const uint64_t bd = umma_desc_k128(p == 1 ? b_lo : b_hi);
 #pragma unroll
           for (int k = 0; k < KD::ROW_ELEMS / KD::UMMA_K; ++k) {   // 4 steps of 32 bytes inside the 128-byte swizzle row
-            const uint32_t acc = p == 0 ? ((kb | k) != 0 ? 1u : 0u) : ((kb | (p - 1) | k) != 0 ? 1u : 0u);
-            umma_issue<KIND>(tmem_base + (p == 0 ? 0u : (uint32_t)BN), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, acc);
+            const uint32_t acc = g.one_acc ? ((kb | p0 | k) != 0 ? 1u : 0u)
+                                           : (p == 0 ? ((kb | k) != 0 ? 1u : 0u) : ((kb | (p - 1) | k) != 0 ? 1u : 0u));
+            umma_issue<KIND>(tmem_base + ((p == 0 || g.one_acc) ? 0u : (uint32_t)BN), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, acc);
           }
         }
         }

@@ -25,6 +25,7 @@
 #include "hx_rng.cuh"
 #include "hx_common.cuh"
 #include "hx_tc_gemm.cuh"
+#include "hx_tc_fused.cuh"
 #include "hx_tc_walk.h"
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
@@ -680,11 +681,7 @@ static int launch_gemm(hx_ctx* ctx, const void* A, int rowsA_pad, const void* B,
   if (int e = make_tmap(ctx, &tmA, A, mapA_rows ? mapA_rows : 2ull * rowsA_pad, Kp, kBM, KIND)) return e;
   if (int e = make_tmap(ctx, &tmB, B, 2ull * rowsB_pad, Kp, BNT, KIND)) return e;
   g.Kp = Kp; g.rowsA_pad = rowsA_pad; g.rowsB_pad = rowsB_pad;
-  static bool attr_done = false;
-  if (!attr_done) {
-    HX_CUDA(cudaFuncSetAttribute(k_tc_gemm<BNT, EPI, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BNT>::BYTES));
-    attr_done = true;
-  }
+  if (int e = ensure_smem_attr(ctx, (const void*)k_tc_gemm<BNT, EPI, KIND>, SmemLayout<BNT>::BYTES)) return e;
   dim3 grid(((n_grid ? n_grid : g.N) + BNT - 1) / BNT, (g.M + kBM - 1) / kBM, slices);
   k_tc_gemm<BNT, EPI, KIND><<<grid, kThreads, SmemLayout<BNT>::BYTES, s>>>(tmA, tmB, g);
   HX_LAUNCH_CHECK("k_tc_gemm");
@@ -701,11 +698,7 @@ static int launch_gemm_pair(hx_ctx* ctx, const void* A, int rowsA_pad, const voi
   if (int e = make_tmap(ctx, &tmA, A, mapA_rows ? mapA_rows : 2ull * rowsA_pad, Kp, kBM, KIND)) return e;
   if (int e = make_tmap(ctx, &tmB, B, 2ull * rowsB_pad, Kp, 128, KIND)) return e;
   g.Kp = Kp; g.rowsA_pad = rowsA_pad; g.rowsB_pad = rowsB_pad; g.n_cover = n_grid;
-  static bool attr_done = false;
-  if (!attr_done) {
-    HX_CUDA(cudaFuncSetAttribute(k_tc_gemm_pair<EPI, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayoutPair::BYTES));
-    attr_done = true;
-  }
+  if (int e = ensure_smem_attr(ctx, (const void*)k_tc_gemm_pair<EPI, KIND>, SmemLayoutPair::BYTES)) return e;
   const int mt = (g.M + kBM - 1) / kBM;
   dim3 grid((((n_grid ? n_grid : g.N) + 255) / 256) * ((mt + 1) & ~1), 1, slices);      // 1-D: see the tile mapping in the kernel
   cudaLaunchConfig_t cfg;
@@ -727,12 +720,81 @@ static int launch_gemm_pair(hx_ctx* ctx, const void* A, int rowsA_pad, const voi
   return 0;
 }
 
+
 static inline int pad_to(int x, int m) { return ((x + m - 1) / m) * m; }
 static inline int grid_for(size_t n, int block) {
   size_t g = (n + block - 1) / block;
   if (g > 148 * 32) g = 148 * 32;
   if (g < 1) g = 1;
   return (int)g;
+}
+
+
+// ---- fused draw + projection (hx_tc_fused.cuh) --------------------------------------------------------------------------
+template <int NW, bool SHARE>
+static int launch_fused_t(hx_ctx* ctx, const CUtensorMap& tmB, const FusedArgs& f, int tiles, int slices, cudaStream_t s) {
+  auto kern = k_tc_proj_fused<NW, SHARE>;
+  if (int e = ensure_smem_attr(ctx, (const void*)kern, FusedSmem::BYTES)) return e;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(SHARE ? 2 * tiles : tiles, slices); cfg.blockDim = dim3(64 + 32 * NW);
+  cfg.dynamicSmemBytes = FusedSmem::BYTES; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = SHARE ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmB, f);
+  if (le != cudaSuccess) {
+    (void)cudaGetLastError();
+    return hx_fail((int)le, "launch k_tc_proj_fused<%d,%d> grid (%u,%u) smem %d failed: %s", NW, (int)SHARE, cfg.gridDim.x, cfg.gridDim.y,
+                   (int)FusedSmem::BYTES, cudaGetErrorString(le));
+  }
+  ctx->launches += 1;
+  return 0;
+}
+static bool fused_eligible(const hx_ctx* ctx, int impl, int nprod, int d) {
+  return ctx->proj_fused && impl == HX_RNG_PARTITIONABLE && nprod == 3 && ctx->precision != HX_PREC_F16F8 && d <= 1024 &&
+         ctx->proj_slices <= 1;
+}
+// split-K of the fused projection: a function of n ONLY (never of the row shard), so that any row sharding reproduces the
+// unsharded result bit for bit.  Two slices halve the wave-quantisation loss of one-CTA-per-SM tiles (c5: 256 pairs on 74
+// pair slots = 3.46 waves -> 6.92 half-length waves) and keep each slice's share of C^T (67 MB) resident in L2.
+static int fused_slices(const hx_ctx* ctx, int nkb) {
+  int s = ctx->fused_slices > 0 ? ctx->fused_slices : (nkb >= 64 ? 2 : 1);
+  if (s > nkb / 16) s = nkb / 16 > 0 ? nkb / 16 : 1;
+  return s;
+}
+// S0[rows, d] = normal(key, (n, n))[row0 : row0 + rows] @ C, C^T given as bf16 hi/lo planes [2, dAB, nK]
+static int launch_proj_fused(hx_ctx* ctx, const void* CT, int dAB, int nK, int n, int row0, int rows, int d, Key key,
+                             const uint32_t* key_ptr, float* S0, cudaStream_t s) {
+  CUtensorMap tmB;
+  if (int e = make_tmap(ctx, &tmB, CT, 2ull * dAB, nK, 256, KIND_BF16)) return e;
+  FusedArgs f;
+  memset(&f, 0, sizeof(f));
+  f.key = key; f.key_ptr = key_ptr; f.n = n; f.row0 = row0; f.rows = rows; f.d = d; f.num_kb = nK / 64;
+  f.rowsB_pad = dAB; f.out = S0; f.ldo = d; f.diag = ctx->fused_diag;
+  const bool share = d > 512;
+  f.units = share ? 2 : (d + 255) / 256;
+  const int tiles = (rows + kBM - 1) / kBM;
+  int slices = fused_slices(ctx, f.num_kb);
+  const int kbs = (f.num_kb + slices - 1) / slices;
+  slices = (f.num_kb + kbs - 1) / kbs;
+  void* pS0P = nullptr;
+  if (slices > 1) {
+    if (int e = ws_get(ctx, WS_TC_S0P, (size_t)slices * rows * d * sizeof(float), &pS0P)) return e;
+    f.out = (float*)pS0P; f.kb_per_slice = kbs; f.slice_stride = (size_t)rows * d;
+  }
+  const int nw = ctx->fused_nw == 8 ? 8 : 16;
+  int e;
+  if (share) e = nw == 8 ? launch_fused_t<8, true>(ctx, tmB, f, tiles, slices, s) : launch_fused_t<16, true>(ctx, tmB, f, tiles, slices, s);
+  else e = nw == 8 ? launch_fused_t<8, false>(ctx, tmB, f, tiles, slices, s) : launch_fused_t<16, false>(ctx, tmB, f, tiles, slices, s);
+  if (e) return e;
+  if (slices > 1) {
+    k_sum_slices_f<<<grid_for((size_t)rows * d, 256), 256, 0, s>>>((const float*)pS0P, slices, (size_t)rows * d, S0);
+    HX_LAUNCH_CHECK("k_sum_slices_f");
+    ctx->launches += 1;
+  }
+  return 0;
 }
 
 struct LeapArgs {
@@ -920,7 +982,9 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   const int nprod = (ctx->precision == HX_PREC_BF16) ? 1 : 3;   // momentum projection / Gram only
   // momentum projection from fp16 + e4m3 operands: explicit mode, and what AUTO picks (measured 0.25 ms per half-move faster at
   // c5 than bf16 hi/lo next to the concurrent draw, S0 within 1.7e-5 instead of 1.3e-5 of an f64 product)
-  const int f8 = (ctx->precision == HX_PREC_F16F8 || ctx->precision == HX_PREC_AUTO) ? 1 : 0;
+  // P0 drawn inside the projection GEMM (bf16 hi/lo operands, one accumulator); otherwise the staged draw + GEMM below
+  const bool fused = fused_eligible(ctx, impl, nprod, d);
+  const int f8 = (!fused && (ctx->precision == HX_PREC_F16F8 || ctx->precision == HX_PREC_AUTO)) ? 1 : 0;
   const int dB = pad_to(d, BN);            // rows of B-operand planes (N side)
   const int dK = pad_to(d, 64);            // K padding when dim is the reduction axis
   const int nK = pad_to(n, 64);            // K padding when the walker index is the reduction axis
@@ -962,7 +1026,9 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   if (int e = ws_get(ctx, WS_TC_MP, (size_t)2 * dB * dK * sizeof(float), &pBoP)) return e;
   if (int e = ws_get(ctx, WS_TC_PP, (size_t)2 * dB * dK * sizeof(float), &pPP)) return e;
   const size_t buf_elems = (size_t)2 * rA * nK;               // one draw buffer = [2 planes, rA, nK]
-  if (int e = ws_get(ctx, WS_TC_P0, 2 * buf_elems * sizeof(bf), &pP0)) return e;
+  pP0 = nullptr;
+  if (!fused)
+    if (int e = ws_get(ctx, WS_TC_P0, 2 * buf_elems * sizeof(bf), &pP0)) return e;
   if (int e = ws_get(ctx, WS_TC_QC, (size_t)2 * rQ * dK * sizeof(float), &pQC)) return e;
   if (int e = ws_get(ctx, WS_TC_QC2, (size_t)2 * (prop ? bRA : rA) * dK * sizeof(float), &pQC2)) return e;
   if (int e = ws_get(ctx, WS_TC_GP, (size_t)2 * (prop ? bRA : rA) * dK * sizeof(float), &pQsP)) return e;
@@ -980,19 +1046,25 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   const int chunk = chunk_rows(ctx, rA, NT);
   const int nchunks = (rows + chunk - 1) / chunk;
   bf* Pbuf[2] = {(bf*)pP0, (bf*)pP0 + buf_elems};
-  if (ctx->p0_base != pP0 || ctx->p0_elems != buf_elems) {    // workspace moved or reshaped: prefetched draws are gone
+  if (!fused && (ctx->p0_base != pP0 || ctx->p0_elems != buf_elems)) {    // workspace moved or reshaped: prefetched draws are gone
     ctx->job[0].valid = ctx->job[1].valid = 0;
     ctx->p0_base = pP0; ctx->p0_elems = buf_elems;
   }
   int cur = -1;
-  for (int b = 0; b < 2; ++b)
-    if (job_matches(ctx->job[b], f8, impl, n, row0, rows, key, key_ptr)) cur = b;
+  if (!fused)
+    for (int b = 0; b < 2; ++b)
+      if (job_matches(ctx->job[b], f8, impl, n, row0, rows, key, key_ptr)) cur = b;
   const bool prefetched = cur >= 0;
-  if (cur < 0) {
-    cur = ctx->job[0].valid ? (ctx->job[1].valid ? 0 : 1) : 0;
-    if (int e = job_launch(ctx, cur, Pbuf[cur], f8, impl, n, row0, rows, rA, nK, chunk, key, key_ptr, s)) return e;
+  if (fused) {
+    cur = 0;
+    next = nullptr;               // nothing to prefetch: the draw lives inside the projection kernel
+  } else {
+    if (cur < 0) {
+      cur = ctx->job[0].valid ? (ctx->job[1].valid ? 0 : 1) : 0;
+      if (int e = job_launch(ctx, cur, Pbuf[cur], f8, impl, n, row0, rows, rA, nK, chunk, key, key_ptr, s)) return e;
+    }
+    ctx->job[cur].valid = 0;       // consumed by this half-move
   }
-  ctx->job[cur].valid = 0;       // consumed by this half-move
 
   // hx_ctx_set_tuning(6, -2 / -1): queue the next half-move's draw already at the start of the complement statistics / of the
   // propagator basis run (a head start over the projection GEMM, at the price of slowing those latency-bound launches)
@@ -1166,7 +1238,11 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
     if (int e = job_launch(ctx, 1 - cur, Pbuf[1 - cur], f8, impl, n, next->row0, next->rows, rA, nK, chunk, next->key, next->key_ptr, s))
       return e;
   }
-  {
+  if (fused) {
+    if (int e = timing_begin(ctx, s)) return e;
+    if (int e = launch_proj_fused(ctx, pCT, dAB, nK, n, row0, rows, d, key, key_ptr, S0, s)) return e;
+    if (int e = timing_mark(ctx, s, HX_PH_LEAP)) return e;
+  } else {
     std::vector<cudaEvent_t>& evs = *ctx->ev_chunk[cur];
     if (int e = timing_begin(ctx, s)) return e;
     // optional split-K (hx_ctx_set_tuning(1, slices)): slices of K summed in fp32 in a fixed order.  Measured on B200
@@ -1193,6 +1269,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
       ga.M = rc; ga.N = d; ga.ldo = d;
       ga.out = slices > 1 ? (float*)pS0P : S0 + (size_t)r0 * d;
       ga.kb_per_slice = slices > 1 ? kbs : 0; ga.slice_stride = (size_t)rc * d;
+      ga.one_acc = (ctx->one_acc && !f8 && !pair && nprod == 3) ? 1 : 0;
       const uint64_t map_rows = (uint64_t)rA + pad_to(rc, kBM);
       const bf* Ac = Pbuf[cur] + (size_t)r0 * nK;
       if (f8) ga.scale_ptr = (const float*)pSc8;
@@ -1212,7 +1289,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
           return e2;
       }
     }
-    ga.kb_per_slice = 0; ga.slice_stride = 0;
+    ga.kb_per_slice = 0; ga.slice_stride = 0; ga.one_acc = 0;
     if (int e = timing_mark(ctx, s, HX_PH_LEAP)) return e;
   }
 
@@ -1314,6 +1391,21 @@ int microbench(hx_ctx* ctx, int mode, int n, int rows, int d, int reps, double* 
   ctx->p0_base = nullptr;
   HX_CUDA(cudaMemsetAsync(pCT, 0x3c, (size_t)2 * dAB * nK * sizeof(bf), s));     // finite bf16 / fp16 / e4m3 pattern
   HX_CUDA(cudaMemsetAsync(pSc8, 0x3c, 16, s));
+  if (mode == 3) {
+    Key key{1u, 2u};
+    cudaEvent_t e0, e1;
+    HX_CUDA(cudaEventCreate(&e0)); HX_CUDA(cudaEventCreate(&e1));
+    HX_CUDA(cudaEventRecord(e0, s));
+    for (int r = 0; r < reps; ++r)
+      if (int e = launch_proj_fused(ctx, pCT, dAB, nK, n, 0, rows, d, key, nullptr, (float*)pS0, s)) return e;
+    HX_CUDA(cudaEventRecord(e1, s));
+    HX_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    HX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    ms_out[0] = ms_out[1] = ms_out[2] = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+  }
   bf* Pbuf[2] = {(bf*)pP0, (bf*)pP0 + buf_elems};
   const int chunk = chunk_rows(ctx, rA, NT);
   const int gchunk = ((ctx->proj_pair && !ctx->pair_chunked) || (!ctx->proj_pair && ctx->proj_one_launch)) ? rA : chunk;        // pair kernel: one launch over all rows (steady state of a batch loop)

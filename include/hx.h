@@ -120,7 +120,7 @@ enum { HX_LEAP_AUTO = 0, HX_LEAP_STEPWISE = 1, HX_LEAP_PROPAGATOR = 2 };
 HX_API int hx_ctx_set_leapfrog_form(hx_ctx* ctx, int form);
 /* Diagnostics for the roofline discussion: wall time [ms] of `reps` repetitions of (mode 0) the momentum draw
  * of a rows x n shard alone, (1) its projection GEMM alone, (2) both running concurrently on two streams.  */
-HX_API int hx_tc_microbench(hx_ctx* ctx, int mode, int32_t n, int32_t rows, int32_t dim, int32_t reps, double* ms_out /*[3]: total,
+HX_API int hx_tc_microbench(hx_ctx* ctx, int mode /* 0 draw, 1 GEMM, 2 both, 3 fused draw + GEMM kernel */, int32_t n, int32_t rows, int32_t dim, int32_t reps, double* ms_out /*[3]: total,
                      GEMM stream, draw stream*/, void* stream);
 /* tuning knobs: what = 0 resident CTAs per SM of the momentum-draw kernel (default 4); what = 1 split-K slices of the
  * projection GEMM, summed in fp32 in a fixed order (default 1 = accumulate all of K = n inside the tensor core; measured:
@@ -142,7 +142,14 @@ HX_API int hx_tc_microbench(hx_ctx* ctx, int mode, int32_t n, int32_t rows, int3
  * error vs f64 1.1e-2 -> 7.7e-4 rms at c5 scale, same MMA rate) and bf16 hi/lo for the propagator form, 1 = fp16 for both,
  * 2 = bf16 for both;
  * what = 12: 0 = Gram and propagator-apply GEMMs by the single-CTA kernel instead of the CTA-pair kernel
- * (default 1: bit-identical, ~0.1 ms per half-move faster at c5; these launches do not overlap the draw)                       */
+ * (default 1: bit-identical, ~0.1 ms per half-move faster at c5; these launches do not overlap the draw);
+ * what = 15: 1 (default) = the momentum draw P0 = normal(key, (n, n)) (hmc_walk.py:36) is generated INSIDE the projection GEMM
+ * (hx_tc_fused.cuh: RNG warps write bf16 hi/lo operand tiles into the shared memory of a CTA pair, P0 never reaches HBM) when
+ * the problem is eligible (partitionable RNG layout, dim <= 1024, three-product modes), 0 = staged draw kernel + GEMM;
+ * what = 16: RNG warps per CTA of the fused kernel (8 or 16; 0 = default 16); what = 17: split-K slices of the fused kernel
+ * (0 = default: 2 from 4096 walkers per group, a function of n only so that row shards stay bit-identical); what = 18: 1 = the staged bf16 hi/lo
+ * projection accumulates its three products in ONE TMEM accumulator like the fused kernel (bit-for-bit comparison of the two);
+ * what = 19: fused-kernel diagnostics (1 = no draw, 2 = no MMA; garbage results)                                                  */
 HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value);
 /* which kernel the timing hooks bracketed last: 0 = fused SIMT half-move, 1 = tcgen05 projection GEMM */
 HX_API int hx_ctx_last_path(const hx_ctx* ctx);
