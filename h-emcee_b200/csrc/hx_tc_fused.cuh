@@ -2,22 +2,32 @@
 // (reference: moves/hamiltonian/hmc_walk.py:36 draws P0, :105 / the first kick consume it only through P0 @ C).
 //
 // The staged path (k_rng_planes + k_tc_gemm) writes the 4.3 GB operand planes of P0 to HBM and reads them back, and
-// its ALU-bound draw and tensor-bound GEMM fight for SMs from two streams.  Here P0 never leaves the SM:
+// its ALU-bound draw and tensor-bound GEMM run as two kernels on two streams.  Here P0 never leaves the SM:
 //
 //   * one CTA owns a 128-row x 512-column tile of S0 (ONE fp32 accumulator = all 512 TMEM columns), so a 128-row
 //     tile of P0 is shared by at most two CTAs (dim <= 1024) -- a CTA PAIR (cluster (2,1,1); pairs pack all 148 SMs,
 //     clusters of four strand 16 of them).  Each CTA of the pair draws HALF of every 128 x 64 K-block of P0
-//     (threefry2x32 + XLA erf_inv in registers), splits it into bf16 hi/lo and stores the 16-byte chunks, already in
-//     the 128-byte-swizzled K-major layout the UMMA descriptor expects, into its own shared memory AND into the
-//     peer's (st.shared::cluster, DSMEM), then arrives on the `fullA` mbarrier of both CTAs;
-//   * warp 0 streams the B operand (C^T planes, bf16 hi/lo) with TMA in units of 256 columns x 64 K;
-//   * warp 1 issues, per unit and K-block, the 12 tcgen05.mma of the three-product split (hi*hi, hi*lo, lo*hi) into
-//     the single accumulator; its commit frees the B stage locally and the A stage in BOTH CTAs (multicast commit);
-//   * the RNG warps drain TMEM at the end (one thread per output row, 128-byte runs).
+//     (threefry2x32 + XLA erf_inv in registers, work items of 4 rows x 64 K dealt round-robin over the RNG warps),
+//     splits it into bf16 hi/lo and stores the 16-byte chunks, already in the 128-byte-swizzled K-major layout the
+//     UMMA descriptor expects, into its own A stage; one lane then hands the item's 2 x 512 contiguous bytes to the
+//     TMA engine, which copies them into the peer's A stage (cp.async.bulk shared::cta -> shared::cluster) and counts
+//     the bytes on the peer's `fullA` mbarrier;
+//   * warp 0 streams the B operand (C^T planes, bf16 hi/lo) with TMA, one plane of 256 columns x 64 K per stage;
+//   * warp 1 issues, per 256-column unit and K-block, the 12 tcgen05.mma of the three-product split in the order
+//     hi*hi, lo*hi (B hi plane), hi*lo (B lo plane) into the single accumulator; its commits free the B stages locally
+//     and the A stage in BOTH CTAs (multicast commit);
+//   * the RNG warps drain TMEM at the end (one thread per output row, 128-byte runs);
+//   * split-K over grid.y (a function of n only): shorter waves, each slice's share of C^T stays in L2.
 //
 // Counters: element (i, j) of the (n, n) draw is counter i * n + j of the partitionable threefry layout (one hash per
 // 32-bit word), so any row range reproduces the rows of the full draw (row shards, App. B of SURVEY.md).  The legacy
 // layout pairs element e with e + n^2/2 in one hash and stays on the staged path.
+//
+// Measured on B200 (c5: 32768 x 32768 draw, dim 1000; scripts/fused_bench.py, profiles/r02_*): 5.0 ms alone at 1965 MHz
+// (staged draw + GEMM on two streams: 5.9), of which the draw arithmetic alone needs 3.5 ms (120 clk per warp and normal and
+// scheduler: 96 instructions, alu pipe (SHF / LOP3 of threefry, 2 clk each) and issue slots saturate together) and the
+// MMA + TMA side alone 3.4 ms (shared-memory bandwidth: 288 KB of operand reads + 192 KB of stage writes per K-block
+// and CTA at 128 B/clk).  The two sides are balanced to 3 %, which is why they couple (5.0 rather than 3.5).
 #pragma once
 #include "hx_tc_gemm.cuh"
 #include "hx_rng.cuh"
@@ -51,21 +61,25 @@ __device__ __noinline__ uint32_t tf_bits_at(Key key, uint32_t ks2, uint64_t e) {
   return tf_bits((uint32_t)(e >> 32) + key.k0, (uint32_t)e + key.k1, key.k0, key.k1, ks2);
 }
 
-// eight consecutive elements of jax.random.normal(key, (n, n), float32) starting at 64-bit counter e (partitionable layout).
-// Same arithmetic, operation by operation, as normal_at<float, false> (hx_rng.cuh) -- the staged path's draw -- with the
-// rare tail branch of erf_inv (|u| > 0.9966, 0.34 % of the draws) hoisted out of the straight-line code of the eight chains.
-__device__ __forceinline__ void normals8(Key key, uint32_t ks2, uint64_t e, float (&x)[8]) {
-  const uint32_t lo0 = (uint32_t)e, hi0 = (uint32_t)(e >> 32);
-  uint32_t b[8];
-  if (lo0 <= 0xFFFFFFF7u) {
-    const uint32_t a0 = hi0 + key.k0, a1 = lo0 + key.k1;
+// random bits of eight consecutive elements of the (n, n) draw starting at 64-bit counter e (partitionable layout): straight-line
+// fast path that assumes the low counter word does not wrap inside the group, and the fix-up for the group where it does
+// (once per 2^32 draws).  Kept apart so that the fast path has no branch and ptxas can interleave it with other work.
+__device__ __forceinline__ void bits8_fast(Key key, uint32_t ks2, uint64_t e, uint32_t (&b)[8]) {
+  const uint32_t a0 = (uint32_t)(e >> 32) + key.k0, a1 = (uint32_t)e + key.k1;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) b[t] = tf_bits(a0, a1 + (uint32_t)t, key.k0, key.k1, ks2);
-  } else {        // the low counter word wraps inside these eight elements (once per 2^32 draws)
+  for (int t = 0; t < 8; ++t) b[t] = tf_bits(a0, a1 + (uint32_t)t, key.k0, key.k1, ks2);
+}
+__device__ __forceinline__ void bits8_fix_wrap(Key key, uint32_t ks2, uint64_t e, uint32_t (&b)[8]) {
+  if ((uint32_t)e > 0xFFFFFFF7u) {
 #pragma unroll
     for (int t = 0; t < 8; ++t) b[t] = tf_bits_at(key, ks2, e + (uint64_t)t);
   }
-  float u[8], w[8];
+}
+
+// jax.random.normal(float32) values of eight random words.  Same arithmetic, operation by operation, as
+// normal_at<float, false> (hx_rng.cuh) -- the staged path's draw.  The central branch of XLA's erf_inv (w < 5) is evaluated
+// for all eight in straight-line code; the tail branch (|u| > 0.9966, 0.34 % of the draws) is a separate fix-up.
+__device__ __forceinline__ bool normals8_central(const uint32_t (&b)[8], float (&x)[8], float (&u)[8], float (&w)[8]) {
   bool tail = false;
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
@@ -87,22 +101,23 @@ __device__ __forceinline__ void normals8(Key key, uint32_t ks2, uint64_t e, floa
     p = fmaf(p, ww, 1.50140941f);
     x[t] = 1.41421354f * (p * u[t]);
   }
-  if (tail) {
+  return tail;
+}
+__device__ __forceinline__ void normals8_fix_tail(float (&x)[8], const float (&u)[8], const float (&w)[8]) {
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      if (!(w[t] < 5.0f)) {
-        const float ww = fast_sqrt(w[t]) - 3.0f;
-        float p = -0.000200214257f;
-        p = fmaf(p, ww, 0.000100950558f);
-        p = fmaf(p, ww, 0.00134934322f);
-        p = fmaf(p, ww, -0.00367342844f);
-        p = fmaf(p, ww, 0.00573950773f);
-        p = fmaf(p, ww, -0.0076224613f);
-        p = fmaf(p, ww, 0.00943887047f);
-        p = fmaf(p, ww, 1.00167406f);
-        p = fmaf(p, ww, 2.83297682f);
-        x[t] = 1.41421354f * (p * u[t]);
-      }
+  for (int t = 0; t < 8; ++t) {
+    if (!(w[t] < 5.0f)) {
+      const float ww = fast_sqrt(w[t]) - 3.0f;
+      float p = -0.000200214257f;
+      p = fmaf(p, ww, 0.000100950558f);
+      p = fmaf(p, ww, 0.00134934322f);
+      p = fmaf(p, ww, -0.00367342844f);
+      p = fmaf(p, ww, 0.00573950773f);
+      p = fmaf(p, ww, -0.0076224613f);
+      p = fmaf(p, ww, 0.00943887047f);
+      p = fmaf(p, ww, 1.00167406f);
+      p = fmaf(p, ww, 2.83297682f);
+      x[t] = 1.41421354f * (p * u[t]);
     }
   }
 }
@@ -123,15 +138,55 @@ __device__ __forceinline__ void split8_bf16(const float (&x)[8], uint4& hi, uint
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// try_wait with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint expires) instead of
+// returning after its default time slice -- the one-thread TMA / MMA warps and blocked RNG warps would otherwise spin on
+// try_wait + branch and take issue slots from the RNG warps of their scheduler (13 % of all issued instructions, measured)
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t ok, polls = 0;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+    if (!ok && ++polls > (1u << 22)) __trap();
+  } while (!ok);
+}
+// Wait of a warp that is AHEAD of its consumer (RNG warps on an `empty` barrier): non-blocking test + fixed sleep.  A parked
+// try_wait is woken by every barrier event of the CTA (item arrivals, bulk-copy completions, TMA completions, MMA commits:
+// ~60 per K-block), and with up to 28 RNG warps parked that was ~900 wake-ups x 6 instructions per K-block and CTA -- a third
+// of all issue slots (ncu: 37 % of the warp samples on NANOSLEEP.SYNCS).  A warp that runs ahead loses nothing by oversleeping.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t ok, polls = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(300);
+    if (++polls > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-// 16-byte asynchronous store into the peer CTA's shared memory; its completion is counted, in bytes, on an mbarrier of the
-// peer (complete_tx).  No fence or release on the writer's side: a cluster-scope release costs MEMBAR.ALL.GPU per warp and
-// K-block (measured: the dominant stall of the first version of this kernel).
-__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, const uint4& v, uint32_t cluster_mbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(cluster_addr),
-               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_mbar)
+// Bulk copy (TMA engine) of `bytes` contiguous bytes of this CTA's shared memory into the peer CTA's shared memory; its
+// completion is counted, in bytes, on an mbarrier of the peer (complete_tx).  No fence or release on the writer's side towards
+// the peer: a cluster-scope release costs MEMBAR.ALL.GPU per warp and K-block (the dominant stall of the first version of this
+// kernel), and per-thread st.async stores (second version) wake every parked waiter of the peer 64 times per item.
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t cluster_mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster_addr),
+               "r"(src_cta_addr), "r"(bytes), "r"(cluster_mbar)
                : "memory");
 }
 // commit of a single-CTA MMA sequence that arrives on the same barrier offset in every CTA of `mask`
@@ -154,13 +209,18 @@ struct FusedArgs {
   int rowsB_pad;    // plane stride of the B planes, in rows
   float* out; int ldo;
   int diag;         // diagnostics: 1 = no draw (A garbage), 2 = no MMA; results are garbage
+  int relaxed_wait; // RNG warps poll their `empty` barrier with test_wait + nanosleep instead of a parked try_wait
 };
 
+#ifndef HX_FUSED_SA
+#define HX_FUSED_SA 3
+#define HX_FUSED_SB 4
+#endif
 struct FusedSmem {
   static constexpr int A_PLANE = kBM * 128;            // 16 KB: 128 rows x 64 bf16
   static constexpr int A_STAGE = 2 * A_PLANE;          // hi + lo
   static constexpr int B_STAGE = 256 * 128;            // 32 KB: ONE plane (hi or lo) of 256 columns x 64 bf16
-  static constexpr int SA = 3, SB = 4;
+  static constexpr int SA = HX_FUSED_SA, SB = HX_FUSED_SB;
   static constexpr int BAR_OFF = SA * A_STAGE + SB * B_STAGE;       // 224 KB
   static constexpr int BYTES = BAR_OFF + 256 + 1024;                // + barriers + alignment slack
 };
@@ -194,7 +254,7 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmB);
-    for (int s = 0; s < L::SA; ++s) { mbar_init(&fullA[s], NW); mbar_init(&emptyA[s], NCTA); }
+    for (int s = 0; s < L::SA; ++s) { mbar_init(&fullA[s], (SHARE ? 64 : 128) / 4); mbar_init(&emptyA[s], NCTA); }
     for (int s = 0; s < L::SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
@@ -217,7 +277,7 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
 #pragma unroll
           for (int pl = 0; pl < 2; ++pl, ++it) {
             const int s = it % L::SB;
-            mbar_wait(&emptyB[s], ((uint32_t)(it / L::SB) & 1u) ^ 1u);
+            mbar_wait_parked(&emptyB[s], ((uint32_t)(it / L::SB) & 1u) ^ 1u);
             mbar_expect_tx(&fullB[s], (uint32_t)L::B_STAGE);
             tma_load_2d(stB + s * L::B_STAGE, &tmB, &fullB[s], (kb0 + kb) * 64, pl * f.rowsB_pad + n0 + u * 256);
           }
@@ -231,7 +291,7 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
       int it = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int sa = kb % L::SA;
-        mbar_wait(&fullA[sa], (uint32_t)(kb / L::SA) & 1u);
+        mbar_wait_parked(&fullA[sa], (uint32_t)(kb / L::SA) & 1u);
         fence_proxy_async();       // the A stage was written through the generic proxy (st.shared / st.async); the MMA reads it through the async proxy
         tc_fence_after();
         const uint32_t a_hi = smem_u32(stA + sa * L::A_STAGE), a_lo = a_hi + L::A_PLANE;
@@ -241,7 +301,7 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
 #pragma unroll
           for (int pl = 0; pl < 2; ++pl, ++it) {
             const int s = it % L::SB;
-            mbar_wait(&fullB[s], (uint32_t)(it / L::SB) & 1u);
+            mbar_wait_parked(&fullB[s], (uint32_t)(it / L::SB) & 1u);
             tc_fence_after();
             const uint64_t bd = umma_desc_k128(smem_u32(stB + s * L::B_STAGE));
             if (f.diag != 2) {
@@ -265,55 +325,69 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
     }
   } else {
     // ---- RNG warps: draw, split, store into the sharing CTAs' A stages -----------------------------------------------------
+    // Work item = 4 rows x 64 K of one K-block (32 lanes x 8 consecutive elements); the RG items of a K-block and the K-blocks
+    // themselves are dealt round-robin over the NW warps, so NW need not divide the tile and neighbouring warps work on
+    // neighbouring K-blocks (at most NW / RG + 1 apart: inside the three-stage A ring).
     Key key = f.key;
     if (f.key_ptr) { key.k0 = f.key_ptr[0]; key.k1 = f.key_ptr[1]; }
     const uint32_t ks2 = key.k0 ^ key.k1 ^ 0x1BD11BDAu;
-    const int tid = (int)threadIdx.x - 64;                       // 0 .. 32 NW - 1
     constexpr int ROWS_CTA = SHARE ? 64 : 128;                    // rows of the A tile this CTA draws
-    constexpr int ITEMS = ROWS_CTA * 8 / (32 * NW);               // (row, 8-element chunk) items per thread and K-block
-    static_assert(ITEMS >= 1 && ROWS_CTA * 8 % (32 * NW) == 0, "RNG warp count");
-    const int chunk = tid & 7;
-    const int rbase = (int)rank * ROWS_CTA + (tid >> 3);          // row of item 0; item i is 4 NW rows further
-    uint64_t ebase[ITEMS];
-    uint32_t soff[ITEMS];
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      const int r = rbase + i * 4 * NW;
-      ebase[i] = (uint64_t)(uint32_t)(f.row0 + m0 + r) * (uint64_t)(uint32_t)f.n + (uint64_t)(kb0 * 64 + chunk * 8);
-      soff[i] = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));   // 128-byte swizzle: 16-byte chunk index ^ (row mod 8)
-    }
+    constexpr int RG = ROWS_CTA / 4;                              // items per K-block
+    const int wr = warp - 2;                                      // 0 .. NW - 1
+    const int chunk = lane & 7, rsub = lane >> 3;
     const uint32_t stA_local = smem_u32(stA);
     const uint32_t stA_peer = SHARE ? mapa_shared(stA_local, rank ^ 1u) : 0u;
     const uint32_t fullA_peer = SHARE ? mapa_shared(smem_u32(fullA), rank ^ 1u) : 0u;
-    for (int kb = 0; kb < num_kb; ++kb) {
+    const uint64_t row_stride = (uint64_t)(uint32_t)f.n;
+    const uint64_t e00 = (uint64_t)(uint32_t)(f.row0 + m0 + (int)rank * ROWS_CTA + rsub) * row_stride + (uint64_t)(kb0 * 64 + chunk * 8);
+    const int nitems = num_kb * RG;
+    // software pipeline: the hash of item g + NW (alu pipe: SHF / LOP3) is issued in the same straight-line block as the
+    // erf_inv polynomial and the operand split of item g (fma pipe), so that each warp keeps both pipes busy by itself
+    uint32_t bcur[8];
+    {
+      const int kb = wr / RG, rg = wr - kb * RG;
+      const uint64_t e = e00 + (uint64_t)(4 * rg) * row_stride + (uint64_t)(kb * 64);
+      bits8_fast(key, ks2, e, bcur);
+      bits8_fix_wrap(key, ks2, e, bcur);
+    }
+    for (int g = wr; g < nitems; g += NW) {
+      const int kb = g / RG, rg = g - kb * RG;
       const int sa = kb % L::SA;
-      uint4 hi[ITEMS], lo[ITEMS];
+      const int r = (int)rank * ROWS_CTA + 4 * rg + rsub;         // row inside the 128-row tile
+      uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+      if (f.diag != 1) {
+        // (the item after the last one is hashed too and dropped: no branch inside the straight-line block)
+        uint32_t bnext[8];
+        const int gn = g + NW;
+        const int kbn = gn / RG, rgn = gn - kbn * RG;
+        const uint64_t en = e00 + (uint64_t)(4 * rgn) * row_stride + (uint64_t)(kbn * 64);
+        float x[8], u[8], w[8];
+        bits8_fast(key, ks2, en, bnext);
+        const bool tail = normals8_central(bcur, x, u, w);
+        if (tail) normals8_fix_tail(x, u, w);
+        bits8_fix_wrap(key, ks2, en, bnext);
+        split8_bf16(x, hi, lo);
 #pragma unroll
-      for (int i = 0; i < ITEMS; ++i) {
-        hi[i] = lo[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (f.diag != 1) {
-          float x[8];
-          normals8(key, ks2, ebase[i] + (uint64_t)(kb * 64), x);
-          split8_bf16(x, hi[i], lo[i]);
-        }
+        for (int t = 0; t < 8; ++t) bcur[t] = bnext[t];
       }
-      mbar_wait(&emptyA[sa], ((uint32_t)(kb / L::SA) & 1u) ^ 1u);
-      const uint32_t so = (uint32_t)(sa * L::A_STAGE);
-#pragma unroll
-      for (int i = 0; i < ITEMS; ++i) {
-        st_shared_v4(stA_local + so + soff[i], hi[i]);
-        st_shared_v4(stA_local + so + L::A_PLANE + soff[i], lo[i]);
-        if (SHARE) {
-          st_async_v4(stA_peer + so + soff[i], hi[i], fullA_peer + 8u * sa);
-          st_async_v4(stA_peer + so + L::A_PLANE + soff[i], lo[i], fullA_peer + 8u * sa);
-        }
-      }
-      fence_proxy_async();         // local generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
+      if (f.relaxed_wait) mbar_wait_relaxed(&emptyA[sa], ((uint32_t)(kb / L::SA) & 1u) ^ 1u);
+      else mbar_wait_parked(&emptyA[sa], ((uint32_t)(kb / L::SA) & 1u) ^ 1u);
+      const uint32_t so = (uint32_t)(sa * L::A_STAGE) + (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));   // 128-byte swizzle
+      st_shared_v4(stA_local + so, hi);
+      st_shared_v4(stA_local + so + L::A_PLANE, lo);
+      fence_proxy_async();         // generic-proxy stores -> visible to the async proxy (the tensor core's operand reads, the bulk copy)
       __syncwarp();
-      // one arrival per warp; in a pair it also announces the bytes the peer's warp of the same index stores into THIS CTA
+      // one arrival per item.  In a pair the item's 4 rows x 128 bytes per plane (contiguous in the swizzled layout) are also
+      // copied into the peer's stage by the TMA engine, and the arrival announces the 1 KB the peer copies into THIS CTA
       if (lane == 0) {
-        if (SHARE) mbar_expect_tx(&fullA[sa], (uint32_t)(ITEMS * 32 * 32));
-        else mbar_arrive(&fullA[sa]);
+        if (SHARE) {
+          const uint32_t io = (uint32_t)(sa * L::A_STAGE) + (uint32_t)(((int)rank * ROWS_CTA + 4 * rg) * 128);
+          bulk_copy_to_peer(stA_peer + io, stA_local + io, 512u, fullA_peer + 8u * sa);
+          bulk_copy_to_peer(stA_peer + io + L::A_PLANE, stA_local + io + L::A_PLANE, 512u, fullA_peer + 8u * sa);
+          mbar_expect_tx(&fullA[sa], 1024u);
+        } else {
+          mbar_arrive(&fullA[sa]);
+        }
       }
     }
     // ---- epilogue: TMEM -> registers -> S0 (one thread per output row) ---------------------------------------------------------
@@ -324,7 +398,7 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
     const bool vec = (f.d & 3) == 0 && (f.ldo & 3) == 0;
     float* out = f.out + (size_t)blockIdx.y * f.slice_stride;
 #pragma unroll 1
-    for (int cc = grp; cc < units * 8; cc += NW / 4) {
+    for (int cc = grp; cc < units * 8; cc += (NW + 3) / 4) {
       const int col0 = n0 + cc * 32;
       if (col0 >= f.d) break;             // warp-uniform
       float v[32];

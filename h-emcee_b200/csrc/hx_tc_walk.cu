@@ -772,7 +772,7 @@ static int launch_proj_fused(hx_ctx* ctx, const void* CT, int dAB, int nK, int n
   FusedArgs f;
   memset(&f, 0, sizeof(f));
   f.key = key; f.key_ptr = key_ptr; f.n = n; f.row0 = row0; f.rows = rows; f.d = d; f.num_kb = nK / 64;
-  f.rowsB_pad = dAB; f.out = S0; f.ldo = d; f.diag = ctx->fused_diag;
+  f.rowsB_pad = dAB; f.out = S0; f.ldo = d; f.diag = ctx->fused_diag; f.relaxed_wait = ctx->fused_relaxed;
   const bool share = d > 512;
   f.units = share ? 2 : (d + 255) / 256;
   const int tiles = (rows + kBM - 1) / kBM;
@@ -784,10 +784,15 @@ static int launch_proj_fused(hx_ctx* ctx, const void* CT, int dAB, int nK, int n
     if (int e = ws_get(ctx, WS_TC_S0P, (size_t)slices * rows * d * sizeof(float), &pS0P)) return e;
     f.out = (float*)pS0P; f.kb_per_slice = kbs; f.slice_stride = (size_t)rows * d;
   }
-  const int nw = ctx->fused_nw == 8 ? 8 : 16;
+  const int nw = ctx->fused_nw > 0 ? ctx->fused_nw : 28;      // measured in the c5 step: 28 >= 20 > 16 warps (17.0-17.4 / 17.3-17.5 / 17.4-17.6 ms per iteration)
   int e;
-  if (share) e = nw == 8 ? launch_fused_t<8, true>(ctx, tmB, f, tiles, slices, s) : launch_fused_t<16, true>(ctx, tmB, f, tiles, slices, s);
-  else e = nw == 8 ? launch_fused_t<8, false>(ctx, tmB, f, tiles, slices, s) : launch_fused_t<16, false>(ctx, tmB, f, tiles, slices, s);
+#define HX_FUSED_NW(NWV) \
+  case NWV: e = share ? launch_fused_t<NWV, true>(ctx, tmB, f, tiles, slices, s) : launch_fused_t<NWV, false>(ctx, tmB, f, tiles, slices, s); break;
+  switch (nw) {
+    HX_FUSED_NW(8) HX_FUSED_NW(16) HX_FUSED_NW(20) HX_FUSED_NW(24) HX_FUSED_NW(28)
+    default: return hx_fail(HX_E_UNSUPPORTED, "fused projection: %d RNG warps per CTA is not instantiated (8, 16, 20, 24, 28)", nw);
+  }
+#undef HX_FUSED_NW
   if (e) return e;
   if (slices > 1) {
     k_sum_slices_f<<<grid_for((size_t)rows * d, 256), 256, 0, s>>>((const float*)pS0P, slices, (size_t)rows * d, S0);

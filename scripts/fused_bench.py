@@ -6,6 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "h-emcee_b200")]
 import hemcee_b200 as hx
 from hemcee_b200 import _lib, _rt
+if os.environ.get("HX_LIB"):
+    _lib.LIB_PATH = os.environ["HX_LIB"]      # diagnostic builds (e.g. other pipeline depths)
 dev = torch.device("cuda", 0); torch.cuda.set_device(0)
 lib = _lib.load(); ctx = _rt.ctx(dev)
 n = int(os.environ.get("N", 32768)); rows = int(os.environ.get("ROWS", n)); d = int(os.environ.get("D", 1000))
@@ -17,8 +19,8 @@ def run(mode, label):
     _lib.check(lib.hx_tc_microbench(ctx, mode, n, rows, d, 2, ms, st))
     _lib.check(lib.hx_tc_microbench(ctx, mode, n, rows, d, reps, ms, st))
     print(f"{label:50s} {ms[0] / reps:8.3f} ms/rep", flush=True)
-NWS = [int(v) for v in os.environ.get("NWS", "16,8").split(",")]
-MASKS = [int(v, 0) for v in os.environ.get("SLICES", "0,1,4").split(",")]
+NWS = [int(v) for v in os.environ.get("NWS", "28,24,20,16").split(",")]
+MASKS = [int(v, 0) for v in os.environ.get("SLICES", "0").split(",")]
 DIAGS = [int(v) for v in os.environ.get("DIAGS", "0,1,2").split(",")]
 NAMES = {0: "", 1: " no draw (MMA + TMA only)", 2: " no MMA (draw + TMA only)", 3: " draw arithmetic only", 4: " draw + local stores only"}
 for nw in NWS:

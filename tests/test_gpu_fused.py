@@ -42,7 +42,7 @@ SHAPES = [(256, 200), (640, 300), (384, 512), (384, 600), (1000, 1000), (200, 72
 
 
 @pytest.mark.parametrize("n,d", SHAPES)
-@pytest.mark.parametrize("nw", [16, 8])
+@pytest.mark.parametrize("nw", [28, 24, 20, 16, 8])
 def test_fused_equals_staged_one_accumulator(hx, knobs, n, d, nw):
     hx.config.update("precision", "bf16x3")
     hx.config.update("leapfrog_form", "stepwise")
