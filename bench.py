@@ -17,11 +17,18 @@ exactly what the reference computes) on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
+import os
+import sys
+
+if "reference" in sys.argv[1:]:
+    # the reference arm is a host-BLAS workload: `torch.distributed.run` exports OMP_NUM_THREADS=1 for nproc > 1, which would
+    # silently run it single-threaded (3x slower, measured in round 1).  Must happen before NumPy loads its BLAS.
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import argparse
 import json
-import os
 import subprocess
-import sys
 import threading
 import time
 
@@ -40,6 +47,10 @@ WORKLOADS = {
     "c3a": dict(target="rosenbrock", d=2, kappa=0, W=8192, L=10, eps=0.01, x64=False, move="walk"),
     "c3": dict(target="rosenbrock", d=50, kappa=0, W=8192, L=10, eps=0.01, x64=False, move="walk"),
     "c4": dict(target="funnel", d=25, kappa=0, W=16384, L=10, eps=0.05, x64=False, move="walk"),
+    # c3 as BASELINE.json states it: "with affine-invariant step-size/trajectory-length tuning" -- run_mcmc with the step-size
+    # heuristic, dual averaging and ChEES on (step_size = 0.01 as docs/tutorials/adaptation.ipynb cell 5); see bench_adaptive()
+    "c3ad": dict(target="rosenbrock", d=50, kappa=0, W=8192, L=10, eps=0.01, x64=False, move="walk", adaptive=True),
+    "c3aad": dict(target="rosenbrock", d=2, kappa=0, W=8192, L=10, eps=0.01, x64=False, move="walk", adaptive=True),
     # mid-size probes of the precision policy (not BASELINE configs)
     "m4": dict(target="gauss", d=128, kappa=1e3, W=2048, L=10, eps=0.1, x64=False, move="walk"),
     "m5": dict(target="gauss", d=64, kappa=1e3, W=8192, L=10, eps=0.1, x64=False, move="walk"),
@@ -49,13 +60,18 @@ WORKLOADS = {
     "m3": dict(target="gauss", d=512, kappa=1e3, W=16384, L=10, eps=0.1, x64=False, move="walk"),
     "c5": dict(target="gauss", d=1000, kappa=1e4, W=65536, L=10, eps=0.1, x64=False, move="walk"),
 }
-CPU_SAMPLE_W = {"m4": 1024, "m5": 1024, "m6": 1024, "m1": 1024, "m2": 1024, "m3": 1024, "c3a": 1024, "c1": 32, "c2": 1024, "c2s": 1024, "c3": 1024, "c4": 2048, "c5": 4096}
+CPU_SAMPLE_W = {"c3ad": 1024, "c3aad": 1024, "m4": 1024, "m5": 1024, "m6": 1024, "m1": 1024, "m2": 1024, "m3": 1024, "c3a": 1024, "c1": 32, "c2": 1024, "c2s": 1024, "c3": 1024, "c4": 2048, "c5": 4096}
 
 
-def make_cov(d, kappa, seed=1):
-    """Sigma = Q diag(0.1 * linspace(1, kappa, d)) Q^T  (reference src/hemcee/tests/distribution.py:92-96)."""
-    rng = np.random.default_rng(seed)
-    Q, _ = np.linalg.qr(rng.standard_normal((d, d)))
+def make_cov(d, kappa, H=None):
+    """Sigma = Q diag(0.1 * linspace(1, kappa, d)) Q^T with Q = qr(normal(PRNGKey(1), (d, d)))  (reference
+    src/hemcee/tests/distribution.py:92-96).  H = the (d, d) float64 normal draw; by default it is drawn with
+    the product's device RNG (bit-compatible with jax.random), the CPU reference arm passes the oracle's draw of the same key."""
+    if H is None:
+        import torch
+        import hemcee_b200 as hx
+        H = hx.random.normal(hx.random.PRNGKey(1), (d, d), torch.float64).cpu().numpy()      # 64-bit draws (the reference's tests run x64)
+    Q, _ = np.linalg.qr(np.asarray(H, dtype=np.float64))
     eig = 0.1 * np.linspace(1.0, kappa, d)
     cov = (Q * eig) @ Q.T
     prec = (Q / eig) @ Q.T
@@ -72,7 +88,7 @@ def cpu_reference(wl, steps, warmup, budget_s=None):
     d, L, eps = cfg["d"], cfg["L"], cfg["eps"]
     dt = np.float64 if cfg["x64"] else np.float32
     if cfg["target"] == "gauss":
-        cov, _ = make_cov(d, cfg["kappa"])
+        cov, _ = make_cov(d, cfg["kappa"], H=R.normal(R.PRNGKey(1), (d, d), np.float64))
         lp, grad = OT.make_gaussian(cov, np.zeros(d))
     elif cfg["target"] == "rosenbrock":
         lp, grad = OT.make_rosenbrock()
@@ -105,6 +121,57 @@ def cpu_reference(wl, steps, warmup, budget_s=None):
               f"{'f64' if cfg['x64'] else 'f32'}); the reference's cost per walker-step grows ~linearly with the "
               f"walker count, so this sample flatters the CPU")
     return dict(value=value, unit="walker-steps/s", cores=os.cpu_count(), kind="port", sample=sample), el / max(done, 1)
+
+
+def bench_adaptive(args, cfg, conf):
+    """c3 with DA + ChEES tuning: one `run_mcmc` = step-size heuristic + `--warmup-iters` adaptive warm-up iterations (adapter
+    state resident on the device: hx_run_warmup) + `--steps` main iterations with the tuned (step, L).  A step of the main phase
+    costs W * L_found leapfrog walker-steps; the warm-up's L changes every half-move, so its throughput is reported in
+    iterations/s with the trajectory lengths it ended on."""
+    import torch
+    import hemcee_b200 as hx
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    hx.config.update("enable_x64", cfg["x64"])
+    W, d = cfg["W"], cfg["d"]
+    tgt = hx.targets.Rosenbrock(d)
+    k_init, k_run = hx.random.split(hx.random.PRNGKey(0), 2)
+    x0 = (hx.random.normal(k_init, (W, d), torch.float32) * 0.3 + 1.0).cpu().pin_memory()
+    Wm, K = args.warmup_iters, args.steps
+
+    def one():
+        s = hx.HamiltonianEnsembleSampler(W, d, tgt, step_size=cfg["eps"], move=hx.hmc_walk_move, verbose=False, store="thinned")
+        t0 = time.perf_counter()
+        out = s.run_mcmc(k_run, x0, K, warmup=Wm)
+        torch.cuda.synchronize(dev)
+        return s, out, time.perf_counter() - t0
+    one()                                   # untimed: workspaces, pinned buffers, graph capture
+    clocks = ClockSampler(0, args.clock_period)
+    if args.clock_period > 0:
+        clocks.start()
+    clocks.mark_begin()
+    s, out, el = one()
+    clocks.mark_end()
+    clk = clocks.stop()
+    step, Lf = float(s.found[0]), int(s.found[1])
+    tm = s.timings
+    main_ws = W * Lf * K / tm["main_s"]
+    line = dict(metric="leapfrog_walker_steps_per_sec", value=main_ws, unit="walker-steps/s", n_gpus=1, steps=K, warmup=Wm,
+                ms_per_step=tm["main_s"] * 1e3 / K, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
+                data="synthetic", config=dict(conf, adaptation="find_reasonable_step_size + dual averaging + ChEES (defaults)",
+                                              warmup_iterations=Wm, main_iterations=K),
+                roofline=None, cpu_baseline=None, clocks=clk,
+                e2e=dict(value=W * Lf * K / tm["main_s"], unit="walker-steps/s", h2d_bytes_per_step=int(W * d * 4 / max(K, 1)),
+                         d2h_bytes_per_step=int(W * d * 4 + W * 4), seconds=el,
+                         api="HamiltonianEnsembleSampler.run_mcmc(store='thinned') with adapt_* defaults (host initial_state -> host chain)"),
+                gpu_launches=None,
+                adaptive=dict(initial_step=float(s.step_size), found_step=step, found_L=Lf,
+                              warmup_iterations_per_s=Wm / tm["warmup_s"], warmup_ms_per_iteration=tm["warmup_s"] * 1e3 / max(Wm, 1),
+                              initial_step_size_s=tm["initial_step_size_s"], main_ms_per_iteration=tm["main_s"] * 1e3 / K,
+                              acceptance_rate_main=float(np.mean(s.diagnostics_main["acceptance_rate"])),
+                              note="value = main phase with the tuned (step, L); the adaptive warm-up changes L every half-move, so "
+                                   "it is reported in iterations/s"))
+    print(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -192,6 +259,11 @@ class ClockSampler:
                     samples=len(rows), power_w_max=max((r[2] for r in rows), default=None))
 
 
+# DRAM traffic of the fused draw + projection of one c5 half-move (ncu --set full, profiles/r02_c5_fused_ncu_summary.txt)
+FUSED_TRAFFIC_BYTES = None
+FUSED_TRAFFIC_SOURCE = "profiles/r02_c5_fused_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of k_tc_proj_fused + k_sum_slices_f)"
+
+
 def algorithmic_flops_half_move(rows, n, d, L, target):
     """minimal (projected-form) flops of one half-move over `rows` walkers."""
     f = 2.0 * rows * n * d + (L + 1) * 2.0 * rows * d * d
@@ -218,6 +290,7 @@ def main():
     ap.add_argument("--tune", action="append", default=[], help="hx_ctx_set_tuning knob as what=value (diagnostics)")
     ap.add_argument("--clock-period", type=float, default=0.01, help="NVML sampling period in s (0 = no clock sampling)")
     ap.add_argument("--ess-iters", type=int, default=192, help="iterations of the ESS/s leg (0 = skip)")
+    ap.add_argument("--warmup-iters", type=int, default=500, help="adaptive workloads (c3ad): warm-up iterations with DA + ChEES")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -233,6 +306,16 @@ def main():
         if rank != 0:
             return
         cb, per_iter = cpu_reference(args.workload, args.steps, max(args.warmup, 0), budget_s=150.0)   # bounded: a few minutes at most
+        Ws = min(cfg["W"], CPU_SAMPLE_W[args.workload])
+        if Ws != cfg["W"]:
+            # the line describes what RAN: the bounded sample, with the full-size cost stated as an extrapolation
+            conf = dict(conf, walkers=Ws, full_size_walkers=cfg["W"],
+                        workload=conf["workload"] + f" -- CPU arm run on a {Ws}-walker sample",
+                        extrapolated_full_size=dict(
+                            walker_steps_per_sec=cb["value"] * Ws / cfg["W"],
+                            how="dense reference form: 4 (L + 1) n^2 d flops per half-move, i.e. cost per walker-step grows linearly with "
+                                "the walkers per group n; value scaled by sample walkers / full walkers (an upper bound for the CPU: the "
+                                "n x n momentum of the full size, 4 GiB in f32, no longer fits any cache)"))
         line = dict(impl="reference", metric="leapfrog_walker_steps_per_sec", value=cb["value"], unit="walker-steps/s",
                     n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=per_iter * 1e3,
                     higher_is_better=True, scaling="strong", vs_baseline=None,
@@ -240,6 +323,11 @@ def main():
                     e2e=dict(value=cb["value"], unit="walker-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                     gpu_launches=0, note="reference = NumPy oracle port of hemcee (JAX not installable here)")
         print(json.dumps(line))
+        return
+
+    if cfg.get("adaptive"):
+        if rank == 0:
+            bench_adaptive(args, cfg, conf)
         return
 
     import torch
@@ -361,6 +449,23 @@ def main():
         dist.all_reduce(tot_acc)
     acc_rate = float(tot_acc.item()) / (W * (K + Wu))
 
+    # ---- 64-bit checksum of the final ensemble, log-probs and accept counters (bit patterns, position-weighted, wrapping
+    #      int64 arithmetic): equal numbers at --gpus 1 / 2 / 4 / 8 prove that the row-sharded runs reproduce the single-GPU
+    #      chain bit for bit (same K, W, workload and leapfrog form)
+    def _cks(t):
+        v = t.contiguous().view(torch.int32).reshape(-1).to(torch.int64)
+        w = torch.arange(v.numel(), device=v.device, dtype=torch.int64) % 65521 + 1
+        return int((v * w).sum().item()) & 0xFFFFFFFFFFFFFFFF
+    if world == 1:
+        Xfin, lpfin, accfin = X, lp, accepts
+    else:
+        Xfin, lpfin = Xf, lpf                       # every rank holds the full exchanged state
+        parts = [torch.empty_like(accepts) for _ in range(world)]
+        dist.all_gather(parts, accepts)
+        accfin = torch.cat([p_[:rows] for p_ in parts] + [p_[rows:] for p_ in parts])     # global order: group 1 rows, group 2 rows
+    checksum = dict(ensemble=f"{_cks(Xfin):016x}", log_prob=f"{_cks(lpfin):016x}", accepts=f"{_cks(accfin):016x}",
+                    note="position-weighted sum of the 32-bit words of the final state after warmup + steps iterations (mod 2^64)")
+
     # ---- roofline of the dominant kernel (fused half-move) -------------------------------------------
     peaks = {}
     try:
@@ -372,6 +477,7 @@ def main():
     k_launches = max(int(c_kn.value), 1)
     k_ms = c_ms.value / k_launches
     path = lib.hx_ctx_last_path(ctx)
+    ctx_sms = torch.cuda.get_device_properties(dev).multi_processor_count
     form = args.leapfrog_form
     if form == "auto":
         el_ = rows * d * 28.0 / 2.6e12           # same cost model as csrc/hx_tc_walk.cu (HX_LEAP_AUTO)
@@ -382,10 +488,18 @@ def main():
         # tensor-core path: the bracketed section is the momentum projection S0 = P0 C of one half-move: tcgen05 GEMM chunks
         # (128 x 256 tiles, K = n) while the counter-based draw of the NEXT half-move's P0 runs concurrently on the ALU pipes
         tune = dict(kv.split("=") for kv in args.tune)
-        f8 = args.precision in ("auto", "f16f8")                      # projection operands: fp16 + 2 x e4m3 (default) or bf16 hi/lo
+        # the momentum draw is generated inside the projection GEMM (k_tc_proj_fused) unless switched off / not eligible
+        fused = (int(tune.get("15", 1)) != 0 and args.precision in ("auto", "bf16x3", "tf32x3") and d <= 1024
+                 and _rt.impl_code() == _lib.HX_RNG_PARTITIONABLE)
+        f8 = (not fused) and args.precision in ("auto", "f16f8")        # staged projection operands: fp16 + 2 x e4m3, or bf16 hi/lo
         ekind = int(tune.get("3", 2)) if args.precision != "tf32x3" else 0   # propagator energy operands: 2 fp16 hi/lo, 0 tf32 hi/lo
-        kname = ("tc::k_tc_gemm<256,EPI_STORE,%s> projection S0 = P0 C (all row chunks of a half-move), "
-                 "tc::k_rng_planes of the next half-move concurrent" % ("fp16 + e4m3" if f8 else "bf16 hi/lo"))
+        if fused:
+            kname = ("tc::k_tc_proj_fused<%s RNG warps, %s> S0 = normal(key,(n,n))[rows] @ C: threefry + erf_inv in registers -> bf16 hi/lo "
+                     "operand tiles in shared memory (CTA pair) -> tcgen05.mma, split-K 2 (+ k_sum_slices_f)"
+                     % (tune.get("16", "28"), "CTA pair" if d > 512 else "single CTA"))
+        else:
+            kname = ("tc::k_tc_gemm<256,EPI_STORE,%s> projection S0 = P0 C (all row chunks of a half-move), "
+                     "tc::k_rng_planes of the next half-move concurrent" % ("fp16 + e4m3" if f8 else "bf16 hi/lo"))
         flops = 2.0 * rows * n * d
         nK, dpad = -(-n // 64) * 64, -(-d // 256) * 256
         # tensor work actually issued, in units of one bf16-rate product: bf16 hi/lo = 3 products; fp16 + e4m3 = one fp16 product
@@ -407,27 +521,60 @@ def main():
                      step_executed_tflops=step_exec * 2 * K / (ms * 1e-3) / 1e12,
                      step_executed_frac=step_exec * 2 * K / (ms * 1e-3) / 1e12 / peak_tf)
         note = ("achieved/frac = ALGORITHMIC flops 2*rows*n*d of the projection (SURVEY §8d first term) / section time. fp32-class "
-                "accuracy on 16-bit tensor-core operands takes 3 products per algorithmic product (hi*hi + hi*lo + lo*hi; by default "
-                "the two correction products run in e4m3 at twice the rate, i.e. 2 bf16-rate units, so frac <= 1/2 by construction, "
-                "1/3 with --precision bf16x3); executed_* counts the bf16-rate units actually issued (incl. d padded to 256); "
-                "step_executed_* is the whole iteration (projection + leapfrog/energy GEMMs + Gram; tf32 products counted double) "
-                "against the same peak.  The section is co-bound by the concurrent momentum draw (ALU: 4.55 ms alone per half-move "
-                "at c5 on one GPU, DESIGN.md section 4), not by the tensor pipe")
+                "accuracy on 16-bit tensor-core operands takes 3 products per algorithmic product (hi*hi + lo*hi + hi*lo: frac <= 1/3 "
+                "by construction; the staged fp16 + e4m3 form runs its two correction products at twice the rate, 2 units); "
+                "executed_* counts the bf16-rate units actually issued (incl. d padded to 256); step_executed_* is the whole "
+                "iteration (projection + leapfrog/energy GEMMs + Gram; tf32 products counted double) against the same peak.  The "
+                "section is bound by the momentum draw it contains (n^2 threefry + erf_inv evaluations per half-move on the alu "
+                "pipe: draw_* keys; 3.5 ms for the arithmetic alone at c5 on one GPU at 1965 MHz), not by the tensor pipe, and the "
+                "whole step runs under the 1 kW power cap (clocks)")
+        # the draw inside the section: achieved normals/s against the measured rate of the draw arithmetic alone (threefry2x32-20
+        # + XLA erf_inv + operand split, 96 instructions per normal: 120.5 clk per warp and normal and scheduler at 1965 MHz on
+        # every SM, scripts/micro/normals_micro.cu -- alu pipe (SHF / LOP3 at 2 clk) and issue slots saturate together)
+        draw_peak = ctx_sms * 4 * 32 / 120.5 * 1.965e9
+        extra.update(draw_gnormals_per_s=rows * float(n) / (k_ms * 1e-3) / 1e9, draw_peak_gnormals_per_s=draw_peak / 1e9,
+                     draw_frac=rows * float(n) / (k_ms * 1e-3) / draw_peak,
+                     draw_peak_source="measured: draw arithmetic alone on all SMs, scripts/micro/normals_micro.cu (round 2)")
         if args.workload == "c5" and world == 1:
-            extra["traffic_source"] = ("profiles/r01e_c5_ncu_full_summary.txt: dram bytes read+write of the 7 chunk launches of one "
-                                       "half-move (6 x 755.0 MB + 704.7 MB read, 28 MB written) = the P0 planes + C^T planes, "
-                                       "i.e. no re-reads (same plane sizes for bf16 hi/lo: profiles/r01c)")
+            if fused:
+                extra["traffic_source"] = FUSED_TRAFFIC_SOURCE
+            else:
+                extra["traffic_source"] = ("profiles/r01e_c5_ncu_full_summary.txt: dram bytes read+write of the 7 chunk launches of one "
+                                           "half-move (6 x 755.0 MB + 704.7 MB read, 28 MB written) = the P0 planes + C^T planes, "
+                                           "i.e. no re-reads (same plane sizes for bf16 hi/lo: profiles/r01c)")
     else:
         kname = "k_walk_half" if mk == 0 else "k_side_half"
         flops = algorithmic_flops_half_move(rows, n, d, L, cfg["target"])
         note = "algorithmic flops = projected form 2*rows*n*d + (L+1)*(2*rows*d^2 [M] + grad) (SURVEY §8d)"
     achieved = flops / (k_ms * 1e-3) / 1e12
-    roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=peak_tf,
-                    unit="TFLOP/s", frac=achieved / peak_tf,
-                    traffic=5.263e9 if "traffic_source" in extra else None, peak_source=peak_src,
-                    flops_per_launch=flops, kernel_ms=k_ms, kernel_share_of_step=c_ms.value / ms, note=note,
-                    half_move_algorithmic_tflops=algorithmic_flops_half_move(rows, n, d, L, cfg["target"]) * 2 * K
-                    / (ms * 1e-3) / 1e12, **extra)
+    traffic = None
+    if "traffic_source" in extra:
+        traffic = FUSED_TRAFFIC_BYTES if extra["traffic_source"] is FUSED_TRAFFIC_SOURCE else 5.263e9
+    if path == 1 or mk == 1:
+        roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=peak_tf,
+                        unit="TFLOP/s", frac=achieved / peak_tf,
+                        traffic=traffic, peak_source=peak_src,
+                        flops_per_launch=flops, kernel_ms=k_ms, kernel_share_of_step=c_ms.value / ms, note=note,
+                        half_move_algorithmic_tflops=algorithmic_flops_half_move(rows, n, d, L, cfg["target"]) * 2 * K
+                        / (ms * 1e-3) / 1e12, **extra)
+        if mk == 1:
+            roofline["note"] = ("side move: RNG / selection-bound (n sort keys per walker and shuffle round), SURVEY section 8d; the tensor "
+                                "fraction is reported for completeness only")
+    else:
+        # SIMT walk half-move (c1-c4 sizes): ALU / RNG-bound -- rows * n normals per launch (n / L normals per walker-step against
+        # <= 2 d^2 + O(d) flops), SURVEY section 8d.  Roofline = normals per second against the measured rate of the draw
+        # arithmetic alone on all SMs (scripts/micro/normals_micro.cu).
+        draw_peak = ctx_sms * 4 * 32 / 120.5 * 1.965e9
+        half_ms = ms / K / 2.0            # whole half-move (narrow targets draw in a separate projection kernel: not only k_ms)
+        gn = rows * float(n) / (half_ms * 1e-3)
+        roofline = dict(bound="alu", kernel=kname + " (RNG-fused projection: threefry2x32 + erf_inv per momentum element)",
+                        achieved=gn / 1e9, peak=draw_peak / 1e9, unit="Gnormal/s", frac=gn / draw_peak, traffic=None,
+                        peak_source="measured: draw arithmetic alone (96 instructions per normal, 120.5 clk per warp and scheduler at "
+                                    "1965 MHz) on all SMs, scripts/micro/normals_micro.cu (round 2)",
+                        normals_per_launch=rows * float(n), half_move_ms=half_ms, kernel_ms=k_ms, kernel_share_of_step=c_ms.value / ms,
+                        tensor_equivalent=dict(achieved_tflops=achieved, frac_of_bf16_peak=achieved / peak_tf, note=note),
+                        note="achieved = normals of one half-move / time of the whole half-move (draw, projection, L + 1 kicks, "
+                             "log-density, accept); latency-bound below ~1e6 normals per half-move (c1, c2: a handful of CTAs)")
 
     # ---- end-to-end through the public API with host buffers (`e2e`) -----------------------------------
     e2e = None
@@ -567,7 +714,7 @@ def main():
                     dtype="f64" if cfg["x64"] else "f32", data="synthetic", config=conf, roofline=roofline,
                     cpu_baseline=cb, clocks=clk, e2e=e2e, gpu_launches=int(c_all.value) if world == 1 else int(c_all.value),
                     acceptance_rate=acc_rate, nonfinite=int(flag.item()), precision=args.precision, leapfrog_form=args.leapfrog_form,
-                    phase_ms_per_half_move=phases, ess=ess, host_enqueue_ms_per_step=host_enqueue_ms)
+                    phase_ms_per_half_move=phases, ess=ess, host_enqueue_ms_per_step=host_enqueue_ms, checksum=checksum)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -180,11 +180,20 @@ class HamiltonianEnsembleSampler(BaseSampler):
         warmup_bs = calculate_batch_size(self.total_chains, self.dim, warmup, batch_size)
         main_bs = calculate_batch_size(self.total_chains, self.dim, num_samples * thin_by, batch_size)
 
+        import time as _time
+        def _now():
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            return _time.perf_counter()
+        t_start = _now()
+        self.timings = {}                                                           # wall time of the phases [s] (diagnostics)
         if self.adapt_inital_step_size:                                             # :115-118
             self.step_size = adaptation.find_reasonable_step_size(
                 keys[0], group1, group2, self.target, self.target, self.step_size, self.move, self.impl)
             self._say(f"Using inital step size of {float(self.step_size)!r}")
 
+        self.timings["initial_step_size_s"] = _now() - t_start
+        t_w = _now()
         if warmup > 0:                                                              # :121-129
             self._say("Starting warmup...")
             group1, group2 = self._mcmc_warmup(keys[1], group1, group2, warmup, self.adapter, warmup_bs, show_progress)
@@ -194,10 +203,13 @@ class HamiltonianEnsembleSampler(BaseSampler):
         else:
             step_size, L = self.step_size, self.L                                   # :131-132
         self.found = (step_size, L)
+        self.timings["warmup_s"] = _now() - t_w
 
         self._say("Starting main sampling...")
+        t_m = _now()
         self._mcmc_main(keys[2], group1, group2, num_samples, thin_by, step_size, L, main_bs, show_progress,
                         warmup_offset=warmup)
+        self.timings["main_s"] = _now() - t_m
         self._say("Main sampling complete.")
         if self._thinned:
             # only the returned iterations were stored; the backend counts the iterations that were RUN

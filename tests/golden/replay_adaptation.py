@@ -1,0 +1,50 @@
+"""Replay of the reference's docs/tutorials/adaptation.ipynb (f32, PRNGKey(0), W = 100, 2-d Rosenbrock) with the oracle.
+
+Stored outputs of the notebook (the only end-to-end numbers the reference publishes for an adaptive run):
+    cell 5 / cell 11 (DA + ChEES, identical outputs):
+        Using inital step size of 0.004999999888241291
+        Found step size 0.010159287601709366 and integration length: 25
+        Autocorrelation time: [41.01967 41.53285]          (on the returned samples, i.e. thinned by 5)
+    cell 13 (no adaptation, step 0.01, L = 10):
+        tau: [210.34383 205.32188]                         (AutocorrError text: N/50 = 200)
+Run:  python tests/golden/replay_adaptation.py adaptive|fixed|conditional [warmup] [num_samples]
+  adaptive     the whole cell-11 run: 1e5 warm-up iterations with DA + ChEES, then 1e4 x 5 main iterations
+  fixed        cell 13: no adaptation, step 0.01, L = 10
+  conditional  main phase only with the notebook's found (step, L) = (0.010159287601709366, 25) after a short fixed warm-up
+Writes tests/golden/adaptation_replay_<mode>.json (full-length runs only).
+"""
+import json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+from oracle import jaxrng as R, moves, targets, sampler, autocorr
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "adaptive"
+warmup = int(sys.argv[2]) if len(sys.argv) > 2 else 10**5
+num = int(sys.argv[3]) if len(sys.argv) > 3 else 10**4
+W, dim, thin = 100, 2, 5
+keys = R.split(R.PRNGKey(0), 2)
+init = R.normal(keys[0], (W, dim), np.float32)
+kw = dict(dtype=np.float32, verbose=True)
+if mode == "adaptive":
+    s = sampler.HamiltonianEnsembleSampler(W, dim, targets.make_rosenbrock(), step_size=0.01, **kw)
+elif mode == "fixed":
+    s = sampler.HamiltonianEnsembleSampler(W, dim, targets.make_rosenbrock(), step_size=0.01, L=10, adapt_inital_step_size=False,
+                                           adapt_step_size=False, adapt_length=False, **kw)
+else:
+    s = sampler.HamiltonianEnsembleSampler(W, dim, targets.make_rosenbrock(), step_size=0.010159287601709366, L=25,
+                                           adapt_inital_step_size=False, adapt_step_size=False, adapt_length=False, **kw)
+t0 = time.time()
+samples = s.run_mcmc(keys[1], init, num_samples=num, warmup=warmup, thin_by=thin)
+t1 = time.time()
+tau = autocorr.integrated_time(samples, quiet=True)
+out = dict(mode=mode, warmup=warmup, num_samples=num, thin_by=thin, initial_step=float(s.step_size),
+           found_step=float(s.found[0]) if getattr(s, "found", None) is not None else None,
+           found_L=int(s.found[1]) if getattr(s, "found", None) is not None else None,
+           acceptance_mean=float(np.mean(s.diagnostics_main["acceptance_rate"])), tau=[float(t) for t in tau],
+           mean=[float(v) for v in samples.reshape(-1, dim).mean(0)], var=[float(v) for v in samples.reshape(-1, dim).var(0)],
+           seconds=t1 - t0)
+print(json.dumps(out, indent=1))
+full = (warmup == 10**5) if mode != "conditional" else (warmup >= 2000)
+if full and num == 10**4:
+    with open(os.path.join(os.path.dirname(__file__), f"adaptation_replay_{mode}.json"), "w") as f:
+        json.dump(out, f, indent=1)

@@ -1,0 +1,87 @@
+"""The reference's tutorial notebooks on the GPU, through the drop-in API (run_mcmc -> hx_run_warmup / hx_run_iterations):
+the only end-to-end numbers the reference publishes (docs/tutorials/adaptation.ipynb cells 5/11/13, quickstart.ipynb cells
+8/10).  Draw-for-draw agreement with a notebook is not defined (unknown JAX build, chaotic f32 dynamics); what is asserted is
+what the oracle replays (tests/test_oracle_golden.py, tests/golden/*.json) establish as reproducible:
+  * the printed initial step sizes, exactly;
+  * the dual-averaging step size after 1e5 warm-up iterations, to 1e-3 relative (1e-7 in x64);
+  * tau of the main phase given the printed (step, L), within 8 % (tau ~ 41) / 20 % (tau ~ 208, N / tau = 50);
+  * the tuned L: a deterministic function of ChEES' running average T_bar, which scatters by +-15 % from stream to stream
+    (oracle: L = 20 ... 27 around the quickstart's printed 23) -- asserted as a range."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import jaxrng as R
+
+pytestmark = pytest.mark.gpu
+
+NB_ADAPT = dict(initial=0.004999999888241291, step=0.010159287601709366, L=25, tau=[41.01967, 41.53285])
+NB_FIXED = dict(step=0.01, L=10, tau=[210.34383, 205.32188])
+NB_QUICK = dict(initial=1.6, step=0.10160634057813525, L=23, tau=[0.4727686, 0.4846164, 0.46748046])
+
+
+def _adaptation_setup(hx):
+    keys = R.split(R.PRNGKey(0), 2)
+    x0 = R.normal(keys[0], (100, 2), np.float32)
+    return hx.targets.Rosenbrock(2), x0, keys[1]
+
+
+def test_adaptation_notebook_main_phase_given_printed_tuning(hx):
+    tgt, x0, key = _adaptation_setup(hx)
+    s = hx.HamiltonianEnsembleSampler(100, 2, tgt, step_size=NB_ADAPT["step"], L=NB_ADAPT["L"], adapt_inital_step_size=False,
+                                      adapt_step_size=False, adapt_length=False, verbose=False)
+    samples = s.run_mcmc(key, x0, 10**4, warmup=2000, thin_by=5)
+    tau = hx.autocorr.integrated_time(samples)
+    np.testing.assert_allclose(tau, NB_ADAPT["tau"], rtol=0.08)
+    flat = samples.reshape(-1, 2)
+    np.testing.assert_allclose(flat.mean(0), [1.0, 1.5], atol=0.04)         # E x0 = 1, E x1 = 1 + Var x0 = 3/2
+
+
+def test_adaptation_notebook_fixed_parameters(hx):
+    """cell 13: no adaptation, step 0.01, L = 10 (warm-up shortened to 2e4 iterations: it only equilibrates)."""
+    tgt, x0, key = _adaptation_setup(hx)
+    s = hx.HamiltonianEnsembleSampler(100, 2, tgt, step_size=0.01, L=10, adapt_inital_step_size=False, adapt_step_size=False,
+                                      adapt_length=False, verbose=False)
+    samples = s.run_mcmc(key, x0, 10**4, warmup=2 * 10**4, thin_by=5)
+    with pytest.raises(hx.autocorr.AutocorrError):          # the notebook prints the error text: N / 50 = 200 < tau
+        hx.autocorr.integrated_time(samples)
+    tau = hx.autocorr.integrated_time(samples, quiet=True)
+    np.testing.assert_allclose(tau, NB_FIXED["tau"], rtol=0.25)
+
+
+def test_adaptation_notebook_full_adaptive_run(hx):
+    """cells 5 / 11: step-size heuristic + DA + ChEES, 1e5 warm-up iterations on the device, 1e4 x 5 main iterations."""
+    tgt, x0, key = _adaptation_setup(hx)
+    s = hx.HamiltonianEnsembleSampler(100, 2, tgt, step_size=0.01, verbose=False)
+    samples = s.run_mcmc(key, x0, 10**4, warmup=10**5, thin_by=5)
+    assert float(s.step_size) == NB_ADAPT["initial"]
+    step, L = float(s.found[0]), int(s.found[1])
+    assert abs(step - NB_ADAPT["step"]) <= 1e-3 * NB_ADAPT["step"], step
+    assert 0.8 * NB_ADAPT["L"] <= L <= 1.2 * NB_ADAPT["L"], L
+    tau = hx.autocorr.integrated_time(samples, quiet=True)
+    assert np.all(tau > 10) and np.all(tau < 120), tau        # tau(L) is steep; the printed 41 belongs to L = 25 exactly
+    if L == NB_ADAPT["L"]:
+        np.testing.assert_allclose(tau, NB_ADAPT["tau"], rtol=0.15)
+    assert samples.shape == (10**4, 100, 2)
+
+
+def test_quickstart_notebook_full_adaptive_run_x64(hx):
+    hx.config.update("enable_x64", True)
+    try:
+        keys = R.split(R.PRNGKey(2), 2)
+        x0 = R.normal(keys[0], (20, 3), np.float64)
+        s = hx.HamiltonianEnsembleSampler(20, 3, hx.targets.GaussianIso(3), verbose=False)
+        samples = s.run_mcmc(keys[1], x0, 10**4, warmup=10**5, thin_by=1)
+        assert float(s.step_size) == NB_QUICK["initial"]
+        step, L = float(s.found[0]), int(s.found[1])
+        assert abs(step - NB_QUICK["step"]) < 2e-8, step
+        assert 19 <= L <= 28, L
+        acc = s.diagnostics_main["acceptance_rate"]
+        assert np.all(np.abs(np.asarray(acc) - 0.999) < 2e-3)
+        # the oracle replay of this very run (tests/golden/quickstart_replay_partitionable.json): x64 chains are equal draw for draw
+        import json, os
+        rec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "quickstart_replay_partitionable.json")))
+        assert L == rec["found_L"] and abs(step - rec["found_step"]) < 1e-12
+        np.testing.assert_allclose(hx.autocorr.integrated_time(samples, quiet=True), rec["tau"], rtol=1e-6)
+    finally:
+        hx.config.update("enable_x64", False)
