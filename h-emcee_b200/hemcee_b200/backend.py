@@ -21,15 +21,44 @@ class Backend:
         self._warmup_end_index = None
         self.accepted = np.zeros(self.nwalkers, dtype=self.dtype)
         self.chain, self.log_prob = [], []
+        # which iterations the stored rows are: row k = iteration stored_first + k * stored_stride.  (0, 1) = every iteration
+        # (the reference's store); the sampler's store="thinned" keeps only the iterations run_mcmc returns
+        # (stored_first = warmup, stored_stride = thin_by) while `iteration` still counts the iterations that were RUN.
+        self.stored_first, self.stored_stride = 0, 1
+        self._last_sample = None
         self.initialized = True
+
+    def set_stored_layout(self, first: int, stride: int, last_sample=None):
+        """Declare that the stored rows are iterations first, first + stride, ... (thinned store); `last_sample` =
+        (coords[nwalkers, ndim], log_prob[nwalkers]) of the final iteration if that iteration itself is not stored."""
+        self.stored_first, self.stored_stride = int(first), max(1, int(stride))
+        self._last_sample = last_sample
+
+    def _rows(self, discard, thin):
+        """Translate the reference's `v[discard::thin]` over ALL iterations into a slice of the stored rows."""
+        f, k = self.stored_first, self.stored_stride
+        if f == 0 and k == 1:
+            return slice(discard, None, thin)
+        if discard < f:
+            raise ValueError(f"iterations before {f} were not stored (thinned store); ask for discard >= {f}")
+        if thin % k != 0:
+            raise ValueError(f"only every {k}-th iteration was stored (thinned store): `thin` must be a multiple of {k}, got {thin}")
+        if (discard - f) % k != 0:
+            raise ValueError(f"iteration {discard} was not stored (thinned store keeps iterations {f} + j * {k})")
+        return slice((discard - f) // k, None, thin // k)
 
     def get_value(self, name, flat=False, thin=1, discard=0):
         if self.iteration <= 0:
             raise AttributeError("you must run the sampler with 'store == True' before accessing the results")
         v = getattr(self, name)
         if name in ("chain", "log_prob"):
-            v = v[0] if len(v) == 1 else np.concatenate(v, axis=0)   # single slice: no copy
-        v = v[discard::thin]
+            if len(v) == 0:
+                v = np.zeros((0, self.nwalkers, self.ndim) if name == "chain" else (0, self.nwalkers), dtype=np.float32)
+            else:
+                v = v[0] if len(v) == 1 else np.concatenate(v, axis=0)   # single slice: no copy
+            v = v[self._rows(discard, thin)]
+        else:
+            v = v[discard::thin]
         if flat:
             s = list(v.shape[1:])
             s[0] = int(np.prod(v.shape[:2]))
@@ -46,7 +75,13 @@ class Backend:
         if (not self.initialized) or self.iteration <= 0:
             raise AttributeError("you must run the sampler with 'store == True' before accessing the results")
         it = self.iteration
-        return self.get_chain(discard=it - 1)[0], self.get_log_prob(discard=it - 1)[0]
+        last_stored = self.stored_first + (sum(len(c) for c in self.chain) - 1) * self.stored_stride
+        if last_stored != it - 1:                            # thinned store whose final iteration is not a stored row
+            if self._last_sample is None:
+                raise AttributeError("the final iteration was not stored (thinned store) and no last sample was recorded")
+            return self._last_sample
+        c = self.chain[-1] if self.chain else None
+        return c[-1], self.log_prob[-1][-1]
 
     def get_autocorr_time(self, discard=0, thin=1, **kwargs):
         return thin * autocorr.integrated_time(self.get_chain(discard=discard, thin=thin), **kwargs)

@@ -31,6 +31,9 @@ from .moves import accept_proposal, hmc_side_move, hmc_walk_move, walk_prefetch
 from .targets import as_target
 
 
+_PIN_LIMIT = 16 << 30      # bytes of page-locked host memory one phase may hold for its chain
+
+
 def calculate_batch_size(total_chains, dim, total_iterations, user_batch_size=None):
     """reference src/hemcee/samplers/sampler_utils.py:10-26."""
     if user_batch_size is not None:
@@ -212,11 +215,27 @@ class HamiltonianEnsembleSampler(BaseSampler):
         self.timings["main_s"] = _now() - t_m
         self._say("Main sampling complete.")
         if self._thinned:
-            # only the returned iterations were stored; the backend counts the iterations that were RUN
+            # only the returned iterations were stored: the backend keeps counting the iterations that were RUN and maps
+            # discard / thin requests onto the stored rows (Backend.set_stored_layout)
             self.backend.iteration = warmup + num_samples * thin_by
             self.backend.iteration_main = num_samples * thin_by
-            return self.backend.get_chain()[-num_samples:] if num_samples > 0 else self.backend.get_chain()[:0]
+            last = None
+            if getattr(self, "last_state", None) is not None:
+                last = (np.asarray(self.last_state.detach().cpu()), np.asarray(self.last_log_prob.detach().cpu())
+                        if getattr(self, "last_log_prob", None) is not None else None)
+            self.backend.set_stored_layout(warmup, thin_by, last)
         return self.get_chain(discard=warmup, thin=thin_by)                         # :139
+
+    def _save_prefix(self, host_chain, host_lp, host_flag, starts, offset, copy_stream):
+        """A stored log-prob became non-finite in some batch: like the reference (sampler_utils.py:74-82 checks each batch
+        BEFORE saving it, so every earlier batch is already in the backend), keep the batches that completed before the
+        offending one.  Their accept counters are not separable from the device total and are left out."""
+        copy_stream.synchronize()
+        bad = next((b for b in range(len(starts)) if int(host_flag[b]) != 0), len(starts))
+        rows = starts[bad] if bad < len(starts) else 0
+        if rows > 0:
+            self.backend.save_slice(host_chain[:rows].numpy().copy(), host_lp[:rows].numpy().copy(),
+                                    np.zeros(self.backend.nwalkers), offset)
 
     # -- batch-level engine (single GPU): T iterations per libhx call ----------------------------------
     def _run_batches(self, key, X, lp, T, step_size, L, batch_size, offset, key_order, show_progress, adapt=None,
@@ -238,14 +257,19 @@ class HamiltonianEnsembleSampler(BaseSampler):
         k = int(thin_store)
         nstore = lambda a, b: (b - a) if k == 1 else (0 if k == 0 else (-(-b // k)) - (-(-a // k)))   # stored iterations in [a, b)
         Ts = nstore(0, T)
-        host_chain = torch.empty((Ts, W, d), dtype=self.dtype, pin_memory=Ts > 0)
-        host_lp = torch.empty((Ts, W), dtype=self.dtype, pin_memory=Ts > 0)
+        # the stored chain of the phase.  Page-locked (asynchronous D2H at full PCIe rate) up to _PIN_LIMIT bytes; beyond that
+        # pageable memory, like the reference's host arrays (cudaHostAlloc of tens of GB is slow, counts against memlock /
+        # cgroup limits and cannot be swapped)
+        pin = Ts > 0 and Ts * W * d * torch.empty((), dtype=self.dtype).element_size() <= _PIN_LIMIT
+        host_chain = torch.empty((Ts, W, d), dtype=self.dtype, pin_memory=pin)
+        host_lp = torch.empty((Ts, W), dtype=self.dtype, pin_memory=pin)
         host_flag = torch.zeros(nb, dtype=torch.int32, pin_memory=True)
         bmax = max(nstore(b * batch_size, min((b + 1) * batch_size, T)) for b in range(nb))
         bufs = [(torch.empty((max(bmax, 1), W, d), dtype=self.dtype, device=dev),
                  torch.empty((max(bmax, 1), W), dtype=self.dtype, device=dev)) for _ in range(min(2, nb))]
         copy_stream = torch.cuda.Stream(dev)
         done = [None, None]
+        starts = []
         main = torch.cuda.current_stream(dev)
         desc = self.target.descriptor(self.dtype, dev)
         it = range(nb)
@@ -286,8 +310,10 @@ class HamiltonianEnsembleSampler(BaseSampler):
                     host_flag[b:b + 1].copy_(flag, non_blocking=True)
                     done[b % 2] = torch.cuda.Event()
                     done[b % 2].record(copy_stream)
+                starts.append(pos)
                 pos += ns
                 if b >= 1 and int(host_flag[b - 1]) != 0 and done[(b - 1) % 2].query():
+                    self._save_prefix(host_chain, host_lp, host_flag, starts, offset, copy_stream)
                     raise ValueError(_NONFINITE_MSG)                                     # sampler_utils.py:74-75
         finally:
             if k > 1:
@@ -295,6 +321,7 @@ class HamiltonianEnsembleSampler(BaseSampler):
         copy_stream.synchronize()
         main.synchronize()
         if int(host_flag.max()) != 0:
+            self._save_prefix(host_chain, host_lp, host_flag, starts, offset, copy_stream)
             raise ValueError(_NONFINITE_MSG)
         acc = accepts.cpu().numpy()
         # one slice for the whole phase: the pinned host buffer becomes the stored chain without another copy
@@ -534,7 +561,7 @@ class HamiltonianEnsembleSampler(BaseSampler):
             lp = self.log_prob(X)                                                    # :325-326
             acc = self._run_batches(key, X, lp, total, step_size, L, batch_size, 0 if self._thinned else warmup_offset, 0,
                                     show_progress, thin_store=thin_by if self._thinned else 1)
-            self.last_state = X
+            self.last_state, self.last_log_prob = X, lp
         elif self._peer_ok:
             acc = self._run_batches_sharded(key, group1, group2, total, step_size, L, batch_size, warmup_offset, 0, show_progress)
             self.last_state = torch.cat([group1, group2])

@@ -8,7 +8,7 @@ Stored outputs of the notebook (the only end-to-end numbers the reference publis
     cell 13 (no adaptation, step 0.01, L = 10):
         tau: [210.34383 205.32188]                         (AutocorrError text: N/50 = 200)
 Run:  python tests/golden/replay_adaptation.py adaptive|fixed|conditional [warmup] [num_samples]
-  adaptive     the whole cell-11 run: 1e5 warm-up iterations with DA + ChEES, then 1e4 x 5 main iterations
+  adaptive     the cell-11 run with DA + ChEES (`adaptive 1500 200` = the affordable short version that is committed)
   fixed        cell 13: no adaptation, step 0.01, L = 10
   conditional  main phase only with the notebook's found (step, L) = (0.010159287601709366, 25) after a short fixed warm-up
 Writes tests/golden/adaptation_replay_<mode>.json (full-length runs only).
@@ -45,6 +45,15 @@ out = dict(mode=mode, warmup=warmup, num_samples=num, thin_by=thin, initial_step
            seconds=t1 - t0)
 print(json.dumps(out, indent=1))
 full = (warmup == 10**5) if mode != "conditional" else (warmup >= 2000)
+if mode == "adaptive":
+    ch = s.adapter_state.chees_state
+    out.update(T_bar=float(np.exp(ch.log_T_bar)), T=float(np.exp(ch.log_T)), chees_iteration=float(ch.iteration))
 if full and num == 10**4:
     with open(os.path.join(os.path.dirname(__file__), f"adaptation_replay_{mode}.json"), "w") as f:
+        json.dump(out, f, indent=1)
+elif mode == "adaptive" and warmup == 1500 and num == 200:
+    # the full-length adaptive run is not affordable on the CPU: with the current revision of chees.py the trajectory length
+    # climbs to T_max = 10, i.e. L ~ 600-700 leapfrog steps per half-move (the notebook's L = 25 = ceil(T_min / step) dates from
+    # an earlier revision, see tests/test_oracle_golden.py)
+    with open(os.path.join(os.path.dirname(__file__), "adaptation_replay_adaptive_short.json"), "w") as f:
         json.dump(out, f, indent=1)

@@ -54,3 +54,38 @@ def test_file_backend_before_warmup_end(tmp_path):
     assert r._warmup_end_index is None and r.iteration_warmup == 3 and r.iteration_main == 0
     with pytest.raises(KeyError):
         FileBackend.load(fn, name="mcmc")
+
+
+def test_thinned_layout_maps_discard_and_thin_onto_stored_rows():
+    """store='thinned' keeps iterations warmup, warmup + thin_by, ...; the backend still counts the iterations RUN and serves
+    the reference's `v[discard::thin]` requests that land on stored rows (reference backend/backend.py:63-66)."""
+    from hemcee_b200.backend import Backend
+    b = Backend()
+    b.reset(4, 2)
+    warmup, thin_by, num = 10, 3, 5
+    full = np.arange((warmup + num * thin_by) * 4 * 2, dtype=np.float32).reshape(-1, 4, 2)
+    stored = full[warmup::thin_by]
+    assert stored.shape[0] == num
+    b.save_slice(stored, stored[:, :, 0], np.zeros(4), 0)
+    b.iteration, b.iteration_main = warmup + num * thin_by, num * thin_by
+    b.set_stored_layout(warmup, thin_by, last_sample=(full[-1], full[-1, :, 0]))
+    np.testing.assert_array_equal(b.get_chain(discard=warmup, thin=thin_by), full[warmup::thin_by])
+    np.testing.assert_array_equal(b.get_chain(discard=warmup + thin_by, thin=2 * thin_by), full[warmup + thin_by::2 * thin_by])
+    with pytest.raises(ValueError):
+        b.get_chain(discard=warmup + 1, thin=thin_by)     # iteration 11 is not a stored row
+    with pytest.raises(ValueError):
+        b.get_chain(discard=0, thin=thin_by)              # warm-up iterations were not stored
+    with pytest.raises(ValueError):
+        b.get_chain(discard=warmup, thin=2)               # not a multiple of the stored stride
+    x, lp = b.get_last_sample()                           # the final iteration itself is not a stored row
+    np.testing.assert_array_equal(x, full[-1])
+    np.testing.assert_array_equal(b.get_autocorr_time.__self__.get_chain(discard=warmup, thin=thin_by, flat=True),
+                                  full[warmup::thin_by].reshape(-1, 2))
+
+
+def test_empty_store_returns_empty_arrays():
+    from hemcee_b200.backend import Backend
+    b = Backend()
+    b.reset(4, 2)
+    b.iteration = 7                                       # iterations were run but none was stored (num_samples = 0)
+    assert b.get_chain().shape == (0, 4, 2) and b.get_log_prob().shape == (0, 4)
