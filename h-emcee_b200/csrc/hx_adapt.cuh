@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256) k_accept_emit(T* cur, const T* __restrict
   const Key key{key_ptr[0], key_ptr[1]};
   const T lo = T(1e-10);
   const T span = T(1.0) - lo;
-  const T u = uniform_rt<T>(key, (uint64_t)(row0 + w), (uint64_t)n, lo, span, legacy != 0);
+  const T u = uniform_rt<T>(key, (uint64_t)(row0 + w), (uint64_t)n, lo, span, legacy);
   const bool acc = log_t(u) < logacc[w];                      // sampler_utils.py:114-115
   const size_t off = (size_t)w * d;
   for (int c = lane; c < d; c += 32) {

@@ -244,6 +244,11 @@ static inline int grid_for(uint64_t n, int block, int cap = 148 * 16) {
   return (int)g;
 }
 static inline int round4(int d) { return (d + 3) & ~3; }
+// RNG flags word of the kernels (hx_rng.cuh HX_RNGF_*): counter layout + the exact f32 normal form under HX_PREC_EXACT
+static inline int rng_flags(const hx_ctx* ctx, int impl) {
+  return (impl == HX_RNG_LEGACY ? HX_RNGF_LEGACY : 0) | (ctx->precision == HX_PREC_EXACT ? HX_RNGF_EXACT : 0);
+}
+
 static inline int check_dtype_impl(int dtype, int impl, const char* who) {
   if (dtype != HX_F32 && dtype != HX_F64) return fail(HX_E_DTYPE, "%s: unknown dtype %d", who, dtype);
   if (impl != HX_RNG_PARTITIONABLE && impl != HX_RNG_LEGACY) return fail(HX_E_DTYPE, "%s: unknown rng impl %d", who, impl);
@@ -330,6 +335,8 @@ extern "C" HX_API int hx_uniform(const uint32_t key[2], int impl, int dtype, dou
 
 extern "C" HX_API int hx_normal(const uint32_t key[2], int impl, int dtype, int64_t count, void* out_dev, void* stream) {
   if (!key || !out_dev) return fail(HX_E_NULL, "hx_normal: NULL argument");
+  const bool exact = (impl & HX_RNG_EXACT_NORMALS) != 0;
+  impl &= ~HX_RNG_EXACT_NORMALS;
   if (count < 0) return fail(HX_E_SHAPE, "hx_normal: count < 0");
   if (int e = check_dtype_impl(dtype, impl, "hx_normal")) return e;
   if (count == 0) return 0;
@@ -337,11 +344,11 @@ extern "C" HX_API int hx_normal(const uint32_t key[2], int impl, int dtype, int6
   cudaStream_t s = (cudaStream_t)stream;
   const int g = grid_for(count, 256);
   if (dtype == HX_F32) {
-    if (impl == HX_RNG_LEGACY) k_normal<float, true><<<g, 256, 0, s>>>(k, (uint64_t)count, (float*)out_dev);
-    else k_normal<float, false><<<g, 256, 0, s>>>(k, (uint64_t)count, (float*)out_dev);
+    if (impl == HX_RNG_LEGACY) k_normal<float, true><<<g, 256, 0, s>>>(k, (uint64_t)count, (float*)out_dev, exact);
+    else k_normal<float, false><<<g, 256, 0, s>>>(k, (uint64_t)count, (float*)out_dev, exact);
   } else {
-    if (impl == HX_RNG_LEGACY) k_normal<double, true><<<g, 256, 0, s>>>(k, (uint64_t)count, (double*)out_dev);
-    else k_normal<double, false><<<g, 256, 0, s>>>(k, (uint64_t)count, (double*)out_dev);
+    if (impl == HX_RNG_LEGACY) k_normal<double, true><<<g, 256, 0, s>>>(k, (uint64_t)count, (double*)out_dev, false);
+    else k_normal<double, false><<<g, 256, 0, s>>>(k, (uint64_t)count, (double*)out_dev, false);
   }
   HX_LAUNCH_CHECK("k_normal");
   return 0;
@@ -529,7 +536,7 @@ static int walk_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1,
   // index, no barrier per draw) and the half-move kernel starts from the given S0.  The choice depends on (n, dim) only, so
   // row shards reproduce the single-GPU chain.
   if (ldd <= 40 && n >= 1024 && !ctx->narrow_off) {       // beyond ~40 columns the per-lane partial sums crowd out occupancy
-    if (int e = launch_project_narrow<T>(key, key_ptr, (impl == HX_RNG_LEGACY) ? 1 : 0, C, n, ldd, d, row0, rows, pproj, ctx->sm_count, s))
+    if (int e = launch_project_narrow<T>(key, key_ptr, rng_flags(ctx, impl), C, n, ldd, d, row0, rows, pproj, ctx->sm_count, s))
       return e;
     W.P.flags |= kFlagGivenMomentum;
     ctx->launches += 1;
@@ -541,7 +548,7 @@ static int walk_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1,
     W.P.accepts = fuse->accepts; W.P.chain_out = fuse->chain_out; W.P.chain_lp = fuse->chain_lp;
     W.P.nonfinite = fuse->nonfinite;
   }
-  W.P.legacy = (impl == HX_RNG_LEGACY) ? 1 : 0;
+  W.P.legacy = rng_flags(ctx, impl);
   ctx->launches += 5 + (ctx->last_gram_slices > 1 ? 1 : 0);   // colsum, mean, centre, gram(+reduce), half-move
   if (int e = timing_begin(ctx, s)) return e;
   if (int e = launch_walk<T>(W.P, ctx->sm_count, s)) return e;
@@ -603,7 +610,7 @@ static int side_move_t(hx_ctx* ctx, int impl, const hx_target* tgt, const T* X1,
     W.P.accepts = fuse->accepts; W.P.chain_out = fuse->chain_out; W.P.chain_lp = fuse->chain_lp;
     W.P.nonfinite = fuse->nonfinite;
   }
-  W.P.legacy = (impl == HX_RNG_LEGACY) ? 1 : 0;
+  W.P.legacy = rng_flags(ctx, impl);
   ctx->launches += 2;   // choice, half-move
   if (int e = timing_begin(ctx, s)) return e;
   if (int e = launch_side<T>(W.P, ctx->sm_count, s)) return e;
@@ -939,7 +946,7 @@ static int vanilla_half_t(hx_ctx* ctx, int impl, int kind, const hx_target* tgt,
                           double stretch, Key key, const uint32_t* key_ptr, T* lp1, T* Q, T* logacc, T* lp_out, int do_accept,
                           int32_t* accepts, T* chain_out, T* chain_lp, int32_t* nonfinite, cudaStream_t s) {
   const int d = tgt->dim;
-  const int legacy = impl == HX_RNG_LEGACY ? 1 : 0;
+  const int legacy = rng_flags(ctx, impl);
   void *pIdx = nullptr, *pExtra, *pShift = nullptr;
   if (int e = ws_get(ctx, WS_LA, (size_t)2 * rows * sizeof(T), &pExtra)) return e;      // [extra | (unused)]
   if (kind == kVanillaStretch || kind == kVanillaSide) {

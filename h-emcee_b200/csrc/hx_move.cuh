@@ -57,7 +57,7 @@ inline int tile_threads(int ldd) {
 template <typename T, int BM>
 struct RngLoader {
   Key key;
-  bool legacy;
+  int legacy;
   uint64_t n;        // group size (P0 is n x n)
   int grow0;         // global row of the tile's first walker
   int rows_valid;
@@ -346,7 +346,7 @@ struct WalkParams {
 };
 
 template <typename T>
-__device__ __forceinline__ void accept_and_emit(bool legacy, T* Q, T* X1w, T* lp1w, const T* lp1, int32_t* accepts, T* chain_out,
+__device__ __forceinline__ void accept_and_emit(int legacy, T* Q, T* X1w, T* lp1w, const T* lp1, int32_t* accepts, T* chain_out,
                                                 T* chain_lp, int32_t* nonfinite, Key akey, int n, int d, int grow0,
                                                 int rows_valid, const T* lp_rows, const T* la_rows, int* mask,
                                                 int tid, int nthreads) {
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(256) k_project_narrow(Key key, const uint32_t*
 #pragma unroll
       for (int w = 0; w < WPW; ++w) {
         const int i = w0 + w;
-        x[w] = (i < rows && j < n) ? normal_rt<T>(key, (uint64_t)(row0 + i) * (uint64_t)n + (uint64_t)j, nn, legacy != 0) : T(0);
+        x[w] = (i < rows && j < n) ? normal_rt<T>(key, (uint64_t)(row0 + i) * (uint64_t)n + (uint64_t)j, nn, legacy) : T(0);
       }
 #pragma unroll
       for (int g = 0; g < DV; ++g) {
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(MAXT) k_walk_half(WalkParams<T> P) {
   T acc[TM][4];
   // S0 = P0[rows,:] @ C  (hmc_walk.py:36 fused with the first use of p)
   if (!(P.flags & kFlagGivenMomentum)) {
-    RngLoader<T, BM> ld{key, P.legacy != 0, (uint64_t)P.n, grow0, rows_valid};
+    RngLoader<T, BM> ld{key, P.legacy, (uint64_t)P.n, grow0, rows_valid};
     gemm_rows<T, BM, TM>(acc, tm, As, ld, P.C, P.ldd, P.n);
     if (tm.active) {
 #pragma unroll
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(MAXT) k_walk_half(WalkParams<T> P) {
   if (P.fuse_accept) {
     Key akey = P.akey;
     if (P.akey_ptr) { akey.k0 = P.akey_ptr[0]; akey.k1 = P.akey_ptr[1]; }
-    accept_and_emit<T>(P.legacy != 0, Q, P.X1w + off, P.lp1w + r0, P.lp1 + r0, P.accepts + r0,
+    accept_and_emit<T>(P.legacy, Q, P.X1w + off, P.lp1w + r0, P.lp1 + r0, P.accepts + r0,
                                P.chain_out ? P.chain_out + off : nullptr, P.chain_lp ? P.chain_lp + r0 : nullptr,
                                P.nonfinite, akey, P.n, d, grow0, rows_valid, lp_rows, la_rows, mask, tm.tid,
                                tm.nthreads);
@@ -626,8 +626,8 @@ __global__ void __launch_bounds__(MAXT) k_side_half(SideParams<T> P) {
       D[idx] = (P.X2[(size_t)j1 * d + c] - P.X2[(size_t)j2 * d + c]) / sc;
     }
     if (tm.tid < rows_valid) {
-      const Key kmom = split_key_rt(key, (uint64_t)P.n, (uint64_t)P.n + 2, P.legacy != 0);
-      const T p0 = normal_rt<T>(kmom, (uint64_t)(grow0 + tm.tid), (uint64_t)P.n, P.legacy != 0);
+      const Key kmom = split_key_rt(key, (uint64_t)P.n, (uint64_t)P.n + 2, P.legacy);
+      const T p0 = normal_rt<T>(kmom, (uint64_t)(grow0 + tm.tid), (uint64_t)P.n, P.legacy);
       p_rows[tm.tid] = p0;
       p0_rows[tm.tid] = p0;
     }
@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(MAXT) k_side_half(SideParams<T> P) {
   if (P.fuse_accept) {
     Key akey = P.akey;
     if (P.akey_ptr) { akey.k0 = P.akey_ptr[0]; akey.k1 = P.akey_ptr[1]; }
-    accept_and_emit<T>(P.legacy != 0, Q, P.X1w + off, P.lp1w + r0, P.lp1 + r0, P.accepts + r0,
+    accept_and_emit<T>(P.legacy, Q, P.X1w + off, P.lp1w + r0, P.lp1 + r0, P.accepts + r0,
                                P.chain_out ? P.chain_out + off : nullptr, P.chain_lp ? P.chain_lp + r0 : nullptr,
                                P.nonfinite, akey, P.n, d, grow0, rows_valid, lp_rows, la_rows, mask, tm.tid,
                                tm.nthreads);

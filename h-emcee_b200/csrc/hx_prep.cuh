@@ -170,9 +170,9 @@ __global__ void k_uniform(Key key, uint64_t m, T lo, T span, T* __restrict__ out
     out[i] = uniform_at<T, LEGACY>(key, i, m, lo, span);
 }
 template <typename T, bool LEGACY>
-__global__ void k_normal(Key key, uint64_t m, T* __restrict__ out) {
+__global__ void k_normal(Key key, uint64_t m, T* __restrict__ out, bool exact) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x)
-    out[i] = normal_at<T, LEGACY>(key, i, m);
+    out[i] = normal_at<T, LEGACY>(key, i, m, exact);
 }
 
 // ---- standalone Metropolis accept (samplers/sampler_utils.py:91-124) ------------------------------

@@ -1,8 +1,10 @@
 // hx_rng.cuh — counter-based Threefry-2x32-20 and the jax.random value maps, device side.
 //
 // Bit-exact with jax.random for bits / split / uniform; normals use the same Giles polynomials
-// as XLA's erf_inv (f32: ErfInv32, f64: ErfInv64) and agree to <= 1-2 ulp (log1p differs per
-// backend even inside JAX).  Reference call sites: moves/hamiltonian/hmc_walk.py:36,
+// as XLA's erf_inv (f32: ErfInv32, f64: ErfInv64).  f32 normals come in two forms selected by the RNG flags word
+// (HX_RNGF_EXACT, set under HX_PREC_EXACT): exact = w from a correctly rounded log1p (<= 1 ulp from the oracle's
+// np.log1p form, measured: tests/test_gpu_rng.py), fast = w from the SFU lg2 (<= 3 ulp, ~84 % bit-equal; log1p
+// differs per backend even inside JAX).  Reference call sites: moves/hamiltonian/hmc_walk.py:36,
 // moves/hamiltonian/hmc_side.py:37-54, samplers/sampler_utils.py:114,
 // samplers/hamiltonian_ensemble.py:90,228,330.
 #pragma once
@@ -147,6 +149,38 @@ __device__ __forceinline__ float erfinv_xla(float x) {
   return p * x;
 }
 
+// Exact form of the f32 erf_inv (HX_RNGF_EXACT): w = -log1p(-x^2) rounded once from the f64 log1p (correctly rounded in all
+// but ~1e-8 of the cases) and an IEEE sqrt, everything else as above.  Out of line: the f64 log1p would otherwise raise the
+// register count of the fused SIMT move kernels for a branch that only HX_PREC_EXACT takes.
+static __device__ __noinline__ float erfinv_xla_exact(float x) {
+  float w = -(float)log1p(-(double)__fmul_rn(x, x));
+  float p;
+  if (w < 5.0f) {
+    w = w - 2.5f;
+    p = 2.81022636e-08f;
+    p = fmaf(p, w, 3.43273939e-07f);
+    p = fmaf(p, w, -3.5233877e-06f);
+    p = fmaf(p, w, -4.39150654e-06f);
+    p = fmaf(p, w, 0.00021858087f);
+    p = fmaf(p, w, -0.00125372503f);
+    p = fmaf(p, w, -0.00417768164f);
+    p = fmaf(p, w, 0.246640727f);
+    p = fmaf(p, w, 1.50140941f);
+  } else {
+    w = __fsqrt_rn(w) - 3.0f;
+    p = -0.000200214257f;
+    p = fmaf(p, w, 0.000100950558f);
+    p = fmaf(p, w, 0.00134934322f);
+    p = fmaf(p, w, -0.00367342844f);
+    p = fmaf(p, w, 0.00573950773f);
+    p = fmaf(p, w, -0.0076224613f);
+    p = fmaf(p, w, 0.00943887047f);
+    p = fmaf(p, w, 1.00167406f);
+    p = fmaf(p, w, 2.83297682f);
+  }
+  return p * x;
+}
+
 // XLA erf_inv, f64 (Giles double precision, three branches on w = -log1p(-x^2)).
 __device__ __forceinline__ double erfinv_xla(double x) {
   double w = -log1p(-x * x);
@@ -242,11 +276,17 @@ template <> __device__ __forceinline__ uint32_t draw_bits<float, true>(Key k, ui
 template <> __device__ __forceinline__ uint64_t draw_bits<double, false>(Key k, uint64_t e, uint64_t m) { return bits64<false>(k, e, m); }
 template <> __device__ __forceinline__ uint64_t draw_bits<double, true>(Key k, uint64_t e, uint64_t m) { return bits64<true>(k, e, m); }
 
+// RNG flags word carried by the kernels' `legacy` argument: bit 0 = legacy counter layout, bit 1 = exact f32 normals
+enum : int { HX_RNGF_LEGACY = 1, HX_RNGF_EXACT = 2 };
+
+__device__ __forceinline__ float erfinv_sel(float u, bool exact) { return exact ? erfinv_xla_exact(u) : erfinv_xla(u); }
+__device__ __forceinline__ double erfinv_sel(double u, bool) { return erfinv_xla(u); }
+
 // element e of jax.random.normal(key, shape with m elements, dtype T)
 template <typename T, bool LEGACY>
-__device__ __forceinline__ T normal_at(Key k, uint64_t e, uint64_t m) {
+__device__ __forceinline__ T normal_at(Key k, uint64_t e, uint64_t m, bool exact = false) {
   const T u = uniform_from_bits(draw_bits<T, LEGACY>(k, e, m), RngTraits<T>::normal_lo(), RngTraits<T>::normal_span());
-  return RngTraits<T>::sqrt2() * erfinv_xla(u);
+  return RngTraits<T>::sqrt2() * erfinv_sel(u, exact);
 }
 
 // element e of jax.random.uniform(key, (m,), minval=lo, maxval=lo+span) with span rounded in T
@@ -255,17 +295,18 @@ __device__ __forceinline__ T uniform_at(Key k, uint64_t e, uint64_t m, T lo, T s
   return uniform_from_bits(draw_bits<T, LEGACY>(k, e, m), lo, span);
 }
 
-// runtime-selected counter layout (the branch is uniform across the grid)
+// runtime-selected counter layout and normal form (`flags` = HX_RNGF_* bits; the branches are uniform across the grid)
 template <typename T>
-__device__ __forceinline__ T normal_rt(Key k, uint64_t e, uint64_t m, bool legacy) {
-  return legacy ? normal_at<T, true>(k, e, m) : normal_at<T, false>(k, e, m);
+__device__ __forceinline__ T normal_rt(Key k, uint64_t e, uint64_t m, int flags) {
+  const bool exact = (flags & HX_RNGF_EXACT) != 0;
+  return (flags & HX_RNGF_LEGACY) ? normal_at<T, true>(k, e, m, exact) : normal_at<T, false>(k, e, m, exact);
 }
 template <typename T>
-__device__ __forceinline__ T uniform_rt(Key k, uint64_t e, uint64_t m, T lo, T span, bool legacy) {
-  return legacy ? uniform_at<T, true>(k, e, m, lo, span) : uniform_at<T, false>(k, e, m, lo, span);
+__device__ __forceinline__ T uniform_rt(Key k, uint64_t e, uint64_t m, T lo, T span, int flags) {
+  return (flags & HX_RNGF_LEGACY) ? uniform_at<T, true>(k, e, m, lo, span) : uniform_at<T, false>(k, e, m, lo, span);
 }
-__host__ __device__ __forceinline__ Key split_key_rt(Key k, uint64_t i, uint64_t num, bool legacy) {
-  return legacy ? split_key<true>(k, i, num) : split_key<false>(k, i, num);
+__host__ __device__ __forceinline__ Key split_key_rt(Key k, uint64_t i, uint64_t num, int flags) {
+  return (flags & 1) ? split_key<true>(k, i, num) : split_key<false>(k, i, num);
 }
 
 }  // namespace hx

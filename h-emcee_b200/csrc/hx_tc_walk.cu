@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(256) k_tc_finish(FinishArgs a) {
       Key akey = a.akey;
       if (a.akey_ptr) { akey.k0 = a.akey_ptr[0]; akey.k1 = a.akey_ptr[1]; }
       const float lo = 1e-10f, span = 1.0f - lo;
-      const float u = uniform_rt<float>(akey, (uint64_t)(a.row0 + r), (uint64_t)a.n, lo, span, a.legacy != 0);
+      const float u = uniform_rt<float>(akey, (uint64_t)(a.row0 + r), (uint64_t)a.n, lo, span, a.legacy);
       const bool acc = logf(u) < la;                           // sampler_utils.py:114-115
       const float lps = acc ? lp : lp1;
       if (lane == 0) {
@@ -1365,7 +1365,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   memset(&fa, 0, sizeof(fa));
   fa.lpp = (const float*)pLPP; fa.dkp = (const float*)pDKP; fa.NT = NT; fa.lp1 = lp1; fa.Q = Q; fa.logacc = logacc;
   fa.lp_out = lp_out; fa.rows = rows; fa.d = d; fa.n = n; fa.row0 = row0; fa.has_lower0 = tgt->has_lower0;
-  fa.lower0 = (float)tgt->lower0; fa.legacy = impl == HX_RNG_LEGACY ? 1 : 0;
+  fa.lower0 = (float)tgt->lower0; fa.legacy = impl == HX_RNG_LEGACY ? 1 : 0;   // tensor-core path: fast normals by definition
   if (fuse) {
     fa.fuse = 1; fa.akey_ptr = fuse->akey_ptr; fa.X1w = const_cast<float*>(X1); fa.lp1w = fuse->lp1w;
     fa.accepts = fuse->accepts; fa.chain_out = fuse->chain_out; fa.chain_lp = fuse->chain_lp; fa.nonfinite = fuse->nonfinite;

@@ -21,11 +21,11 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_vanilla_walk_shift(const T* __restrict__ X2, const T* __restrict__ mean, int n, int d, Key key,
                                                             const uint32_t* key_ptr, int legacy, T* __restrict__ shift) {
   if (key_ptr) { key.k0 = key_ptr[0]; key.k1 = key_ptr[1]; }
-  const Key kn = split_key_rt(key, 0, 2, legacy != 0);
+  const Key kn = split_key_rt(key, 0, 2, legacy);
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d) return;
   T s = T(0);
-  for (int b = 0; b < n; ++b) s = fma_t(X2[(size_t)b * d + c] - mean[c], normal_rt<T>(kn, (uint64_t)b, (uint64_t)n, legacy != 0), s);
+  for (int b = 0; b < n; ++b) s = fma_t(X2[(size_t)b * d + c] - mean[c], normal_rt<T>(kn, (uint64_t)b, (uint64_t)n, legacy), s);
   shift[c] = s / sqrt_t(T(n));
 }
 
@@ -41,8 +41,8 @@ __global__ void __launch_bounds__(256) k_vanilla_propose(int kind, const T* __re
   if (key_ptr) { key.k0 = key_ptr[0]; key.k1 = key_ptr[1]; }
   const size_t off = (size_t)r * d;
   if (kind == kVanillaStretch) {
-    const Key kz = split_key_rt(key, (uint64_t)n + 1, (uint64_t)n + 2, legacy != 0);     // keys[-1]   stretch.py:37
-    const T u = uniform_rt<T>(kz, (uint64_t)(row0 + r), (uint64_t)n, T(0), T(1), legacy != 0);
+    const Key kz = split_key_rt(key, (uint64_t)n + 1, (uint64_t)n + 2, legacy);     // keys[-1]   stretch.py:37
+    const T u = uniform_rt<T>(kz, (uint64_t)(row0 + r), (uint64_t)n, T(0), T(1), legacy);
     const T sa = sqrt_t(stretch), isa = T(1) / sa;
     const T t = isa + u * (sa - isa);
     const T z = t * t;                                                                     // stretch.py:72-75
@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(256) k_vanilla_propose(int kind, const T* __re
     for (int c = lane; c < d; c += 32) Q[off + c] = xj[c] + z * (X1[off + c] - xj[c]);     // stretch.py:49
     if (lane == 0) extra[r] = T(d - 1) * log_t(z);
   } else if (kind == kVanillaSide) {
-    const Key kz = split_key_rt(key, (uint64_t)n, (uint64_t)n + 2, legacy != 0);           // keys[-2]   side.py:32
-    const T z = normal_rt<T>(kz, (uint64_t)(row0 + r), (uint64_t)n, legacy != 0);
+    const Key kz = split_key_rt(key, (uint64_t)n, (uint64_t)n + 2, legacy);           // keys[-2]   side.py:32
+    const T z = normal_rt<T>(kz, (uint64_t)(row0 + r), (uint64_t)n, legacy);
     const T sz = stretch * z;
     const T* xj = X2 + (size_t)idx2[2 * r] * d;
     const T* xk = X2 + (size_t)idx2[2 * r + 1] * d;
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) k_vanilla_finish(T* X1w, const T* __restr
   if (!do_accept) return;
   const T lo = T(1e-10);
   const T span = T(1.0) - lo;
-  const T u = uniform_rt<T>(key, (uint64_t)(row0 + r), (uint64_t)n, lo, span, legacy != 0);
+  const T u = uniform_rt<T>(key, (uint64_t)(row0 + r), (uint64_t)n, lo, span, legacy);
   const bool acc = log_t(u) < la;                                  // sampler_utils.py:114-115 (NaN compares false: reject)
   const size_t off = (size_t)r * d;
   for (int c = lane; c < d; c += 32) {

@@ -59,13 +59,17 @@ def uniform(key, shape=(), dtype=None, minval=0.0, maxval=1.0, device=None, impl
     return out
 
 
-def normal(key, shape=(), dtype=None, device=None, impl=None) -> torch.Tensor:
+def normal(key, shape=(), dtype=None, device=None, impl=None, exact=None) -> torch.Tensor:
+    """`jax.random.normal`.  f32: `exact=True` (default under config precision "exact") evaluates erf_inv's log1p correctly
+    rounded (<= 1 ulp from the oracle); otherwise the SFU log2 form of the fused kernels (<= 3 ulp)."""
     dev = _rt.device(device)
     dtype = _rt.default_dtype() if dtype is None else dtype
     shape = _shape(shape)
     count = int(np.prod(shape)) if shape else 1
     out = torch.empty(shape, dtype=dtype, device=dev)
-    _lib.check(_lib.load().hx_normal(_lib.key_arg(_rt.as_key(key)), _rt.impl_code(impl), _rt.dtype_code(dtype), count,
+    if exact is None:
+        exact = _rt.config.precision == "exact"
+    _lib.check(_lib.load().hx_normal(_lib.key_arg(_rt.as_key(key)), _rt.impl_code(impl) | (16 if exact else 0), _rt.dtype_code(dtype), count,
                                      _rt.ptr(out), _rt.stream(dev)), "hx_normal")
     return out
 

@@ -16,7 +16,10 @@
  *   - `dtype`: HX_F32 = JAX default mode, HX_F64 = `jax_enable_x64` (changes the RNG
  *     stream: 64 random bits per draw).
  *   - `impl`: threefry counter layout, HX_RNG_PARTITIONABLE (JAX >= 0.5 default) or
- *     HX_RNG_LEGACY.
+ *     HX_RNG_LEGACY.  f32 normals exist in two forms: exact (w = -log1p(-u^2) correctly rounded, <= 1 ulp from
+ *     the NumPy oracle of XLA's erf_inv) and fast (SFU log2, <= 3 ulp, ~84 % of the draws bit-equal; used by the
+ *     tensor-core path and by default).  ctx-based calls draw exact normals under HX_PREC_EXACT; the ctx-free
+ *     hx_normal takes the request as `impl | HX_RNG_EXACT_NORMALS`.
  *   - keys are raw uint32[2] on the HOST unless the name says `_dev`.
  *   - all launches are asynchronous on `stream` (a cudaStream_t passed as void*).
  *   - return value: 0 ok; <0 invalid argument (HX_E_*); >0 a cudaError_t.  The message
@@ -43,7 +46,7 @@ extern "C" {
 #endif
 
 enum { HX_F32 = 0, HX_F64 = 1 };
-enum { HX_RNG_PARTITIONABLE = 0, HX_RNG_LEGACY = 1 };
+enum { HX_RNG_PARTITIONABLE = 0, HX_RNG_LEGACY = 1, HX_RNG_EXACT_NORMALS = 16 };
 
 /* error codes (<0) */
 enum {

@@ -6,7 +6,8 @@ what the oracle replays (tests/test_oracle_golden.py, tests/golden/*.json) estab
   * the dual-averaging step size after 1e5 warm-up iterations, to 1e-3 relative (1e-7 in x64);
   * tau of the main phase given the printed (step, L), within 8 % (tau ~ 41) / 20 % (tau ~ 208, N / tau = 50);
   * the tuned L: a deterministic function of ChEES' running average T_bar, which scatters by +-15 % from stream to stream
-    (oracle: L = 20 ... 27 around the quickstart's printed 23) -- asserted as a range."""
+    (oracle: L = 20 ... 27 around the quickstart's printed 23) -- asserted as a range.  The adaptation notebook's printed
+    L = 25 is NOT reproducible with chees.py as shipped (test_adaptation_notebook_full_adaptive_run says why)."""
 import numpy as np
 import pytest
 import torch
@@ -50,19 +51,28 @@ def test_adaptation_notebook_fixed_parameters(hx):
 
 
 def test_adaptation_notebook_full_adaptive_run(hx):
-    """cells 5 / 11: step-size heuristic + DA + ChEES, 1e5 warm-up iterations on the device, 1e4 x 5 main iterations."""
+    """cells 5 / 11: step-size heuristic + DA + ChEES with 1e5 warm-up iterations on the device.
+
+    Reproduced: the printed initial step, and the printed dual-averaging step size to 1e-3.  NOT reproduced, and not by the
+    oracle either (tests/golden/adaptation_replay_adaptive_short.json: L = 594 after 1500 warm-up iterations): the printed
+    L = 25.  25 = ceil(T_min / step) = ceil(0.25 / 0.0101593) exactly, i.e. the notebook's revision of chees.py drove T to its
+    LOWER bound (its progress bar, 1e5 warm-up iterations in 40 s on a laptop, rules out anything but a short trajectory),
+    while chees.py as shipped ascends the ChEES criterion (chees.py:147-149 "Gradient ASCENT (note sign ...)") and drives T
+    to T_max = 10 on this target, for the oracle and for the device adapter alike.  Asserted for L: the saturated range
+    ceil(T_max * [1 - jitter, 1] / step) of finalize() (chees.py:176-192)."""
     tgt, x0, key = _adaptation_setup(hx)
     s = hx.HamiltonianEnsembleSampler(100, 2, tgt, step_size=0.01, verbose=False)
-    samples = s.run_mcmc(key, x0, 10**4, warmup=10**5, thin_by=5)
+    samples = s.run_mcmc(key, x0, 400, warmup=10**5, thin_by=5)
     assert float(s.step_size) == NB_ADAPT["initial"]
     step, L = float(s.found[0]), int(s.found[1])
     assert abs(step - NB_ADAPT["step"]) <= 1e-3 * NB_ADAPT["step"], step
-    assert 0.8 * NB_ADAPT["L"] <= L <= 1.2 * NB_ADAPT["L"], L
+    T_max, jitter = 10.0, 0.6
+    assert np.ceil(0.97 * T_max * (1 - jitter) / step) <= L <= np.ceil(T_max / step), L
+    assert samples.shape == (400, 100, 2)
+    flat = samples.reshape(-1, 2)
+    np.testing.assert_allclose(flat.mean(0), [1.0, 1.5], atol=0.1)          # E x0 = 1, E x1 = 1 + Var x0 = 3/2
     tau = hx.autocorr.integrated_time(samples, quiet=True)
-    assert np.all(tau > 10) and np.all(tau < 120), tau        # tau(L) is steep; the printed 41 belongs to L = 25 exactly
-    if L == NB_ADAPT["L"]:
-        np.testing.assert_allclose(tau, NB_ADAPT["tau"], rtol=0.15)
-    assert samples.shape == (10**4, 100, 2)
+    assert np.all(tau < 3), tau                                             # trajectories of length ~7: nearly independent draws
 
 
 def test_quickstart_notebook_full_adaptive_run_x64(hx):
