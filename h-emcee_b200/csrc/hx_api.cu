@@ -6,6 +6,7 @@
 #include <cmath>
 #include <new>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/hx.h"
 #include "hx_common.cuh"
@@ -58,7 +59,13 @@ int ensure_smem_attr(hx_ctx* ctx, const void* func, int bytes) {
   return 0;
 }
 
+// Phase boundary of a half-move on the launch stream: an NVTX range per phase (nsys / ncu --nvtx attribute the launches enqueued
+// inside it; header-only NVTX3, a no-op unless a tool is attached) and, when hx_ctx_set_timing is on, a CUDA event.
+static const char* const kPhaseName[HX_PH_COUNT] = {"hx:project(draw+GEMM)", "hx:prep(mean,C^T,Gram,MP)", "hx:propagator-basis", "hx:leapfrog+energies",
+                                                    "hx:finish(accept,emit)", "hx:wait-peers", "hx:push-rows", "hx:stats"};
 int timing_mark(hx_ctx* ctx, cudaStream_t s, int phase) {
+  if (ctx->nvtx_open) { nvtxRangePop(); ctx->nvtx_open = 0; }
+  if (phase >= 0 && phase < HX_PH_COUNT) { nvtxRangePushA(kPhaseName[phase]); ctx->nvtx_open = 1; }
   if (!ctx->timing) return 0;
   if (!ctx->ev) { ctx->ev = new (std::nothrow) std::vector<cudaEvent_t>(); ctx->ev_tag = new (std::nothrow) std::vector<int>(); }
   if (!ctx->ev || !ctx->ev_tag) return hx_fail(HX_E_NULL, "out of host memory");
@@ -896,6 +903,8 @@ static int run_iterations_body(hx_ctx* ctx, int impl, int move_kind, int key_ord
         e = side_move_t<T>(ctx, impl, tgt, Xa, Xb, n, 0, n, eps, Key{0, 0}, kmove, L, lpa, (T*)pQ, (T*)pLa, nullptr, (T*)pLp, 0, &f, s);
       if (e) return e;
     }
+    if (ctx->stats_on)
+      if (int e = stats_feed(ctx, sizeof(T) == 4 ? HX_F32 : HX_F64, &ctx->stats, X, s)) return e;
   }
   return 0;
 }
@@ -912,8 +921,9 @@ static int run_iterations_t(hx_ctx* ctx, int impl, int move_kind, int key_order,
     return run_iterations_body<T>(ctx, impl, move_kind, key_order, tgt, X, lp, n, eps, L, keys, Tn, chain, chain_lp, accepts, nonfinite, s);
   const uint32_t* staged = nullptr;
   if (int e = stage_keys(ctx, keys, (size_t)Tn * 8, &staged, s)) return e;
-  struct { int impl, move_kind, key_order, n, L, every, phase, dt, narrow_off, leap_form; double eps; int64_t Tn; const void *X, *lp, *chain, *clp, *acc, *nf; hx_target tg; } K;
+  struct { int impl, move_kind, key_order, n, L, every, phase, dt, narrow_off, leap_form, stats_on; double eps; int64_t Tn; const void *X, *lp, *chain, *clp, *acc, *nf; hx_target tg; hx_chain_stats st; } K;
   memset(&K, 0, sizeof(K));
+  K.stats_on = ctx->stats_on; if (ctx->stats_on) K.st = ctx->stats;
   K.impl = impl; K.move_kind = move_kind; K.key_order = key_order; K.n = n; K.L = L; K.every = ctx->chain_every; K.phase = ctx->chain_phase;
   K.dt = (int)sizeof(T); K.narrow_off = ctx->narrow_off; K.leap_form = ctx->leap_form; K.eps = eps; K.Tn = Tn; K.X = X; K.lp = lp; K.chain = chain; K.clp = chain_lp; K.acc = accepts; K.nf = nonfinite;
   K.tg = *tgt;
@@ -1011,6 +1021,8 @@ static int run_vanilla_t(hx_ctx* ctx, int impl, int kind, const hx_target* tgt, 
                                     chain_lp ? chain_lp + (size_t)t * W2 + (size_t)half * n : nullptr, nonfinite, s))
         return e;
     }
+    if (ctx->stats_on)
+      if (int e = stats_feed(ctx, sizeof(T) == 4 ? HX_F32 : HX_F64, &ctx->stats, X, s)) return e;
   }
   return 0;
 }

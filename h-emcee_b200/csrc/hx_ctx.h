@@ -6,6 +6,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "hx_err.h"
+#include "../../include/hx.h"
 
 enum Slot {
   WS_C = 0, WS_M, WS_MEAN, WS_PART, WS_G, WS_S, WS_Q, WS_LA, WS_LP, WS_IDX, WS_GRAMP,
@@ -53,6 +54,7 @@ struct hx_ctx {
   size_t ev_used;
   double phase_ms[8]; int64_t phase_n[8];   // last hx_ctx_timing_read, by phase
   int64_t launches;               // all kernels launched through this ctx
+  int nvtx_open;                  // an NVTX phase range is open on this host thread (timing_mark)
   int last_gram_slices;
   int precision;                  // HX_PREC_*
   int last_path;                  // 0 fused SIMT half-move, 1 tcgen05 projection GEMM
@@ -70,6 +72,7 @@ struct hx_ctx {
   std::vector<GraphEntry>* graphs; cudaStream_t gstream; uint64_t graph_tick; int graphs_off;
   uint64_t ws_generation;                  // bumped whenever ws_get moves a workspace slot: captured graphs from before are stale
   void* key_stage; size_t key_stage_cap;    // fixed-address copy of a batch's keys (graph replays read the keys from here)
+  hx_chain_stats stats; int stats_on;      // on-device chain statistics fed by the batch loops after every iteration (hx_stats.cu)
   int chain_every, chain_phase;            // thinned chain emit of the batch loops (hx_ctx_set_chain_thinning); 0/1 = every iteration
   const void* ctl_eps; const int* ctl_L;   // device-resident (step, L) the SIMT move kernels read during adaptive warm-up
   int narrow_off;                          // 1: keep the momentum projection of narrow targets inside the half-move kernel
@@ -94,6 +97,7 @@ struct hx_ctx {
   std::vector<const void*>* attr_done;     // kernels whose dynamic-shared-memory attribute was set on THIS ctx's device (attributes are per device)
 };
 
+namespace hx { int stats_feed(hx_ctx* ctx, int dtype, const hx_chain_stats* st, const void* X, cudaStream_t s); }
 // cudaFuncAttributeMaxDynamicSharedMemorySize once per (ctx = device, kernel)
 int ensure_smem_attr(hx_ctx* ctx, const void* func, int bytes);
 // grow-only scratch slot

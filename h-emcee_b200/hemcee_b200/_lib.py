@@ -45,6 +45,14 @@ class hx_adapt_state(C.Structure):
                 ("ch_iteration", C.c_double), ("ch_halton", C.c_double)]
 
 
+class hx_chain_stats(C.Structure):
+    _fields_ = [("nwalkers", C.c_int32), ("dim", C.c_int32),
+                ("n_track", C.c_int32), ("walker_stride", C.c_int32), ("n_dims", C.c_int32), ("max_lag", C.c_int32),
+                ("dims_dev", C.c_void_p), ("count_dev", C.c_void_p),
+                ("sum_dev", C.c_void_p), ("sumsq_dev", C.c_void_p), ("partial_dev", C.c_void_p),
+                ("lagsum_dev", C.c_void_p), ("ring_dev", C.c_void_p), ("first_dev", C.c_void_p), ("total_dev", C.c_void_p)]
+
+
 _P = C.c_void_p
 _KEY = C.POINTER(C.c_uint32)
 _PROTOS = {
@@ -80,6 +88,9 @@ _PROTOS = {
     "hx_run_iterations": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.c_double,
                                     C.c_int32, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "hx_ctx_set_chain_thinning": (C.c_int, [_P, C.c_int32, C.c_int32]),
+    "hx_stats_row_blocks": (C.c_int32, []),
+    "hx_stats_feed": (C.c_int, [_P, C.c_int, C.POINTER(hx_chain_stats), _P, _P]),
+    "hx_ctx_set_chain_stats": (C.c_int, [_P, C.POINTER(hx_chain_stats)]),
     "hx_run_warmup": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.POINTER(hx_adapt_params),
                                 C.POINTER(hx_adapt_state), _P, C.c_int64, _P, _P, _P, _P, _P]),
     "hx_vanilla_move": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.c_int32, C.c_int32,

@@ -26,6 +26,7 @@ class Backend:
         # (stored_first = warmup, stored_stride = thin_by) while `iteration` still counts the iterations that were RUN.
         self.stored_first, self.stored_stride = 0, 1
         self._last_sample = None
+        self.stats = None               # on-device accumulators of the main phase (hemcee_b200.stats.ChainStats), if the sampler keeps them
         self.initialized = True
 
     def set_stored_layout(self, first: int, stride: int, last_sample=None):
@@ -84,6 +85,12 @@ class Backend:
         return c[-1], self.log_prob[-1][-1]
 
     def get_autocorr_time(self, discard=0, thin=1, **kwargs):
+        if self.stats is not None and sum(len(c) for c in self.chain) == 0:
+            # no chain was stored (store="none"): the estimate comes from the on-device accumulators of the main phase
+            if thin != 1:
+                raise ValueError("the on-device accumulators see every main-phase iteration: thin must be 1")
+            kwargs.pop("has_walkers", None)
+            return self.stats.integrated_time(**kwargs)
         return thin * autocorr.integrated_time(self.get_chain(discard=discard, thin=thin), **kwargs)
 
     @property

@@ -90,7 +90,7 @@ class BaseSampler:
 class HamiltonianEnsembleSampler(BaseSampler):
     def __init__(self, total_chains, dim, log_prob, step_size=0.1, L=10, move=hmc_walk_move, backend=None,
                  adapt_inital_step_size=True, adapt_step_size=True, adapt_length=True, *, device=None, group=None,
-                 chain_store="full", exchange="peer", store="full", verbose=True):
+                 chain_store="full", exchange="peer", store="full", online_stats=None, verbose=True):
         super().__init__(total_chains, dim, log_prob, move, backend)
         if getattr(move, "__name__", None) not in ("hmc_walk_move", "hmc_side_move"):
             raise ValueError("HamiltonianEnsembleSampler on B200 supports move=hmc_walk_move or hmc_side_move")
@@ -105,10 +105,17 @@ class HamiltonianEnsembleSampler(BaseSampler):
         self.verbose = verbose
         self.group = group
         self.chain_store = chain_store
-        if store not in ("full", "thinned"):
-            raise ValueError("store must be 'full' (every iteration, like the reference) or 'thinned' (only the iterations "
-                             "run_mcmc returns: no warm-up, every thin_by-th main iteration)")
+        if store not in ("full", "thinned", "none"):
+            raise ValueError("store must be 'full' (every iteration, like the reference), 'thinned' (only the iterations "
+                             "run_mcmc returns: no warm-up, every thin_by-th main iteration) or 'none' (no chain leaves the "
+                             "device: results through online_stats / get_last_sample)")
         self.store = store
+        # on-device chain statistics of the MAIN phase (hemcee_b200.stats.ChainStats: moments over all walkers, lagged products
+        # of the tracked series -> integrated_time without a stored chain).  True = defaults, dict = ChainStats keyword arguments.
+        if online_stats is True:
+            online_stats = {}
+        self.online_stats = online_stats if isinstance(online_stats, dict) else None
+        self.stats = None
         if exchange not in ("peer", "nccl"):
             raise ValueError("exchange must be 'peer' (NVLink peer-memory stores from the kernels) or 'nccl' (all-gather)")
         self.exchange = exchange
@@ -165,7 +172,7 @@ class HamiltonianEnsembleSampler(BaseSampler):
 
     @property
     def _thinned(self):
-        return self.store == "thinned" and self.world == 1
+        return self.store in ("thinned", "none") and self.world == 1
 
     @property
     def _move_kind(self):
@@ -559,8 +566,20 @@ class HamiltonianEnsembleSampler(BaseSampler):
         if self.world == 1:
             X = torch.cat([group1, group2]).contiguous()
             lp = self.log_prob(X)                                                    # :325-326
-            acc = self._run_batches(key, X, lp, total, step_size, L, batch_size, 0 if self._thinned else warmup_offset, 0,
-                                    show_progress, thin_store=thin_by if self._thinned else 1)
+            if self.online_stats is not None:
+                from .stats import ChainStats
+                cfg = dict(max_lag=128, walkers=min(self.total_chains, 1024), dims=None if self.dim <= 64 else list(range(16)))
+                cfg.update(self.online_stats)
+                self.stats = ChainStats(self.total_chains, self.dim, self.dtype, self.device, **cfg)
+                self.backend.stats = self.stats
+                self.stats.attach()
+            try:
+                thin_store = 0 if self.store == "none" else (thin_by if self._thinned else 1)
+                acc = self._run_batches(key, X, lp, total, step_size, L, batch_size, 0 if self._thinned else warmup_offset, 0,
+                                        show_progress, thin_store=thin_store)
+            finally:
+                if self.stats is not None:
+                    self.stats.detach()
             self.last_state, self.last_log_prob = X, lp
         elif self._peer_ok:
             acc = self._run_batches_sharded(key, group1, group2, total, step_size, L, batch_size, warmup_offset, 0, show_progress)

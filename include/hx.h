@@ -261,6 +261,33 @@ HX_API int hx_run_iterations(hx_ctx* ctx, int dtype, int impl, int move_kind, in
  * (backend/backend.py:63-66), which is 262 MB per iteration at c5.  every = 1 restores the default.               */
 HX_API int hx_ctx_set_chain_thinning(hx_ctx* ctx, int32_t every, int32_t phase);
 
+/* ---- (4a) on-device chain statistics ------------------------------------------------------------
+ * The reference estimates moments and the integrated autocorrelation time from the stored chain
+ * (backend/backend.py:174-211 keeps every iteration, autocorr.py:15-34,44-118 FFT estimator).  These accumulators give the
+ * same numbers without storing the chain: per iteration `hx_stats_feed` adds the ensemble X[nwalkers, dim] to
+ *   count[1], sum[dim], sumsq[dim]          over ALL walkers (fixed-order partial sums: bit-reproducible)
+ * and, for the tracked series s = j * n_dims + i  (walker row j * walker_stride, parameter dims_dev[i] or i), to
+ *   lagsum[k, s] = sum_{t >= k} x_t x_{t-k}  (k < max_lag),  total[s] = sum_t x_t,
+ *   first[t, s] = x_t (t < max_lag),  ring[t mod max_lag, s] = x_t (the last max_lag values)
+ * from which sum_t (x_t - m)(x_{t+k} - m) of autocorr.py:30-31 follows exactly for k < max_lag (csrc/hx_stats.cu).
+ * All pointers are DEVICE buffers owned and ZEROED by the caller; `ring`/`first` have the run dtype, the rest is f64;
+ * partial_dev is scratch of 2 * hx_stats_row_blocks() * dim doubles.  hx_ctx_set_chain_stats(ctx, stats) makes the
+ * single-GPU batch loops (hx_run_iterations, hx_run_vanilla_iterations) feed `stats` after EVERY iteration (thinning of the
+ * chain emit does not apply); NULL switches it off.  The struct is copied.                                            */
+typedef struct hx_chain_stats {
+  int32_t nwalkers, dim;
+  int32_t n_track, walker_stride, n_dims, max_lag;
+  const int32_t* dims_dev;      /* int32 [n_dims] or NULL = parameters 0 .. n_dims-1 */
+  int64_t* count_dev;
+  double *sum_dev, *sumsq_dev, *partial_dev;
+  double* lagsum_dev;           /* [max_lag, n_track * n_dims] */
+  void *ring_dev, *first_dev;   /* [max_lag, n_track * n_dims], run dtype */
+  double* total_dev;            /* [n_track * n_dims] */
+} hx_chain_stats;
+HX_API int32_t hx_stats_row_blocks(void);
+HX_API int hx_stats_feed(hx_ctx* ctx, int dtype, const hx_chain_stats* stats, const void* X_dev, void* stream);
+HX_API int hx_ctx_set_chain_stats(hx_ctx* ctx, const hx_chain_stats* stats);
+
 /* ---- (4b) batch level: the WARM-UP scan with live adapters (device-resident adaptation) ---------------------
  * Replaces the warm-up scan body of samplers/hamiltonian_ensemble.py:165-217 for the dual-averaging step-size adapter
  * (adaptation/dual_averaging.py:16-96), the ChEES trajectory-length adapter (adaptation/chees.py:18-219) and their

@@ -186,24 +186,45 @@ _ERFINV64_GE16 = (
 )
 
 
-def _horner(coeffs, w, dtype):
+# How the f32 erf_inv is ROUNDED is not part of the algorithm and differs between XLA backends; the oracle fixes one
+# well-defined, platform-independent form (ERFINV32_FORM = "cr-fma"):
+#   * w = -log1p(-x*x) correctly rounded to f32 (evaluated in f64 and rounded once).  glibc's log1pf ("libm" form) is
+#     not correctly rounded (it differs from this in ~1 % of the draws, which moves ~1 % of the normals by 1-3 ulp), and
+#     XLA itself expands log1p as log(1 + x) with its own polynomial logf, so no libm is "the" reference;
+#   * the Horner steps p*w + c are FUSED (one rounding): XLA's CPU compiler always allows FMA fusion
+#     (cpu_compiler.cc CompilerTargetOptions: AllowFPOpFusion = Fast) and NVPTX contracts by default.
+# The "libm" form (np.log1p in f32, unfused Horner) is kept for comparison: the two agree to <= 3 ulp, ~95 % bit-equal
+# (tests/test_oracle_rng.py).  f64 has no such ambiguity at the tolerances used (1e-13).
+ERFINV32_FORM = "cr-fma"
+
+
+def _horner(coeffs, w, dtype, fma=False):
     p = np.full_like(w, dtype(coeffs[0]))
     for c in coeffs[1:]:
-        p = dtype(c) + p * w
+        if fma:      # f32 fma: the f64 product of two f32 is exact, the sum is rounded to f64 and then to f32
+            p = (p.astype(np.float64) * w.astype(np.float64) + np.float64(dtype(c))).astype(dtype)
+        else:
+            p = dtype(c) + p * w
     return p
 
 
-def erf_inv(x: np.ndarray) -> np.ndarray:
-    """XLA's `erf_inv` (Giles' polynomials), evaluated in the dtype of `x`."""
+def erf_inv(x: np.ndarray, form: str = None) -> np.ndarray:
+    """XLA's `erf_inv` (Giles' polynomials), evaluated in the dtype of `x`; `form` selects the f32 rounding ("cr-fma" |
+    "libm", default ERFINV32_FORM)."""
     x = np.asarray(x)
     dt = x.dtype.type
+    form = ERFINV32_FORM if form is None else form
     with np.errstate(divide="ignore", invalid="ignore"):
-        w = -np.log1p(-x * x)
+        if dt == np.float32 and form == "cr-fma":
+            w = (-np.log1p(-(x * x).astype(np.float64))).astype(np.float32)
+        else:
+            w = -np.log1p(-x * x)
         if dt == np.float32:
+            fma = form == "cr-fma"
             lt = w < dt(5.0)
             wa = w - dt(2.5)
             wb = np.sqrt(w) - dt(3.0)
-            p = np.where(lt, _horner(_ERFINV32_LT5, wa, dt), _horner(_ERFINV32_GE5, wb, dt))
+            p = np.where(lt, _horner(_ERFINV32_LT5, wa, dt, fma), _horner(_ERFINV32_GE5, wb, dt, fma))
         else:
             lt1 = w < dt(6.25)
             lt2 = w < dt(16.0)
@@ -220,12 +241,12 @@ def erf_inv(x: np.ndarray) -> np.ndarray:
     return res.astype(dt)
 
 
-def normal(key, shape=(), dtype=np.float32, impl: str = DEFAULT_IMPL) -> np.ndarray:
+def normal(key, shape=(), dtype=np.float32, impl: str = DEFAULT_IMPL, form: str = None) -> np.ndarray:
     """`jax.random.normal`: sqrt(2) * erf_inv(uniform(key, shape, nextafter(-1, 0), 1))."""
     dtype = np.dtype(dtype).type
     lo = np.nextafter(dtype(-1.0), dtype(0.0))
     u = uniform(key, shape, dtype, lo, dtype(1.0), impl)
-    return (dtype(np.sqrt(2)) * erf_inv(u)).astype(dtype)
+    return (dtype(np.sqrt(2)) * erf_inv(u, form)).astype(dtype)
 
 
 def shuffle_rounds(n: int) -> int:

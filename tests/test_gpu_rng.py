@@ -45,16 +45,19 @@ def test_uniform_exact(hx, impl, dtype):
 
 @pytest.mark.parametrize("impl", IMPLS)
 def test_normal_f32_ulp(hx, impl):
-    """f32 normals against the oracle's XLA erf_inv (np.log1p form).  Exact form (HX_PREC_EXACT / HX_RNG_EXACT_NORMALS):
-    <= 1 ulp everywhere and > 99 % of the draws bit-equal; fast form (SFU log2, what the fused kernels draw): <= 3 ulp and
-    > 80 % bit-equal (measured on B200: 84 %)."""
+    """f32 normals against the oracle's XLA erf_inv (jaxrng.ERFINV32_FORM: correctly rounded log1p, fused Horner).
+    Exact form (HX_PREC_EXACT / HX_RNG_EXACT_NORMALS; same definition: f64 log1p rounded once, fmaf Horner, IEEE sqrt):
+    <= 1 ulp and > 99.99 % of the draws bit-equal (a mismatch needs the f64 log1p to land within 2^-29 of an f32 rounding
+    boundary).  Fast form (SFU log2 of 1 - u^2, what the fused kernels draw): <= 3 ulp, > 80 % bit-equal."""
     key = R.PRNGKey(5)
     ref = R.normal(key, (1000, 1001), np.float32, impl)
     ulp = np.spacing(np.abs(ref).astype(np.float32))
     exact = hx.random.normal(key, (1000, 1001), torch.float32, impl=impl, exact=True).cpu().numpy()
-    assert np.max(np.abs(exact - ref) / ulp) <= 1.0         # tolerance: 1 ulp (f32), exact form
-    assert np.mean(exact == ref) > 0.99
     fast = hx.random.normal(key, (1000, 1001), torch.float32, impl=impl, exact=False).cpu().numpy()
+    print(f"exact: max {np.max(np.abs(exact - ref) / ulp)} ulp, bit-equal {np.mean(exact == ref):.6f}; "
+          f"fast: max {np.max(np.abs(fast - ref) / ulp)} ulp, bit-equal {np.mean(fast == ref):.4f}")
+    assert np.max(np.abs(exact - ref) / ulp) <= 1.0         # tolerance: 1 ulp (f32), exact form
+    assert np.mean(exact == ref) > 0.9999
     assert np.max(np.abs(fast - ref) / ulp) <= 3.0          # tolerance: 3 ulp (f32), fast form
     assert np.mean(fast == ref) > 0.8
 

@@ -29,6 +29,26 @@ def test_split_kat():
         np.testing.assert_array_equal(R.split(R.PRNGKey(v["seed"]), v["num"], v["impl"]), np.array(v["out"], np.uint32))
 
 
+def test_erfinv32_forms_agree_to_3_ulp():
+    """The two roundings of the f32 erf_inv the oracle knows (jaxrng.ERFINV32_FORM: correctly rounded log1p + fused Horner, the
+    default; and libm log1pf + unfused Horner) are the same algorithm: <= 3 ulp apart, > 90 % of the draws bit-equal."""
+    key = R.PRNGKey(5)
+    a = R.normal(key, (400, 401), np.float32, "partitionable", form="cr-fma")
+    b = R.normal(key, (400, 401), np.float32, "partitionable", form="libm")
+    np.testing.assert_array_equal(a, R.normal(key, (400, 401), np.float32, "partitionable"))      # the default form
+    ulp = np.spacing(np.abs(a))
+    assert np.max(np.abs(a - b) / ulp) <= 3.0
+    assert np.mean(a == b) > 0.9
+
+
+@pytest.mark.parametrize("form", ["cr-fma", "libm"])
+def test_normal_f32_doc_values_both_forms(form):
+    for v in KAT["normal_f32"]:
+        key = np.array(v["key"], np.uint32) if "key" in v else R.PRNGKey(v["seed"])
+        got = R.normal(key, tuple(v["shape"]), np.float32, v["impl"], form=form)
+        np.testing.assert_allclose(np.atleast_1d(got), v["out"], atol=KAT["normal_tol"], rtol=0)
+
+
 def test_normal_f32_doc_values():
     for v in KAT["normal_f32"]:
         key = R.PRNGKey(v["seed"]) if "seed" in v else np.array(v["key"], np.uint32)
