@@ -639,37 +639,39 @@ def main():
     #      quiet) on a fixed subset of <= 16 dims x <= 1024 walkers, after a burn-in; device-resident state, untimed by `value`
     ess = None
     if world == 1 and args.ess_iters > 0 and not args.no_e2e:
-        from hemcee_b200 import autocorr as hac
-        Tb, Te, Bq = 48, args.ess_iters, 8
+        # no chain leaves the kernels here: the on-device accumulators (hemcee_b200.stats.ChainStats, csrc/hx_stats.cu) are fed
+        # after every iteration inside hx_run_iterations and give the reference estimator's tau for lags < max_lag
+        from hemcee_b200.stats import ChainStats
+        Tb, Te = 48, args.ess_iters
         Xe = x0.clone(); lpe = tgt.log_prob(Xe)
         ke = hx.random.split_device(hx.random.PRNGKey(12345), 4 * (Tb + Te))
         acc_e = torch.zeros(W, dtype=torch.int32, device=dev)
-        cbuf = torch.empty((Bq, W, d), dtype=tdt, device=dev)
-        dims = torch.linspace(0, d - 1, min(16, d)).long().to(dev)
-        wsel = torch.linspace(0, W - 1, min(1024, W)).long().to(dev)
-        sub = torch.empty((Te, wsel.numel(), dims.numel()), dtype=tdt, device=dev)
+        dims = [int(v) for v in np.linspace(0, d - 1, min(16, d)).round()]
+        st = ChainStats(W, d, tdt, dev, max_lag=min(96, Te), walkers=min(1024, W), dims=dims)
 
-        def run_e(t0, T, store):
-            for b0 in range(0, T, Bq):
-                nb_ = min(Bq, T - b0)
-                _lib.check(lib.hx_run_iterations(ctx, _rt.dtype_code(tdt), _rt.impl_code(), mk, 0, desc, _rt.ptr(Xe), _rt.ptr(lpe), n,
-                                                 eps, L, _rt.ptr(ke[4 * (t0 + b0):]), nb_, _rt.ptr(cbuf), None, _rt.ptr(acc_e),
-                                                 _rt.ptr(flag), _rt.stream(dev)), "run_ess")
-                if store:
-                    sub[b0:b0 + nb_] = cbuf[:nb_][:, wsel][:, :, dims]
-        run_e(0, Tb, False)
+        def run_e(t0, T):
+            _lib.check(lib.hx_run_iterations(ctx, _rt.dtype_code(tdt), _rt.impl_code(), mk, 0, desc, _rt.ptr(Xe), _rt.ptr(lpe), n,
+                                             eps, L, _rt.ptr(ke[4 * t0:]), T, None, None, _rt.ptr(acc_e),
+                                             _rt.ptr(flag), _rt.stream(dev)), "run_ess")
+        run_e(0, Tb)
         torch.cuda.synchronize(dev)
+        st.attach()
         t0 = time.perf_counter()
-        run_e(Tb, Te, True)
-        torch.cuda.synchronize(dev)
+        try:
+            run_e(Tb, Te)
+            torch.cuda.synchronize(dev)
+        finally:
+            st.detach()
         el = time.perf_counter() - t0
-        tau = np.asarray(hac.integrated_time(sub, c=5, tol=50, quiet=True))
+        tau = np.asarray(st.integrated_time(c=5, tol=50, quiet=True))
         tmax = float(np.nanmax(tau))
         ess = dict(value=Te * W / tmax / el, unit="ESS/s", tau_max=tmax, tau_min=float(np.nanmin(tau)), iterations=Te, burn_in=Tb,
-                   seconds=el, reliable=bool(50 * tmax <= Te), dims=int(dims.numel()), walkers_in_estimate=int(wsel.numel()),
-                   note="min over the sampled dims of (iterations * walkers / tau_int) / wall time of those iterations; fixed "
-                        "step size and L (no adaptation), chain started from N(0, I)")
-        del sub, cbuf
+                   seconds=el, reliable=bool(50 * tmax <= Te), dims=len(dims), walkers_in_estimate=int(st.n_track),
+                   mean_abs_max=float(np.abs(st.mean()).max()), var_minmax=[float(st.var().min()), float(st.var().max())],
+                   note="min over the sampled dims of (iterations * walkers / tau_int) / wall time of those iterations; tau_int = the "
+                        "reference's estimator (autocorr.py:44-118, c=5, tol=50) evaluated from on-device accumulators (no chain is "
+                        "stored or copied: hx_ctx_set_chain_stats); fixed step size and L (no adaptation), chain started from "
+                        "N(0, I); mean / var = running moments over all walkers and those iterations")
 
     # ESS/s at N > 1: the sharded loop continues from the timed state; every rank estimates tau_int on a subset of ITS rows
     if world > 1 and args.ess_iters > 0 and not args.no_e2e:

@@ -31,6 +31,8 @@
 #pragma once
 #include "hx_tc_gemm.cuh"
 #include "hx_rng.cuh"
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 namespace hx {
 namespace tc {
@@ -138,6 +140,25 @@ __device__ __forceinline__ void split8_bf16(const float (&x)[8], uint4& hi, uint
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// fp16 + fp8 form of eight values at TRUE scale (FMT 1): p16 = fp16(x) (main operand), v8 = e4m3(x), r8 = e5m2(x - fp16(x)).
+// The correction products e4m3(x) * e5m2(res b) and e5m2(res x) * e4m3(b) need no rescaling (e5m2 reaches down to 2^-16, the
+// fp16 residual of |x| < 6 is < 2^-9.6), so they accumulate into the SAME accumulator as the main product.
+__device__ __forceinline__ void split8_f16e(const float (&x)[8], uint4& p16, uint2& v8, uint2& r8) {
+  uint32_t h[4];
+  uint16_t v[4], r[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const __half2 hp = __floats2half2_rn(x[2 * t], x[2 * t + 1]);
+    h[t] = *reinterpret_cast<const uint32_t*>(&hp);
+    const float2 hf = __half22float2(hp);
+    v[t] = __nv_cvt_float2_to_fp8x2(make_float2(x[2 * t], x[2 * t + 1]), __NV_SATFINITE, __NV_E4M3);
+    r[t] = __nv_cvt_float2_to_fp8x2(make_float2(x[2 * t] - hf.x, x[2 * t + 1] - hf.y), __NV_SATFINITE, __NV_E5M2);
+  }
+  p16 = make_uint4(h[0], h[1], h[2], h[3]);
+  v8 = make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
+  r8 = make_uint2((uint32_t)r[0] | ((uint32_t)r[1] << 16), (uint32_t)r[2] | ((uint32_t)r[3] << 16));
+}
+
 // try_wait with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint expires) instead of
 // returning after its default time slice -- the one-thread TMA / MMA warps and blocked RNG warps would otherwise spin on
 // try_wait + branch and take issue slots from the RNG warps of their scheduler (13 % of all issued instructions, measured)
@@ -177,6 +198,9 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     if (++polls > (1u << 24)) __trap();
   }
 }
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, const uint2& v) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -210,6 +234,7 @@ struct FusedArgs {
   float* out; int ldo;
   int diag;         // diagnostics: 1 = no draw (A garbage), 2 = no MMA; results are garbage
   int relaxed_wait; // RNG warps poll their `empty` barrier with test_wait + nanosleep instead of a parked try_wait
+  const float* scale_ptr;   // FMT 1: {sc, 1/sc}, the power-of-two scale of the B planes; the epilogue multiplies by scale_ptr[1]
 };
 
 #ifndef HX_FUSED_SA
@@ -227,7 +252,11 @@ struct FusedSmem {
 
 // SHARE: the two CTAs of a (2,1,1) cluster own the two 512-column halves of one 128-row tile and each draws half of the
 // A tile for both; otherwise every CTA is on its own (dim <= 512).  NW = RNG warps per CTA.
-template <int NW, bool SHARE>
+// FMT 0: bf16 hi/lo operands, three kind::f16 products.  FMT 1: fp16 main product + two fp8 correction products at twice the
+// rate (A stage: plane 0 = fp16(x), plane 1 rows = [64 x e4m3(x) | 64 x e5m2(x - fp16(x))]; B planes (k_center_planes_T fmt 2):
+// plane 0 = fp16(b sc), plane 1 rows = [64 x e5m2(res) | 64 x e4m3(b sc)]): 8 instead of 12 MMAs and 192 KB instead of 288 KB of
+// shared-memory operand reads per K-block and CTA -- the resource that bounds the MMA side of this kernel.
+template <int NW, bool SHARE, int FMT>
 __global__ void __launch_bounds__(64 + 32 * NW, 1)
 k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
   using L = FusedSmem;
@@ -304,7 +333,21 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
             mbar_wait_parked(&fullB[s], (uint32_t)(it / L::SB) & 1u);
             tc_fence_after();
             const uint64_t bd = umma_desc_k128(smem_u32(stB + s * L::B_STAGE));
-            if (f.diag != 2) {
+            if (f.diag != 2 && FMT == 1) {
+              constexpr uint32_t dims = ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+              constexpr uint32_t idesc16 = (1u << 4) | dims;                    // kind::f16, A = B = F16 (format 0)
+              constexpr uint32_t idesc_vr = (1u << 4) | (1u << 10) | dims;      // kind::f8f6f4, A = E4M3 (0), B = E5M2 (1)
+              constexpr uint32_t idesc_rv = (1u << 4) | (1u << 7) | dims;       // kind::f8f6f4, A = E5M2 (1), B = E4M3 (0)
+              if (pl == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(dcol, ad_hi + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc16, (kb | k) != 0 ? 1u : 0u);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) umma_f8(dcol, ad_lo + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_vr, 1u);
+#pragma unroll
+                for (int k = 2; k < 4; ++k) umma_f8(dcol, ad_lo + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_rv, 1u);
+              }
+            } else if (f.diag != 2) {
               if (pl == 0) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_bf16(dcol, ad_hi + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
@@ -366,7 +409,13 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
         const bool tail = normals8_central(bcur, x, u, w);
         if (tail) normals8_fix_tail(x, u, w);
         bits8_fix_wrap(key, ks2, en, bnext);
-        split8_bf16(x, hi, lo);
+        if (FMT == 1) {
+          uint2 v8, r8;
+          split8_f16e(x, hi, v8, r8);
+          lo = make_uint4(v8.x, v8.y, r8.x, r8.y);
+        } else {
+          split8_bf16(x, hi, lo);
+        }
 #pragma unroll
         for (int t = 0; t < 8; ++t) bcur[t] = bnext[t];
       }
@@ -374,7 +423,14 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
       else mbar_wait_parked(&emptyA[sa], ((uint32_t)(kb / L::SA) & 1u) ^ 1u);
       const uint32_t so = (uint32_t)(sa * L::A_STAGE) + (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));   // 128-byte swizzle
       st_shared_v4(stA_local + so, hi);
-      st_shared_v4(stA_local + so + L::A_PLANE, lo);
+      if (FMT == 1) {
+        // fp8 plane row = [64 x e4m3(x) | 64 x e5m2(res)]: this lane's 8 bytes of each at byte chunk * 8 / 64 + chunk * 8
+        const uint32_t rowb = stA_local + (uint32_t)(sa * L::A_STAGE + L::A_PLANE + r * 128) + (uint32_t)((chunk & 1) << 3);
+        st_shared_v2(rowb + ((uint32_t)((chunk >> 1) ^ (r & 7)) << 4), make_uint2(lo.x, lo.y));
+        st_shared_v2(rowb + ((uint32_t)((4 + (chunk >> 1)) ^ (r & 7)) << 4), make_uint2(lo.z, lo.w));
+      } else {
+        st_shared_v4(stA_local + so + L::A_PLANE, lo);
+      }
       fence_proxy_async();         // generic-proxy stores -> visible to the async proxy (the tensor core's operand reads, the bulk copy)
       __syncwarp();
       // one arrival per item.  In a pair the item's 4 rows x 128 bytes per plane (contiguous in the swizzled layout) are also
@@ -397,12 +453,17 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
     const int row = m0 + 32 * q + lane;
     const bool vec = (f.d & 3) == 0 && (f.ldo & 3) == 0;
     float* out = f.out + (size_t)blockIdx.y * f.slice_stride;
+    const float inv_sc = (FMT == 1) ? f.scale_ptr[1] : 1.0f;
 #pragma unroll 1
     for (int cc = grp; cc < units * 8; cc += (NW + 3) / 4) {
       const int col0 = n0 + cc * 32;
       if (col0 >= f.d) break;             // warp-uniform
       float v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cc * 32), v);
+      if (FMT == 1) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[t] *= inv_sc;
+      }
       if (row < f.rows) {
         const int nval = min(32, f.d - col0);
         store32(out + (size_t)row * f.ldo + col0, v, nval, vec && nval == 32);

@@ -75,23 +75,27 @@ static int make_tmap(hx_ctx* ctx, CUtensorMap* out, const void* base, uint64_t r
 // x ~= fp16(x) + residual; the tensor core gets fp16(x) for the main product and e4m3(x), e4m3(residual * 2^11) for the two
 // correction products.  8 consecutive K elements at a time: 16 bytes of the fp16 plane, 8 + 8 bytes of the e4m3 plane whose
 // 128-byte rows hold [64 values | 64 residuals] per 64-element K-block.
+// fmt8 = 2 (B operand of the fused projection, hx_tc_fused.cuh FMT 1): residuals at TRUE scale in e5m2 and the halves swapped,
+// rows = [64 x e5m2(residual) | 64 x e4m3(value)], so that they pair with the A rows [e4m3(value) | e5m2(residual)].
 __device__ __forceinline__ void store_f16f8_x8(uint16_t* __restrict__ plane16, uint8_t* __restrict__ plane8_row, size_t o16, int j0,
-                                               const float (&x)[8]) {
+                                               const float (&x)[8], int fmt8) {
   __align__(16) __half h[8];
   __align__(8) __nv_fp8x2_storage_t v8[4], r8[4];
 #pragma unroll
   for (int t = 0; t < 8; ++t) h[t] = __float2half_rn(x[t]);
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    const float r0 = (x[2 * t] - __half2float(h[2 * t])) * kF8ResidualScale;
-    const float r1 = (x[2 * t + 1] - __half2float(h[2 * t + 1])) * kF8ResidualScale;
+    const float rs = fmt8 == 2 ? 1.0f : kF8ResidualScale;
+    const float r0 = (x[2 * t] - __half2float(h[2 * t])) * rs;
+    const float r1 = (x[2 * t + 1] - __half2float(h[2 * t + 1])) * rs;
     v8[t] = __nv_cvt_float2_to_fp8x2(make_float2(x[2 * t], x[2 * t + 1]), __NV_SATFINITE, __NV_E4M3);
-    r8[t] = __nv_cvt_float2_to_fp8x2(make_float2(r0, r1), __NV_SATFINITE, __NV_E4M3);
+    r8[t] = fmt8 == 2 ? __nv_cvt_float2_to_fp8x2(make_float2(r0, r1), __NV_SATFINITE, __NV_E5M2)
+                      : __nv_cvt_float2_to_fp8x2(make_float2(r0, r1), __NV_SATFINITE, __NV_E4M3);
   }
   *reinterpret_cast<uint4*>(plane16 + o16) = *reinterpret_cast<const uint4*>(h);
   uint8_t* p8 = plane8_row + (size_t)(j0 >> 6) * 128 + (j0 & 63);
-  *reinterpret_cast<uint2*>(p8) = *reinterpret_cast<const uint2*>(v8);
-  *reinterpret_cast<uint2*>(p8 + 64) = *reinterpret_cast<const uint2*>(r8);
+  *reinterpret_cast<uint2*>(p8 + (fmt8 == 2 ? 64 : 0)) = *reinterpret_cast<const uint2*>(v8);
+  *reinterpret_cast<uint2*>(p8 + (fmt8 == 2 ? 0 : 64)) = *reinterpret_cast<const uint2*>(r8);
 }
 
 // power-of-two scale of the centred complement C = (X2 - mean)/sqrt(n): max |C| * sc lies in [32, 64), inside the fp16 and
@@ -157,7 +161,7 @@ __global__ void k_f8_scale(const uint32_t* __restrict__ amax_bits, int n, float*
 __global__ void __launch_bounds__(256) k_center_planes_T(const float* __restrict__ X2, const float* __restrict__ mean, int n, int d,
                                                          int dB_pad, int Kp, __nv_bfloat16* __restrict__ planes,
                                                          float* __restrict__ planes32, uint16_t* __restrict__ planes8,
-                                                         const float* __restrict__ scale8) {
+                                                         const float* __restrict__ scale8, int fmt8) {
   constexpr int TJ = 256, TC = 32;
   __shared__ float tile[TJ][TC + 1];
   const int j0 = blockIdx.x * TJ, c0 = blockIdx.y * TC;
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(256) k_center_planes_T(const float* __restrict
       float xs[8];
 #pragma unroll
       for (int t = 0; t < 8; ++t) xs[t] = tile[jc * 8 + t][cc] * sc;
-      store_f16f8_x8(planes8, reinterpret_cast<uint8_t*>(planes8 + plane + (size_t)crow * Kp), o, jb, xs);
+      store_f16f8_x8(planes8, reinterpret_cast<uint8_t*>(planes8 + plane + (size_t)crow * Kp), o, jb, xs, fmt8);
     }
     *reinterpret_cast<uint4*>(planes + o) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(planes + plane + o) = *reinterpret_cast<const uint4*>(lo);
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(256) k_rng_planes(Key key, const uint32_t* key
       if (t == 12345.678f) planes[i] = __float2bfloat16_rn(t);
     } else if (FMT == 1) {
       uint16_t* p16 = reinterpret_cast<uint16_t*>(planes);
-      store_f16f8_x8(p16, reinterpret_cast<uint8_t*>(p16 + plane + (size_t)r * Kp), i, j0, x);
+      store_f16f8_x8(p16, reinterpret_cast<uint8_t*>(p16 + plane + (size_t)r * Kp), i, j0, x, 1);
     } else {
       __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
@@ -731,9 +735,9 @@ static inline int grid_for(size_t n, int block) {
 
 
 // ---- fused draw + projection (hx_tc_fused.cuh) --------------------------------------------------------------------------
-template <int NW, bool SHARE>
+template <int NW, bool SHARE, int FMT>
 static int launch_fused_t(hx_ctx* ctx, const CUtensorMap& tmB, const FusedArgs& f, int tiles, int slices, cudaStream_t s) {
-  auto kern = k_tc_proj_fused<NW, SHARE>;
+  auto kern = k_tc_proj_fused<NW, SHARE, FMT>;
   if (int e = ensure_smem_attr(ctx, (const void*)kern, FusedSmem::BYTES)) return e;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -764,15 +768,22 @@ static int fused_slices(const hx_ctx* ctx, int nkb) {
   if (s > nkb / 16) s = nkb / 16 > 0 ? nkb / 16 : 1;
   return s;
 }
-// S0[rows, d] = normal(key, (n, n))[row0 : row0 + rows] @ C, C^T given as bf16 hi/lo planes [2, dAB, nK]
+// operand form of the fused projection: 1 = bf16 hi/lo (three kind::f16 products), 2 = fp16 main + two fp8 products at true scale
+static int fused_format(const hx_ctx* ctx) {
+  if (ctx->fused_fmt == 1 || ctx->fused_fmt == 2) return ctx->fused_fmt;
+  return ctx->precision == HX_PREC_AUTO ? 2 : 1;
+}
+// S0[rows, d] = normal(key, (n, n))[row0 : row0 + rows] @ C, C^T given as bf16 hi/lo planes [2, dAB, nK] (scale8 == NULL) or as
+// fp16 + fp8 planes scaled by scale8[0] (k_center_planes_T fmt8 = 2)
 static int launch_proj_fused(hx_ctx* ctx, const void* CT, int dAB, int nK, int n, int row0, int rows, int d, Key key,
-                             const uint32_t* key_ptr, float* S0, cudaStream_t s) {
+                             const uint32_t* key_ptr, float* S0, cudaStream_t s, const float* scale8 = nullptr) {
   CUtensorMap tmB;
   if (int e = make_tmap(ctx, &tmB, CT, 2ull * dAB, nK, 256, KIND_BF16)) return e;
   FusedArgs f;
   memset(&f, 0, sizeof(f));
   f.key = key; f.key_ptr = key_ptr; f.n = n; f.row0 = row0; f.rows = rows; f.d = d; f.num_kb = nK / 64;
   f.rowsB_pad = dAB; f.out = S0; f.ldo = d; f.diag = ctx->fused_diag; f.relaxed_wait = ctx->fused_relaxed;
+  f.scale_ptr = scale8;
   const bool share = d > 512;
   f.units = share ? 2 : (d + 255) / 256;
   const int tiles = (rows + kBM - 1) / kBM;
@@ -787,7 +798,8 @@ static int launch_proj_fused(hx_ctx* ctx, const void* CT, int dAB, int nK, int n
   const int nw = ctx->fused_nw > 0 ? ctx->fused_nw : 28;      // measured in the c5 step: 28 >= 20 > 16 warps (17.0-17.4 / 17.3-17.5 / 17.4-17.6 ms per iteration)
   int e;
 #define HX_FUSED_NW(NWV) \
-  case NWV: e = share ? launch_fused_t<NWV, true>(ctx, tmB, f, tiles, slices, s) : launch_fused_t<NWV, false>(ctx, tmB, f, tiles, slices, s); break;
+  case NWV: e = scale8 ? (share ? launch_fused_t<NWV, true, 1>(ctx, tmB, f, tiles, slices, s) : launch_fused_t<NWV, false, 1>(ctx, tmB, f, tiles, slices, s)) \
+                       : (share ? launch_fused_t<NWV, true, 0>(ctx, tmB, f, tiles, slices, s) : launch_fused_t<NWV, false, 0>(ctx, tmB, f, tiles, slices, s)); break;
   switch (nw) {
     HX_FUSED_NW(8) HX_FUSED_NW(16) HX_FUSED_NW(20) HX_FUSED_NW(24) HX_FUSED_NW(28)
     default: return hx_fail(HX_E_UNSUPPORTED, "fused projection: %d RNG warps per CTA is not instantiated (8, 16, 20, 24, 28)", nw);
@@ -990,6 +1002,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   // P0 drawn inside the projection GEMM (bf16 hi/lo operands, one accumulator); otherwise the staged draw + GEMM below
   const bool fused = fused_eligible(ctx, impl, nprod, d);
   const int f8 = (!fused && (ctx->precision == HX_PREC_F16F8 || ctx->precision == HX_PREC_AUTO)) ? 1 : 0;
+  const int fmt8 = f8 ? 1 : ((fused && fused_format(ctx) == 2) ? 2 : 0);      // form of the fp16 + fp8 copy of C^T (0: none)
   const int dB = pad_to(d, BN);            // rows of B-operand planes (N side)
   const int dK = pad_to(d, 64);            // K padding when dim is the reduction axis
   const int nK = pad_to(n, 64);            // K padding when the walker index is the reduction axis
@@ -1088,7 +1101,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   if (gram32)
     if (int e = ws_get(ctx, WS_TC_CT32, (size_t)2 * dAB * nK * sizeof(float), &pCT32)) return e;
   void *pCT8 = nullptr, *pSc8 = nullptr;
-  if (f8) {
+  if (fmt8) {
     // power-of-two scale of C from max |X2 - mean| (order-independent reduction: bit-reproducible)
     if (int e = ws_get(ctx, WS_TC_CT8, (size_t)2 * dAB * nK * sizeof(uint16_t), &pCT8)) return e;
     if (int e = ws_get(ctx, WS_TC_SC8, 16, &pSc8)) return e;
@@ -1102,7 +1115,7 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   }
   {
     dim3 g((nK + 255) / 256, (dAB + 31) / 32);
-    k_center_planes_T<<<g, 256, 0, s>>>(X2, mean_dev, n, d, dAB, nK, (bf*)pCT, (float*)pCT32, (uint16_t*)pCT8, (const float*)pSc8);
+    k_center_planes_T<<<g, 256, 0, s>>>(X2, mean_dev, n, d, dAB, nK, (bf*)pCT, (float*)pCT32, (uint16_t*)pCT8, (const float*)pSc8, fmt8);
     HX_LAUNCH_CHECK("k_center_planes_T");
   }
   GemmArgs ga;
@@ -1245,7 +1258,8 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   }
   if (fused) {
     if (int e = timing_begin(ctx, s)) return e;
-    if (int e = launch_proj_fused(ctx, pCT, dAB, nK, n, row0, rows, d, key, key_ptr, S0, s)) return e;
+    if (int e = fmt8 == 2 ? launch_proj_fused(ctx, pCT8, dAB, nK, n, row0, rows, d, key, key_ptr, S0, s, (const float*)pSc8)
+                          : launch_proj_fused(ctx, pCT, dAB, nK, n, row0, rows, d, key, key_ptr, S0, s)) return e;
     if (int e = timing_mark(ctx, s, HX_PH_LEAP)) return e;
   } else {
     std::vector<cudaEvent_t>& evs = *ctx->ev_chunk[cur];
@@ -1402,7 +1416,8 @@ int microbench(hx_ctx* ctx, int mode, int n, int rows, int d, int reps, double* 
     HX_CUDA(cudaEventCreate(&e0)); HX_CUDA(cudaEventCreate(&e1));
     HX_CUDA(cudaEventRecord(e0, s));
     for (int r = 0; r < reps; ++r)
-      if (int e = launch_proj_fused(ctx, pCT, dAB, nK, n, 0, rows, d, key, nullptr, (float*)pS0, s)) return e;
+      if (int e = launch_proj_fused(ctx, pCT, dAB, nK, n, 0, rows, d, key, nullptr, (float*)pS0, s,
+                                    fused_format(ctx) == 2 ? (const float*)pSc8 : nullptr)) return e;
     HX_CUDA(cudaEventRecord(e1, s));
     HX_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;

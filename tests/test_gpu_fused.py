@@ -22,7 +22,7 @@ def knobs(hx):
     def set_(what, value):
         _lib.check(lib.hx_ctx_set_tuning(ctx, what, value), "hx_ctx_set_tuning")
     yield set_
-    for what, value in ((1, 0), (15, 1), (16, 0), (17, 0), (18, 0), (19, 0)):
+    for what, value in ((1, 0), (15, 1), (16, 0), (17, 0), (18, 0), (19, 0), (21, 0)):
         lib.hx_ctx_set_tuning(ctx, what, value)
     hx.config.update("precision", "auto")
     hx.config.update("leapfrog_form", "auto")
@@ -76,13 +76,14 @@ def test_fused_split_k_equals_staged_split_k(hx, knobs, n, d, slices):
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("fmt", [1, 2])
 @pytest.mark.parametrize("n,d", [(384, 600), (640, 300)])
-def test_fused_matches_oracle(hx, knobs, n, d):
+def test_fused_matches_oracle(hx, knobs, n, d, fmt):
     hx.config.update("precision", "bf16x3")
     tgt, (olp, og), g1, g2, key = _problem(hx, n, d)
     G1, G2 = torch.from_numpy(g1).cuda(), torch.from_numpy(g2).cuda()
     LP1 = tgt.log_prob(G1)
-    knobs(15, 1)
+    knobs(15, 1); knobs(21, fmt)
     q, la, pp, lp = hx.hmc_walk_move(G1, G2, 0.03, key, tgt, tgt, 4, LP1)
     a64, b64 = g1.astype(np.float64), g2.astype(np.float64)
     q64, la64, pp64, lp64 = OM.hmc_walk_move(a64, b64, 0.03, key, olp, og, 4, olp(a64), rng_dtype=np.float32)
@@ -92,9 +93,36 @@ def test_fused_matches_oracle(hx, knobs, n, d):
     np.testing.assert_allclose(la.cpu().numpy(), la64, rtol=0, atol=5e-3)
 
 
-def test_fused_row_shards_and_reruns_are_bit_identical(hx, knobs):
+@pytest.mark.parametrize("n,d", SHAPES + [(4160, 1000)])
+def test_fused_projection_error_of_both_operand_forms(hx, knobs, n, d):
+    """S0 = P0 C of the fused kernel against an f64 product of the same draws, for the bf16 hi/lo form (FMT 0, three products) and
+    the fp16 + fp8 form (FMT 1: fp16 main product, e4m3 x e5m2 correction products at true scale; the default under "auto").
+    With step 1e-9 and L = 1 the returned projected momentum IS S0.  Bounds: rms error / rms S0 <= 1e-5 (bf16 hi/lo, measured
+    ~3e-6) and <= 3e-5 (fp16 + fp8); both forms agree with each other to 1e-4 of the scale everywhere."""
     hx.config.update("precision", "bf16x3")
-    knobs(15, 1)
+    hx.config.update("leapfrog_form", "stepwise")
+    tgt, (olp, og), g1, g2, key = _problem(hx, n, d)
+    rows = min(n, 384)
+    G1, G2 = torch.from_numpy(g1[:rows]).cuda(), torch.from_numpy(g2).cuda()
+    LP1 = tgt.log_prob(G1)
+    p0 = R.normal(key, (n, n), np.float32)[:rows].astype(np.float64)
+    c = g2.astype(np.float64)
+    ref = p0 @ ((c - c.mean(0)) / np.sqrt(n))
+    out = {}
+    for fmt in (1, 2):
+        knobs(15, 1); knobs(21, fmt)
+        pp = hx.hmc_walk_move(G1, G2, 1e-9, key, tgt, tgt, 1, LP1, row0=0, n=n)[2].cpu().numpy().astype(np.float64)
+        out[fmt] = pp
+        err = np.sqrt(np.mean((pp - ref) ** 2)) / np.sqrt(np.mean(ref ** 2))
+        print(f"n={n} d={d} fmt={fmt}: rms error {err:.2e}, max {np.abs(pp - ref).max() / np.abs(ref).max():.2e}")
+        assert err <= (1e-5 if fmt == 1 else 3e-5)
+    assert np.abs(out[1] - out[2]).max() <= 1e-4 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("fmt", [1, 2])
+def test_fused_row_shards_and_reruns_are_bit_identical(hx, knobs, fmt):
+    hx.config.update("precision", "bf16x3")
+    knobs(15, 1); knobs(21, fmt)
     tgt, _, g1, g2, key = _problem(hx, 512, 600)
     G1, G2 = torch.from_numpy(g1).cuda(), torch.from_numpy(g2).cuda()
     LP1 = tgt.log_prob(G1)
