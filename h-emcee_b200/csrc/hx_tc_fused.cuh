@@ -237,9 +237,12 @@ struct FusedArgs {
   const float* scale_ptr;   // FMT 1: {sc, 1/sc}, the power-of-two scale of the B planes; the epilogue multiplies by scale_ptr[1]
 };
 
+#ifndef HX_FUSED_IR
+#define HX_FUSED_IR 8          // rows of a work item of the RNG warps: 4 or 8 (measured at c5: 8 rows, A ring 4 / B ring 3: 15.96 ms per iteration; 4 rows, 3 / 4: 16.22)
+#endif
 #ifndef HX_FUSED_SA
-#define HX_FUSED_SA 3
-#define HX_FUSED_SB 4
+#define HX_FUSED_SA 4
+#define HX_FUSED_SB 3
 #endif
 struct FusedSmem {
   static constexpr int A_PLANE = kBM * 128;            // 16 KB: 128 rows x 64 bf16
@@ -283,7 +286,7 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmB);
-    for (int s = 0; s < L::SA; ++s) { mbar_init(&fullA[s], (SHARE ? 64 : 128) / 4); mbar_init(&emptyA[s], NCTA); }
+    for (int s = 0; s < L::SA; ++s) { mbar_init(&fullA[s], (SHARE ? 64 : 128) / HX_FUSED_IR); mbar_init(&emptyA[s], NCTA); }
     for (int s = 0; s < L::SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
@@ -368,14 +371,21 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
     }
   } else {
     // ---- RNG warps: draw, split, store into the sharing CTAs' A stages -----------------------------------------------------
-    // Work item = 4 rows x 64 K of one K-block (32 lanes x 8 consecutive elements); the RG items of a K-block and the K-blocks
+    // Work item = IR rows x 64 K of one K-block (batches of 4 rows: 32 lanes x 8 consecutive elements); the RG items of a K-block and the K-blocks
     // themselves are dealt round-robin over the NW warps, so NW need not divide the tile and neighbouring warps work on
     // neighbouring K-blocks (at most NW / RG + 1 apart: inside the three-stage A ring).
     Key key = f.key;
     if (f.key_ptr) { key.k0 = f.key_ptr[0]; key.k1 = f.key_ptr[1]; }
     const uint32_t ks2 = key.k0 ^ key.k1 ^ 0x1BD11BDAu;
     constexpr int ROWS_CTA = SHARE ? 64 : 128;                    // rows of the A tile this CTA draws
-    constexpr int RG = ROWS_CTA / 4;                              // items per K-block
+    constexpr int IR = HX_FUSED_IR;                               // rows per work item
+    constexpr int NB = IR / 4;                                    // batches of 4 rows x 64 K (32 lanes x 8 elements) per item
+    constexpr int RG = ROWS_CTA / IR;                             // items per K-block
+    // A warp's consecutive items are NW / RG K-blocks apart.  It may not skip a whole cycle of the A ring: the parity wait on
+    // `emptyA` only tells the last two phases of a stage apart, so a warp that touches a stage for the first time two uses late
+    // would pass while the stage is still waiting to be consumed (seen on B200 with 8-row items, 28 warps and a 3-stage ring:
+    // overwritten stages and surplus arrivals on fullA -> launch failure).
+    static_assert((NW + RG - 1) / RG <= L::SA, "RNG warps would skip a full cycle of the A ring: fewer warps, smaller items or a deeper ring");
     const int wr = warp - 2;                                      // 0 .. NW - 1
     const int chunk = lane & 7, rsub = lane >> 3;
     const uint32_t stA_local = smem_u32(stA);
@@ -384,63 +394,70 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
     const uint64_t row_stride = (uint64_t)(uint32_t)f.n;
     const uint64_t e00 = (uint64_t)(uint32_t)(f.row0 + m0 + (int)rank * ROWS_CTA + rsub) * row_stride + (uint64_t)(kb0 * 64 + chunk * 8);
     const int nitems = num_kb * RG;
-    // software pipeline: the hash of item g + NW (alu pipe: SHF / LOP3) is issued in the same straight-line block as the
-    // erf_inv polynomial and the operand split of item g (fma pipe), so that each warp keeps both pipes busy by itself
+    // first element of batch b of item g (for this lane)
+    auto elem = [&](int g, int b) -> uint64_t {
+      const int kb = g / RG, rg = g - kb * RG;
+      return e00 + (uint64_t)(IR * rg + 4 * b) * row_stride + (uint64_t)(kb * 64);
+    };
+    // software pipeline: the hash of the NEXT batch (alu pipe: SHF / LOP3) is issued in the same straight-line block as the
+    // erf_inv polynomial and the operand split of the current one (fma pipe), so that each warp keeps both pipes busy by itself
     uint32_t bcur[8];
     {
-      const int kb = wr / RG, rg = wr - kb * RG;
-      const uint64_t e = e00 + (uint64_t)(4 * rg) * row_stride + (uint64_t)(kb * 64);
+      const uint64_t e = elem(wr, 0);
       bits8_fast(key, ks2, e, bcur);
       bits8_fix_wrap(key, ks2, e, bcur);
     }
     for (int g = wr; g < nitems; g += NW) {
       const int kb = g / RG, rg = g - kb * RG;
       const int sa = kb % L::SA;
-      const int r = (int)rank * ROWS_CTA + 4 * rg + rsub;         // row inside the 128-row tile
-      uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-      if (f.diag != 1) {
-        // (the item after the last one is hashed too and dropped: no branch inside the straight-line block)
-        uint32_t bnext[8];
-        const int gn = g + NW;
-        const int kbn = gn / RG, rgn = gn - kbn * RG;
-        const uint64_t en = e00 + (uint64_t)(4 * rgn) * row_stride + (uint64_t)(kbn * 64);
-        float x[8], u[8], w[8];
-        bits8_fast(key, ks2, en, bnext);
-        const bool tail = normals8_central(bcur, x, u, w);
-        if (tail) normals8_fix_tail(x, u, w);
-        bits8_fix_wrap(key, ks2, en, bnext);
-        if (FMT == 1) {
-          uint2 v8, r8;
-          split8_f16e(x, hi, v8, r8);
-          lo = make_uint4(v8.x, v8.y, r8.x, r8.y);
-        } else {
-          split8_bf16(x, hi, lo);
-        }
 #pragma unroll
-        for (int t = 0; t < 8; ++t) bcur[t] = bnext[t];
-      }
-      if (f.relaxed_wait) mbar_wait_relaxed(&emptyA[sa], ((uint32_t)(kb / L::SA) & 1u) ^ 1u);
-      else mbar_wait_parked(&emptyA[sa], ((uint32_t)(kb / L::SA) & 1u) ^ 1u);
-      const uint32_t so = (uint32_t)(sa * L::A_STAGE) + (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));   // 128-byte swizzle
-      st_shared_v4(stA_local + so, hi);
-      if (FMT == 1) {
-        // fp8 plane row = [64 x e4m3(x) | 64 x e5m2(res)]: this lane's 8 bytes of each at byte chunk * 8 / 64 + chunk * 8
-        const uint32_t rowb = stA_local + (uint32_t)(sa * L::A_STAGE + L::A_PLANE + r * 128) + (uint32_t)((chunk & 1) << 3);
-        st_shared_v2(rowb + ((uint32_t)((chunk >> 1) ^ (r & 7)) << 4), make_uint2(lo.x, lo.y));
-        st_shared_v2(rowb + ((uint32_t)((4 + (chunk >> 1)) ^ (r & 7)) << 4), make_uint2(lo.z, lo.w));
-      } else {
-        st_shared_v4(stA_local + so + L::A_PLANE, lo);
+      for (int b = 0; b < NB; ++b) {
+        const int r = (int)rank * ROWS_CTA + IR * rg + 4 * b + rsub;         // row inside the 128-row tile
+        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+        if (f.diag != 1) {
+          // (the batch after the last one is hashed too and dropped: no branch inside the straight-line block)
+          uint32_t bnext[8];
+          const uint64_t en = (b + 1 < NB) ? elem(g, b + 1) : elem(g + NW, 0);
+          float x[8], u[8], w[8];
+          bits8_fast(key, ks2, en, bnext);
+          const bool tail = normals8_central(bcur, x, u, w);
+          if (tail) normals8_fix_tail(x, u, w);
+          bits8_fix_wrap(key, ks2, en, bnext);
+          if (FMT == 1) {
+            uint2 v8, r8;
+            split8_f16e(x, hi, v8, r8);
+            lo = make_uint4(v8.x, v8.y, r8.x, r8.y);
+          } else {
+            split8_bf16(x, hi, lo);
+          }
+#pragma unroll
+          for (int t = 0; t < 8; ++t) bcur[t] = bnext[t];
+        }
+        if (b == 0) {
+          if (f.relaxed_wait) mbar_wait_relaxed(&emptyA[sa], ((uint32_t)(kb / L::SA) & 1u) ^ 1u);
+          else mbar_wait_parked(&emptyA[sa], ((uint32_t)(kb / L::SA) & 1u) ^ 1u);
+        }
+        const uint32_t so = (uint32_t)(sa * L::A_STAGE) + (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));   // 128-byte swizzle
+        st_shared_v4(stA_local + so, hi);
+        if (FMT == 1) {
+          // fp8 plane row = [64 x e4m3(x) | 64 x e5m2(res)]: this lane's 8 bytes of each at byte chunk * 8 / 64 + chunk * 8
+          const uint32_t rowb = stA_local + (uint32_t)(sa * L::A_STAGE + L::A_PLANE + r * 128) + (uint32_t)((chunk & 1) << 3);
+          st_shared_v2(rowb + ((uint32_t)((chunk >> 1) ^ (r & 7)) << 4), make_uint2(lo.x, lo.y));
+          st_shared_v2(rowb + ((uint32_t)((4 + (chunk >> 1)) ^ (r & 7)) << 4), make_uint2(lo.z, lo.w));
+        } else {
+          st_shared_v4(stA_local + so + L::A_PLANE, lo);
+        }
       }
       fence_proxy_async();         // generic-proxy stores -> visible to the async proxy (the tensor core's operand reads, the bulk copy)
       __syncwarp();
-      // one arrival per item.  In a pair the item's 4 rows x 128 bytes per plane (contiguous in the swizzled layout) are also
-      // copied into the peer's stage by the TMA engine, and the arrival announces the 1 KB the peer copies into THIS CTA
+      // one arrival per item.  In a pair the item's IR rows x 128 bytes per plane (contiguous in the swizzled layout) are also
+      // copied into the peer's stage by the TMA engine, and the arrival announces the bytes the peer copies into THIS CTA
       if (lane == 0) {
         if (SHARE) {
-          const uint32_t io = (uint32_t)(sa * L::A_STAGE) + (uint32_t)(((int)rank * ROWS_CTA + 4 * rg) * 128);
-          bulk_copy_to_peer(stA_peer + io, stA_local + io, 512u, fullA_peer + 8u * sa);
-          bulk_copy_to_peer(stA_peer + io + L::A_PLANE, stA_local + io + L::A_PLANE, 512u, fullA_peer + 8u * sa);
-          mbar_expect_tx(&fullA[sa], 1024u);
+          const uint32_t io = (uint32_t)(sa * L::A_STAGE) + (uint32_t)(((int)rank * ROWS_CTA + IR * rg) * 128);
+          bulk_copy_to_peer(stA_peer + io, stA_local + io, IR * 128u, fullA_peer + 8u * sa);
+          bulk_copy_to_peer(stA_peer + io + L::A_PLANE, stA_local + io + L::A_PLANE, IR * 128u, fullA_peer + 8u * sa);
+          mbar_expect_tx(&fullA[sa], 2u * IR * 128u);
         } else {
           mbar_arrive(&fullA[sa]);
         }

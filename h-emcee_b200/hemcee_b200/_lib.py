@@ -15,7 +15,7 @@ HX_TARGET_GAUSS_ISO, HX_TARGET_GAUSS_FULL, HX_TARGET_ROSENBROCK, HX_TARGET_FUNNE
 HX_MOVE_FROZEN_GRAD = 1
 HX_PREC_AUTO, HX_PREC_EXACT, HX_PREC_BF16X3, HX_PREC_BF16 = 0, 1, 2, 3
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libhx.so")
+LIB_PATH = os.environ.get("HX_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libhx.so")   # HX_LIB: diagnostic builds
 
 
 class HxError(RuntimeError):

@@ -58,23 +58,43 @@ def test_c2_chain_parity_x64(hx, move, start, eps_by_move):
 @pytest.mark.parametrize("start,eps_by_move", CASES)
 @pytest.mark.parametrize("move", ["walk", "side"])
 def test_c2_chain_parity_f32(hx, move, start, eps_by_move):
-    """f32 (the dtype the throughput numbers are quoted in): per (iteration, walker) the position agrees with the f32 oracle
-    within 2e-3 of the ensemble scale unless an accept decision flipped inside the f32 energy noise; at least 95 % of the
-    (iteration, walker) pairs agree over the first 4 iterations and the accept counts differ by < 3 %."""
+    """f32 (the dtype the throughput numbers are quoted in) under precision "exact" (draws bit-equal to the oracle's): over the
+    first 4 iterations every half-move of the main-phase schedule (keys[t,0] move1, [t,2] accept1, [t,1] move2, [t,3] accept2,
+    hamiltonian_ensemble.py:284-318) is run from the ORACLE's current f32 state by both sides.  Per half-move: proposals within
+    2e-3 of the ensemble scale and log-accept within 2e-2 for every walker (f32 energy noise of a kappa = 1e4 target), log-probs
+    within 2e-3 relative; accept decisions equal except where log u lies inside that noise (< 1 % of the walkers).  Continuing
+    from the oracle's state keeps a single flipped decision from decorrelating the rest of the run (one changed complement row
+    moves every walk proposal by ~4 % of the scale), which is what a free-running f32 comparison measures instead."""
     T, EPS = 4, eps_by_move[move]
-    tgt, otgt, x0, k_run = _c2(hx, np.float32, start)
+    tgt, (olp, og), x0, k_run = _c2(hx, np.float32, start)
     pm = hx.hmc_walk_move if move == "walk" else hx.hmc_side_move
     om = OM.hmc_walk_move if move == "walk" else OM.hmc_side_move
-    s = hx.HamiltonianEnsembleSampler(W, D, tgt, step_size=EPS, L=L_STEPS, move=pm, adapt_inital_step_size=False,
-                                      adapt_step_size=False, adapt_length=False, verbose=False)
-    chain = s.run_mcmc(k_run, x0, T, warmup=0)
-    o = OS.HamiltonianEnsembleSampler(W, D, otgt, step_size=EPS, L=L_STEPS, move=om, adapt_inital_step_size=False,
-                                      adapt_step_size=False, adapt_length=False, dtype=np.float32)
-    ref = o.run_mcmc(k_run, x0, T, warmup=0)
-    same = np.all(np.abs(chain - ref) <= 2e-3 * np.abs(ref).max(), axis=2)
-    assert same.mean() > 0.95, same.mean()
-    assert same[0].mean() > 0.98, same[0].mean()
-    assert abs(int(s.diagnostics_main["accepts"].sum()) - int(o.diagnostics_main["accepts"].sum())) <= 0.03 * W * T
+    n = W // 2
+    keys = R.split(R.split(k_run, 3)[2], 4 * T).reshape(T, 4, 2)            # run_mcmc: keys[2] drives the main phase
+    g = [x0[:n].copy(), x0[n:].copy()]
+    lp = [olp(g[0]).astype(np.float32), olp(g[1]).astype(np.float32)]
+    scale = np.abs(x0).max()
+    flips = total = 0
+    hx.config.update("precision", "exact")
+    try:
+        for t in range(T):
+            for half, (im, ia) in enumerate(((0, 2), (1, 3))):
+                cur, comp, lpc = g[half], g[1 - half], lp[half]
+                qo, lao, _, lpo = om(cur, comp, np.float32(EPS), keys[t, im], olp, og, L_STEPS, lpc)
+                C, Cc, LPC = torch.from_numpy(cur).cuda(), torch.from_numpy(comp).cuda(), torch.from_numpy(lpc).cuda()
+                qg, lag, _, lpg = pm(C, Cc, EPS, keys[t, im], tgt, tgt, L_STEPS, LPC)
+                np.testing.assert_allclose(qg.cpu().numpy(), qo, rtol=0, atol=2e-3 * scale)
+                np.testing.assert_allclose(lpg.cpu().numpy(), lpo, rtol=2e-3, atol=2e-2)
+                np.testing.assert_allclose(lag.cpu().numpy(), lao, rtol=0, atol=2e-2)
+                new, acc_o = OM.accept_proposal(cur, qo, lao, keys[t, ia])
+                new_lp, _ = OM.accept_proposal(lpc, lpo, lao, keys[t, ia])
+                _, _, acc_g = hx.moves.accept_proposal(C.clone(), qg, LPC.clone(), lpg, lag, keys[t, ia])
+                flips += int(np.sum(acc_g.cpu().numpy().astype(bool) != acc_o.astype(bool)))
+                total += n
+                g[half], lp[half] = new.astype(np.float32), new_lp.astype(np.float32)
+    finally:
+        hx.config.update("precision", "auto")
+    assert flips <= 0.01 * total, (flips, total)
 
 
 def test_side_move_two_shuffle_rounds_matches_oracle(hx):
