@@ -124,6 +124,7 @@ extern "C" HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value) {
   else if (what == 19) ctx->fused_diag = value;
   else if (what == 20) ctx->fused_relaxed = value ? 1 : 0;
   else if (what == 21) ctx->fused_fmt = value;
+  else if (what == 22) ctx->fused_no_atomic = value ? 1 : 0;
   else return hx_fail(HX_E_DTYPE, "hx_ctx_set_tuning: unknown knob %d", what);
   return 0;
 }

@@ -234,6 +234,8 @@ struct FusedArgs {
   float* out; int ldo;
   int diag;         // diagnostics: 1 = no draw (A garbage), 2 = no MMA; results are garbage
   int relaxed_wait; // RNG warps poll their `empty` barrier with test_wait + nanosleep instead of a parked try_wait
+  int atomic_out;   // split-K with exactly two slices: both add into the zeroed output with red.global.add (x + y is commutative and
+                    // 0 + x exact, so the result does not depend on which slice lands first) -- no slice buffers, no sum kernel
   const float* scale_ptr;   // FMT 1: {sc, 1/sc}, the power-of-two scale of the B planes; the epilogue multiplies by scale_ptr[1]
 };
 
@@ -483,7 +485,20 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
       }
       if (row < f.rows) {
         const int nval = min(32, f.d - col0);
-        store32(out + (size_t)row * f.ldo + col0, v, nval, vec && nval == 32);
+        float* o = out + (size_t)row * f.ldo + col0;
+        if (!f.atomic_out) {
+          store32(o, v, nval, vec && nval == 32);
+        } else if (vec && nval == 32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * j), "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]),
+                         "f"(v[4 * j + 3])
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nval) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(o + j), "f"(v[j]) : "memory");
+        }
       }
     }
     tc_fence_before();

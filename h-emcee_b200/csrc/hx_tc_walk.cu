@@ -791,7 +791,11 @@ static int launch_proj_fused(hx_ctx* ctx, const void* CT, int dAB, int nK, int n
   const int kbs = (f.num_kb + slices - 1) / slices;
   slices = (f.num_kb + kbs - 1) / kbs;
   void* pS0P = nullptr;
-  if (slices > 1) {
+  const bool atomic2 = slices == 2 && !ctx->fused_no_atomic;
+  if (atomic2) {
+    HX_CUDA(cudaMemsetAsync(S0, 0, (size_t)rows * d * sizeof(float), s));
+    f.kb_per_slice = kbs; f.slice_stride = 0; f.atomic_out = 1;
+  } else if (slices > 1) {
     if (int e = ws_get(ctx, WS_TC_S0P, (size_t)slices * rows * d * sizeof(float), &pS0P)) return e;
     f.out = (float*)pS0P; f.kb_per_slice = kbs; f.slice_stride = (size_t)rows * d;
   }
@@ -806,7 +810,7 @@ static int launch_proj_fused(hx_ctx* ctx, const void* CT, int dAB, int nK, int n
   }
 #undef HX_FUSED_NW
   if (e) return e;
-  if (slices > 1) {
+  if (slices > 1 && !atomic2) {
     k_sum_slices_f<<<grid_for((size_t)rows * d, 256), 256, 0, s>>>((const float*)pS0P, slices, (size_t)rows * d, S0);
     HX_LAUNCH_CHECK("k_sum_slices_f");
     ctx->launches += 1;
