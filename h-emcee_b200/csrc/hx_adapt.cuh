@@ -159,6 +159,45 @@ __global__ void __launch_bounds__(128) k_adapt_rows(const T* __restrict__ la, co
   stat_accg[i] = a * g;
 }
 
+// Per-walker adapter statistics beyond kAdaptMaxDim (float runs on the tensor-core path): one warp per walker; the ChEES inner
+// product arrives as column-tile partial sums ip_part[i * nt + t] of <pproj_i cov^-1, Xprop_i - mean_prop> (tc::chees_inner).
+__global__ void __launch_bounds__(256) k_adapt_rows_big(const float* __restrict__ la, const float* __restrict__ Xcur,
+                                                        const float* __restrict__ Xprop, const float* __restrict__ mean_prev,
+                                                        const float* __restrict__ mean_prop, const float* __restrict__ ip_part, int nt,
+                                                        int rows, int d, const AdaptDev<float>* st, hx_adapt_params p,
+                                                        float* __restrict__ stat_da, float* __restrict__ stat_acc,
+                                                        float* __restrict__ stat_accg) {
+  const int lane = threadIdx.x & 31, i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= rows) return;
+  float a = expf(la[i]);
+  a = a < 0.f ? 0.f : (a > 1.f ? 1.f : a);
+  if (p.use_da && lane == 0) stat_da[i] = p.agg_harmonic ? 1.f / a : a;
+  if (!p.use_chees) return;
+  const float* xc = Xcur + (size_t)i * d;
+  const float* xp = Xprop + (size_t)i * d;
+  float sq_prop = 0.f, sq_prev = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float cp = xp[c] - mean_prop[c], cv = xc[c] - mean_prev[c];
+    sq_prop = fmaf(cp, cp, sq_prop);
+    sq_prev = fmaf(cv, cv, sq_prev);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sq_prop += __shfl_xor_sync(0xffffffffu, sq_prop, o);
+    sq_prev += __shfl_xor_sync(0xffffffffu, sq_prev, o);
+  }
+  if (lane != 0) return;
+  float ip = 0.f;
+  for (int t = 0; t < nt; ++t) ip += ip_part[(size_t)i * nt + t];
+  const float Tt = expf(st->ch_lT);
+  const float t_n = st->ch_halton * Tt;
+  float g = t_n * (sq_prop - sq_prev) * ip;                                     // chees.py:112-131
+  if (!(a > 1e-4f)) g = 0.f;
+  if (!isfinite(g)) g = 0.f;
+  stat_acc[i] = a;
+  stat_accg[i] = a * g;
+}
+
 // fixed-order sum of v[0..n) by one CTA of 1024 threads: strided per-thread partials, then a shared-memory tree
 template <typename T>
 __device__ __forceinline__ T block_sum_fixed(const T* __restrict__ v, int n, T* sh) {

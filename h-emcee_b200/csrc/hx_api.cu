@@ -17,6 +17,7 @@
 #include "hx_tc_walk.h"
 #include "hx_dist.cuh"
 #include "hx_adapt.cuh"
+#include "hx_spd.cuh"
 #include "hx_vanilla.cuh"
 #include <type_traits>
 
@@ -1065,7 +1066,13 @@ static int run_warmup_t(hx_ctx* ctx, int impl, int move_kind, const hx_target* t
                         hx_adapt_state* st_host, const uint32_t* keys, int64_t Tn, T* chain, T* chain_lp, int32_t* accepts,
                         int32_t* nonfinite, cudaStream_t s) {
   const int d = tgt->dim, ldd = round4(d);
-  if (P.use_chees && d > kAdaptMaxDim) return fail(HX_E_UNSUPPORTED, "hx_run_warmup: ChEES on the device needs dim <= %d (got %d)", kAdaptMaxDim, d);
+  // Problems the precision policy sends to the tcgen05 path: the adapter state and its update kernels stay on the device, but
+  // the launch sequence of that path depends on (step, L), so the two words are read back once per half-move (no other host
+  // work; the Python loop this replaces spent 165 ms per iteration at c5 against 16 ms for the moves themselves)
+  bool tcp = false;
+  if constexpr (std::is_same<T, float>::value) tcp = move_kind == 0 && tc::walk_eligible(ctx, HX_F32, tgt, n, n, 0);
+  if (P.use_chees && d > kAdaptMaxDim && !tcp)
+    return fail(HX_E_UNSUPPORTED, "hx_run_warmup: ChEES on the device needs dim <= %d (got %d) unless the tensor-core path applies", kAdaptMaxDim, d);
   void *pQ, *pLa, *pLp, *pS, *pSt, *pMean, *pChol, *pStat;
   if (int e = ws_get(ctx, WS_AD_PROP, (size_t)n * d * sizeof(T), &pQ)) return e;
   if (int e = ws_get(ctx, WS_LA, (size_t)n * sizeof(T), &pLa)) return e;
@@ -1073,7 +1080,9 @@ static int run_warmup_t(hx_ctx* ctx, int impl, int move_kind, const hx_target* t
   if (int e = ws_get(ctx, WS_S, (size_t)n * d * sizeof(T), &pS)) return e;
   if (int e = ws_get(ctx, WS_AD_STATE, sizeof(AdaptDev<T>), &pSt)) return e;
   if (int e = ws_get(ctx, WS_AD_MEAN, (size_t)2 * d * sizeof(T), &pMean)) return e;
-  if (int e = ws_get(ctx, WS_AD_CHOL, (size_t)d * d * sizeof(T), &pChol)) return e;
+  const bool big = P.use_chees && d > kAdaptMaxDim;
+  const size_t ldw = (size_t)((d + spd::NB - 1) / spd::NB) * spd::NB;
+  if (int e = ws_get(ctx, WS_AD_CHOL, big ? 2 * ldw * ldw * sizeof(double) : (size_t)d * d * sizeof(T), &pChol)) return e;
   if (int e = ws_get(ctx, WS_AD_STAT, (size_t)3 * n * sizeof(T), &pStat)) return e;
   AdaptDev<T>* st = (AdaptDev<T>*)pSt;
   T* mean_prev = (T*)pMean;
@@ -1090,8 +1099,10 @@ static int run_warmup_t(hx_ctx* ctx, int impl, int move_kind, const hx_target* t
   HX_CUDA(cudaStreamSynchronize(s));                    // `h` is a stack object
   k_adapt_value<T><<<1, 32, 0, s>>>(st, P);
   HX_LAUNCH_CHECK("k_adapt_value");
-  ctx->ctl_eps = &st->eps;
-  ctx->ctl_L = &st->L;
+  if (!tcp) {
+    ctx->ctl_eps = &st->eps;
+    ctx->ctl_L = &st->L;
+  }
   const size_t W2 = (size_t)2 * n;
   int err = 0;
   for (int64_t t = 0; t < Tn && !err; ++t) {
@@ -1103,7 +1114,14 @@ static int run_warmup_t(hx_ctx* ctx, int impl, int move_kind, const hx_target* t
       T* Xa = X + (size_t)half * n * d;
       T* Xb = X + (size_t)(1 - half) * n * d;
       T* lpa = lp + (size_t)half * n;
-      if (move_kind == 0)
+      if (tcp) {
+        AdaptDev<T> cur;
+        cudaError_t ce = cudaMemcpyAsync(&cur, st, sizeof(cur), cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        if (ce != cudaSuccess) { err = fail((int)ce, "hx_run_warmup: reading (step, L) back failed: %s", cudaGetErrorString(ce)); break; }
+        err = walk_move_t<T>(ctx, impl, tgt, Xa, Xb, n, 0, n, (double)cur.eps, Key{0, 0}, kmove, cur.L, lpa, (T*)pQ, (T*)pLa, (T*)pS, (T*)pLp,
+                             0, nullptr, nullptr, s);
+      } else if (move_kind == 0)
         err = walk_move_t<T>(ctx, impl, tgt, Xa, Xb, n, 0, n, 0.0, Key{0, 0}, kmove, 1, lpa, (T*)pQ, (T*)pLa, (T*)pS, (T*)pLp, 0, nullptr, nullptr, s);
       else
         err = side_move_t<T>(ctx, impl, tgt, Xa, Xb, n, 0, n, 0.0, Key{0, 0}, kmove, 1, lpa, (T*)pQ, (T*)pLa, (T*)pS, (T*)pLp, 0, nullptr, s);
@@ -1119,11 +1137,29 @@ static int run_warmup_t(hx_ctx* ctx, int impl, int move_kind, const hx_target* t
         }
         if ((err = column_mean<T>(ctx, Xa, n, d, mean_prev, s))) break;
         if ((err = column_mean<T>(ctx, (const T*)pQ, n, d, mean_prop, s))) break;
-        k_chol<T><<<1, 256, 0, s>>>(M, ldd, d, (T)n / (T)(n - 1), (T*)pChol, d);
-        Lf = (const T*)pChol;
+        if (!big) {
+          k_chol<T><<<1, 256, 0, s>>>(M, tcp ? d : ldd, d, (T)n / (T)(n - 1), (T*)pChol, d);      // the tensor-core path keeps M unpadded
+          Lf = (const T*)pChol;
+        }
       }
-      k_adapt_rows<T><<<(n + 127) / 128, 128, 0, s>>>((const T*)pLa, Xa, (const T*)pQ, (const T*)pS, mean_prev, mean_prop, Lf, d, n, d,
-                                                      st, P, stat_da, stat_acc, stat_accg);
+      bool rows_done = false;
+      if constexpr (std::is_same<T, float>::value) {
+        if (big) {
+          // cov(group2)^-1 = (n / (n - 1) M)^-1 in fp64 once per half-move, then ONE tensor-core GEMM with a row-dot epilogue
+          // gives <cen_prop_i, cov^-1 pproj_i> for all walkers (chees.py:57-73 solves with n right-hand sides instead)
+          void* pInv;
+          if ((err = ws_get(ctx, WS_TC_BO, (size_t)d * d * sizeof(float), &pInv))) break;
+          if ((err = spd::spd_inverse(ctx, (const float*)ctx->buf[WS_M], d, d, (double)n / (double)(n - 1), (double*)pChol, (float*)pInv, d, s))) break;
+          float* part = nullptr; int nt = 0;
+          if ((err = tc::chees_inner(ctx, (const float*)pS, n, d, (const float*)pInv, (const float*)pQ, mean_prop, &part, &nt, s))) break;
+          k_adapt_rows_big<<<(n * 32 + 255) / 256, 256, 0, s>>>((const float*)pLa, Xa, (const float*)pQ, mean_prev, mean_prop, part, nt, n, d,
+                                                                st, P, stat_da, stat_acc, stat_accg);
+          rows_done = true;
+        }
+      }
+      if (!rows_done)
+        k_adapt_rows<T><<<(n + 127) / 128, 128, 0, s>>>((const T*)pLa, Xa, (const T*)pQ, (const T*)pS, mean_prev, mean_prop, Lf, d, n, d,
+                                                        st, P, stat_da, stat_acc, stat_accg);
       k_adapt_update<T><<<1, 1024, 0, s>>>(st, P, stat_da, stat_acc, stat_accg, n);
       k_accept_emit<T><<<(n + 7) / 8, 256, 0, s>>>(Xa, (const T*)pQ, lpa, (const T*)pLp, (const T*)pLa, kacc, impl == HX_RNG_LEGACY ? 1 : 0,
                                                    n, 0, n, d, accepts + (size_t)half * n,
@@ -1144,6 +1180,17 @@ static int run_warmup_t(hx_ctx* ctx, int impl, int move_kind, const hx_target* t
   st_host->ch_m1 = (double)h.ch_m1; st_host->ch_m2 = (double)h.ch_m2; st_host->ch_iteration = (double)h.ch_it;
   st_host->ch_halton = (double)h.ch_halton;
   return 0;
+}
+
+extern "C" HX_API int hx_spd_inverse(hx_ctx* ctx, const float* M_dev, int32_t ldm, int32_t d, double scale, float* inv_out_dev, int32_t ldo,
+                              void* stream) {
+  if (!ctx || !M_dev || !inv_out_dev) return fail(HX_E_NULL, "hx_spd_inverse: NULL argument");
+  if (d < 1 || ldm < d || ldo < d) return fail(HX_E_SHAPE, "hx_spd_inverse: need d >= 1 and leading dimensions >= d");
+  HX_CUDA(cudaSetDevice(ctx->device));
+  const size_t ldw = (size_t)((d + spd::NB - 1) / spd::NB) * spd::NB;
+  void* work;
+  if (int e = ws_get(ctx, WS_AD_CHOL, 2 * ldw * ldw * sizeof(double), &work)) return e;
+  return spd::spd_inverse(ctx, M_dev, ldm, d, scale, (double*)work, inv_out_dev, ldo, (cudaStream_t)stream);
 }
 
 extern "C" HX_API int hx_run_warmup(hx_ctx* ctx, int dtype, int impl, int move_kind, const hx_target* tgt, void* X, void* lp, int32_t n,

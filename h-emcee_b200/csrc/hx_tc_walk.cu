@@ -996,6 +996,27 @@ static int job_launch(hx_ctx* ctx, int b, __nv_bfloat16* buf, int fmt, int impl,
   return 0;
 }
 
+int chees_inner(hx_ctx* ctx, const float* pproj, int rows, int d, const float* covinv, const float* Xprop, const float* mean_prop,
+                float** part_out, int* nt_out, cudaStream_t s) {
+  typedef __nv_bfloat16 bf;
+  const int dB = pad_to(d, BN), dK = pad_to(d, 64), rA = pad_to(rows, kBM), NT = (d + BN - 1) / BN;
+  void *pA, *pB, *pPart;
+  if (int e = ws_get(ctx, WS_TC_QC, (size_t)2 * rA * dK * sizeof(float), &pA)) return e;
+  if (int e = ws_get(ctx, WS_TC_MP, (size_t)2 * dB * dK * sizeof(float), &pB)) return e;
+  if (int e = ws_get(ctx, WS_TC_DKP, (size_t)rows * NT * sizeof(float), &pPart)) return e;
+  k_split_planes<KIND_BF16><<<grid_for((size_t)rA * dK, 256), 256, 0, s>>>(pproj, rows, d, d, rA, dK, (bf*)pA);
+  k_split_planes<KIND_BF16><<<grid_for((size_t)dB * dK, 256), 256, 0, s>>>(covinv, d, d, d, dB, dK, (bf*)pB);
+  HX_LAUNCH_CHECK("k_split_planes");
+  ctx->launches += 2;
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.nprod = 3; g.M = rows; g.N = d; g.NT = NT; g.X = Xprop; g.mu = mean_prop; g.part = (float*)pPart;
+  if (int e = launch_gemm<EPI_DOT, KIND_BF16>(ctx, pA, rA, pB, dB, dK, g, s)) return e;
+  *part_out = (float*)pPart;
+  *nt_out = NT;
+  return 0;
+}
+
 int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev, const float* X1, const float* X2, int n,
               int row0, int rows, double eps, Key key, const uint32_t* key_ptr, int L, const float* lp1, float* Q,
               float* logacc, float* S, float* lp_out, const FuseF32* fuse, const NextDraw* next, cudaStream_t s) {

@@ -34,6 +34,12 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
               int row0, int rows, double eps, Key key, const uint32_t* key_ptr, int L, const float* lp1, float* Q,
               float* logacc, float* S, float* lp_out, const FuseF32* fuse, const NextDraw* next, cudaStream_t s);
 
+// ChEES inner product beyond dim 128 (adaptation/chees.py:57-73): part[i * nt_out + t], t < nt_out, are the column-tile partial
+// sums of <(pproj_i covinv), Xprop_i - mean_prop> for rows i < rows; covinv[d, d] (fp32, symmetric) = cov(group2)^-1.
+// bf16 hi/lo operands, three products; overwrites the leapfrog operand workspaces (the half-move is finished by then).
+int chees_inner(hx_ctx* ctx, const float* pproj, int rows, int d, const float* covinv, const float* Xprop, const float* mean_prop,
+                float** part_out, int* nt_out, cudaStream_t s);
+
 int microbench(hx_ctx* ctx, int mode, int n, int rows, int d, int reps, double* ms_out, cudaStream_t s);
 
 }  // namespace tc

@@ -91,6 +91,7 @@ _PROTOS = {
     "hx_stats_row_blocks": (C.c_int32, []),
     "hx_stats_feed": (C.c_int, [_P, C.c_int, C.POINTER(hx_chain_stats), _P, _P]),
     "hx_ctx_set_chain_stats": (C.c_int, [_P, C.POINTER(hx_chain_stats)]),
+    "hx_spd_inverse": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_double, _P, C.c_int32, _P]),
     "hx_run_warmup": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.POINTER(hx_adapt_params),
                                 C.POINTER(hx_adapt_state), _P, C.c_int64, _P, _P, _P, _P, _P]),
     "hx_vanilla_move": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(hx_target), _P, _P, C.c_int32, C.c_int32, C.c_int32,

@@ -22,6 +22,8 @@ def split_device(key, num: int = 2, device=None, impl=None) -> torch.Tensor:
     """split(key, num) kept on the device as an int32 [num, 2] tensor (bit pattern of uint32)."""
     dev = _rt.device(device)
     out = torch.empty((int(num), 2), dtype=torch.int32, device=dev)
+    if int(num) == 0:
+        return out
     _lib.check(_lib.load().hx_split(_lib.key_arg(_rt.as_key(key)), _rt.impl_code(impl), int(num), _rt.ptr(out),
                                     _rt.stream(dev)), "hx_split")
     return out

@@ -150,18 +150,21 @@ class HamiltonianEnsembleSampler(BaseSampler):
         dist.all_gather_into_tensor(full, local, group=self.group)
 
     def _device_adapt_ok(self):
-        """Device-resident adaptation (hx_run_warmup) runs the exact SIMT kernels; problems that the precision policy sends to
-        the tensor-core path (whose launch sequence depends on L on the host) and ChEES beyond dim 128 keep the host loop."""
+        """Device-resident adaptation (hx_run_warmup): adapter state and update kernels on the device.  The exact SIMT kernels
+        read (step, L) from device memory (no host round trip; ChEES up to dim 128); problems the precision policy sends to the
+        tensor-core path (fp32 full-covariance Gaussians) read the two words back once per half-move and take ChEES at any dim
+        (cov(group2)^-1 by an fp64 blocked Cholesky + one tensor-core GEMM).  Everything else keeps the host loop."""
         if adaptation.device_params(self.adapter) is None or not _rt.config.device_adaptation:
-            return False
-        ch_on = isinstance(self.adapter, (adaptation.ChEESAdapter, adaptation.CompositeAdapter))
-        if ch_on and self.dim > 128:
             return False
         from .targets import GaussianFull
         n = self.total_chains // 2
-        tc = (_rt.config.precision != "exact" and self.dtype == torch.float32 and isinstance(self.target, GaussianFull)
+        tc = (self._move_kind == 0 and _rt.config.precision != "exact" and self.dtype == torch.float32
+              and isinstance(self.target, GaussianFull)
               and ((self.dim >= 128 and n >= 2048) if _rt.config.precision == "auto" else (self.dim >= 16 and n >= 64)))
-        return not tc
+        ch_on = isinstance(self.adapter, (adaptation.ChEESAdapter, adaptation.CompositeAdapter))
+        if ch_on and self.dim > 128 and not tc:
+            return False
+        return True
 
     @property
     def _peer_ok(self):
@@ -255,10 +258,10 @@ class HamiltonianEnsembleSampler(BaseSampler):
         dev, W, d = self.device, self.total_chains, self.dim
         n = W // 2
         lib = _lib.load()
-        keys_dev = hrandom.split_device(key, 4 * T, dev, self.impl)                 # :227-228 / :328-330
         accepts = torch.zeros(W, dtype=torch.int32, device=dev)
         if T == 0:
             return accepts.cpu().numpy()
+        keys_dev = hrandom.split_device(key, 4 * T, dev, self.impl)                 # :227-228 / :328-330
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
         nb = (T + batch_size - 1) // batch_size
         k = int(thin_store)

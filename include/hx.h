@@ -294,8 +294,13 @@ HX_API int hx_ctx_set_chain_stats(hx_ctx* ctx, const hx_chain_stats* stats);
  * composite (adaptation/adapter.py:44-78): per half-move (step, L) = adapter.value(state) is read by the move kernel from
  * device memory, adapter.update runs on the device after the move and before the accept, keys are used in the warm-up
  * order (keys[t,0] move1, [t,1] accept1, [t,2] move2, [t,3] accept2).  `state_inout` is a HOST struct (doubles hold the
- * run dtype's values exactly); the call synchronises the stream once at the end to return it.  Exact SIMT kernels only;
- * ChEES needs dim <= 128 (HX_E_UNSUPPORTED otherwise: the caller keeps its host-driven loop).                       */
+ * run dtype's values exactly); the call synchronises the stream once at the end to return it.
+ * Exact SIMT kernels: (step, L) never leave the device; ChEES needs dim <= 128 there (HX_E_UNSUPPORTED otherwise: the
+ * caller keeps its host-driven loop).  Problems the precision policy sends to the tensor-core path (fp32 full-covariance
+ * Gaussians, walk move): the launch sequence depends on (step, L), which are read back once per half-move (16 bytes, the
+ * only host work); ChEES at any dim <= 1024: cov(group2)^-1 = (n/(n-1) M)^-1 by hx_spd_inverse on the Gram matrix the move
+ * already forms, then one tensor-core GEMM with a row-dot epilogue for <cen_prop_i, cov^-1 pproj_i> of all walkers
+ * (chees.py:57-73 solves an LU system with n right-hand sides).                                                      */
 typedef struct hx_adapt_params {
   int32_t use_da, use_chees, agg_harmonic, pass_L;
   double da_target_accept, da_t0, da_gamma, da_kappa, da_init_step;
@@ -307,6 +312,10 @@ typedef struct hx_adapt_state {
   double da_log_step, da_log_step_bar, da_H_bar;
   double ch_log_T, ch_log_T_bar, ch_m1, ch_m2, ch_iteration, ch_halton;
 } hx_adapt_state;
+/* inv_out[d, ldo] (fp32) = (scale * M)^-1 for a symmetric positive definite M[d, ldm] (fp32, lower triangle read): blocked
+ * Cholesky, blocked inverse of the factor and X^T X in fp64 (csrc/hx_spd.cuh).  A non-positive pivot yields NaNs.         */
+HX_API int hx_spd_inverse(hx_ctx* ctx, const float* M_dev, int32_t ldm, int32_t d, double scale, float* inv_out_dev,
+                   int32_t ldo, void* stream);
 HX_API int hx_run_warmup(hx_ctx* ctx, int dtype, int impl, int move_kind, const hx_target* tgt, void* X_inout_dev,
                   void* lp_inout_dev, int32_t n, const hx_adapt_params* params, hx_adapt_state* state_inout,
                   const uint32_t* keys_dev, int64_t T, void* chain_out_dev, void* lp_out_dev,
