@@ -126,6 +126,7 @@ extern "C" HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value) {
   else if (what == 20) ctx->fused_relaxed = value ? 1 : 0;
   else if (what == 21) ctx->fused_fmt = value;
   else if (what == 22) ctx->fused_no_atomic = value ? 1 : 0;
+  else if (what == 23) ctx->row_epilogue = value;
   else return hx_fail(HX_E_DTYPE, "hx_ctx_set_tuning: unknown knob %d", what);
   return 0;
 }
@@ -195,6 +196,8 @@ extern "C" HX_API int hx_ctx_create(hx_ctx** out, int device) {
   c->aux_pair = 1;
   c->energy_bf16 = 2;
   c->proj_fused = 1;
+  c->row_epilogue = (1 << 2) | (1 << 3);      // EPI_DOT, EPI_PROP: row-per-lane epilogue (measured: coalescing costs 0.4 ms / nothing there); STORE, KICKB: coalesced
+
   cudaDeviceProp prop;
   HX_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;

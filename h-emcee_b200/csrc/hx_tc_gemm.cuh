@@ -90,6 +90,7 @@ struct GemmArgs {
   // KIND_F16 with EPI_KICKB / EPI_PROP: acc is divided by row_scale[row] * f16_scale(amax[unscale_idx]) before use
   int unscale_idx;
   int n_cover;       // pair kernel: padded N the grid covers (0: N); EPI_PROP covers two column blocks
+  int row_epilogue;  // bit EPI set: row-per-lane epilogue for that epilogue kind, clear: coalesced chunks through shared memory (hx_ctx_set_tuning(23, mask))
   int one_acc;       // single-CTA kernel, bf16 hi/lo: all three products into ONE accumulator in the order (hi hi, lo hi, hi lo) per
                      // K-block -- the accumulation structure of the fused draw + projection kernel (hx_tc_fused.cuh), kept here
                      // so that the two can be compared bit for bit (hx_ctx_set_tuning(18, 1))
@@ -220,14 +221,69 @@ __device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint64_t ad, uint64_
   }
 }
 
+// ---- coalesced epilogue (round 2) ---------------------------------------------------------------------------------------------
+// tcgen05.ld hands every lane 32 consecutive columns of ITS row, so a row-per-lane epilogue issues global accesses whose 32
+// lanes touch 32 different cache lines (16 bytes each): the kick GEMM of the propagator basis run spent ~25 of its 43 us in
+// those 32-wavefront requests (ncu: tensor pipe 13 % active, stalls on L1TEX scoreboards).  The warp therefore transposes each
+// 32 x 32 chunk through a 4.6 KB tile of the (by then idle) operand stages: afterwards lane l holds, for i < 8, the four values
+// of local row (l >> 3) + 4 i at columns 4 (l & 7) .. + 3, i.e. eight lanes cover 128 contiguous bytes of one row and a warp
+// request touches 4 full lines.  Ragged chunks (fewer than 32 valid columns) keep the row-per-lane path.
+// Measured at c5 (hx_ctx_set_tuning(23, mask), bit EPI = row path): the kick GEMM gains 6 % (basis run 0.647 -> 0.605 ms per
+// half-move) -- its epilogue turned out to be bound by the latency of four lone warps, not by LSU wavefronts --, EPI_STORE and
+// EPI_PROP are unchanged (stores do not stall), EPI_DOT loses 0.4 ms per half-move (eight shuffle hand-overs per row and chunk on
+// warps that have no one to hide behind), so the default keeps DOT and PROP on the row path.
+constexpr int kTilePitch = 36;                               // floats per tile row: 16-byte aligned, conflict-free both ways
+constexpr int kTileBytes = 32 * kTilePitch * 4;
+__device__ __forceinline__ void warp_transpose32(const float (&v)[32], float* tile, int lane, float4 (&o)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(tile + lane * kTilePitch + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = *reinterpret_cast<const float4*>(tile + ((lane >> 3) + 4 * i) * kTilePitch + 4 * (lane & 7));
+  __syncwarp();
+}
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+// hi/lo planes of four consecutive values (same splits as store_planes32)
+template <int KIND>
+__device__ __forceinline__ void store_planes4(void* planes, size_t pbase, size_t plane, const float4& v, float scale = 1.f) {
+  const float x[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+  if (KIND == KIND_F16) {
+    __half* P = reinterpret_cast<__half*>(planes);
+    __align__(8) __half hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_f16(x[j], hi[j], lo[j]);
+    *reinterpret_cast<uint2*>(P + pbase) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(P + plane + pbase) = *reinterpret_cast<const uint2*>(lo);
+  } else if (KIND == KIND_BF16) {
+    __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(planes);
+    __align__(8) __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_bf16(x[j], hi[j], lo[j]);
+    *reinterpret_cast<uint2*>(P + pbase) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(P + plane + pbase) = *reinterpret_cast<const uint2*>(lo);
+  } else {
+    float* P = reinterpret_cast<float*>(planes);
+    float hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_tf32(x[j], hi[j], lo[j]);
+    st4(P + pbase, make_float4(hi[0], hi[1], hi[2], hi[3]));
+    st4(P + plane + pbase, make_float4(lo[0], lo[1], lo[2], lo[3]));
+  }
+}
+
 // Epilogue of one 128 x BN accumulator tile held in this CTA's TMEM (main product at columns [0, BN), correction products at
 // [BN, 2 BN)): warp quadrant q owns TMEM lanes [32 q, 32 q + 32), one thread per output row.
 template <int BN, int EPI, int KIND>
-__device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t tmem_base, int m0, int n0, int ntile, int q, int lane) {
+__device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t tmem_base, int m0, int n0, int ntile, int q, int lane,
+                                              float* tile = nullptr) {
   const int row = m0 + 32 * q + lane;
   const bool rok = row < g.M;
   const bool vec = (g.N & 3) == 0 && (EPI == EPI_STORE ? (g.ldo & 3) == 0 : true);
   float rowacc = 0.f;
+  float dot8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // EPI_DOT, coalesced chunks: partial sums of local rows (lane >> 3) + 4 i
+  float amax4 = 0.f;
   float f16_inv = 1.f;
   if (KIND == KIND_F16 && (EPI == EPI_KICKB || EPI == EPI_PROP) && rok)
     f16_inv = 1.f / (g.row_scale[row] * f16_scale(g.amax[g.unscale_idx], kF16TopB));
@@ -252,13 +308,71 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t tmem_b
         for (int j = 0; j < 32; ++j) v[j] += vc[j];
       }
     }
-    if (!rok) continue;
     if (KIND == KIND_F16 && (EPI == EPI_KICKB || EPI == EPI_PROP)) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] *= f16_inv;
     }
     const int nval = min(32, g.N - col0);
     const bool fast = vec && nval == 32;
+    if (tile && fast) {
+      // ---- coalesced path: full 32-column chunk, eight lanes per row ----------------------------------------------------------
+      float4 o[8];
+      warp_transpose32(v, tile, lane, o);
+      const int c4 = col0 + 4 * (lane & 7);
+      float4 mu4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (EPI != EPI_STORE && g.mu && !(EPI == EPI_PROP && blk != 0)) mu4 = ld4(g.mu + c4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = m0 + 32 * q + (lane >> 3) + 4 * i;
+        if (r >= g.M) continue;
+        const float4 a = o[i];
+        if (EPI == EPI_STORE) {
+          st4(g.out + (size_t)blockIdx.z * g.slice_stride + (size_t)r * g.ldo + c4, a);
+          if (g.amax_out) amax4 = fmaxf(fmaxf(amax4, fmaxf(fabsf(a.x), fabsf(a.y))), fmaxf(fabsf(a.z), fabsf(a.w)));
+        } else if (EPI == EPI_PROP) {
+          const size_t base = (size_t)r * g.N + c4;
+          if (blk == 0) {
+            st4(g.Q + base, make_float4(a.x + mu4.x, a.y + mu4.y, a.z + mu4.z, a.w + mu4.w));
+            const size_t pb = (size_t)r * g.Kout_p + c4, pl = (size_t)g.rows_out_pad * g.Kout_p;
+            if (g.planes_bf16 == 2) store_planes4<KIND_F16>(g.planes_out, pb, pl, a, g.row_scale[r]);
+            else if (g.planes_bf16) store_planes4<KIND_BF16>(g.planes_out, pb, pl, a);
+            else store_planes4<KIND_TF32>(g.planes_out, pb, pl, a);
+          } else {
+            st4(g.S + base, a);
+          }
+        } else if (EPI == EPI_DOT) {
+          const size_t base = (size_t)r * g.N + c4;
+          float4 x = ld4(g.X + base);
+          if (g.Y) {
+            const float4 y = ld4(g.Y + base);
+            x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+          }
+          float t = dot8[i];
+          t = fmaf(a.x, x.x - mu4.x, t); t = fmaf(a.y, x.y - mu4.y, t); t = fmaf(a.z, x.z - mu4.z, t); t = fmaf(a.w, x.w - mu4.w, t);
+          dot8[i] = t;
+        } else {
+          // EPI_KICKB
+          const size_t base = (size_t)r * g.N + c4;
+          float4 sv = ld4(g.S_in + base), qv = ld4(g.Q + base);
+          float4 ws = g.first ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4(g.Qs + base);
+          ws.x = fmaf(g.a, qv.x - mu4.x, ws.x); ws.y = fmaf(g.a, qv.y - mu4.y, ws.y);
+          ws.z = fmaf(g.a, qv.z - mu4.z, ws.z); ws.w = fmaf(g.a, qv.w - mu4.w, ws.w);
+          sv.x = sv.x - g.a * a.x; sv.y = sv.y - g.a * a.y; sv.z = sv.z - g.a * a.z; sv.w = sv.w - g.a * a.w;
+          qv.x = qv.x + g.eps * sv.x; qv.y = qv.y + g.eps * sv.y; qv.z = qv.z + g.eps * sv.z; qv.w = qv.w + g.eps * sv.w;
+          st4(g.S + base, sv);
+          st4(g.Qs + base, ws);
+          if (g.drift) {
+            st4(g.Q + base, qv);
+            const float4 qc = make_float4(qv.x - mu4.x, qv.y - mu4.y, qv.z - mu4.z, qv.w - mu4.w);
+            const size_t pb = (size_t)r * g.Kout_p + c4, pl = (size_t)g.rows_out_pad * g.Kout_p;
+            if (KIND == KIND_F16) store_planes4<KIND_F16>(g.planes_out, pb, pl, qc, g.row_scale[r]);
+            else store_planes4<KIND == KIND_F16F8 ? KIND_BF16 : KIND>(g.planes_out, pb, pl, qc);
+          }
+        }
+      }
+      continue;
+    }
+    if (!rok) continue;
     if (EPI == EPI_STORE) {
       store32(g.out + (size_t)blockIdx.z * g.slice_stride + (size_t)row * g.ldo + col0, v, nval, fast);
       if (g.amax_out) {
@@ -339,6 +453,19 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t tmem_b
       }
     }
   }
+  if (EPI == EPI_DOT && tile) {
+    // hand the coalesced partial sums to the row owners: the eight lanes of group (lane >> 3) hold local rows (lane >> 3) + 4 i
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = dot8[i];
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      const float mine = __shfl_sync(0xffffffffu, t, 8 * (lane & 3));      // local row `lane` lives in group lane & 3 at i = lane >> 2
+      if ((lane >> 2) == i) rowacc += mine;
+    }
+  }
+  if (EPI == EPI_STORE && g.amax_out) rowacc = fmaxf(rowacc, amax4);
   if (EPI == EPI_DOT && rok) {
     float sc = 1.f;
     if (g.dot_pair) sc = 1.f / (g.row_scale[row] * f16_scale(g.amax[g.dot_pair == 1 ? 1 : 0], kF16TopB));
@@ -457,7 +584,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); thread = one output row ----------
     mbar_wait_backoff(tmem_full, 0, 512);
     tc_fence_after();
-    epilogue_rows<BN, EPI, KIND>(g, tmem_base, m0, n0, (int)blockIdx.x, warp & 3, lane);
+    epilogue_rows<BN, EPI, KIND>(g, tmem_base, m0, n0, (int)blockIdx.x, warp & 3, lane,
+                                 ((g.row_epilogue >> EPI) & 1) ? nullptr : reinterpret_cast<float*>(stage_base + (warp & 3) * kTileBytes));
     tc_fence_before();
   }
   __syncthreads();
@@ -588,7 +716,8 @@ k_tc_gemm_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     mbar_wait_backoff(tmem_full, 0, 512);
     tc_fence_after();
-    epilogue_rows<BN, EPI, KIND>(g, tmem_base, m0, n0, ntile, warp & 3, lane);
+    epilogue_rows<BN, EPI, KIND>(g, tmem_base, m0, n0, ntile, warp & 3, lane,
+                                 ((g.row_epilogue >> EPI) & 1) ? nullptr : reinterpret_cast<float*>(smem + (warp & 3) * kTileBytes));
     tc_fence_before();
   }
   __syncwarp();

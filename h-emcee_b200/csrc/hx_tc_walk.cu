@@ -684,7 +684,7 @@ static int launch_gemm(hx_ctx* ctx, const void* A, int rowsA_pad, const void* B,
   CUtensorMap tmA, tmB;
   if (int e = make_tmap(ctx, &tmA, A, mapA_rows ? mapA_rows : 2ull * rowsA_pad, Kp, kBM, KIND)) return e;
   if (int e = make_tmap(ctx, &tmB, B, 2ull * rowsB_pad, Kp, BNT, KIND)) return e;
-  g.Kp = Kp; g.rowsA_pad = rowsA_pad; g.rowsB_pad = rowsB_pad;
+  g.Kp = Kp; g.rowsA_pad = rowsA_pad; g.rowsB_pad = rowsB_pad; g.row_epilogue = ctx->row_epilogue;
   if (int e = ensure_smem_attr(ctx, (const void*)k_tc_gemm<BNT, EPI, KIND>, SmemLayout<BNT>::BYTES)) return e;
   dim3 grid(((n_grid ? n_grid : g.N) + BNT - 1) / BNT, (g.M + kBM - 1) / kBM, slices);
   k_tc_gemm<BNT, EPI, KIND><<<grid, kThreads, SmemLayout<BNT>::BYTES, s>>>(tmA, tmB, g);
@@ -701,7 +701,7 @@ static int launch_gemm_pair(hx_ctx* ctx, const void* A, int rowsA_pad, const voi
   CUtensorMap tmA, tmB;
   if (int e = make_tmap(ctx, &tmA, A, mapA_rows ? mapA_rows : 2ull * rowsA_pad, Kp, kBM, KIND)) return e;
   if (int e = make_tmap(ctx, &tmB, B, 2ull * rowsB_pad, Kp, 128, KIND)) return e;
-  g.Kp = Kp; g.rowsA_pad = rowsA_pad; g.rowsB_pad = rowsB_pad; g.n_cover = n_grid;
+  g.Kp = Kp; g.rowsA_pad = rowsA_pad; g.rowsB_pad = rowsB_pad; g.n_cover = n_grid; g.row_epilogue = ctx->row_epilogue;
   if (int e = ensure_smem_attr(ctx, (const void*)k_tc_gemm_pair<EPI, KIND>, SmemLayoutPair::BYTES)) return e;
   const int mt = (g.M + kBM - 1) / kBM;
   dim3 grid((((n_grid ? n_grid : g.N) + 255) / 256) * ((mt + 1) & ~1), 1, slices);      // 1-D: see the tile mapping in the kernel
