@@ -90,6 +90,7 @@ struct GemmArgs {
   // KIND_F16 with EPI_KICKB / EPI_PROP: acc is divided by row_scale[row] * f16_scale(amax[unscale_idx]) before use
   int unscale_idx;
   int n_cover;       // pair kernel: padded N the grid covers (0: N); EPI_PROP covers two column blocks
+  int epi_force_row; // launch-site override: 1 = row-per-lane epilogue for this launch whatever the ctx mask says
   int row_epilogue;  // bit EPI set: row-per-lane epilogue for that epilogue kind, clear: coalesced chunks through shared memory (hx_ctx_set_tuning(23, mask))
   int one_acc;       // single-CTA kernel, bf16 hi/lo: all three products into ONE accumulator in the order (hi hi, lo hi, hi lo) per
                      // K-block -- the accumulation structure of the fused draw + projection kernel (hx_tc_fused.cuh), kept here
@@ -287,6 +288,15 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t tmem_b
   float f16_inv = 1.f;
   if (KIND == KIND_F16 && (EPI == EPI_KICKB || EPI == EPI_PROP) && rok)
     f16_inv = 1.f / (g.row_scale[row] * f16_scale(g.amax[g.unscale_idx], kF16TopB));
+  // coalesced path: power-of-two operand scales of this lane's eight rows (fp16 hi/lo planes), read once
+  float rs8[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+  if (tile && ((EPI == EPI_KICKB && KIND == KIND_F16 && g.drift) || (EPI == EPI_PROP && g.planes_bf16 == 2))) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = m0 + 32 * q + (lane >> 3) + 4 * i;
+      if (r < g.M) rs8[i] = g.row_scale[r];
+    }
+  }
   const int NC = BN / 32;
   const int blk = (EPI == EPI_PROP) ? n0 / g.blk_cols : 0;
   const int cn0 = (EPI == EPI_PROP) ? n0 - blk * g.blk_cols : n0;
@@ -334,7 +344,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t tmem_b
           if (blk == 0) {
             st4(g.Q + base, make_float4(a.x + mu4.x, a.y + mu4.y, a.z + mu4.z, a.w + mu4.w));
             const size_t pb = (size_t)r * g.Kout_p + c4, pl = (size_t)g.rows_out_pad * g.Kout_p;
-            if (g.planes_bf16 == 2) store_planes4<KIND_F16>(g.planes_out, pb, pl, a, g.row_scale[r]);
+            if (g.planes_bf16 == 2) store_planes4<KIND_F16>(g.planes_out, pb, pl, a, rs8[i]);
             else if (g.planes_bf16) store_planes4<KIND_BF16>(g.planes_out, pb, pl, a);
             else store_planes4<KIND_TF32>(g.planes_out, pb, pl, a);
           } else {
@@ -365,7 +375,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmArgs& g, uint32_t tmem_b
             st4(g.Q + base, qv);
             const float4 qc = make_float4(qv.x - mu4.x, qv.y - mu4.y, qv.z - mu4.z, qv.w - mu4.w);
             const size_t pb = (size_t)r * g.Kout_p + c4, pl = (size_t)g.rows_out_pad * g.Kout_p;
-            if (KIND == KIND_F16) store_planes4<KIND_F16>(g.planes_out, pb, pl, qc, g.row_scale[r]);
+            if (KIND == KIND_F16) store_planes4<KIND_F16>(g.planes_out, pb, pl, qc, rs8[i]);
             else store_planes4<KIND == KIND_F16F8 ? KIND_BF16 : KIND>(g.planes_out, pb, pl, qc);
           }
         }

@@ -684,7 +684,8 @@ static int launch_gemm(hx_ctx* ctx, const void* A, int rowsA_pad, const void* B,
   CUtensorMap tmA, tmB;
   if (int e = make_tmap(ctx, &tmA, A, mapA_rows ? mapA_rows : 2ull * rowsA_pad, Kp, kBM, KIND)) return e;
   if (int e = make_tmap(ctx, &tmB, B, 2ull * rowsB_pad, Kp, BNT, KIND)) return e;
-  g.Kp = Kp; g.rowsA_pad = rowsA_pad; g.rowsB_pad = rowsB_pad; g.row_epilogue = ctx->row_epilogue;
+  g.Kp = Kp; g.rowsA_pad = rowsA_pad; g.rowsB_pad = rowsB_pad;
+  g.row_epilogue = ctx->row_epilogue | (g.epi_force_row ? (1 << EPI) : 0);
   if (int e = ensure_smem_attr(ctx, (const void*)k_tc_gemm<BNT, EPI, KIND>, SmemLayout<BNT>::BYTES)) return e;
   dim3 grid(((n_grid ? n_grid : g.N) + BNT - 1) / BNT, (g.M + kBM - 1) / kBM, slices);
   k_tc_gemm<BNT, EPI, KIND><<<grid, kThreads, SmemLayout<BNT>::BYTES, s>>>(tmA, tmB, g);
@@ -872,6 +873,9 @@ static int leapfrog_bform(hx_ctx* ctx, const LeapArgs& a, cudaStream_t s) {
     x.planes_out = planes[(k + 1) & 1]; x.rows_out_pad = rA; x.Kout_p = dK;
     x.a = (float)((k == 0 || k == a.L) ? 0.5 * (float)a.eps : (float)a.eps);
     x.drift = k < a.L ? 1 : 0;
+    // many rows (stepwise kicks over the walkers): the epilogue is bound by its HBM traffic and the coalesced chunk path only adds
+    // shared-memory round trips (c5, 32768 rows: 5.9 -> 7.0 ms per half-move); few rows (latency-bound): coalesced (-6 %)
+    x.epi_force_row = !(narrow || narrow64);
     // few rows (the propagator's 2d basis trajectories): 128-wide tiles double the CTAs and halve both the MMA chain and
     // the per-thread epilogue of these latency-bound launches
     if (narrow64) {
@@ -1046,7 +1050,10 @@ int walk_half(hx_ctx* ctx, int impl, const hx_target* tgt, const float* mean_dev
   bool prop = ctx->leap_form == HX_LEAP_PROPAGATOR;
   if (ctx->leap_form == HX_LEAP_AUTO) {
     const double bw = 2.6e12, elems = (double)rows * d * 28.0;
-    const double t_kick = elems / bw > 25e-6 ? elems / bw : 25e-6;
+    // (+ the kick GEMM's own main loop, ~1 us per 64-wide K-block: without it the model picked the stepwise form for 8 ranks at
+    //  c5, 4096 rows each, where the propagator form measures 0.75 ms against 0.82-1.0 ms per half-move -- and keeps the 8-GPU
+    //  chain bit-equal to the 1/2/4-GPU chains)
+    const double t_kick = (elems / bw > 25e-6 ? elems / bw : 25e-6) + 16e-6 * (d / 1000.0);
     const double t_bk = 27e-6 + 15e-6 * (d / 1000.0) * (d / 1000.0);
     const double t_apply = 4.0 * elems / bw > 80e-6 ? 4.0 * elems / bw : 80e-6;
     prop = (L + 3) * t_kick > (L + 1) * t_bk + 60e-6 + t_apply;
