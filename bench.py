@@ -8,7 +8,8 @@ integrated for L leapfrog steps and accepted/rejected).  Default workload = BASE
 1000-dim ill-conditioned Gaussian (kappa 1e4, full covariance), 65,536 walkers, walk move, L = 10,
 fp32 — the configuration the metric is quoted on; it fits one GPU because the walk move runs in
 projected form (no n x n momentum in HBM).  N > 1 shards the walkers of both halves by rows over the
-ranks (strong scaling: total work fixed) with one NCCL all-gather of the updated half per half-move.
+ranks (strong scaling: total work fixed); after every half-move the kernels store the updated rows into the peers' copies over NVLink
+(csrc/hx_dist.cuh: peer-memory stores + epoch flags, no collective on the data path).
 
 Prints ONE JSON line (contract in the task statement) with `roofline`, `cpu_baseline`, `e2e`,
 `clocks`, `gpu_launches`.  `--impl reference` times the reference algorithm on the host CPU: JAX is
@@ -483,8 +484,8 @@ def main():
     form = args.leapfrog_form
     if form == "auto":
         el_ = rows * d * 28.0 / 2.6e12           # same cost model as csrc/hx_tc_walk.cu (HX_LEAP_AUTO)
-        form = ("propagator" if (L + 3) * max(el_, 25e-6) > (L + 1) * (27e-6 + 15e-6 * (d / 1000.0) ** 2) + 60e-6 + max(4 * el_, 80e-6)
-                else "stepwise")
+        form = ("propagator" if (L + 3) * (max(el_, 25e-6) + 16e-6 * (d / 1000.0)) > (L + 1) * (27e-6 + 15e-6 * (d / 1000.0) ** 2) + 60e-6
+                + max(4 * el_, 80e-6) else "stepwise")
     extra = {}
     if path == 1:
         # tensor-core path: the bracketed section is the momentum projection S0 = P0 C of one half-move: tcgen05 GEMM chunks
@@ -494,11 +495,13 @@ def main():
         fused = (int(tune.get("15", 1)) != 0 and args.precision in ("auto", "bf16x3", "tf32x3") and d <= 1024
                  and _rt.impl_code() == _lib.HX_RNG_PARTITIONABLE)
         f8 = (not fused) and args.precision in ("auto", "f16f8")        # staged projection operands: fp16 + 2 x e4m3, or bf16 hi/lo
+        ffmt = int(tune.get("21", 0)) or (2 if args.precision == "auto" else 1)   # fused operand form: 1 bf16 hi/lo, 2 fp16 + fp8 (hx_tc_fused.cuh)
         ekind = int(tune.get("3", 2)) if args.precision != "tf32x3" else 0   # propagator energy operands: 2 fp16 hi/lo, 0 tf32 hi/lo
         if fused:
-            kname = ("tc::k_tc_proj_fused<%s RNG warps, %s> S0 = normal(key,(n,n))[rows] @ C: threefry + erf_inv in registers -> bf16 hi/lo "
-                     "operand tiles in shared memory (CTA pair) -> tcgen05.mma, split-K 2 (+ k_sum_slices_f)"
-                     % (tune.get("16", "28"), "CTA pair" if d > 512 else "single CTA"))
+            kname = ("tc::k_tc_proj_fused<%s RNG warps, %s, %s> S0 = normal(key,(n,n))[rows] @ C: threefry + erf_inv in registers -> "
+                     "operand tiles in shared memory -> tcgen05.mma into one TMEM accumulator, split-K 2 added with red.global.add"
+                     % (tune.get("16", "28"), "CTA pair" if d > 512 else "single CTA",
+                        "fp16 + e4m3 x e5m2 operands at true scale (kind::f16 + 2 x kind::f8f6f4)" if ffmt == 2 else "bf16 hi/lo operands (3 x kind::f16)"))
         else:
             kname = ("tc::k_tc_gemm<256,EPI_STORE,%s> projection S0 = P0 C (all row chunks of a half-move), "
                      "tc::k_rng_planes of the next half-move concurrent" % ("fp16 + e4m3" if f8 else "bf16 hi/lo"))
@@ -506,7 +509,7 @@ def main():
         nK, dpad = -(-n // 64) * 64, -(-d // 256) * 256
         # tensor work actually issued, in units of one bf16-rate product: bf16 hi/lo = 3 products; fp16 + e4m3 = one fp16 product
         # + two e4m3 products at twice the rate = 2 units; single bf16 = 1
-        units = 1.0 if args.precision == "bf16" else (2.0 if f8 else 3.0)
+        units = 1.0 if args.precision == "bf16" else (2.0 if (f8 or (fused and ffmt == 2)) else 3.0)
         executed = units * 2.0 * (-(-rows // 128) * 128) * nK * dpad
         dB, dK = dpad, -(-d // 64) * 64
         # executed tensor flops of the whole half-move in bf16 units (tf32 products count double: half the MMA rate)
@@ -524,7 +527,7 @@ def main():
                      step_executed_frac=step_exec * 2 * K / (ms * 1e-3) / 1e12 / peak_tf)
         note = ("achieved/frac = ALGORITHMIC flops 2*rows*n*d of the projection (SURVEY §8d first term) / section time. fp32-class "
                 "accuracy on 16-bit tensor-core operands takes 3 products per algorithmic product (hi*hi + lo*hi + hi*lo: frac <= 1/3 "
-                "by construction; the staged fp16 + e4m3 form runs its two correction products at twice the rate, 2 units); "
+                "by construction; the fp16 + fp8 forms run their two correction products at twice the rate, 2 units: frac <= 1/2); "
                 "executed_* counts the bf16-rate units actually issued (incl. d padded to 256); step_executed_* is the whole "
                 "iteration (projection + leapfrog/energy GEMMs + Gram; tf32 products counted double) against the same peak.  The "
                 "section is bound by the momentum draw it contains (n^2 threefry + erf_inv evaluations per half-move on the alu "

@@ -16,8 +16,14 @@ projection, leapfrog, energy and Metropolis accept, and writes the new state str
 on-device chain buffer, which is copied to pinned host memory per batch on a side stream.
 
 With `group=` (a torch.distributed process group) the walkers of both halves are row-sharded over
-the ranks; each half-move updates the local rows against the all-gathered complement (one NCCL
-all-gather per half-move).
+the ranks.  Default `exchange="peer"`: every rank keeps a full copy of the ensemble that its peers map
+through CUDA IPC; after a half-move the finish kernel stores the rank's updated rows straight into the
+peers' copies over NVLink and publishes an epoch flag (csrc/hx_dist.cuh; no collective library on the data
+path).  `exchange="nccl"` all-gathers the updated rows instead (used for warm-up with live adapters).
+
+Also here, beyond the reference: `store="thinned" | "none"` (only the returned iterations / no chain leave
+the device), `online_stats=` (on-device moments and lagged products: `sampler.stats.integrated_time()`
+without a stored chain, hemcee_b200/stats.py), device-resident adaptation (`hx_run_warmup`).
 """
 from __future__ import annotations
 
