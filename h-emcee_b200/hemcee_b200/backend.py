@@ -127,13 +127,28 @@ class FileBackend(Backend):
     attributes `version`, `nwalkers`, `ndim`, `iteration`, `iteration_warmup`, `iteration_main`, `warmup_end_index` with -1 for
     "warm-up not complete").  h5py is not a dependency here, so the container is NumPy's .npz; a maintainer with h5py can copy
     the arrays into an HDF5 group one to one.  During sampling it behaves like the in-memory Backend (the chain batches arrive
-    from pinned host buffers); `save()` writes what has been stored so far."""
+    from pinned host buffers); `save()` writes what has been stored so far.
+
+    Differences from the reference's HDFBackend, stated rather than hidden: (1) the reference appends to the HDF5 file on every
+    `save_slice` (hdf.py:155-170), so a crashed run keeps its completed batches; here that needs `autosave=True`, which REWRITES the
+    .npz after every slice (atomic rename; cost grows with the stored chain -- meant for long batches, the sampler stores one slice
+    per phase on a single GPU); (2) the file is .npz, which the reference's HDFBackend cannot open."""
 
     VERSION = 0
 
-    def __init__(self, filename: str, name: str = "mcmc", read_only: bool = False, dtype=None):
+    def __init__(self, filename: str, name: str = "mcmc", read_only: bool = False, dtype=None, autosave: bool = False):
         super().__init__(dtype)
-        self.filename, self.name, self.read_only = filename, name, read_only
+        self.filename, self.name, self.read_only, self.autosave = filename, name, read_only, autosave
+
+    def save_slice(self, coords, log_prob, accepted, index: int):
+        super().save_slice(coords, log_prob, accepted, index)
+        if self.autosave and not self.read_only:
+            self.save()
+
+    def mark_warmup_end(self):
+        super().mark_warmup_end()
+        if self.autosave and not self.read_only and self.iteration > 0:
+            self.save()
 
     def save(self):
         if self.read_only:
@@ -149,8 +164,11 @@ class FileBackend(Backend):
                      warmup_end_index=-1 if self._warmup_end_index is None else self._warmup_end_index)
         arrays = {f"{n}/chain": np.asarray(chain), f"{n}/log_prob": np.asarray(lp), f"{n}/accepted": self.accepted}
         arrays.update({f"{n}/attrs/{k}": np.asarray(v) for k, v in attrs.items()})
-        with open(self.filename, "wb") as f:
+        tmp = self.filename + ".tmp"
+        with open(tmp, "wb") as f:
             np.savez(f, **arrays)
+        import os
+        os.replace(tmp, self.filename)                    # atomic: a crash during save keeps the previous file
 
     @classmethod
     def load(cls, filename: str, name: str = "mcmc", read_only: bool = True):

@@ -89,3 +89,24 @@ def test_empty_store_returns_empty_arrays():
     b.reset(4, 2)
     b.iteration = 7                                       # iterations were run but none was stored (num_samples = 0)
     assert b.get_chain().shape == (0, 4, 2) and b.get_log_prob().shape == (0, 4)
+
+
+def test_file_backend_autosave_keeps_completed_slices(tmp_path):
+    """autosave=True: the file on disk holds every completed slice (what the reference's HDFBackend guarantees by appending in
+    save_slice, hdf.py:155-170), so a run that dies later loses only the unfinished batch."""
+    from hemcee_b200.backend import FileBackend
+    fn = str(tmp_path / "auto.npz")
+    b = FileBackend(fn, autosave=True)
+    b.reset(4, 2)
+    rng = np.random.default_rng(0)
+    c1, c2 = rng.standard_normal((3, 4, 2)).astype(np.float32), rng.standard_normal((2, 4, 2)).astype(np.float32)
+    b.save_slice(c1, c1[:, :, 0], np.ones(4), 0)
+    r = FileBackend.load(fn)
+    assert r.iteration == 3 and r._warmup_end_index is None
+    np.testing.assert_array_equal(r.get_chain(), c1)
+    b.mark_warmup_end()
+    b.save_slice(c2, c2[:, :, 0], np.ones(4), 3)
+    r = FileBackend.load(fn)
+    assert r.iteration == 5 and r.iteration_warmup == 3 and r.iteration_main == 2
+    np.testing.assert_array_equal(r.get_chain(), np.concatenate([c1, c2]))
+    np.testing.assert_array_equal(r.accepted, 2 * np.ones(4))
