@@ -261,10 +261,10 @@ class ClockSampler:
 
 
 # DRAM traffic of the fused draw + projection of one c5 half-move (ncu --set full, profiles/r02_c5_fused_ncu_summary.txt)
-FUSED_TRAFFIC_BYTES = 7.384e8
-FUSED_TRAFFIC_SOURCE = ("profiles/r02_c5_fused_ncu_summary.txt: dram__bytes_read.sum 508.0 MB + dram__bytes_write.sum 230.4 MB of the one "
-                        "k_tc_proj_fused launch of a half-move (C^T planes 134 MB + two split-K slices of S0, 262 MB, are the algorithmic "
-                        "bytes; the k_sum_slices_f launch that adds the slices moves another 393 MB); staged path of round 1: 9.6 GB")
+FUSED_TRAFFIC_BYTES = 1.0097e9
+FUSED_TRAFFIC_SOURCE = ("profiles/r02_c5_fused_ncu_summary.txt: dram__bytes_read.sum 772.8 MB + dram__bytes_write.sum 236.8 MB of the one "
+                        "k_tc_proj_fused launch of a half-move (algorithmic: C^T planes 134 MB + S0 131 MB; the two split-K slices add into "
+                        "S0 with red.global.add, which reads it back once); staged path of round 1: 9.6 GB per half-move")
 
 
 def algorithmic_flops_half_move(rows, n, d, L, target):
