@@ -93,7 +93,7 @@ def test_fused_matches_oracle(hx, knobs, n, d, fmt):
     np.testing.assert_allclose(la.cpu().numpy(), la64, rtol=0, atol=5e-3)
 
 
-@pytest.mark.parametrize("n,d", SHAPES + [(4160, 1000)])
+@pytest.mark.parametrize("n,d", SHAPES + [(4160, 1000), (4160, 203), (4100, 64)])      # from 4096 walkers: split-K 2 with red.add (d = 203: scalar path)
 def test_fused_projection_error_of_both_operand_forms(hx, knobs, n, d):
     """S0 = P0 C of the fused kernel against an f64 product of the same draws, for the bf16 hi/lo form (FMT 0, three products) and
     the fp16 + fp8 form (FMT 1: fp16 main product, e4m3 x e5m2 correction products at true scale; the default under "auto").
