@@ -127,6 +127,7 @@ extern "C" HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value) {
   else if (what == 21) ctx->fused_fmt = value;
   else if (what == 22) ctx->fused_no_atomic = value ? 1 : 0;
   else if (what == 23) ctx->row_epilogue = value;
+  else if (what == 24) ctx->fused_stagger_ns = value;
   else return hx_fail(HX_E_DTYPE, "hx_ctx_set_tuning: unknown knob %d", what);
   return 0;
 }

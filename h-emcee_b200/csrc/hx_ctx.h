@@ -94,6 +94,7 @@ struct hx_ctx {
   int fused_relaxed;                       // 1: RNG warps wait for a free A stage with test_wait + nanosleep (0: parked try_wait)
   int fused_fmt;                           // operand form of the fused projection: 0 by precision (AUTO: fp16 + fp8, BF16X3: bf16 hi/lo), 1 bf16 hi/lo, 2 fp16 + fp8
   int row_epilogue;                        // 1: row-per-lane GEMM epilogues (diagnostics; default: coalesced through shared memory)
+  int fused_stagger_ns;                    // start-up stagger of the fused kernel's RNG warps per K-block position, in ns
   int fused_no_atomic;                     // 1: two split-K slices of the fused projection go through slice buffers + a sum kernel instead of red.add
   int fused_diag;                          // diagnostics: 1 no draw, 2 no MMA (results are garbage)
   int one_acc;                             // staged bf16 hi/lo projection accumulates all three products in one accumulator (bit-compare with the fused kernel)

@@ -234,6 +234,7 @@ struct FusedArgs {
   float* out; int ldo;
   int diag;         // diagnostics: 1 = no draw (A garbage), 2 = no MMA; results are garbage
   int relaxed_wait; // RNG warps poll their `empty` barrier with test_wait + nanosleep instead of a parked try_wait
+  int stagger_ns;   // RNG warps assigned to the p-th K-block of a round start p * stagger_ns late (see the RNG loop)
   int atomic_out;   // split-K with exactly two slices: both add into the zeroed output with red.global.add (x + y is commutative and
                     // 0 + x exact, so the result does not depend on which slice lands first) -- no slice buffers, no sum kernel
   const float* scale_ptr;   // FMT 1: {sc, 1/sc}, the power-of-two scale of the B planes; the epilogue multiplies by scale_ptr[1]
@@ -403,6 +404,12 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
     };
     // software pipeline: the hash of the NEXT batch (alu pipe: SHF / LOP3) is issued in the same straight-line block as the
     // erf_inv polynomial and the operand split of the current one (fma pipe), so that each warp keeps both pipes busy by itself
+    // All RNG warps run at the same rate, so without a stagger the NW / RG K-blocks of a round are completed at the same moment:
+    // the MMA warp then works through a burst while the warps of the next round wait for free stages (ncu: a third of their
+    // samples parked on emptyA although the draw is the slower side).  Starting the warps of the p-th K-block p * stagger late
+    // would spread the completions evenly.  Measured on B200 (hx_ctx_set_tuning(24, ns), scripts/fused_knob.py): 0 ... 3200 ns per
+    // position change nothing (4.644 +- 0.003 ms at c5) -- the first blocked wait re-aligns the warps -- so the default is 0.
+    if (f.stagger_ns > 0 && wr >= RG) __nanosleep((unsigned)(f.stagger_ns * (wr / RG)));
     uint32_t bcur[8];
     {
       const uint64_t e = elem(wr, 0);

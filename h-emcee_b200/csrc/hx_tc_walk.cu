@@ -784,7 +784,7 @@ static int launch_proj_fused(hx_ctx* ctx, const void* CT, int dAB, int nK, int n
   memset(&f, 0, sizeof(f));
   f.key = key; f.key_ptr = key_ptr; f.n = n; f.row0 = row0; f.rows = rows; f.d = d; f.num_kb = nK / 64;
   f.rowsB_pad = dAB; f.out = S0; f.ldo = d; f.diag = ctx->fused_diag; f.relaxed_wait = ctx->fused_relaxed;
-  f.scale_ptr = scale8;
+  f.scale_ptr = scale8; f.stagger_ns = ctx->fused_stagger_ns;
   const bool share = d > 512;
   f.units = share ? 2 : (d + 255) / 256;
   const int tiles = (rows + kBM - 1) / kBM;
