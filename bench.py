@@ -354,7 +354,7 @@ def main():
     rows = n // world
     row0 = rank * rows
     if cfg["target"] == "gauss":
-        _, prec = make_cov(d, cfg["kappa"])
+        cov_t, prec = make_cov(d, cfg["kappa"])
         tgt = hx.targets.GaussianFull(precision=prec)
     elif cfg["target"] == "rosenbrock":
         tgt = hx.targets.Rosenbrock(d)
@@ -671,10 +671,13 @@ def main():
         ess = dict(value=Te * W / tmax / el, unit="ESS/s", tau_max=tmax, tau_min=float(np.nanmin(tau)), iterations=Te, burn_in=Tb,
                    seconds=el, reliable=bool(50 * tmax <= Te), dims=len(dims), walkers_in_estimate=int(st.n_track),
                    mean_abs_max=float(np.abs(st.mean()).max()), var_minmax=[float(st.var().min()), float(st.var().max())],
+                   var_over_target_minmax=([float((st.var() / np.diag(cov_t)).min()), float((st.var() / np.diag(cov_t)).max())]
+                                           if cfg["target"] == "gauss" else None),
                    note="min over the sampled dims of (iterations * walkers / tau_int) / wall time of those iterations; tau_int = the "
                         "reference's estimator (autocorr.py:44-118, c=5, tol=50) evaluated from on-device accumulators (no chain is "
                         "stored or copied: hx_ctx_set_chain_stats); fixed step size and L (no adaptation), chain started from "
-                        "N(0, I); mean / var = running moments over all walkers and those iterations")
+                        "N(0, I); mean / var = running moments over all walkers and those iterations; var_over_target = their ratio to the target's "
+                        "coordinate variances diag(Sigma) (long-run moments at full size: ~1 once the slow directions have equilibrated)")
 
     # ESS/s at N > 1: the sharded loop continues from the timed state; every rank estimates tau_int on a subset of ITS rows
     if world > 1 and args.ess_iters > 0 and not args.no_e2e:
