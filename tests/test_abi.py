@@ -41,6 +41,22 @@ def test_argument_validation_without_gpu():
     assert lib.hx_walk_move(None, 0, 0, None, None, None, 4, 0, 4, 0.1, key, 1, None, None, None, None, None, 0, None) == -1
 
 
+def test_round2_entry_points_validate_arguments_without_gpu():
+    """hx_stats_feed / hx_ctx_set_chain_stats / hx_spd_inverse reject NULL handles before touching the device; the Python mirror of
+    hx_chain_stats has the header's field order."""
+    from hemcee_b200 import _lib
+    lib = _lib.load()
+    st = _lib.hx_chain_stats()
+    assert lib.hx_stats_feed(None, 0, ctypes.byref(st), ctypes.c_void_p(8), None) == -1
+    assert lib.hx_ctx_set_chain_stats(None, ctypes.byref(st)) == -1
+    assert lib.hx_spd_inverse(None, ctypes.c_void_p(8), 4, 4, ctypes.c_double(1.0), ctypes.c_void_p(8), 4, None) == -1
+    assert lib.hx_stats_row_blocks() >= 1
+    src = open(os.path.join(ROOT, "include", "hx.h")).read()
+    body = src[src.index("typedef struct hx_chain_stats {"):src.index("} hx_chain_stats;")]
+    names = re.findall(r"[\*\s,](\w+_dev|nwalkers|dim|n_track|walker_stride|n_dims|max_lag)\b(?=[,;])", body)
+    assert names == [f[0] for f in _lib.hx_chain_stats._fields_], names
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "h-emcee_b200", "hemcee_b200")
     for fn in os.listdir(pkg):
