@@ -82,7 +82,7 @@ __device__ __forceinline__ void bits8_fix_wrap(Key key, uint32_t ks2, uint64_t e
 // normal_at<float, false> (hx_rng.cuh) -- the staged path's draw.  The central branch of XLA's erf_inv (w < 5) is evaluated
 // for all eight in straight-line code; the tail branch (|u| > 0.9966, 0.34 % of the draws) is a separate fix-up.
 __device__ __forceinline__ bool normals8_central(const uint32_t (&b)[8], float (&x)[8], float (&u)[8], float (&w)[8]) {
-  bool tail = false;
+  float wmax = 0.f;                  // w >= 0; one FMNMX per draw instead of FSETP + PLOP3
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
     // (bits >> 9) | 0x3F800000 as one IMAD.HI: hi32(bits * 2^23) + 0x3F800000 (the two fields do not overlap)
@@ -90,7 +90,7 @@ __device__ __forceinline__ bool normals8_central(const uint32_t (&b)[8], float (
     const float f = __uint_as_float(m) - 1.0f;
     u[t] = fmaxf(-0.99999994f, fmaf(f, 2.0f, -0.99999994f));      // 2 f is exact: one rounding, like fmul_rn + fadd_rn
     w[t] = -0.693147182f * fast_lg2(__fsub_rn(1.0f, __fmul_rn(u[t], u[t])));
-    tail = tail || !(w[t] < 5.0f);
+    wmax = fmaxf(wmax, w[t]);
     const float ww = w[t] - 2.5f;
     float p = 2.81022636e-08f;
     p = fmaf(p, ww, 3.43273939e-07f);
@@ -103,7 +103,7 @@ __device__ __forceinline__ bool normals8_central(const uint32_t (&b)[8], float (
     p = fmaf(p, ww, 1.50140941f);
     x[t] = 1.41421354f * (p * u[t]);
   }
-  return tail;
+  return !(wmax < 5.0f);
 }
 __device__ __forceinline__ void normals8_fix_tail(float (&x)[8], const float (&u)[8], const float (&w)[8]) {
 #pragma unroll
@@ -416,8 +416,13 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
       bits8_fast(key, ks2, e, bcur);
       bits8_fix_wrap(key, ks2, e, bcur);
     }
+    // NW a multiple of RG (28 RNG warps are not, 24 are for a CTA pair): a warp keeps its row group and advances NW / RG
+    // K-blocks per item, so the element index of the next batch is the current one plus a constant
+    constexpr bool kAligned = (NW % RG) == 0;
+    const uint64_t rs4 = 4ull * row_stride;
+    uint64_t e_item = elem(wr, 0);
     for (int g = wr; g < nitems; g += NW) {
-      const int kb = g / RG, rg = g - kb * RG;
+      const int kb = g / RG, rg = g - kb * RG;        // (keeping rg loop-invariant by hand for the aligned case costs registers: slower)
       const int sa = kb % L::SA;
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
@@ -426,7 +431,13 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
         if (f.diag != 1) {
           // (the batch after the last one is hashed too and dropped: no branch inside the straight-line block)
           uint32_t bnext[8];
-          const uint64_t en = (b + 1 < NB) ? elem(g, b + 1) : elem(g + NW, 0);
+          uint64_t en;
+          if (kAligned) {
+            en = (b + 1 < NB) ? e_item + (uint64_t)(b + 1) * rs4 : e_item + (uint64_t)((NW / RG) * 64);
+            if (b + 1 == NB) e_item = en;
+          } else {
+            en = (b + 1 < NB) ? elem(g, b + 1) : elem(g + NW, 0);
+          }
           float x[8], u[8], w[8];
           bits8_fast(key, ks2, en, bnext);
           const bool tail = normals8_central(bcur, x, u, w);

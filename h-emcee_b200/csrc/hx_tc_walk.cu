@@ -800,7 +800,9 @@ static int launch_proj_fused(hx_ctx* ctx, const void* CT, int dAB, int nK, int n
     if (int e = ws_get(ctx, WS_TC_S0P, (size_t)slices * rows * d * sizeof(float), &pS0P)) return e;
     f.out = (float*)pS0P; f.kb_per_slice = kbs; f.slice_stride = (size_t)rows * d;
   }
-  const int nw = ctx->fused_nw > 0 ? ctx->fused_nw : 28;      // measured in the c5 step: 28 >= 20 > 16 warps (17.0-17.4 / 17.3-17.5 / 17.4-17.6 ms per iteration)
+  // RNG warps per CTA.  A CTA pair deals 8 items per K-block: with 24 warps every warp keeps its row group and steps 3 K-blocks per
+  // item (constant index increments, loop-invariant store offsets): 4.53 ms alone at c5 against 4.67 with 28 warps (round 2)
+  const int nw = ctx->fused_nw > 0 ? ctx->fused_nw : (share ? 24 : 28);
   int e;
 #define HX_FUSED_NW(NWV) \
   case NWV: e = scale8 ? (share ? launch_fused_t<NWV, true, 1>(ctx, tmB, f, tiles, slices, s) : launch_fused_t<NWV, false, 1>(ctx, tmB, f, tiles, slices, s)) \
