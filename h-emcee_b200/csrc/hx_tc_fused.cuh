@@ -220,6 +220,17 @@ __device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) 
                : "memory");
 }
 
+// K-major SWIZZLE_128B operand whose 8-row groups (1 KB atoms) are `sbo` bytes apart (umma_desc_k128 fixes 1024)
+__device__ __forceinline__ uint64_t umma_desc_k128_sbo(uint32_t smem_addr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 struct FusedArgs {
   Key key; const uint32_t* key_ptr;   // key by value, or device-resident (batch loops / graph replays)
   int n;            // walkers per group: row length of the (n, n) draw and the K extent
@@ -249,7 +260,10 @@ struct FusedArgs {
 #endif
 struct FusedSmem {
   static constexpr int A_PLANE = kBM * 128;            // 16 KB: 128 rows x 64 bf16
-  static constexpr int A_STAGE = 2 * A_PLANE;          // hi + lo
+  static constexpr int A_STAGE = 2 * A_PLANE;          // hi + lo, INTERLEAVED per 8-row group: [group g: plane 0 (1 KB) | plane 1 (1 KB)], so
+                                                       // that an 8-row work item is 2 KB contiguous (one bulk copy to the peer, one byte-count
+                                                       // event on its barrier instead of two); the UMMA descriptors step 2 KB between groups
+  static constexpr int A_GROUP = 2048;
   static constexpr int B_STAGE = 256 * 128;            // 32 KB: ONE plane (hi or lo) of 256 columns x 64 bf16
   static constexpr int SA = HX_FUSED_SA, SB = HX_FUSED_SB;
   static constexpr int BAR_OFF = SA * A_STAGE + SB * B_STAGE;       // 224 KB
@@ -329,8 +343,8 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
         mbar_wait_parked(&fullA[sa], (uint32_t)(kb / L::SA) & 1u);
         fence_proxy_async();       // the A stage was written through the generic proxy (st.shared / st.async); the MMA reads it through the async proxy
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(stA + sa * L::A_STAGE), a_lo = a_hi + L::A_PLANE;
-        const uint64_t ad_hi = umma_desc_k128(a_hi), ad_lo = umma_desc_k128(a_lo);
+        const uint32_t a_hi = smem_u32(stA + sa * L::A_STAGE), a_lo = a_hi + 1024u;
+        const uint64_t ad_hi = umma_desc_k128_sbo(a_hi, L::A_GROUP), ad_lo = umma_desc_k128_sbo(a_lo, L::A_GROUP);
         for (int u = 0; u < units; ++u) {
           const uint32_t dcol = tmem_base + (uint32_t)(u * 256);
 #pragma unroll
@@ -457,15 +471,16 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
           if (f.relaxed_wait) mbar_wait_relaxed(&emptyA[sa], ((uint32_t)(kb / L::SA) & 1u) ^ 1u);
           else mbar_wait_parked(&emptyA[sa], ((uint32_t)(kb / L::SA) & 1u) ^ 1u);
         }
-        const uint32_t so = (uint32_t)(sa * L::A_STAGE) + (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));   // 128-byte swizzle
+        // row r of plane p lives at (r >> 3) * 2 KB + p * 1 KB + (r & 7) * 128, 16-byte chunks XOR-swizzled with the row (128B swizzle)
+        const uint32_t so = (uint32_t)(sa * L::A_STAGE) + (uint32_t)((r >> 3) * L::A_GROUP + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
         st_shared_v4(stA_local + so, hi);
         if (FMT == 1) {
           // fp8 plane row = [64 x e4m3(x) | 64 x e5m2(res)]: this lane's 8 bytes of each at byte chunk * 8 / 64 + chunk * 8
-          const uint32_t rowb = stA_local + (uint32_t)(sa * L::A_STAGE + L::A_PLANE + r * 128) + (uint32_t)((chunk & 1) << 3);
+          const uint32_t rowb = stA_local + (uint32_t)(sa * L::A_STAGE + (r >> 3) * L::A_GROUP + 1024 + (r & 7) * 128) + (uint32_t)((chunk & 1) << 3);
           st_shared_v2(rowb + ((uint32_t)((chunk >> 1) ^ (r & 7)) << 4), make_uint2(lo.x, lo.y));
           st_shared_v2(rowb + ((uint32_t)((4 + (chunk >> 1)) ^ (r & 7)) << 4), make_uint2(lo.z, lo.w));
         } else {
-          st_shared_v4(stA_local + so + L::A_PLANE, lo);
+          st_shared_v4(stA_local + so + 1024u, lo);
         }
       }
       fence_proxy_async();         // generic-proxy stores -> visible to the async proxy (the tensor core's operand reads, the bulk copy)
@@ -474,9 +489,15 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
       // copied into the peer's stage by the TMA engine, and the arrival announces the bytes the peer copies into THIS CTA
       if (lane == 0) {
         if (SHARE) {
-          const uint32_t io = (uint32_t)(sa * L::A_STAGE) + (uint32_t)(((int)rank * ROWS_CTA + IR * rg) * 128);
-          bulk_copy_to_peer(stA_peer + io, stA_local + io, IR * 128u, fullA_peer + 8u * sa);
-          bulk_copy_to_peer(stA_peer + io + L::A_PLANE, stA_local + io + L::A_PLANE, IR * 128u, fullA_peer + 8u * sa);
+          if (IR == 8) {      // the item is one 8-row group: both planes in one 2 KB copy
+            const uint32_t io = (uint32_t)(sa * L::A_STAGE) + (uint32_t)((((int)rank * ROWS_CTA + IR * rg) >> 3) * L::A_GROUP);
+            bulk_copy_to_peer(stA_peer + io, stA_local + io, 2048u, fullA_peer + 8u * sa);
+          } else {            // half a group: 4 rows x 128 bytes of each plane
+            const int r0 = (int)rank * ROWS_CTA + IR * rg;
+            const uint32_t io = (uint32_t)(sa * L::A_STAGE) + (uint32_t)((r0 >> 3) * L::A_GROUP + (r0 & 7) * 128);
+            bulk_copy_to_peer(stA_peer + io, stA_local + io, IR * 128u, fullA_peer + 8u * sa);
+            bulk_copy_to_peer(stA_peer + io + 1024u, stA_local + io + 1024u, IR * 128u, fullA_peer + 8u * sa);
+          }
           mbar_expect_tx(&fullA[sa], 2u * IR * 128u);
         } else {
           mbar_arrive(&fullA[sa]);
