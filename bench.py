@@ -500,7 +500,7 @@ def main():
         if fused:
             kname = ("tc::k_tc_proj_fused<%s RNG warps, %s, %s> S0 = normal(key,(n,n))[rows] @ C: threefry + erf_inv in registers -> "
                      "operand tiles in shared memory -> tcgen05.mma into one TMEM accumulator, split-K 2 added with red.global.add"
-                     % (tune.get("16", "28"), "CTA pair" if d > 512 else "single CTA",
+                     % (tune.get("16", "24" if d > 512 else "28"), "CTA pair" if d > 512 else "single CTA",
                         "fp16 + e4m3 x e5m2 operands at true scale (kind::f16 + 2 x kind::f8f6f4)" if ffmt == 2 else "bf16 hi/lo operands (3 x kind::f16)"))
         else:
             kname = ("tc::k_tc_gemm<256,EPI_STORE,%s> projection S0 = P0 C (all row chunks of a half-move), "
@@ -531,7 +531,8 @@ def main():
                 "executed_* counts the bf16-rate units actually issued (incl. d padded to 256); step_executed_* is the whole "
                 "iteration (projection + leapfrog/energy GEMMs + Gram; tf32 products counted double) against the same peak.  The "
                 "section is bound by the momentum draw it contains (n^2 threefry + erf_inv evaluations per half-move on the alu "
-                "pipe: draw_* keys; 3.5 ms for the arithmetic alone at c5 on one GPU at 1965 MHz), not by the tensor pipe, and the "
+                "pipe: draw_* keys -- draw_frac is the fraction of THAT roofline, the one that binds; 3.5 ms for the arithmetic alone at c5 on "
+                "one GPU at 1965 MHz), not by the tensor pipe, and the "
                 "whole step runs under the 1 kW power cap (clocks)")
         # the draw inside the section: achieved normals/s against the measured rate of the draw arithmetic alone (threefry2x32-20
         # + XLA erf_inv + operand split, 96 instructions per normal: 120.5 clk per warp and normal and scheduler at 1965 MHz on
