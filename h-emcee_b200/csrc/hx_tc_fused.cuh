@@ -82,13 +82,18 @@ __device__ __forceinline__ void bits8_fix_wrap(Key key, uint32_t ks2, uint64_t e
 // normal_at<float, false> (hx_rng.cuh) -- the staged path's draw.  The central branch of XLA's erf_inv (w < 5) is evaluated
 // for all eight in straight-line code; the tail branch (|u| > 0.9966, 0.34 % of the draws) is a separate fix-up.
 __device__ __forceinline__ bool normals8_central(const uint32_t (&b)[8], float (&x)[8], float (&u)[8], float (&w)[8]) {
-  float wmax = 0.f;                  // w >= 0; one FMNMX per draw instead of FSETP + PLOP3
+  // The alu pipe (SHF / LOP3 of the hash) is what binds this kernel: every alu instruction per draw costs ~2 % (dropping the no-op
+  // FMNMX of the uniform map: 4.52 -> 4.43 ms at c5).  Tail detection = running maximum of w (one FMNMX per draw; FSETP + PLOP3
+  // took two, a sum of w^2 on the fma pipe is a superset that sends most batches through the fix-up: 4.49 ms)
+  float wmax = 0.f;
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
     // (bits >> 9) | 0x3F800000 as one IMAD.HI: hi32(bits * 2^23) + 0x3F800000 (the two fields do not overlap)
     const uint32_t m = __umulhi(b[t], c_shr9mul) + 0x3F800000u;
     const float f = __uint_as_float(m) - 1.0f;
-    u[t] = fmaxf(-0.99999994f, fmaf(f, 2.0f, -0.99999994f));      // 2 f is exact: one rounding, like fmul_rn + fadd_rn
+    // jax.random.uniform's max(minval, .) is a no-op here: f >= 0 and rounding is monotonic, so fl(2 f + lo) >= lo always -- one
+    // alu-pipe instruction (FMNMX) less per draw, same bits as normal_at (hx_rng.cuh) keeps the max for arbitrary minval
+    u[t] = fmaf(f, 2.0f, -0.99999994f);                           // 2 f is exact: one rounding, like fmul_rn + fadd_rn
     w[t] = -0.693147182f * fast_lg2(__fsub_rn(1.0f, __fmul_rn(u[t], u[t])));
     wmax = fmaxf(wmax, w[t]);
     const float ww = w[t] - 2.5f;
