@@ -42,18 +42,33 @@ __constant__ uint32_t c_shr9mul = 1u << 23;      // hi32(bits * 2^23) = bits >> 
 // y0 ^ y1 of threefry2x32-20(key, (x0, x1)) with x0 = hi + ks0, x1 = lo + ks1 already injected.  70 instructions per hash:
 // 20 x (IADD/IMAD, SHF.L.W, LOP3) + 5 key injections folded into three-input adds.  (Routing rotations through the fma pipe as
 // IMAD.WIDE by 2^r with the OR folded into the round's LOP3 was measured on B200: every such rotation made the kernel slower.)
+#ifndef HX_FUSED_IMAD_INJ
+#define HX_FUSED_IMAD_INJ 1      // hash adds as IMAD by a constant-bank 1 (fma pipe) instead of IADD3 / VIADD (alu pipe, which binds): 4.43 -> 4.36 ms at c5
+#endif
+__constant__ uint32_t c_one = 1u;                // multiplier from the constant bank: ptxas cannot fold a * c[..] + b back into an IADD3
+__device__ __forceinline__ uint32_t add_fma_pipe(uint32_t a, uint32_t b) {
+#if HX_FUSED_IMAD_INJ
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(c_one), "r"(b));
+  return r;
+#else
+  return a + b;
+#endif
+}
 __device__ __forceinline__ uint32_t tf_bits(uint32_t x0, uint32_t x1, uint32_t ks0, uint32_t ks1, uint32_t ks2) {
-#define HX_R(r) x0 += x1; x1 = __funnelshift_l(x1, x1, r) ^ x0;
+#define HX_R(r) x0 = add_fma_pipe(x0, x1); x1 = __funnelshift_l(x1, x1, r) ^ x0;
+#define HX_INJ(ka, kb) x0 = add_fma_pipe(x0, ka); x1 = add_fma_pipe(x1, kb);
   HX_R(13) HX_R(15) HX_R(26) HX_R(6)
-  x0 += ks1; x1 += ks2 + 1u;
+  HX_INJ(ks1, ks2 + 1u)
   HX_R(17) HX_R(29) HX_R(16) HX_R(24)
-  x0 += ks2; x1 += ks0 + 2u;
+  HX_INJ(ks2, ks0 + 2u)
   HX_R(13) HX_R(15) HX_R(26) HX_R(6)
-  x0 += ks0; x1 += ks1 + 3u;
+  HX_INJ(ks0, ks1 + 3u)
   HX_R(17) HX_R(29) HX_R(16) HX_R(24)
-  x0 += ks1; x1 += ks2 + 4u;
+  HX_INJ(ks1, ks2 + 4u)
   HX_R(13) HX_R(15) HX_R(26) HX_R(6)
-  x0 += ks2; x1 += ks0 + 5u;
+  HX_INJ(ks2, ks0 + 5u)
+#undef HX_INJ
 #undef HX_R
   return x0 ^ x1;
 }
@@ -69,7 +84,7 @@ __device__ __noinline__ uint32_t tf_bits_at(Key key, uint32_t ks2, uint64_t e) {
 __device__ __forceinline__ void bits8_fast(Key key, uint32_t ks2, uint64_t e, uint32_t (&b)[8]) {
   const uint32_t a0 = (uint32_t)(e >> 32) + key.k0, a1 = (uint32_t)e + key.k1;
 #pragma unroll
-  for (int t = 0; t < 8; ++t) b[t] = tf_bits(a0, a1 + (uint32_t)t, key.k0, key.k1, ks2);
+  for (int t = 0; t < 8; ++t) b[t] = tf_bits(a0, add_fma_pipe(a1, (uint32_t)t), key.k0, key.k1, ks2);
 }
 __device__ __forceinline__ void bits8_fix_wrap(Key key, uint32_t ks2, uint64_t e, uint32_t (&b)[8]) {
   if ((uint32_t)e > 0xFFFFFFF7u) {
@@ -446,8 +461,10 @@ k_tc_proj_fused(const __grid_constant__ CUtensorMap tmB, const FusedArgs f) {
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
         const int r = (int)rank * ROWS_CTA + IR * rg + 4 * b + rsub;         // row inside the 128-row tile
-        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-        if (f.diag != 1) {
+        uint4 hi, lo;
+        if (f.diag == 1) {
+          hi = make_uint4(0u, 0u, 0u, 0u); lo = hi;
+        } else {
           // (the batch after the last one is hashed too and dropped: no branch inside the straight-line block)
           uint32_t bnext[8];
           uint64_t en;
