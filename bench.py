@@ -271,8 +271,8 @@ class ClockSampler:
 
 
 # DRAM traffic of the fused draw + projection of one c5 half-move (ncu --set full, profiles/r02_c5_fused_ncu_summary.txt)
-FUSED_TRAFFIC_BYTES = 9.943e8
-FUSED_TRAFFIC_SOURCE = ("profiles/r02_c5_fused_ncu_summary.txt: dram__bytes_read.sum 765.4 MB + dram__bytes_write.sum 228.9 MB of the one "
+FUSED_TRAFFIC_BYTES = 1.002e9
+FUSED_TRAFFIC_SOURCE = ("profiles/r02_c5_fused_ncu_summary.txt: dram__bytes_read.sum 769.4 MB + dram__bytes_write.sum 232.6 MB of the one "
                         "k_tc_proj_fused launch of a half-move (algorithmic: C^T planes 134 MB + S0 131 MB; the two split-K slices add into "
                         "S0 with red.global.add, which reads it back once); staged path of round 1: 9.6 GB per half-move")
 
