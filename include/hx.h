@@ -149,10 +149,18 @@ HX_API int hx_tc_microbench(hx_ctx* ctx, int mode /* 0 draw, 1 GEMM, 2 both, 3 f
  * what = 15: 1 (default) = the momentum draw P0 = normal(key, (n, n)) (hmc_walk.py:36) is generated INSIDE the projection GEMM
  * (hx_tc_fused.cuh: RNG warps write bf16 hi/lo operand tiles into the shared memory of a CTA pair, P0 never reaches HBM) when
  * the problem is eligible (partitionable RNG layout, dim <= 1024, three-product modes), 0 = staged draw kernel + GEMM;
- * what = 16: RNG warps per CTA of the fused kernel (8 or 16; 0 = default 16); what = 17: split-K slices of the fused kernel
+ * what = 16: RNG warps per CTA of the fused kernel (8, 16, 20, 24, 28; 0 = default: 24 for a CTA pair, 28 otherwise); what = 17: split-K slices of the fused kernel
  * (0 = default: 2 from 4096 walkers per group, a function of n only so that row shards stay bit-identical); what = 18: 1 = the staged bf16 hi/lo
  * projection accumulates its three products in ONE TMEM accumulator like the fused kernel (bit-for-bit comparison of the two);
- * what = 19: fused-kernel diagnostics (1 = no draw, 2 = no MMA; garbage results)                                                  */
+ * what = 19: fused-kernel diagnostics (1 = no draw, 2 = no MMA; garbage results); what = 20: 1 = RNG warps poll for a free stage
+ * with test_wait + nanosleep instead of a parked try_wait;
+ * what = 21: operand form of the fused projection: 0 (default) by precision (AUTO: fp16 main product + e4m3 x e5m2 correction
+ * products at true scale, one accumulator; BF16X3 / TF32X3: bf16 hi/lo, three products, bit-equal to the staged kernel), 1 = bf16
+ * hi/lo, 2 = fp16 + fp8;  what = 22: 1 = the two split-K slices of the fused projection go through slice buffers and a sum kernel
+ * instead of red.global.add into the zeroed output (same bits);  what = 23: bit mask over the GEMM epilogue kinds (bit 0 STORE,
+ * 1 KICKB, 2 DOT, 3 PROP): set = row-per-lane epilogue, clear = 32 x 32 chunks transposed through shared memory for coalesced
+ * global accesses (default 0b1100; launches over many rows keep the row path for KICKB);  what = 24: start-up stagger of the fused
+ * kernel's RNG warps in ns per K-block position (default 0: measured to change nothing)                                       */
 HX_API int hx_ctx_set_tuning(hx_ctx* ctx, int what, int value);
 /* which kernel the timing hooks bracketed last: 0 = fused SIMT half-move, 1 = tcgen05 projection GEMM */
 HX_API int hx_ctx_last_path(const hx_ctx* ctx);
